@@ -1,0 +1,128 @@
+/* onnxstream_b200_kernels.h -- internal C ABI between the C++ host (engine.cpp) and the hand-written sm_100a CUDA
+ * kernels.  Device pointers + explicit shapes/strides/dtype enums in, `int` status (cudaError_t value, 0 = OK) out,
+ * no exceptions and no torch types across it.  Each entry point replaces one method of the reference's private
+ * `class XnnPack` (src/onnxstream.cpp:657-2150) or one inline pthreadpool lambda of `Model::run()`
+ * (src/onnxstream.cpp:3550-8269); the reference location is cited per function.
+ *
+ * All kernels are asynchronous on `stream` (a cudaStream_t passed as void*).
+ */
+#ifndef ONNXSTREAM_B200_KERNELS_H
+#define ONNXSTREAM_B200_KERNELS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* TensorDataType order of the reference (src/onnxstream.h:147-154). */
+enum { OSB_NONE = 0, OSB_U8 = 1, OSB_F16 = 2, OSB_F32 = 3, OSB_I64 = 4 };
+
+#define OSB_MAX_DIMS 6
+
+/* XnnPack::convert / convert_qu8 (src/onnxstream.cpp:757-834); also int64 <-> float casts (src/onnxstream.cpp:7352-7424).
+ * u8 -> float: (q - zp) * scale.  float -> u8: clamp(rint(x / scale) + zp, 0, 255). */
+int osb_convert(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, float scale, int zero_point, void* stream);
+
+/* Unary elementwise: Sigmoid (src/onnxstream.cpp:1217-1280), Cos/Sin/Sqrt/Erf (4001-4139), Pow with scalar exponent
+ * (5478-5604), Neg (7475-7542); plus the fused chains the engine recognises: SiLU (Sigmoid*x) and erf-GELU. */
+enum { OSB_UN_SIGMOID = 0, OSB_UN_SILU, OSB_UN_ERF, OSB_UN_SQRT, OSB_UN_SIN, OSB_UN_COS, OSB_UN_POW, OSB_UN_NEG,
+       OSB_UN_GELU_ERF, OSB_UN_COPY, OSB_UN_MULC, OSB_UN_ADDC, OSB_UN_RECIP_SQRT };
+int osb_unary(int op, const void* x, void* y, int dtype, size_t n, float alpha, void* stream);
+
+/* N-d broadcasting binary ops: XnnPack::add/subtract/multiply/divide (src/onnxstream.cpp:846-927, 1666-1949).
+ * Shapes are right-aligned and padded to `ndim` by the caller; stride 0 marks a broadcast dimension.
+ * OSB_BIN_MUL_GELU computes a * gelu_erf(b) (GEGLU gate), OSB_BIN_MUL_SIGMOID a * sigmoid(b). */
+enum { OSB_BIN_ADD = 0, OSB_BIN_SUB, OSB_BIN_MUL, OSB_BIN_DIV, OSB_BIN_MUL_GELU, OSB_BIN_MUL_SIGMOID };
+int osb_binary(int op, const void* a, const int64_t* a_strides, const void* b, const int64_t* b_strides,
+               void* out, const int64_t* out_shape, int ndim, int dtype, void* stream);
+
+/* Generic strided gather-copy: out[i0..] = in[in_offset + sum_k (i_k / in_div[k]) * in_stride[k]], written at
+ * out_offset + sum_k i_k * out_stride[k].  Covers XnnPack::transpose (src/onnxstream.cpp:1748-1809), Concat
+ * (4140-4299), Split (5999-6119), Slice (6499-6695), Expand (7154-7351) and nearest Resize (6120-6315, in_div = scale). */
+int osb_strided_copy(const void* in, void* out, int elem_size, int ndim, const int64_t* shape,
+                     const int64_t* in_stride, const int64_t* in_div, int64_t in_offset,
+                     const int64_t* out_stride, int64_t out_offset, void* stream);
+
+/* Tiled 2-D batched transpose [B, R, C] -> [B, C, R] (NCHW <-> NHWC relayout, src/onnxstream.cpp:2914-2955). */
+int osb_transpose2d(const void* in, void* out, int elem_size, int64_t batch, int64_t rows, int64_t cols, void* stream);
+
+/* Softmax over the last axis: XnnPack::softmax (src/onnxstream.cpp:1958-2051). */
+int osb_softmax(const void* x, void* y, int dtype, int64_t rows, int64_t cols, void* stream);
+
+/* Softmax over the last axis of (x * scale + mask[row % mask_rows]): the Mul + Softmax pair of the attention pattern
+ * (src/onnxstream.cpp:6837-6887) and the mask add of the SDPA pattern; mask may be NULL. */
+int osb_softmax_scaled(const void* x, void* y, int dtype, int64_t rows, int64_t cols, float scale, const void* mask, int64_t mask_rows, void* stream);
+
+/* InstanceNormalization on [1, C, N] contiguous (src/onnxstream.cpp:4788-5055): two-pass mean/variance per channel
+ * (the reference accumulates in double), y = scale[c] * (x - mean) / sqrt(var + eps) + bias[c]. scale/bias in `dtype`. */
+int osb_instance_norm(const void* x, void* y, int dtype, int64_t channels, int64_t n_per_channel,
+                      const void* scale, const void* bias, float eps, void* stream);
+
+/* Fused GroupNorm (+SiLU): the Reshape/InstanceNormalization/Reshape/Mul/Add[/Sigmoid/Mul] chain of the diffusers export
+ *  in one pass pair. x is [1,C,H,W] in NCHW (nhwc=0) or NHWC (nhwc=1) physical order; gamma/beta [C].
+ * `stats` is caller-provided device scratch of 2*groups doubles (sum, sum of squares per group). */
+int osb_group_norm(const void* x, void* y, int dtype, int nhwc, int64_t C, int64_t HW, int groups,
+                   const void* gamma, const void* beta, float eps, int fuse_silu, void* stats, void* stream);
+
+/* Fused LayerNorm over the last axis (ReduceMean,Sub,Pow,ReduceMean,Add,Sqrt,Div,Mul,Add chain; src/onnxstream.cpp
+ * 5237-5393 et al.).  gamma/beta may be NULL. */
+int osb_layer_norm(const void* x, void* y, int dtype, int64_t rows, int64_t cols, const void* gamma, const void* beta,
+                   float eps, void* stream);
+
+/* ReduceMean over the last axis (src/onnxstream.cpp:5237-5393). */
+int osb_reduce_mean(const void* x, void* y, int dtype, int64_t rows, int64_t cols, void* stream);
+
+/* Row gather: out[i, :] = table[idx[i], :]  (Gather axis 0, src/onnxstream.cpp:6316-6498). idx is int64 on device. */
+int osb_gather_rows(const void* table, const int64_t* idx, void* out, int64_t n_idx, int64_t table_rows, int64_t row_bytes, void* stream);
+
+/* Batched GEMM  C[b] = A[b] (M x K, row-major) * B[b] (K x N, row-major) (+ bias[N]) (+ residual[b] M x N):
+ * XnnPack::matrix_multiply / matrix_multiply_dynamic (src/onnxstream.cpp:929-1215) and the MatMul/Gemm branches
+ * (4300-4375, 5669-5861).  stride_* are element strides between batches (0 = shared operand).
+ * b_transposed: B[b] is stored N x K row-major.  Accumulation is fp32 for both dtypes.
+ * `impl`: 0 = auto (tcgen05 when dtype == f16 and the shape is eligible), 1 = force the CUDA-core reference kernel,
+ * 2 = force tcgen05 (returns an error if ineligible). */
+int osb_gemm(const void* A, const void* B, void* C, const void* bias, const void* residual,
+             int64_t batch, int64_t M, int64_t N, int64_t K,
+             int64_t stride_a, int64_t stride_b, int64_t stride_c, int b_transposed, int dtype, int impl, void* stream);
+
+/* 2-D convolution, batch 1, groups 1, dilation 1: XnnPack::convolution (src/onnxstream.cpp:1292-1534).
+ * x NHWC [H,W,Cin], w OHWI [Cout,kh,kw,Cin], bias [Cout] or NULL, y NHWC [Ho,Wo,Cout]; optional residual (same shape
+ * as y) added in the epilogue.  Padding follows the reference's re-symmetrisation: callers pass pad_top/pad_left
+ * computed as (p0+p2)/2, (p1+p3)/2 (src/onnxstream.cpp:1315-1329). */
+int osb_conv2d(const void* x, const void* w, const void* bias, const void* residual, void* y,
+               int64_t H, int64_t W, int64_t Cin, int64_t Cout, int kh, int kw, int stride, int pad_top, int pad_left,
+               int64_t Ho, int64_t Wo, int dtype, int impl, void* stream);
+
+/* Fused attention softmax(Q K^T * scale) V per head: the AttentionFusedOps branch (src/onnxstream.cpp:6696-6929).
+ * q [h,Tq,d], k [h,d,Tk] when k_transposed (the diffusers export) else [h,Tk,d], v [h,Tk,d], out [h,Tq,d].
+ * `mask` (optional, [Tq,Tk], additive, same dtype) and `kv_group` (query heads per kv head) cover the
+ * ScaledDotProductAttention branch (src/onnxstream.cpp:7767-7882). */
+int osb_attention(const void* q, const void* k, const void* v, const void* mask, void* out,
+                  int64_t heads, int64_t Tq, int64_t Tk, int64_t d, int64_t dv, float scale, int k_transposed,
+                  int64_t kv_group, int dtype, void* stream);
+
+/* qu8 GEMM / conv with XNNPACK's requantisation (bit-exact target):
+ * acc = sum (x - zx)(w - zw) + bias_i32; y = clamp(lrintf(acc * (sx*sw/sy)) + zy, 0, 255). */
+int osb_gemm_qu8(const uint8_t* A, const uint8_t* B, uint8_t* C, const int32_t* bias, int64_t M, int64_t N, int64_t K,
+                 int zx, float sx, int zw, float sw, int zy, float sy, void* stream);
+int osb_conv2d_qu8(const uint8_t* x, const uint8_t* w, const int32_t* bias, uint8_t* y,
+                   int64_t H, int64_t W, int64_t Cin, int64_t Cout, int kh, int kw, int stride, int pad_top, int pad_left,
+                   int64_t Ho, int64_t Wo, int zx, float sx, int zw, float sw, int zy, float sy, void* stream);
+
+/* Fill `n` bytes-worth of elements with a constant (ConstantOfShape, src/onnxstream.cpp:7543-7588). */
+int osb_fill(void* dst, int dtype, size_t n, float value, void* stream);
+
+/* 1 when the tcgen05/TMA GEMM path can take this problem (used by tests and the bench to assert the fast path ran). */
+int osb_gemm_tc_eligible(int64_t M, int64_t N, int64_t K, int dtype);
+
+/* Counters: number of kernel launches issued through this ABI since the last reset (bench.py's gpu_launches). */
+uint64_t osb_launch_count(void);
+void osb_launch_count_reset(void);
+uint64_t osb_tc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

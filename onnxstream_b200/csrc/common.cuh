@@ -1,0 +1,88 @@
+// common.cuh -- shared device helpers for the sm_100a kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <algorithm>
+#include "../../include/onnxstream_b200_kernels.h"
+
+using std::min;
+using std::max;
+
+extern "C" void osb_count_launch(int tensor_core);
+
+// ---- launch bookkeeping --------------------------------------------------------------------------------------
+static inline int launched(int tensor_core = 0)
+{
+    osb_count_launch(tensor_core);
+    return (int)cudaGetLastError();
+}
+
+static inline int grid_for(size_t work_items, int threads)
+{
+    size_t blocks = (work_items + threads - 1) / threads;
+    size_t cap = 148ull * 16;  // persistent-ish: at most 16 CTAs per SM, grid-stride loops cover the rest
+    if (blocks < 1) blocks = 1;
+    return (int)(blocks < cap ? blocks : cap);
+}
+
+static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+// ---- scalar conversions ----------------------------------------------------------------------------------------
+__device__ __forceinline__ float to_float(float v) { return v; }
+__device__ __forceinline__ float to_float(__half v) { return __half2float(v); }
+__device__ __forceinline__ float to_float(uint8_t v) { return (float)v; }
+template <typename T> __device__ __forceinline__ T from_float(float v);
+template <> __device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_float<__half>(float v) { return __float2half_rn(v); }
+
+// ---- 128-bit vectors -------------------------------------------------------------------------------------------
+template <typename T, int N> struct alignas(sizeof(T) * N) Vec { T v[N]; };
+
+template <typename T, int N>
+__device__ __forceinline__ Vec<T, N> load_vec(const T* p)
+{
+    return *reinterpret_cast<const Vec<T, N>*>(p);
+}
+template <typename T, int N>
+__device__ __forceinline__ void store_vec(T* p, const Vec<T, N>& v)
+{
+    *reinterpret_cast<Vec<T, N>*>(p) = v;
+}
+
+// ---- block reductions (blockDim.x multiple of 32, <= 1024) -------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float block_reduce_sum(float v, float* red)
+{
+    v = warp_sum(v);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    v = l < nw ? red[l] : 0.f;
+    v = warp_sum(v);
+    return v;
+}
+__device__ __forceinline__ float block_reduce_max(float v, float* red)
+{
+    v = warp_max(v);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    v = l < nw ? red[l] : -INFINITY;
+    v = warp_max(v);
+    return v;
+}

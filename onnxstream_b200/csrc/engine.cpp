@@ -1,0 +1,411 @@
+// engine.cpp -- infrastructure of the B200 engine: device pool, model.txt parser, weight sources, the streaming
+// HBM weight ring.  The op interpreter lives in engine_run.cpp.
+#include "engine_impl.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
+
+namespace osb {
+
+void check_cuda(int err, const char* what)
+{
+    if (err != 0) {
+        const char* s = cudaGetErrorString((cudaError_t)err);
+        throw std::runtime_error(std::string(what) + ": CUDA error " + std::to_string(err) + " (" + (s ? s : "?") + ")");
+    }
+}
+
+size_t dtype_size(DType t)
+{
+    switch (t) {
+    case DType::u8: return 1;
+    case DType::f16: return 2;
+    case DType::f32: return 4;
+    case DType::i64: return 8;
+    default: return 0;
+    }
+}
+
+const char* dtype_name(DType t)
+{
+    switch (t) {
+    case DType::u8: return "uint8";
+    case DType::f16: return "float16";
+    case DType::f32: return "float32";
+    case DType::i64: return "int64";
+    default: return "none";
+    }
+}
+
+// ================================================================================================================
+// DevicePool
+// ================================================================================================================
+
+DevBlock::~DevBlock() { if (pool && ptr) pool->release(ptr, bytes); }
+
+DevicePool::~DevicePool()
+{
+    for (auto& s : m_slabs) cudaFree(s.base);
+}
+
+void DevicePool::add_slab(size_t min_bytes)
+{
+    if (frozen) throw std::runtime_error("DevicePool: cannot grow while a CUDA graph owns the pool addresses");
+    size_t bytes = std::max<size_t>(min_bytes, m_slabs.empty() ? (size_t)256 << 20 : (size_t)512 << 20);
+    bytes = (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+    void* p = nullptr;
+    check_cuda(cudaMalloc(&p, bytes), "DevicePool cudaMalloc");
+    m_slabs.push_back({ p, bytes });
+    m_reserved += bytes;
+    release(p, bytes);
+    m_in_use += bytes;  // release() subtracts
+}
+
+DevPtr DevicePool::alloc(size_t bytes)
+{
+    if (bytes == 0) bytes = 256;
+    bytes = (bytes + 255) & ~(size_t)255;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        // best fit
+        auto best = m_free.end();
+        for (auto it = m_free.begin(); it != m_free.end(); ++it)
+            if (it->second >= bytes && (best == m_free.end() || it->second < best->second)) best = it;
+        if (best != m_free.end()) {
+            uintptr_t addr = best->first;
+            size_t sz = best->second;
+            m_free.erase(best);
+            if (sz > bytes) m_free[addr + bytes] = sz - bytes;
+            m_in_use += bytes;
+            m_high_water = std::max(m_high_water, m_in_use);
+            auto blk = std::make_shared<DevBlock>();
+            blk->ptr = (void*)addr; blk->bytes = bytes; blk->pool = this;
+            return blk;
+        }
+        add_slab(bytes);
+    }
+    throw std::runtime_error("DevicePool: allocation failed");
+}
+
+void DevicePool::release(void* ptr, size_t bytes)
+{
+    uintptr_t addr = (uintptr_t)ptr;
+    m_in_use -= std::min(m_in_use, bytes);
+    auto next = m_free.lower_bound(addr);
+    // never merge across slab boundaries
+    auto same_slab = [&](uintptr_t a, uintptr_t b) {
+        for (auto& s : m_slabs) {
+            uintptr_t lo = (uintptr_t)s.base, hi = lo + s.bytes;
+            if (a >= lo && a < hi) return b >= lo && b < hi;
+        }
+        return false;
+    };
+    if (next != m_free.end() && addr + bytes == next->first && same_slab(addr, next->first)) {
+        bytes += next->second;
+        next = m_free.erase(next);
+    }
+    if (next != m_free.begin()) {
+        auto prev = std::prev(next);
+        if (prev->first + prev->second == addr && same_slab(prev->first, addr)) {
+            prev->second += bytes;
+            return;
+        }
+    }
+    m_free[addr] = bytes;
+}
+
+// ================================================================================================================
+// parser (format: src/onnxstream.cpp:2445-2616)
+// ================================================================================================================
+
+static std::vector<std::string> split(const std::string& s, char delim)
+{
+    std::vector<std::string> out;
+    size_t start = 0;
+    while (true) {
+        size_t pos = s.find(delim, start);
+        if (pos == std::string::npos) { out.push_back(s.substr(start)); break; }
+        out.push_back(s.substr(start, pos - start));
+        start = pos + 1;
+    }
+    return out;
+}
+
+const std::string* OpDef::attr(const char* key) const
+{
+    for (auto& a : attrs) if (a.first == key) return &a.second;
+    return nullptr;
+}
+
+static TensorRef parse_tensor(const std::string& str, bool dynamic_shapes)
+{
+    TensorRef t;
+    if (str.empty()) return t;
+    size_t open = str.find('(');
+    if (open == std::string::npos || open == 0 || str.back() != ')' || str.find('(', open + 1) != std::string::npos)
+        throw std::invalid_argument("Model::parse_tensor_string: invalid tensor format.");
+    t.present = true;
+    t.name = str.substr(0, open);
+    std::string inner = str.substr(open + 1, str.size() - open - 2);
+    std::string shape;
+    size_t colon = inner.find(':');
+    if (colon == std::string::npos) {
+        shape = inner;
+    } else {
+        if (inner.find(':', colon + 1) != std::string::npos) throw std::invalid_argument("Model::parse_tensor_string: invalid tensor format.");
+        std::string ty = inner.substr(0, colon);
+        shape = inner.substr(colon + 1);
+        if (ty.rfind("uint8[", 0) == 0 && ty.back() == ']') {
+            auto rv = split(ty.substr(6, ty.size() - 7), ',');
+            if (rv.size() != 2) throw std::invalid_argument("Model::parse_tensor_string: invalid uint8 range.");
+            t.wtype = DType::u8;
+            t.scale = (float)std::stod(rv[0]);
+            t.zero_point = std::stoi(rv[1]);
+        } else if (ty == "float16") t.wtype = DType::f16;
+        else if (ty == "float32") t.wtype = DType::f32;
+        else if (ty == "int64") t.wtype = DType::i64;
+        else throw std::invalid_argument("Model::parse_tensor_string: unsupported tensor data format.");
+    }
+    if (!shape.empty()) {
+        for (auto& d : split(shape, ',')) {
+            int v = std::stoi(d);
+            if (v < 0) throw std::invalid_argument("Model::parse_tensor_string: invalid shape (dim < 0).");
+            if (v == 0 && !dynamic_shapes) throw std::invalid_argument("Model::parse_tensor_string: invalid shape (dim == 0).");
+            t.shape.push_back(v);
+        }
+    }
+    return t;
+}
+
+std::vector<OpDef> parse_model_text(const std::string& text, bool dynamic_shapes)
+{
+    std::vector<OpDef> ops;
+    size_t pos = 0, n = text.size();
+    while (pos < n) {
+        size_t end = pos;
+        while (end < n && text[end] != '\n' && text[end] != '\r') end++;
+        std::string line = text.substr(pos, end - pos);
+        size_t line_pos = pos;
+        pos = end;
+        while (pos < n && (text[pos] == '\n' || text[pos] == '\r')) pos++;
+        if (line.empty()) continue;
+        auto sections = split(line, '*');
+        if (sections.size() != 3 && sections.size() != 4) throw std::invalid_argument("Model::next_op: invalid format of model line.");
+        OpDef op;
+        auto first = split(sections[0], ':');
+        if (first.size() != 2) throw std::invalid_argument("Model::next_op: invalid format of model line.");
+        op.name = first[0];
+        op.type = first[1];
+        if (op.name.empty()) op.name = "onnxstream_fallback_name_" + std::to_string(line_pos);
+        if (sections[1].rfind("input:", 0) != 0 || sections[2].rfind("output:", 0) != 0)
+            throw std::invalid_argument("Model::next_op: invalid format of model line.");
+        for (auto& s : split(sections[1].substr(6), ';')) op.in.push_back(parse_tensor(s, dynamic_shapes));
+        for (auto& s : split(sections[2].substr(7), ';')) op.out.push_back(parse_tensor(s, dynamic_shapes));
+        if (sections.size() == 4) {
+            for (auto& kv : split(sections[3], ';')) {
+                auto p = split(kv, ':');
+                if (p.size() != 2) throw std::invalid_argument("Model::next_op: invalid format of model line.");
+                op.attrs.emplace_back(p[0], p[1]);
+            }
+        }
+        ops.push_back(std::move(op));
+    }
+    return ops;
+}
+
+// ================================================================================================================
+// weight sources
+// ================================================================================================================
+
+static void read_blob(const std::string& fn, void* dst, size_t bytes)
+{
+    FILE* f = fopen(fn.c_str(), "rb");
+    if (!f) throw std::runtime_error("read_file: unable to open file (" + fn + ").");
+    fseek(f, 0, SEEK_END);
+    long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    if (sz < 0 || (size_t)sz != bytes) { fclose(f); throw std::invalid_argument("Model::get_tensor_data: mismatch between tensor shape and data size (" + fn + ")."); }
+    size_t got = bytes ? fread(dst, 1, bytes, f) : 0;
+    fclose(f);
+    if (got != bytes) throw std::runtime_error("read_file: unable to read file.");
+}
+
+namespace {
+
+// DiskNoCacheWeightsProvider analogue (src/onnxstream.h:331-354): one read per request, straight into pinned staging.
+class DiskSource : public WeightSource {
+public:
+    const void* fetch(const std::string& name, DType, size_t bytes, void* dst) override
+    {
+        read_blob(path + name, dst, bytes);
+        return dst;
+    }
+    const char* kind() const override { return "nocache"; }
+};
+
+// RamWeightsProvider analogue (src/onnxstream.h:666-900): blobs stay in *pinned* host memory after the first load so
+// every later run streams them to HBM with cudaMemcpyAsync at full PCIe rate.
+class RamSource : public WeightSource {
+public:
+    explicit RamSource(std::unique_ptr<WeightSource> inner) : m_inner(std::move(inner)) {}
+    ~RamSource() override { for (auto& kv : m_blobs) cudaFreeHost(kv.second.ptr); }
+    struct Blob { void* ptr; size_t bytes; };
+    std::unordered_map<std::string, Blob> m_blobs;
+    std::unique_ptr<WeightSource> m_inner;
+
+    void* add(const std::string& name, size_t bytes)
+    {
+        auto it = m_blobs.find(name);
+        if (it != m_blobs.end()) { cudaFreeHost(it->second.ptr); m_blobs.erase(it); }
+        void* p = nullptr;
+        check_cuda(cudaHostAlloc(&p, std::max<size_t>(bytes, 16), cudaHostAllocDefault), "cudaHostAlloc(weights)");
+        m_blobs[name] = { p, bytes };
+        return p;
+    }
+    const void* fetch(const std::string& name, DType type, size_t bytes, void* dst) override
+    {
+        auto it = m_blobs.find(name);
+        if (it == m_blobs.end()) {
+            if (!m_inner) throw std::invalid_argument("RamWeightsProvider: weights not found: " + name);
+            m_inner->path = path;
+            void* p = add(name, bytes);
+            m_inner->fetch(name, type, bytes, p);
+            it = m_blobs.find(name);
+        }
+        if (it->second.bytes != bytes) throw std::invalid_argument("Model::get_tensor_data: mismatch between tensor shape and data size (" + name + ").");
+        return it->second.ptr;
+    }
+    bool stable_pinned() const override { return true; }
+    const char* kind() const override { return "ram"; }
+};
+
+}  // namespace
+
+std::unique_ptr<WeightSource> make_disk_source(bool) { return std::make_unique<DiskSource>(); }
+std::unique_ptr<WeightSource> make_ram_source(std::unique_ptr<WeightSource> inner) { return std::make_unique<RamSource>(std::move(inner)); }
+void* ram_source_add(WeightSource* ram, const std::string& name, size_t bytes)
+{
+    auto* r = dynamic_cast<RamSource*>(ram);
+    if (!r) return nullptr;
+    return r->add(name, bytes);
+}
+
+// ================================================================================================================
+// WeightStreamer: pinned host -> HBM ring on the copy stream
+// ================================================================================================================
+
+WeightStreamer::WeightStreamer(size_t capacity, bool host_mirror, ncclComm* comm, int rank, int nranks)
+    : m_cap((capacity + 255) & ~(size_t)255), m_comm(comm), m_rank(rank), m_nranks(nranks)
+{
+    check_cuda(cudaStreamCreateWithFlags(&m_copy, cudaStreamNonBlocking), "cudaStreamCreate(copy)");
+    check_cuda(cudaMalloc(&m_ring, m_cap), "cudaMalloc(weight ring)");
+    if (host_mirror) check_cuda(cudaHostAlloc(&m_host, m_cap, cudaHostAllocDefault), "cudaHostAlloc(weight staging)");
+}
+
+WeightStreamer::~WeightStreamer()
+{
+    cudaStreamSynchronize(m_copy);
+    for (auto& s : m_slots) { if (s.ready) cudaEventDestroy(s.ready); if (s.released_ev) cudaEventDestroy(s.released_ev); }
+    for (auto e : m_event_pool) cudaEventDestroy(e);
+    if (m_ring) cudaFree(m_ring);
+    if (m_host) cudaFreeHost(m_host);
+    cudaStreamDestroy(m_copy);
+}
+
+cudaEvent_t WeightStreamer::get_event()
+{
+    if (!m_event_pool.empty()) { auto e = m_event_pool.back(); m_event_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    check_cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+    return e;
+}
+
+void WeightStreamer::begin_run()
+{
+    m_live = 0;
+    m_streamed = 0;
+}
+
+// Reserve [off, off+bytes) in the ring.  Slots are FIFO in graph order; a slot can be overwritten once its consumer
+// has been *enqueued* (release event recorded) -- the copy stream then waits on that event, so the host never blocks
+// on the GPU except when it must overwrite the pinned host mirror of a slot whose H2D has not finished (disk modes).
+bool WeightStreamer::try_reserve(size_t bytes, size_t& off)
+{
+    if (bytes > m_cap) throw std::runtime_error("WeightStreamer: node footprint exceeds ring capacity");
+    size_t cand = m_head;
+    if (cand + bytes > m_cap) cand = 0;  // wrap; the tail remainder is skipped
+    auto overlaps = [&](const Slot& s) { return s.off < cand + bytes && cand < s.off + s.bytes; };
+    while (true) {
+        bool any = false;
+        for (auto& s : m_slots) if (overlaps(s)) { any = true; break; }
+        if (!any) break;
+        Slot& f = m_slots.front();
+        if (!f.released) return false;
+        check_cuda(cudaStreamWaitEvent(m_copy, f.released_ev, 0), "cudaStreamWaitEvent(copy, released)");
+        if (m_host) check_cuda(cudaEventSynchronize(f.ready), "cudaEventSynchronize(h2d done)");
+        m_live -= f.bytes;
+        m_event_pool.push_back(f.ready);
+        m_event_pool.push_back(f.released_ev);
+        m_slots.pop_front();
+    }
+    off = cand;
+    m_head = cand + bytes;
+    return true;
+}
+
+WeightStreamer::Slot* WeightStreamer::stage(WeightSource& src, const std::vector<Request>& node, bool must)
+{
+    size_t total = 0;
+    for (auto& r : node) total += (r.bytes + 255) & ~(size_t)255;
+    if (total == 0) total = 256;
+    size_t off = 0;
+    if (!try_reserve(total, off)) {
+        if (must) throw std::runtime_error("WeightStreamer: ring full although all previous nodes were released");
+        return nullptr;
+    }
+    m_slots.emplace_back();
+    Slot& s = m_slots.back();
+    s.off = off;
+    s.bytes = total;
+    s.ready = get_event();
+    s.released_ev = get_event();
+    s.released = false;
+    bool do_h2d = (m_nranks == 1) || (m_rank == 0);
+    size_t cur = off;
+    for (auto& r : node) {
+        Blob b;
+        b.dev = (char*)m_ring + cur;
+        b.bytes = r.bytes;
+        // every rank reads the host bytes (small constants are evaluated on the host); only the root uploads them
+        b.host = src.fetch(r.name, r.type, r.bytes, m_host ? (char*)m_host + cur : nullptr);
+        if (r.bytes && r.type != DType::i64) {
+            if (do_h2d) check_cuda(cudaMemcpyAsync(b.dev, b.host, r.bytes, cudaMemcpyHostToDevice, m_copy), "cudaMemcpyAsync(weights H2D)");
+            if (m_nranks > 1) nccl_broadcast(b.dev, r.bytes);
+            m_streamed += r.bytes;
+        }
+        s.blobs.push_back(b);
+        cur += (r.bytes + 255) & ~(size_t)255;
+    }
+    check_cuda(cudaEventRecord(s.ready, m_copy), "cudaEventRecord(ready)");
+    m_live += s.bytes;
+    m_peak_live = std::max(m_peak_live, m_live);
+    return &s;
+}
+
+void WeightStreamer::release(Slot* s, cudaStream_t compute)
+{
+    check_cuda(cudaEventRecord(s->released_ev, compute), "cudaEventRecord(released)");
+    s->released = true;
+}
+
+void WeightStreamer::end_run(cudaStream_t compute)
+{
+    // everything staged must have been consumed; keep slots (their events order the next run's copies)
+    for (auto& s : m_slots) if (!s.released) { check_cuda(cudaEventRecord(s.released_ev, compute), "cudaEventRecord"); s.released = true; }
+}
+
+}  // namespace osb

@@ -1,0 +1,725 @@
+// kernels_basic.cu -- bandwidth-bound node kernels for sm_100a: dtype conversion, unary / broadcasting binary
+// elementwise, strided copies (transpose / concat / slice / expand / nearest resize), softmax, InstanceNorm,
+// fused GroupNorm(+SiLU), fused LayerNorm, ReduceMean, row gather.  Each replaces an XnnPack method or an inline
+// pthreadpool lambda of the reference's Model::run(); see include/onnxstream_b200_kernels.h for file:line citations.
+//
+// Design rules (HBM-bound work): 128-bit vectorised accesses where alignment allows, grid-stride loops sized as a
+// multiple of the SM count, fp32 math on fp16 storage, every tensor read once and written once.
+
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------
+// convert
+// ------------------------------------------------------------------------------------------------------------
+
+template <typename S, typename D>
+__global__ void convert_kernel(const S* __restrict__ src, D* __restrict__ dst, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = from_float<D>(to_float(src[i]));
+}
+
+template <typename D>
+__global__ void dequant_kernel(const uint8_t* __restrict__ src, D* __restrict__ dst, size_t n, float scale, int zp)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = from_float<D>((float)((int)src[i] - zp) * scale);
+}
+
+template <typename S>
+__global__ void quant_kernel(const S* __restrict__ src, uint8_t* __restrict__ dst, size_t n, float scale, int zp)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float q = rintf(to_float(src[i]) / scale) + (float)zp;
+        dst[i] = (uint8_t)fminf(fmaxf(q, 0.f), 255.f);
+    }
+}
+
+__global__ void i64_to_float_kernel(const int64_t* __restrict__ src, float* __restrict__ dst, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = (float)src[i];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// unary
+// ------------------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ float apply_unary(int op, float x, float alpha)
+{
+    switch (op) {
+    case OSB_UN_SIGMOID: return 1.f / (1.f + expf(-x));
+    case OSB_UN_SILU: return x / (1.f + expf(-x));
+    case OSB_UN_ERF: return erff(x);
+    case OSB_UN_SQRT: return sqrtf(x);
+    case OSB_UN_SIN: return sinf(x);
+    case OSB_UN_COS: return cosf(x);
+    case OSB_UN_POW: return alpha == 2.f ? x * x : powf(x, alpha);
+    case OSB_UN_NEG: return -x;
+    case OSB_UN_GELU_ERF: return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+    case OSB_UN_MULC: return x * alpha;
+    case OSB_UN_ADDC: return x + alpha;
+    case OSB_UN_RECIP_SQRT: return rsqrtf(x);
+    default: return x;
+    }
+}
+
+template <typename T, int VEC>
+__global__ void unary_kernel(int op, const T* __restrict__ x, T* __restrict__ y, size_t n, float alpha)
+{
+    size_t nvec = n / VEC;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+        Vec<T, VEC> v = load_vec<T, VEC>(x + i * VEC);
+#pragma unroll
+        for (int k = 0; k < VEC; k++) v.v[k] = from_float<T>(apply_unary(op, to_float(v.v[k]), alpha));
+        store_vec<T, VEC>(y + i * VEC, v);
+    }
+    if (blockIdx.x == 0) {
+        for (size_t i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x)
+            y[i] = from_float<T>(apply_unary(op, to_float(x[i]), alpha));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// binary with broadcasting
+// ------------------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ float apply_binary(int op, float a, float b)
+{
+    switch (op) {
+    case OSB_BIN_ADD: return a + b;
+    case OSB_BIN_SUB: return a - b;
+    case OSB_BIN_MUL: return a * b;
+    case OSB_BIN_DIV: return a / b;
+    case OSB_BIN_MUL_GELU: return a * (0.5f * b * (1.f + erff(b * 0.70710678118654752f)));
+    case OSB_BIN_MUL_SIGMOID: return a / (1.f + expf(-b));
+    default: return a;
+    }
+}
+
+struct BinParams {
+    int64_t shape[OSB_MAX_DIMS];
+    int64_t as[OSB_MAX_DIMS];
+    int64_t bs[OSB_MAX_DIMS];
+    int ndim;
+};
+
+// fast path: both operands contiguous & same shape, or one of them a scalar
+template <typename T, int VEC>
+__global__ void binary_flat_kernel(int op, const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, size_t n, int a_scalar, int b_scalar)
+{
+    float sa = a_scalar ? to_float(a[0]) : 0.f, sb = b_scalar ? to_float(b[0]) : 0.f;
+    size_t nvec = n / VEC;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+        Vec<T, VEC> va, vb, vo;
+        if (!a_scalar) va = load_vec<T, VEC>(a + i * VEC);
+        if (!b_scalar) vb = load_vec<T, VEC>(b + i * VEC);
+#pragma unroll
+        for (int k = 0; k < VEC; k++)
+            vo.v[k] = from_float<T>(apply_binary(op, a_scalar ? sa : to_float(va.v[k]), b_scalar ? sb : to_float(vb.v[k])));
+        store_vec<T, VEC>(out + i * VEC, vo);
+    }
+    if (blockIdx.x == 0)
+        for (size_t i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x)
+            out[i] = from_float<T>(apply_binary(op, a_scalar ? sa : to_float(a[i]), b_scalar ? sb : to_float(b[i])));
+}
+
+// inner-broadcast path: out[r, c] = a[r, c] (op) b[c]  (or b[r]); covers bias adds and gamma/beta in channel-last tensors
+template <typename T, int VEC>
+__global__ void binary_rowcol_kernel(int op, const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out,
+                                     int64_t rows, int64_t cols, int b_per_row, int swap)
+{
+    int64_t cvec = cols / VEC;
+    int64_t total = rows * cvec;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / cvec, c = (i % cvec) * VEC;
+        Vec<T, VEC> va = load_vec<T, VEC>(a + r * cols + c), vb, vo;
+        float sb = 0.f;
+        if (b_per_row) sb = to_float(b[r]); else vb = load_vec<T, VEC>(b + c);
+#pragma unroll
+        for (int k = 0; k < VEC; k++) {
+            float x = to_float(va.v[k]), y = b_per_row ? sb : to_float(vb.v[k]);
+            vo.v[k] = from_float<T>(swap ? apply_binary(op, y, x) : apply_binary(op, x, y));
+        }
+        store_vec<T, VEC>(out + r * cols + c, vo);
+    }
+}
+
+template <typename T>
+__global__ void binary_generic_kernel(int op, const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, BinParams p, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        size_t rem = i;
+        int64_t ao = 0, bo = 0;
+#pragma unroll
+        for (int d = OSB_MAX_DIMS - 1; d >= 0; d--) {
+            if (d < p.ndim) {
+                int64_t idx = rem % p.shape[d];
+                rem /= p.shape[d];
+                ao += idx * p.as[d];
+                bo += idx * p.bs[d];
+            }
+        }
+        out[i] = from_float<T>(apply_binary(op, to_float(a[ao]), to_float(b[bo])));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// strided copy
+// ------------------------------------------------------------------------------------------------------------
+
+struct CopyParams {
+    int64_t shape[OSB_MAX_DIMS];
+    int64_t is[OSB_MAX_DIMS];
+    int64_t idiv[OSB_MAX_DIMS];
+    int64_t os[OSB_MAX_DIMS];
+    int64_t in_off, out_off;
+    int ndim;
+};
+
+template <typename T>
+__global__ void strided_copy_kernel(const T* __restrict__ in, T* __restrict__ out, CopyParams p, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        size_t rem = i;
+        int64_t io = p.in_off, oo = p.out_off;
+#pragma unroll
+        for (int d = OSB_MAX_DIMS - 1; d >= 0; d--) {
+            if (d < p.ndim) {
+                int64_t idx = rem % p.shape[d];
+                rem /= p.shape[d];
+                io += (idx / p.idiv[d]) * p.is[d];
+                oo += idx * p.os[d];
+            }
+        }
+        out[oo] = in[io];
+    }
+}
+
+// [B, R, C] -> [B, C, R] through a 32x33 shared tile (coalesced on both sides)
+template <typename T>
+__global__ void transpose2d_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t rows, int64_t cols)
+{
+    __shared__ T tile[32][33];
+    int64_t b = blockIdx.z;
+    const T* src = in + b * rows * cols;
+    T* dst = out + b * rows * cols;
+    int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int64_t r = r0 + j, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[j][threadIdx.x] = src[r * cols + c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int64_t c = c0 + j, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) dst[c * rows + r] = tile[threadIdx.x][j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// reductions: softmax / layernorm / reduce-mean (one CTA per row, row cached in registers when it fits)
+// ------------------------------------------------------------------------------------------------------------
+
+template <typename T>
+__global__ void softmax_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int64_t cols)
+{
+    __shared__ float red[32];
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        const T* xr = x + r * cols;
+        T* yr = y + r * cols;
+        float mx = -INFINITY;
+        for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) mx = fmaxf(mx, to_float(xr[c]));
+        mx = block_reduce_max(mx, red);
+        float sum = 0.f;
+        for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) sum += expf(to_float(xr[c]) - mx);
+        sum = block_reduce_sum(sum, red);
+        float inv = 1.f / sum;
+        for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) yr[c] = from_float<T>(expf(to_float(xr[c]) - mx) * inv);
+    }
+}
+
+template <typename T>
+__global__ void layer_norm_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int64_t cols,
+                                  const T* __restrict__ gamma, const T* __restrict__ beta, float eps)
+{
+    __shared__ float red[32];
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        const T* xr = x + r * cols;
+        T* yr = y + r * cols;
+        float s = 0.f;
+        for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) s += to_float(xr[c]);
+        float mean = block_reduce_sum(s, red) / (float)cols;
+        float v = 0.f;
+        for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) { float d = to_float(xr[c]) - mean; v += d * d; }
+        float var = block_reduce_sum(v, red) / (float)cols;
+        float rstd = 1.f / sqrtf(var + eps);
+        for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) {
+            float o = (to_float(xr[c]) - mean) * rstd;
+            if (gamma) o *= to_float(gamma[c]);
+            if (beta) o += to_float(beta[c]);
+            yr[c] = from_float<T>(o);
+        }
+    }
+}
+
+template <typename T>
+__global__ void reduce_mean_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int64_t cols)
+{
+    __shared__ float red[32];
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        const T* xr = x + r * cols;
+        float s = 0.f;
+        for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) s += to_float(xr[c]);
+        s = block_reduce_sum(s, red);
+        if (threadIdx.x == 0) y[r] = from_float<T>(s / (float)cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// InstanceNorm on [C, N]: one CTA cluster-free design -- grid (C, splits); stats via fp32 partials + double finish
+// ------------------------------------------------------------------------------------------------------------
+
+// pass 1: per (channel, split) partial sum and sum of squares, accumulated in double like the reference.
+template <typename T>
+__global__ void inorm_stats_kernel(const T* __restrict__ x, double* __restrict__ partial, int64_t n_per_c, int splits)
+{
+    __shared__ double red[64];
+    int64_t c = blockIdx.x;
+    int s = blockIdx.y;
+    int64_t chunk = (n_per_c + splits - 1) / splits;
+    int64_t lo = s * chunk, hi = min(lo + chunk, n_per_c);
+    const T* xc = x + c * n_per_c;
+    double sum = 0.0, sq = 0.0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) { double v = (double)to_float(xc[i]); sum += v; sq += v * v; }
+    // block reduce (double)
+    for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (l == 0) { red[w] = sum; red[32 + w] = sq; }
+    __syncthreads();
+    if (w == 0) {
+        sum = l < nw ? red[l] : 0.0; sq = l < nw ? red[32 + l] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+        if (l == 0) { partial[(c * splits + s) * 2] = sum; partial[(c * splits + s) * 2 + 1] = sq; }
+    }
+}
+
+template <typename T>
+__global__ void inorm_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const double* __restrict__ partial, int64_t n_per_c, int splits,
+                                   const T* __restrict__ scale, const T* __restrict__ bias, float eps)
+{
+    int64_t c = blockIdx.x;
+    double sum = 0.0, sq = 0.0;
+    for (int s = 0; s < splits; s++) { sum += partial[(c * splits + s) * 2]; sq += partial[(c * splits + s) * 2 + 1]; }
+    double mean = sum / (double)n_per_c;
+    double var = sq / (double)n_per_c - mean * mean;
+    if (var < 0) var = 0;
+    float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    float g = scale ? to_float(scale[c]) : 1.f, b = bias ? to_float(bias[c]) : 0.f;
+    float m = (float)mean;
+    int64_t chunk = (n_per_c + gridDim.y - 1) / gridDim.y;
+    int64_t lo = blockIdx.y * chunk, hi = min(lo + chunk, n_per_c);
+    const T* xc = x + c * n_per_c;
+    T* yc = y + c * n_per_c;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) yc[i] = from_float<T>((to_float(xc[i]) - m) * rstd * g + b);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// GroupNorm (+SiLU) on [C, HW] (NCHW) or [HW, C] (NHWC)
+// ------------------------------------------------------------------------------------------------------------
+
+// NCHW: group g = contiguous slab of (C/G)*HW elements -> same as instance norm stats with C := G.
+// NHWC: each pixel row holds C channels; a CTA takes a strip of pixels, accumulates per-channel partials in registers
+// (thread t owns channels t, t+blockDim, ...), folds them to groups through shared memory, then atomically adds to stats.
+template <typename T>
+__global__ void gn_stats_nhwc_kernel(const T* __restrict__ x, double* __restrict__ stats, int64_t C, int64_t HW, int groups, int64_t pix_per_cta)
+{
+    extern __shared__ float sm[];  // 2 * groups
+    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    int64_t p0 = (int64_t)blockIdx.x * pix_per_cta, p1 = min(p0 + pix_per_cta, HW);
+    int cpg = (int)(C / groups);
+    for (int64_t c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f, q = 0.f;
+        for (int64_t p = p0; p < p1; p++) { float v = to_float(x[p * C + c]); s += v; q += v * v; }
+        int g = (int)(c / cpg);
+        atomicAdd(&sm[2 * g], s);
+        atomicAdd(&sm[2 * g + 1], q);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(&stats[i], (double)sm[i]);
+}
+
+template <typename T>
+__global__ void gn_stats_nchw_kernel(const T* __restrict__ x, double* __restrict__ stats, int64_t n_per_g, int splits)
+{
+    __shared__ float red[32];
+    int64_t g = blockIdx.x;
+    int64_t chunk = (n_per_g + splits - 1) / splits;
+    int64_t lo = blockIdx.y * chunk, hi = min(lo + chunk, n_per_g);
+    const T* xg = x + g * n_per_g;
+    float s = 0.f, q = 0.f;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) { float v = to_float(xg[i]); s += v; q += v * v; }
+    s = block_reduce_sum(s, red);
+    q = block_reduce_sum(q, red);
+    if (threadIdx.x == 0) { atomicAdd(&stats[2 * g], (double)s); atomicAdd(&stats[2 * g + 1], (double)q); }
+}
+
+template <typename T, int VEC>
+__global__ void gn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const double* __restrict__ stats, int nhwc, int64_t C, int64_t HW, int groups,
+                                const T* __restrict__ gamma, const T* __restrict__ beta, float eps, int silu)
+{
+    int cpg = (int)(C / groups);
+    double inv_n = 1.0 / (double)((int64_t)cpg * HW);
+    size_t n = (size_t)C * HW, nvec = n / VEC;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+        size_t e = i * VEC;
+        Vec<T, VEC> v = load_vec<T, VEC>(x + e);
+#pragma unroll
+        for (int k = 0; k < VEC; k++) {
+            int64_t c = nhwc ? (int64_t)((e + k) % C) : (int64_t)((e + k) / HW);
+            int g = (int)(c / cpg);
+            double meand = stats[2 * g] * inv_n;
+            double vard = stats[2 * g + 1] * inv_n - meand * meand;
+            float mean = (float)meand;
+            float rstd = rsqrtf(fmaxf((float)vard, 0.f) + eps);
+            float o = (to_float(v.v[k]) - mean) * rstd;
+            o = o * (gamma ? to_float(gamma[c]) : 1.f) + (beta ? to_float(beta[c]) : 0.f);
+            if (silu) o = o / (1.f + expf(-o));
+            v.v[k] = from_float<T>(o);
+        }
+        store_vec<T, VEC>(y + e, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// gather rows, fill
+// ------------------------------------------------------------------------------------------------------------
+
+__global__ void gather_rows_kernel(const uint8_t* __restrict__ table, const int64_t* __restrict__ idx, uint8_t* __restrict__ out,
+                                   int64_t n_idx, int64_t table_rows, int64_t row_bytes)
+{
+    for (int64_t r = blockIdx.x; r < n_idx; r += gridDim.x) {
+        int64_t src = idx[r];
+        if (src < 0) src += table_rows;
+        const uint8_t* s = table + src * row_bytes;
+        uint8_t* d = out + r * row_bytes;
+        if ((row_bytes & 15) == 0 && (((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
+            for (int64_t i = threadIdx.x; i < row_bytes / 16; i += blockDim.x) ((int4*)d)[i] = ((const int4*)s)[i];
+        } else {
+            for (int64_t i = threadIdx.x; i < row_bytes; i += blockDim.x) d[i] = s[i];
+        }
+    }
+}
+
+template <typename T>
+__global__ void fill_kernel(T* dst, size_t n, float v)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = from_float<T>(v);
+}
+
+bool contiguous_like(const int64_t* strides, const int64_t* shape, int ndim)
+{
+    int64_t s = 1;
+    for (int d = ndim - 1; d >= 0; d--) {
+        if (shape[d] != 1 && strides[d] != s) return false;
+        s *= shape[d];
+    }
+    return true;
+}
+
+bool all_zero(const int64_t* strides, const int64_t* shape, int ndim)
+{
+    for (int d = 0; d < ndim; d++) if (shape[d] != 1 && strides[d] != 0) return false;
+    return true;
+}
+
+} // namespace
+
+template <typename T, int VEC>
+static int binary_dispatch(int op, const T* a, const int64_t* as, const T* b, const int64_t* bs, T* out, const int64_t* shape, int ndim, cudaStream_t st)
+{
+    size_t n = 1;
+    for (int d = 0; d < ndim; d++) n *= (size_t)shape[d];
+    if (n == 0) return 0;
+    bool al = aligned16(a) && aligned16(b) && aligned16(out);
+    bool a_contig = contiguous_like(as, shape, ndim), b_contig = contiguous_like(bs, shape, ndim);
+    bool a_scalar = all_zero(as, shape, ndim), b_scalar = all_zero(bs, shape, ndim);
+    if ((a_contig || a_scalar) && (b_contig || b_scalar)) {
+        if (al || (a_scalar && aligned16(b) && aligned16(out)) || (b_scalar && aligned16(a) && aligned16(out)))
+            binary_flat_kernel<T, VEC><<<grid_for(n / VEC + 1, 256), 256, 0, st>>>(op, a, b, out, n, a_scalar && !a_contig, b_scalar && !b_contig);
+        else
+            binary_flat_kernel<T, 1><<<grid_for(n, 256), 256, 0, st>>>(op, a, b, out, n, a_scalar && !a_contig, b_scalar && !b_contig);
+        return launched();
+    }
+    // one operand contiguous, the other varies only along the last dim (per-column) or is constant along it (per-row)
+    for (int swap = 0; swap < 2; swap++) {
+        const int64_t* fs = swap ? bs : as;      // full operand
+        const int64_t* ps = swap ? as : bs;      // partial operand
+        const T* full = swap ? b : a;
+        const T* part = swap ? a : b;
+        if (!contiguous_like(fs, shape, ndim)) continue;
+        int64_t cols = shape[ndim - 1], rows = (int64_t)(n / (size_t)cols);
+        // per-column: strides zero on all but the last dim, last dim stride 1
+        bool percol = (cols == 1 || ps[ndim - 1] == 1);
+        for (int d = 0; d < ndim - 1 && percol; d++) if (shape[d] != 1 && ps[d] != 0) percol = false;
+        if (percol && cols % VEC == 0 && aligned16(full) && aligned16(part) && aligned16(out)) {
+            binary_rowcol_kernel<T, VEC><<<grid_for((size_t)rows * (cols / VEC), 256), 256, 0, st>>>(op, full, part, out, rows, cols, 0, swap);
+            return launched();
+        }
+        // per-row: [R, 1] against [R, cols] where the partial operand is contiguous over the leading dims
+        if (ps[ndim - 1] == 0 || cols == 1) {
+            bool perrow = true;
+            int64_t s = 1;
+            for (int d = ndim - 2; d >= 0; d--) { if (shape[d] != 1 && ps[d] != s) perrow = false; s *= shape[d]; }
+            if (perrow && cols % VEC == 0 && aligned16(full) && aligned16(out)) {
+                binary_rowcol_kernel<T, VEC><<<grid_for((size_t)rows * (cols / VEC), 256), 256, 0, st>>>(op, full, part, out, rows, cols, 1, swap);
+                return launched();
+            }
+        }
+    }
+    BinParams p;
+    p.ndim = ndim;
+    for (int d = 0; d < OSB_MAX_DIMS; d++) { p.shape[d] = d < ndim ? shape[d] : 1; p.as[d] = d < ndim ? as[d] : 0; p.bs[d] = d < ndim ? bs[d] : 0; }
+    binary_generic_kernel<T><<<grid_for(n, 256), 256, 0, st>>>(op, a, b, out, p, n);
+    return launched();
+}
+
+// ================================================================================================================
+// C ABI
+// ================================================================================================================
+
+extern "C" {
+
+int osb_convert(const void* src, int sd, void* dst, int dd, size_t n, float scale, int zp, void* stream)
+{
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int grid = grid_for(n, 256);
+    if (sd == OSB_F16 && dd == OSB_F32) convert_kernel<__half, float><<<grid, 256, 0, st>>>((const __half*)src, (float*)dst, n);
+    else if (sd == OSB_F32 && dd == OSB_F16) convert_kernel<float, __half><<<grid, 256, 0, st>>>((const float*)src, (__half*)dst, n);
+    else if (sd == OSB_U8 && dd == OSB_F32) dequant_kernel<float><<<grid, 256, 0, st>>>((const uint8_t*)src, (float*)dst, n, scale, zp);
+    else if (sd == OSB_U8 && dd == OSB_F16) dequant_kernel<__half><<<grid, 256, 0, st>>>((const uint8_t*)src, (__half*)dst, n, scale, zp);
+    else if (sd == OSB_F32 && dd == OSB_U8) quant_kernel<float><<<grid, 256, 0, st>>>((const float*)src, (uint8_t*)dst, n, scale, zp);
+    else if (sd == OSB_F16 && dd == OSB_U8) quant_kernel<__half><<<grid, 256, 0, st>>>((const __half*)src, (uint8_t*)dst, n, scale, zp);
+    else if (sd == OSB_I64 && dd == OSB_F32) i64_to_float_kernel<<<grid, 256, 0, st>>>((const int64_t*)src, (float*)dst, n);
+    else return (int)cudaErrorInvalidValue;
+    return launched();
+}
+
+int osb_unary(int op, const void* x, void* y, int dtype, size_t n, float alpha, void* stream)
+{
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    bool al = aligned16(x) && aligned16(y);
+    if (dtype == OSB_F16) {
+        if (al) unary_kernel<__half, 8><<<grid_for(n / 8 + 1, 256), 256, 0, st>>>(op, (const __half*)x, (__half*)y, n, alpha);
+        else unary_kernel<__half, 1><<<grid_for(n, 256), 256, 0, st>>>(op, (const __half*)x, (__half*)y, n, alpha);
+    } else if (dtype == OSB_F32) {
+        if (al) unary_kernel<float, 4><<<grid_for(n / 4 + 1, 256), 256, 0, st>>>(op, (const float*)x, (float*)y, n, alpha);
+        else unary_kernel<float, 1><<<grid_for(n, 256), 256, 0, st>>>(op, (const float*)x, (float*)y, n, alpha);
+    } else return (int)cudaErrorInvalidValue;
+    return launched();
+}
+
+int osb_binary(int op, const void* a, const int64_t* as, const void* b, const int64_t* bs, void* out, const int64_t* shape, int ndim, int dtype, void* stream)
+{
+    if (ndim < 1 || ndim > OSB_MAX_DIMS) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == OSB_F16) return binary_dispatch<__half, 8>(op, (const __half*)a, as, (const __half*)b, bs, (__half*)out, shape, ndim, st);
+    if (dtype == OSB_F32) return binary_dispatch<float, 4>(op, (const float*)a, as, (const float*)b, bs, (float*)out, shape, ndim, st);
+    return (int)cudaErrorInvalidValue;
+}
+
+int osb_strided_copy(const void* in, void* out, int elem_size, int ndim, const int64_t* shape, const int64_t* in_stride, const int64_t* in_div,
+                     int64_t in_offset, const int64_t* out_stride, int64_t out_offset, void* stream)
+{
+    if (ndim < 1 || ndim > OSB_MAX_DIMS) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = (cudaStream_t)stream;
+    CopyParams p;
+    p.ndim = ndim; p.in_off = in_offset; p.out_off = out_offset;
+    size_t n = 1;
+    for (int d = 0; d < OSB_MAX_DIMS; d++) {
+        p.shape[d] = d < ndim ? shape[d] : 1;
+        p.is[d] = d < ndim ? in_stride[d] : 0;
+        p.idiv[d] = (d < ndim && in_div) ? in_div[d] : 1;
+        p.os[d] = d < ndim ? out_stride[d] : 0;
+        if (d < ndim) n *= (size_t)shape[d];
+    }
+    if (n == 0) return 0;
+    // widen the element when the innermost dimension is contiguous on both sides and everything is aligned
+    int es = elem_size;
+    if (p.is[ndim - 1] == 1 && p.os[ndim - 1] == 1 && p.idiv[ndim - 1] == 1) {
+        for (int wide = 16; wide > es; wide >>= 1) {
+            int f = wide / es;
+            bool ok = (p.shape[ndim - 1] % f == 0) && (p.in_off % f == 0) && (p.out_off % f == 0) &&
+                      ((uintptr_t)in % wide == 0) && ((uintptr_t)out % wide == 0);
+            for (int d = 0; d < ndim - 1 && ok; d++) ok = (p.is[d] % f == 0) && (p.os[d] % f == 0);
+            if (ok) {
+                p.shape[ndim - 1] /= f; p.in_off /= f; p.out_off /= f;
+                for (int d = 0; d < ndim - 1; d++) { p.is[d] /= f; p.os[d] /= f; }
+                n /= f; es = wide;
+                break;
+            }
+        }
+    }
+    int grid = grid_for(n, 256);
+    switch (es) {
+    case 1: strided_copy_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)in, (uint8_t*)out, p, n); break;
+    case 2: strided_copy_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)in, (uint16_t*)out, p, n); break;
+    case 4: strided_copy_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)in, (uint32_t*)out, p, n); break;
+    case 8: strided_copy_kernel<uint2><<<grid, 256, 0, st>>>((const uint2*)in, (uint2*)out, p, n); break;
+    case 16: strided_copy_kernel<uint4><<<grid, 256, 0, st>>>((const uint4*)in, (uint4*)out, p, n); break;
+    default: return (int)cudaErrorInvalidValue;
+    }
+    return launched();
+}
+
+int osb_transpose2d(const void* in, void* out, int elem_size, int64_t batch, int64_t rows, int64_t cols, void* stream)
+{
+    if (batch * rows * cols == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)batch), block(32, 8);
+    if (grid.y > 65535 || grid.z > 65535) return (int)cudaErrorInvalidValue;
+    switch (elem_size) {
+    case 1: transpose2d_kernel<uint8_t><<<grid, block, 0, st>>>((const uint8_t*)in, (uint8_t*)out, rows, cols); break;
+    case 2: transpose2d_kernel<uint16_t><<<grid, block, 0, st>>>((const uint16_t*)in, (uint16_t*)out, rows, cols); break;
+    case 4: transpose2d_kernel<uint32_t><<<grid, block, 0, st>>>((const uint32_t*)in, (uint32_t*)out, rows, cols); break;
+    default: return (int)cudaErrorInvalidValue;
+    }
+    return launched();
+}
+
+int osb_softmax(const void* x, void* y, int dtype, int64_t rows, int64_t cols, void* stream)
+{
+    if (rows * cols == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int threads = cols >= 1024 ? 256 : (cols >= 256 ? 128 : 32);
+    int grid = (int)min<int64_t>(rows, 148 * 16);
+    if (dtype == OSB_F16) softmax_kernel<__half><<<grid, threads, 0, st>>>((const __half*)x, (__half*)y, rows, cols);
+    else if (dtype == OSB_F32) softmax_kernel<float><<<grid, threads, 0, st>>>((const float*)x, (float*)y, rows, cols);
+    else return (int)cudaErrorInvalidValue;
+    return launched();
+}
+
+int osb_layer_norm(const void* x, void* y, int dtype, int64_t rows, int64_t cols, const void* gamma, const void* beta, float eps, void* stream)
+{
+    if (rows * cols == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int threads = cols >= 1024 ? 256 : (cols >= 256 ? 128 : 32);
+    int grid = (int)min<int64_t>(rows, 148 * 16);
+    if (dtype == OSB_F16) layer_norm_kernel<__half><<<grid, threads, 0, st>>>((const __half*)x, (__half*)y, rows, cols, (const __half*)gamma, (const __half*)beta, eps);
+    else if (dtype == OSB_F32) layer_norm_kernel<float><<<grid, threads, 0, st>>>((const float*)x, (float*)y, rows, cols, (const float*)gamma, (const float*)beta, eps);
+    else return (int)cudaErrorInvalidValue;
+    return launched();
+}
+
+int osb_reduce_mean(const void* x, void* y, int dtype, int64_t rows, int64_t cols, void* stream)
+{
+    if (rows * cols == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int threads = cols >= 1024 ? 256 : (cols >= 256 ? 128 : 32);
+    int grid = (int)min<int64_t>(rows, 148 * 16);
+    if (dtype == OSB_F16) reduce_mean_kernel<__half><<<grid, threads, 0, st>>>((const __half*)x, (__half*)y, rows, cols);
+    else if (dtype == OSB_F32) reduce_mean_kernel<float><<<grid, threads, 0, st>>>((const float*)x, (float*)y, rows, cols);
+    else return (int)cudaErrorInvalidValue;
+    return launched();
+}
+
+// scratch for instance-norm partials: grown on demand, reused across calls (single compute stream)
+static double* g_inorm_partial = nullptr;
+static size_t g_inorm_partial_cap = 0;
+
+int osb_instance_norm(const void* x, void* y, int dtype, int64_t channels, int64_t n_per_c, const void* scale, const void* bias, float eps, void* stream)
+{
+    if (channels * n_per_c == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int splits = (int)max<int64_t>(1, min<int64_t>(64, (148 * 4 + channels - 1) / channels));
+    while (splits > 1 && n_per_c / splits < 1024) splits--;
+    size_t need = (size_t)channels * splits * 2;
+    if (need > g_inorm_partial_cap) {
+        cudaError_t cap_status;
+        cudaStreamCaptureStatus cs;
+        cap_status = cudaStreamIsCapturing(st, &cs);
+        if (cap_status == cudaSuccess && cs != cudaStreamCaptureStatusNone) return (int)cudaErrorStreamCaptureUnsupported;
+        if (g_inorm_partial) cudaFree(g_inorm_partial);
+        g_inorm_partial_cap = need * 2 + 4096;
+        cudaError_t e = cudaMalloc(&g_inorm_partial, g_inorm_partial_cap * sizeof(double));
+        if (e != cudaSuccess) { g_inorm_partial = nullptr; g_inorm_partial_cap = 0; return (int)e; }
+    }
+    dim3 grid((unsigned)channels, (unsigned)splits);
+    if (dtype == OSB_F16) {
+        inorm_stats_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, g_inorm_partial, n_per_c, splits);
+        inorm_apply_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, (__half*)y, g_inorm_partial, n_per_c, splits, (const __half*)scale, (const __half*)bias, eps);
+    } else if (dtype == OSB_F32) {
+        inorm_stats_kernel<float><<<grid, 256, 0, st>>>((const float*)x, g_inorm_partial, n_per_c, splits);
+        inorm_apply_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, g_inorm_partial, n_per_c, splits, (const float*)scale, (const float*)bias, eps);
+    } else return (int)cudaErrorInvalidValue;
+    launched();
+    return launched();
+}
+
+int osb_group_norm(const void* x, void* y, int dtype, int nhwc, int64_t C, int64_t HW, int groups, const void* gamma, const void* beta,
+                   float eps, int fuse_silu, void* stats_, void* stream)
+{
+    double* stats = (double*)stats_;
+    if (C * HW == 0) return 0;
+    if (C % groups) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups, st);
+    if (e != cudaSuccess) return (int)e;
+    size_t n = (size_t)C * HW;
+    if (nhwc) {
+        int64_t ctas = min<int64_t>(HW, 148 * 4);
+        int64_t ppc = (HW + ctas - 1) / ctas;
+        ctas = (HW + ppc - 1) / ppc;
+        int threads = (int)min<int64_t>(1024, ((C + 31) / 32) * 32);
+        size_t smem = sizeof(float) * 2 * groups;
+        if (dtype == OSB_F16) gn_stats_nhwc_kernel<__half><<<(unsigned)ctas, threads, smem, st>>>((const __half*)x, stats, C, HW, groups, ppc);
+        else if (dtype == OSB_F32) gn_stats_nhwc_kernel<float><<<(unsigned)ctas, threads, smem, st>>>((const float*)x, stats, C, HW, groups, ppc);
+        else return (int)cudaErrorInvalidValue;
+    } else {
+        int64_t n_per_g = (C / groups) * HW;
+        int splits = (int)max<int64_t>(1, min<int64_t>(64, (148 * 4 + groups - 1) / groups));
+        while (splits > 1 && n_per_g / splits < 2048) splits--;
+        dim3 grid((unsigned)groups, (unsigned)splits);
+        if (dtype == OSB_F16) gn_stats_nchw_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, stats, n_per_g, splits);
+        else if (dtype == OSB_F32) gn_stats_nchw_kernel<float><<<grid, 256, 0, st>>>((const float*)x, stats, n_per_g, splits);
+        else return (int)cudaErrorInvalidValue;
+    }
+    launched();
+    bool al = aligned16(x) && aligned16(y);
+    if (dtype == OSB_F16) {
+        if (al && n % 8 == 0 && (nhwc ? C % 8 == 0 : HW % 8 == 0))
+            gn_apply_kernel<__half, 8><<<grid_for(n / 8, 256), 256, 0, st>>>((const __half*)x, (__half*)y, stats, nhwc, C, HW, groups, (const __half*)gamma, (const __half*)beta, eps, fuse_silu);
+        else
+            gn_apply_kernel<__half, 1><<<grid_for(n, 256), 256, 0, st>>>((const __half*)x, (__half*)y, stats, nhwc, C, HW, groups, (const __half*)gamma, (const __half*)beta, eps, fuse_silu);
+    } else {
+        if (al && n % 4 == 0 && (nhwc ? C % 4 == 0 : HW % 4 == 0))
+            gn_apply_kernel<float, 4><<<grid_for(n / 4, 256), 256, 0, st>>>((const float*)x, (float*)y, stats, nhwc, C, HW, groups, (const float*)gamma, (const float*)beta, eps, fuse_silu);
+        else
+            gn_apply_kernel<float, 1><<<grid_for(n, 256), 256, 0, st>>>((const float*)x, (float*)y, stats, nhwc, C, HW, groups, (const float*)gamma, (const float*)beta, eps, fuse_silu);
+    }
+    return launched();
+}
+
+int osb_gather_rows(const void* table, const int64_t* idx, void* out, int64_t n_idx, int64_t table_rows, int64_t row_bytes, void* stream)
+{
+    if (n_idx * row_bytes == 0) return 0;
+    int threads = row_bytes >= 4096 ? 256 : 64;
+    gather_rows_kernel<<<(unsigned)min<int64_t>(n_idx, 148 * 8), threads, 0, (cudaStream_t)stream>>>((const uint8_t*)table, idx, (uint8_t*)out, n_idx, table_rows, row_bytes);
+    return launched();
+}
+
+int osb_fill(void* dst, int dtype, size_t n, float value, void* stream)
+{
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == OSB_F16) fill_kernel<__half><<<grid_for(n, 256), 256, 0, st>>>((__half*)dst, n, value);
+    else if (dtype == OSB_F32) fill_kernel<float><<<grid_for(n, 256), 256, 0, st>>>((float*)dst, n, value);
+    else return (int)cudaErrorInvalidValue;
+    return launched();
+}
+
+} // extern "C"

@@ -1,0 +1,383 @@
+// kernels_gemm.cu -- dispatch for MatMul/Gemm/Conv plus the CUDA-core implicit-GEMM kernels that serve as
+//   (a) the fp32 path (bit-faithful fp32 FMA accumulation, needed for parity with the reference's f32 XNNPACK path),
+//   (b) the fallback for fp16 problems the tcgen05 kernel (gemm_tcgen05.cu) does not take (ragged K, tiny M/N),
+//   (c) the qu8 (W8A8) path with XNNPACK's exact requantisation.
+// The tensor-core path for fp16 lives in gemm_tcgen05.cu; osb_gemm/osb_conv2d choose between them.
+//
+// One kernel template covers GEMM and convolution: a convolution is a GEMM whose A operand is gathered on the fly
+// from the NHWC input (M = Ho*Wo, K = kh*kw*Cin in OHWI order, N = Cout, B = the OHWI weights read as [N, K]).
+
+#include "common.cuh"
+
+// implemented in gemm_tcgen05.cu
+int osb_tc_gemm_launch(const void* A, const void* B, void* C, const void* bias, const void* residual,
+                       int64_t batch, int64_t M, int64_t N, int64_t K, int64_t sa, int64_t sb, int64_t sc,
+                       int b_transposed, cudaStream_t st);
+int osb_tc_conv_launch(const void* x, const void* w, const void* bias, const void* residual, void* y,
+                       int64_t H, int64_t W, int64_t Cin, int64_t Cout, int kh, int kw, int stride, int pad_top, int pad_left,
+                       int64_t Ho, int64_t Wo, cudaStream_t st);
+bool osb_tc_gemm_ok(int64_t M, int64_t N, int64_t K, int b_transposed, const void* A, const void* B, const void* C, int64_t sa, int64_t sb, int64_t sc);
+bool osb_tc_conv_ok(int64_t H, int64_t W, int64_t Cin, int64_t Cout, int kh, int kw, int stride, const void* x, const void* w, const void* y);
+
+namespace {
+
+struct ConvGeom {
+    int H, W, Cin, kh, kw, stride, pad_top, pad_left, Ho, Wo;
+};
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+// acc type: float for f32/f16, int for u8
+template <typename T, bool CONV, bool QU8>
+__global__ void __launch_bounds__(256)
+igemm_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C,
+             const void* __restrict__ bias, const T* __restrict__ residual,
+             int M, int N, int K, int64_t sa, int64_t sb, int64_t sc, int b_transposed, ConvGeom g,
+             int zx, int zw, int zy, float requant)
+{
+    using Acc = typename std::conditional<QU8, int, float>::type;
+    __shared__ Acc As[BK][BM + 4];
+    __shared__ Acc Bs[BK][BN + 4];
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each 4x4 outputs
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int64_t bz = blockIdx.z;
+    A += bz * sa; B += bz * sb; C += bz * sc;
+    if (residual) residual += bz * sc;
+
+    Acc acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0;
+
+    // loader mapping: A tile 64x16 -> 1024 elements, 4 per thread; B tile 16x64 likewise
+    for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            int idx = tid + e * 256;
+            // A: idx -> (m, k) with k fastest (contiguous in memory for GEMM rows / conv channels)
+            int am = idx / BK, ak = idx % BK;
+            int m = m0 + am, k = k0 + ak;
+            Acc v = 0;
+            if (m < M && k < K) {
+                if (CONV) {
+                    int oy = m / g.Wo, ox = m % g.Wo;
+                    int ci = k % g.Cin, t = k / g.Cin;
+                    int kx = t % g.kw, ky = t / g.kw;
+                    int iy = oy * g.stride - g.pad_top + ky, ix = ox * g.stride - g.pad_left + kx;
+                    if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) {
+                        T raw = A[((int64_t)iy * g.W + ix) * g.Cin + ci];
+                        if (QU8) v = (Acc)((int)raw - zx); else v = (Acc)to_float(raw);
+                    }
+                } else {
+                    T raw = A[(int64_t)m * K + k];
+                    if (QU8) v = (Acc)((int)raw - zx); else v = (Acc)to_float(raw);
+                }
+            }
+            As[ak][am] = v;
+            // B
+            int bk, bn;
+            if (b_transposed) { bn = idx / BK; bk = idx % BK; } else { bk = idx / BN; bn = idx % BN; }
+            int kk = k0 + bk, n = n0 + bn;
+            Acc w = 0;
+            if (kk < K && n < N) {
+                T raw = b_transposed ? B[(int64_t)n * K + kk] : B[(int64_t)kk * N + n];
+                if (QU8) w = (Acc)((int)raw - zw); else w = (Acc)to_float(raw);
+            }
+            Bs[bk][bn] = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; k++) {
+            Acc a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] += a[i] * b[j];
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            if constexpr (QU8) {
+                int a = acc[i][j];
+                if (bias) a += ((const int32_t*)bias)[n];
+                float scaled = (float)a * requant;
+                scaled = fmaxf(scaled, (float)(0 - zy));
+                scaled = fminf(scaled, (float)(255 - zy));
+                int q = (int)lrintf(scaled) + zy;
+                C[(int64_t)m * N + n] = (uint8_t)q;
+            } else {
+                float v = acc[i][j];
+                if (bias) v += to_float(((const T*)bias)[n]);
+                if (residual) v += to_float(residual[(int64_t)m * N + n]);
+                C[(int64_t)m * N + n] = from_float<T>(v);
+            }
+        }
+    }
+}
+
+// Skinny GEMM (M <= 8): weight-bandwidth bound (time-embedding Gemms, llm decode).  One warp per output column
+// block; each lane strides K; B is read exactly once, coalesced along N.
+template <typename T, int MAXM>
+__global__ void __launch_bounds__(256)
+skinny_gemm_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C, const T* __restrict__ bias, const T* __restrict__ residual,
+                   int M, int N, int K, int b_transposed)
+{
+    // block handles 64 columns x all M rows; 256 threads = 4 k-slices x 64 columns (non-transposed B, coalesced over n)
+    __shared__ float red[4][MAXM][64];
+    if (!b_transposed) {
+        int nl = threadIdx.x & 63, ks = threadIdx.x >> 6;
+        int n = blockIdx.x * 64 + nl;
+        float acc[MAXM];
+#pragma unroll
+        for (int m = 0; m < MAXM; m++) acc[m] = 0.f;
+        if (n < N) {
+            for (int k = ks; k < K; k += 4) {
+                float b = to_float(B[(int64_t)k * N + n]);
+#pragma unroll
+                for (int m = 0; m < MAXM; m++) if (m < M) acc[m] += to_float(A[(int64_t)m * K + k]) * b;
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < MAXM; m++) red[ks][m][nl] = acc[m];
+        __syncthreads();
+        if (ks == 0 && n < N) {
+            for (int m = 0; m < M; m++) {
+                float v = red[0][m][nl] + red[1][m][nl] + red[2][m][nl] + red[3][m][nl];
+                if (bias) v += to_float(bias[n]);
+                if (residual) v += to_float(residual[(int64_t)m * N + n]);
+                C[(int64_t)m * N + n] = from_float<T>(v);
+            }
+        }
+    } else {
+        // B is [N, K]: one warp per column, lanes stride K (coalesced along K)
+        int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int n = blockIdx.x * 8 + warp; n < N; n += gridDim.x * 8) {
+            float acc[MAXM];
+#pragma unroll
+            for (int m = 0; m < MAXM; m++) acc[m] = 0.f;
+            for (int k = lane; k < K; k += 32) {
+                float b = to_float(B[(int64_t)n * K + k]);
+#pragma unroll
+                for (int m = 0; m < MAXM; m++) if (m < M) acc[m] += to_float(A[(int64_t)m * K + k]) * b;
+            }
+#pragma unroll
+            for (int m = 0; m < MAXM; m++) {
+                float v = warp_sum(acc[m]);
+                if (lane == 0 && m < M) {
+                    if (bias) v += to_float(bias[n]);
+                    if (residual) v += to_float(residual[(int64_t)m * N + n]);
+                    C[(int64_t)m * N + n] = from_float<T>(v);
+                }
+            }
+        }
+    }
+}
+
+// ---- softmax with scale + additive mask (score tile of the attention decomposition) ---------------------------
+template <typename T>
+__global__ void softmax_scaled_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int64_t cols, float scale,
+                                      const T* __restrict__ mask, int64_t mask_rows)
+{
+    __shared__ float red[32];
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        const T* xr = x + r * cols;
+        const T* mr = mask ? mask + (r % mask_rows) * cols : nullptr;
+        T* yr = y + r * cols;
+        float mx = -INFINITY;
+        for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) mx = fmaxf(mx, to_float(xr[c]) * scale + (mr ? to_float(mr[c]) : 0.f));
+        mx = block_reduce_max(mx, red);
+        float sum = 0.f;
+        for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) sum += expf(to_float(xr[c]) * scale + (mr ? to_float(mr[c]) : 0.f) - mx);
+        sum = block_reduce_sum(sum, red);
+        float inv = 1.f / sum;
+        for (int64_t c = threadIdx.x; c < cols; c += blockDim.x)
+            yr[c] = from_float<T>(expf(to_float(xr[c]) * scale + (mr ? to_float(mr[c]) : 0.f) - mx) * inv);
+    }
+}
+
+// ---- direct attention for short query lengths (decode): one warp per (head, query row), online softmax -------
+template <typename T>
+__global__ void attention_rows_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ mask,
+                                      T* __restrict__ out, int64_t heads, int64_t Tq, int64_t Tk, int d, int dv, float scale,
+                                      int k_transposed, int64_t kv_group)
+{
+    extern __shared__ float smem[];  // per warp: q row [d] + acc [dv] + p [32]
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    float* qs = smem + warp * (d + dv + 32);
+    float* acc = qs + d;
+    float* ps = acc + dv;
+    int64_t total = heads * Tq;
+    for (int64_t row = (int64_t)blockIdx.x * nwarps + warp; row < total; row += (int64_t)gridDim.x * nwarps) {
+        int64_t h = row / Tq, t = row % Tq, hk = h / kv_group;
+        const T* qr = q + row * d;
+        for (int c = lane; c < d; c += 32) qs[c] = to_float(qr[c]) * scale;
+        for (int c = lane; c < dv; c += 32) acc[c] = 0.f;
+        __syncwarp();
+        float m = -INFINITY, l = 0.f;
+        const T* kb = k + hk * Tk * d;
+        const T* vb = v + hk * Tk * dv;
+        for (int64_t s0 = 0; s0 < Tk; s0 += 32) {
+            int64_t s = s0 + lane;
+            float logit = -INFINITY;
+            if (s < Tk) {
+                float dot = 0.f;
+                if (k_transposed) for (int c = 0; c < d; c++) dot += qs[c] * to_float(kb[(int64_t)c * Tk + s]);
+                else for (int c = 0; c < d; c++) dot += qs[c] * to_float(kb[s * d + c]);
+                if (mask) dot += to_float(mask[t * Tk + s]);
+                logit = dot;
+            }
+            float mnew = fmaxf(m, warp_max(logit));
+            float corr = expf(m - mnew);
+            float p = s < Tk ? expf(logit - mnew) : 0.f;
+            l = l * corr + warp_sum(p);
+            // acc = acc * corr + sum_s p_s * v[s]   (p staged through shared memory: trip counts differ per lane)
+            ps[lane] = p;
+            __syncwarp();
+            int jn = (Tk - s0) < 32 ? (int)(Tk - s0) : 32;
+            for (int c = lane; c < dv; c += 32) {
+                float a = acc[c] * corr;
+                for (int j = 0; j < jn; j++) a += ps[j] * to_float(vb[(s0 + j) * dv + c]);
+                acc[c] = a;
+            }
+            m = mnew;
+            __syncwarp();
+        }
+        float inv = 1.f / l;
+        T* orow = out + row * dv;
+        for (int c = lane; c < dv; c += 32) orow[c] = from_float<T>(acc[c] * inv);
+        __syncwarp();
+    }
+}
+
+template <typename T>
+int launch_igemm(const T* A, const T* B, T* C, const void* bias, const T* residual, int64_t batch, int64_t M, int64_t N, int64_t K,
+                 int64_t sa, int64_t sb, int64_t sc, int bt, bool conv, ConvGeom g, cudaStream_t st)
+{
+    dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)batch);
+    if (grid.y > 65535 || grid.z > 65535) return (int)cudaErrorInvalidValue;
+    if (conv) igemm_kernel<T, true, false><<<grid, 256, 0, st>>>(A, B, C, bias, residual, (int)M, (int)N, (int)K, sa, sb, sc, bt, g, 0, 0, 0, 0.f);
+    else igemm_kernel<T, false, false><<<grid, 256, 0, st>>>(A, B, C, bias, residual, (int)M, (int)N, (int)K, sa, sb, sc, bt, g, 0, 0, 0, 0.f);
+    return launched();
+}
+
+} // namespace
+
+extern "C" {
+
+int osb_gemm_tc_eligible(int64_t M, int64_t N, int64_t K, int dtype)
+{
+    return dtype == OSB_F16 && osb_tc_gemm_ok(M, N, K, 0, nullptr, nullptr, nullptr, 0, 0, 0) ? 1 : 0;
+}
+
+int osb_gemm(const void* A, const void* B, void* C, const void* bias, const void* residual, int64_t batch, int64_t M, int64_t N, int64_t K,
+             int64_t sa, int64_t sb, int64_t sc, int bt, int dtype, int impl, void* stream)
+{
+    if (batch * M * N == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype != OSB_F16 && dtype != OSB_F32) return (int)cudaErrorInvalidValue;
+    if (K == 0) return (int)cudaErrorInvalidValue;
+    bool tc_ok = dtype == OSB_F16 && osb_tc_gemm_ok(M, N, K, bt, A, B, C, sa, sb, sc);
+    if (impl == 2 && !tc_ok) return (int)cudaErrorInvalidValue;
+    if (tc_ok && impl != 1) return osb_tc_gemm_launch(A, B, C, bias, residual, batch, M, N, K, sa, sb, sc, bt, st);
+    ConvGeom g{};
+    if (M <= 8 && batch == 1) {
+        int grid = bt ? (int)min<int64_t>((N + 7) / 8, 148 * 8) : (int)((N + 63) / 64);
+        if (dtype == OSB_F16) skinny_gemm_kernel<__half, 8><<<grid, 256, 0, st>>>((const __half*)A, (const __half*)B, (__half*)C, (const __half*)bias, (const __half*)residual, (int)M, (int)N, (int)K, bt);
+        else skinny_gemm_kernel<float, 8><<<grid, 256, 0, st>>>((const float*)A, (const float*)B, (float*)C, (const float*)bias, (const float*)residual, (int)M, (int)N, (int)K, bt);
+        return launched();
+    }
+    if (dtype == OSB_F16) return launch_igemm<__half>((const __half*)A, (const __half*)B, (__half*)C, bias, (const __half*)residual, batch, M, N, K, sa, sb, sc, bt, false, g, st);
+    return launch_igemm<float>((const float*)A, (const float*)B, (float*)C, bias, (const float*)residual, batch, M, N, K, sa, sb, sc, bt, false, g, st);
+}
+
+int osb_conv2d(const void* x, const void* w, const void* bias, const void* residual, void* y, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+               int kh, int kw, int stride, int pad_top, int pad_left, int64_t Ho, int64_t Wo, int dtype, int impl, void* stream)
+{
+    if (Ho * Wo * Cout == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype != OSB_F16 && dtype != OSB_F32) return (int)cudaErrorInvalidValue;
+    bool tc_ok = dtype == OSB_F16 && osb_tc_conv_ok(H, W, Cin, Cout, kh, kw, stride, x, w, y);
+    if (impl == 2 && !tc_ok) return (int)cudaErrorInvalidValue;
+    if (tc_ok && impl != 1) return osb_tc_conv_launch(x, w, bias, residual, y, H, W, Cin, Cout, kh, kw, stride, pad_top, pad_left, Ho, Wo, st);
+    ConvGeom g{ (int)H, (int)W, (int)Cin, kh, kw, stride, pad_top, pad_left, (int)Ho, (int)Wo };
+    int64_t M = Ho * Wo, N = Cout, K = (int64_t)kh * kw * Cin;
+    if (dtype == OSB_F16) return launch_igemm<__half>((const __half*)x, (const __half*)w, (__half*)y, bias, (const __half*)residual, 1, M, N, K, 0, 0, 0, 1, true, g, st);
+    return launch_igemm<float>((const float*)x, (const float*)w, (float*)y, bias, (const float*)residual, 1, M, N, K, 0, 0, 0, 1, true, g, st);
+}
+
+int osb_gemm_qu8(const uint8_t* A, const uint8_t* B, uint8_t* C, const int32_t* bias, int64_t M, int64_t N, int64_t K,
+                 int zx, float sx, int zw, float sw, int zy, float sy, void* stream)
+{
+    if (M * N == 0) return 0;
+    ConvGeom g{};
+    float requant = sx * sw / sy;
+    dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), 1);
+    igemm_kernel<uint8_t, false, true><<<grid, 256, 0, (cudaStream_t)stream>>>(A, B, C, bias, nullptr, (int)M, (int)N, (int)K, 0, 0, 0, 0, g, zx, zw, zy, requant);
+    return launched();
+}
+
+int osb_conv2d_qu8(const uint8_t* x, const uint8_t* w, const int32_t* bias, uint8_t* y, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                   int kh, int kw, int stride, int pad_top, int pad_left, int64_t Ho, int64_t Wo,
+                   int zx, float sx, int zw, float sw, int zy, float sy, void* stream)
+{
+    if (Ho * Wo * Cout == 0) return 0;
+    ConvGeom g{ (int)H, (int)W, (int)Cin, kh, kw, stride, pad_top, pad_left, (int)Ho, (int)Wo };
+    int64_t M = Ho * Wo, N = Cout, K = (int64_t)kh * kw * Cin;
+    float requant = sx * sw / sy;
+    dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), 1);
+    igemm_kernel<uint8_t, true, true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, y, bias, nullptr, (int)M, (int)N, (int)K, 0, 0, 0, 1, g, zx, zw, zy, requant);
+    return launched();
+}
+
+int osb_softmax_scaled(const void* x, void* y, int dtype, int64_t rows, int64_t cols, float scale, const void* mask, int64_t mask_rows, void* stream)
+{
+    if (rows * cols == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int threads = cols >= 1024 ? 256 : (cols >= 256 ? 128 : 32);
+    int grid = (int)min<int64_t>(rows, 148 * 16);
+    if (mask_rows <= 0) mask_rows = 1;
+    if (dtype == OSB_F16) softmax_scaled_kernel<__half><<<grid, threads, 0, st>>>((const __half*)x, (__half*)y, rows, cols, scale, (const __half*)mask, mask_rows);
+    else if (dtype == OSB_F32) softmax_scaled_kernel<float><<<grid, threads, 0, st>>>((const float*)x, (float*)y, rows, cols, scale, (const float*)mask, mask_rows);
+    else return (int)cudaErrorInvalidValue;
+    return launched();
+}
+
+int osb_attention(const void* q, const void* k, const void* v, const void* mask, void* out, int64_t heads, int64_t Tq, int64_t Tk,
+                  int64_t d, int64_t dv, float scale, int k_transposed, int64_t kv_group, int dtype, void* stream)
+{
+    if (heads * Tq * dv == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (kv_group < 1) kv_group = 1;
+    int warps = 4;
+    size_t smem = (size_t)warps * (d + dv + 32) * sizeof(float);
+    if (smem > 48 * 1024) return (int)cudaErrorInvalidValue;
+    int grid = (int)min<int64_t>((heads * Tq + warps - 1) / warps, 148 * 8);
+    if (dtype == OSB_F16) attention_rows_kernel<__half><<<grid, warps * 32, smem, st>>>((const __half*)q, (const __half*)k, (const __half*)v, (const __half*)mask, (__half*)out, heads, Tq, Tk, (int)d, (int)dv, scale, k_transposed, kv_group);
+    else if (dtype == OSB_F32) attention_rows_kernel<float><<<grid, warps * 32, smem, st>>>((const float*)q, (const float*)k, (const float*)v, (const float*)mask, (float*)out, heads, Tq, Tk, (int)d, (int)dv, scale, k_transposed, kv_group);
+    else return (int)cudaErrorInvalidValue;
+    return launched();
+}
+
+// ---- launch counters -----------------------------------------------------------------------------------------
+static uint64_t g_launches = 0, g_tc_launches = 0;
+void osb_count_launch(int tensor_core) { g_launches++; if (tensor_core) g_tc_launches++; }
+uint64_t osb_launch_count(void) { return g_launches; }
+uint64_t osb_tc_launch_count(void) { return g_tc_launches; }
+void osb_launch_count_reset(void) { g_launches = 0; g_tc_launches = 0; }
+
+} // extern "C"
