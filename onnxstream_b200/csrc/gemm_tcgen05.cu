@@ -1,6 +1,458 @@
-// gemm_tcgen05.cu -- placeholder until the tcgen05 path lands (next commit): reports "not eligible".
+// gemm_tcgen05.cu -- the tensor-core path for fp16 MatMul / Gemm / Conv / attention GEMMs on sm_100a.
+//
+// One persistent, warp-specialised kernel:
+//   warp 0      TMA producer: cp.async.bulk.tensor tiles of A and B into 128B-swizzled shared memory, mbarrier-tracked
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma (kind::f16, M=128, N=128, K=16) into TMEM
+//   warps 2..5  epilogue: tcgen05.ld the fp32 accumulator, add bias / residual, round to fp16, store
+// The accumulator is double-buffered in TMEM (2 x 128 columns) so the epilogue of tile i overlaps the main loop of
+// tile i+1; shared memory holds a STAGES-deep ring of (A,B) k-blocks.
+//
+// A is always K-major ([M,K] activations).  B is either MN-major ([K,N] row-major: ONNX MatMul weights, the
+// pre-transposed K of the attention pattern, V) or K-major ([N,K] row-major: OHWI conv weights).  A convolution is the
+// same kernel with the A tiles fetched as 3-D boxes of the NHWC input -- one box per filter tap and 64-channel block,
+// out-of-bounds (padding) elements zero-filled by TMA -- i.e. an implicit GEMM with no im2col buffer.
+//
+// Replaces: XnnPack::matrix_multiply / matrix_multiply_dynamic / convolution for T = uint16_t
+// (src/onnxstream.cpp:929-1215, 1292-1534) and the cuBLAS offload CublasOps::OpFullyConnected::run (src/onnxstream.cpp:308-352).
+
 #include "common.cuh"
-int osb_tc_gemm_launch(const void*, const void*, void*, const void*, const void*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int, cudaStream_t) { return (int)cudaErrorNotSupported; }
-int osb_tc_conv_launch(const void*, const void*, const void*, const void*, void*, int64_t, int64_t, int64_t, int64_t, int, int, int, int, int, int64_t, int64_t, cudaStream_t) { return (int)cudaErrorNotSupported; }
-bool osb_tc_gemm_ok(int64_t, int64_t, int64_t, int, const void*, const void*, const void*, int64_t, int64_t, int64_t) { return false; }
-bool osb_tc_conv_ok(int64_t, int64_t, int64_t, int64_t, int, int, int, const void*, const void*, const void*) { return false; }
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 128;
+constexpr int BLOCK_K = 64;            // 64 fp16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 6;
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;   // 256
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;  // 16 KiB
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 192;       // 6 warps
+
+struct TcParams {
+    int M, N, K;                 // GEMM view of the problem (conv: M = Ho*Wo, K = Cin per tap)
+    int batch;
+    int m_tiles, n_tiles;
+    int b_kmajor;                // 1: B is [N,K] row-major
+    // conv geometry (taps == 1 for a plain GEMM)
+    int taps, kw, pad_top, pad_left, Wo, Ho, bw, bh, tiles_x;
+    int k_blocks_per_tap;
+    // output
+    __half* C;
+    const __half* bias;
+    const __half* residual;
+    long long stride_c;          // elements between batches
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t addr = smem_u32(bar);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(addr), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], single CTA, fp16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs have completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (see cute/arch/mma_sm100_desc.hpp SmemDescriptor): SWIZZLE_128B, version 1
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;   // LayoutType::SWIZZLE_128B
+    return d;
+}
+
+// instruction descriptor for kind::f16: fp16 x fp16 -> fp32, A K-major, B K- or MN-major
+__device__ __forceinline__ uint32_t make_idesc(int b_mn_major)
+{
+    uint32_t d = 0;
+    d |= 1u << 4;                              // c_format = F32
+    d |= 0u << 7;                              // a_format = F16
+    d |= 0u << 10;                             // b_format = F16
+    d |= 0u << 15;                             // a_major  = K
+    d |= (uint32_t)(b_mn_major ? 1 : 0) << 16; // b_major
+    d |= (uint32_t)(BLOCK_N >> 3) << 17;       // n_dim
+    d |= (uint32_t)(BLOCK_M >> 4) << 24;       // m_dim
+    return d;
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment for the 128B swizzle atoms
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+    uint64_t* bars = (uint64_t*)(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+    uint64_t* full = bars;                       // [STAGES]
+    uint64_t* empty = bars + STAGES;             // [STAGES]
+    uint64_t* acc_full = bars + 2 * STAGES;      // [ACC_STAGES]
+    uint64_t* acc_empty = acc_full + ACC_STAGES; // [ACC_STAGES]
+    uint32_t* tmem_slot = (uint32_t*)(acc_empty + ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < ACC_STAGES; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_per_batch = p.m_tiles * p.n_tiles;
+    const int total_tiles = tiles_per_batch * p.batch;
+    const int k_blocks = p.taps * p.k_blocks_per_tap;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int b = tile / tiles_per_batch, r = tile % tiles_per_batch;
+                int mt = r % p.m_tiles, nt = r / p.m_tiles;
+                int n0 = nt * BLOCK_N;
+                int y0 = 0, x0 = 0, m0 = mt * BLOCK_M;
+                if (p.taps > 1 || p.bh > 0) { y0 = (mt / p.tiles_x) * p.bh; x0 = (mt % p.tiles_x) * p.bw; }
+                for (int kb = 0; kb < k_blocks; kb++) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+                    int tap = kb / p.k_blocks_per_tap, kc = (kb % p.k_blocks_per_tap) * BLOCK_K;
+                    uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
+                    uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
+                    if (p.bh > 0) {
+                        int ky = tap / p.kw, kx = tap % p.kw;
+                        tma_load_3d(sa, &map_a, &full[stage], kc, x0 + kx - p.pad_left, y0 + ky - p.pad_top);
+                    } else {
+                        tma_load_3d(sa, &map_a, &full[stage], kc, m0, b);
+                    }
+                    int kglob = tap * p.K + kc;   // K index into B (conv: taps are concatenated along K)
+                    if (p.b_kmajor) {
+                        tma_load_3d(sb, &map_b, &full[stage], kglob, n0, b);
+                    } else {
+                        tma_load_3d(sb, &map_b, &full[stage], n0, kglob, b);
+                        tma_load_3d(sb + B_STAGE_BYTES / 2, &map_b, &full[stage], n0 + 64, kglob, b);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = make_idesc(p.b_kmajor ? 0 : 1);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            if (lane == 0) mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+            __syncwarp();
+            tc_fence_after();
+            uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+            for (int kb = 0; kb < k_blocks; kb++) {
+                if (lane == 0) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    uint32_t a_addr = smem_u32(smem_a + stage * A_STAGE_BYTES);
+                    uint32_t b_addr = smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
+                        // A, K-major SW128: 8-row groups 1024 B apart; K advances 32 B inside the swizzle row
+                        uint64_t adesc = make_smem_desc(a_addr + k * (UMMA_K * 2), 16, 1024);
+                        uint64_t bdesc;
+                        if (p.b_kmajor) bdesc = make_smem_desc(b_addr + k * (UMMA_K * 2), 16, 1024);
+                        // B, MN-major SW128: two 64-column atoms 8192 B apart (LBO), 8-row k-groups 1024 B apart (SBO);
+                        // K advances 16 rows = 2048 B
+                        else bdesc = make_smem_desc(b_addr + k * (UMMA_K * 128), B_STAGE_BYTES / 2, 1024);
+                        umma_f16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[stage]);                       // frees the smem slot when these MMAs retire
+                    if (kb == k_blocks - 1) umma_commit(&acc_full[acc]);  // accumulator complete -> epilogue
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int b = tile / tiles_per_batch, r = tile % tiles_per_batch;
+            int mt = r % p.m_tiles, nt = r / p.m_tiles;
+            int n0 = nt * BLOCK_N;
+            int row_in_tile = q * 32 + lane;
+            long long out_row;   // row index into C (conv: output pixel index)
+            bool row_ok;
+            if (p.bh > 0) {
+                int y = (mt / p.tiles_x) * p.bh + row_in_tile / p.bw, x = (mt % p.tiles_x) * p.bw + row_in_tile % p.bw;
+                row_ok = y < p.Ho && x < p.Wo;
+                out_row = (long long)y * p.Wo + x;
+            } else {
+                int m = mt * BLOCK_M + row_in_tile;
+                row_ok = m < p.M;
+                out_row = m;
+            }
+            mbar_wait(&acc_full[acc], acc_phase);
+            tc_fence_after();
+            __half* crow = p.C + (long long)b * p.stride_c + out_row * p.N;
+            const __half* rrow = p.residual ? p.residual + (long long)b * p.stride_c + out_row * p.N : nullptr;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N; c += 32) {
+                if (n0 + c >= p.N) break;       // warp-uniform
+                uint32_t v[32];
+                uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c);
+                tmem_ld_32x32b_x32(taddr, v);
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        int n = n0 + c + j;
+                        if (n >= p.N) break;    // N % 8 == 0 is an eligibility requirement
+                        float f[8];
+#pragma unroll
+                        for (int t = 0; t < 8; t++) f[t] = __uint_as_float(v[j + t]);
+                        if (p.bias) {
+                            Vec<__half, 8> bv = load_vec<__half, 8>(p.bias + n);
+#pragma unroll
+                            for (int t = 0; t < 8; t++) f[t] += __half2float(bv.v[t]);
+                        }
+                        if (rrow) {
+                            Vec<__half, 8> rv = load_vec<__half, 8>(rrow + n);
+#pragma unroll
+                            for (int t = 0; t < 8; t++) f[t] += __half2float(rv.v[t]);
+                        }
+                        Vec<__half, 8> o;
+#pragma unroll
+                        for (int t = 0; t < 8; t++) o.v[t] = __float2half_rn(f[t]);
+                        store_vec<__half, 8>(crow + n, o);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[acc]);
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode()
+{
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+    });
+    return fn;
+}
+
+// rank-3 fp16 tensor map with 128B swizzle; dims/strides innermost first
+bool make_map(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes, uint64_t s2_bytes,
+              uint32_t b0, uint32_t b1, uint32_t b2)
+{
+    auto enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[3] = { d0, d1, d2 };
+    cuuint64_t strides[2] = { s1_bytes, s2_bytes };
+    cuuint32_t box[3] = { b0, b1, b2 };
+    cuuint32_t estr[3] = { 1, 1, 1 };
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+int num_sms()
+{
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+    return n;
+}
+
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    int total = p.m_tiles * p.n_tiles * p.batch;
+    int grid = std::min(total, num_sms());
+    tc_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, p);
+    return launched(1);
+}
+
+inline uint32_t next_pow2(uint32_t v) { uint32_t r = 1; while (r < v) r <<= 1; return r; }
+
+}  // namespace
+
+bool osb_tc_gemm_ok(int64_t M, int64_t N, int64_t K, int bt, const void* A, const void* B, const void* C, int64_t sa, int64_t sb, int64_t sc)
+{
+    if (M < 32 || N < 8 || K < 8) return false;
+    if (N % 8 || K % 8) return false;
+    if (M > (1 << 30) || N > (1 << 30) || K > (1 << 30)) return false;
+    if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) return false;
+    if ((sa % 8) || (sb % 8) || (sc % 8)) return false;
+    (void)bt;
+    return get_encode() != nullptr || A == nullptr;
+}
+
+int osb_tc_gemm_launch(const void* A, const void* B, void* C, const void* bias, const void* residual, int64_t batch, int64_t M, int64_t N, int64_t K,
+                       int64_t sa, int64_t sb, int64_t sc, int bt, cudaStream_t st)
+{
+    CUtensorMap ma, mb;
+    // A: [batch][M][K]; a shared operand (stride 0) is presented as batch extent 1 and the batch coordinate ignored
+    uint64_t abatch = sa ? (uint64_t)batch : 1, bbatch = sb ? (uint64_t)batch : 1;
+    if (batch > 1 && (!sa || !sb)) {
+        // shared operands across the batch: fold the batch into per-batch launches (rare: 2-D weights with n > 1)
+        for (int64_t i = 0; i < batch; i++) {
+            int r = osb_tc_gemm_launch((const __half*)A + i * sa, (const __half*)B + i * sb, (__half*)C + i * sc, bias,
+                                       residual ? (const __half*)residual + i * sc : nullptr, 1, M, N, K, M * K, bt ? N * K : K * N, sc, bt, st);
+            if (r) return r;
+        }
+        return 0;
+    }
+    if (!make_map(&ma, A, (uint64_t)K, (uint64_t)M, abatch, (uint64_t)K * 2, (uint64_t)(sa ? sa : M * K) * 2, BLOCK_K, BLOCK_M, 1)) return (int)cudaErrorInvalidValue;
+    bool okb = bt ? make_map(&mb, B, (uint64_t)K, (uint64_t)N, bbatch, (uint64_t)K * 2, (uint64_t)(sb ? sb : N * K) * 2, BLOCK_K, BLOCK_N, 1)
+                  : make_map(&mb, B, (uint64_t)N, (uint64_t)K, bbatch, (uint64_t)N * 2, (uint64_t)(sb ? sb : N * K) * 2, 64, BLOCK_K, 1);
+    if (!okb) return (int)cudaErrorInvalidValue;
+    TcParams p{};
+    p.M = (int)M; p.N = (int)N; p.K = (int)K; p.batch = (int)batch;
+    p.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M); p.n_tiles = (int)((N + BLOCK_N - 1) / BLOCK_N);
+    p.b_kmajor = bt ? 1 : 0;
+    p.taps = 1; p.kw = 1; p.bh = 0; p.bw = 0; p.tiles_x = 1;
+    p.k_blocks_per_tap = (int)((K + BLOCK_K - 1) / BLOCK_K);
+    p.C = (__half*)C; p.bias = (const __half*)bias; p.residual = (const __half*)residual; p.stride_c = sc;
+    return launch(ma, mb, p, st);
+}
+
+bool osb_tc_conv_ok(int64_t H, int64_t W, int64_t Cin, int64_t Cout, int kh, int kw, int stride, const void* x, const void* w, const void* y)
+{
+    if (stride != 1) return false;           // strided convs: CUDA-core implicit GEMM (3 nodes in the UNet)
+    if (Cin % 8 || Cout % 8 || Cin < 16) return false;
+    if (H * W < 64) return false;
+    if (kh > 7 || kw > 7) return false;
+    if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) return false;
+    return get_encode() != nullptr;
+}
+
+int osb_tc_conv_launch(const void* x, const void* w, const void* bias, const void* residual, void* y, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                       int kh, int kw, int stride, int pad_top, int pad_left, int64_t Ho, int64_t Wo, cudaStream_t st)
+{
+    (void)stride;
+    uint32_t bw = std::min<uint32_t>(128, next_pow2((uint32_t)Wo)), bh = 128 / bw;
+    CUtensorMap ma, mb;
+    // A: NHWC input as (C, W, H); one box = bh rows x bw pixels x 64 channels, zero-filled outside the image
+    if (!make_map(&ma, x, (uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)Cin * 2, (uint64_t)W * Cin * 2, BLOCK_K, bw, bh)) return (int)cudaErrorInvalidValue;
+    // B: OHWI weights = [Cout][kh*kw*Cin], K-major
+    int64_t Ktot = (int64_t)kh * kw * Cin;
+    if (!make_map(&mb, w, (uint64_t)Ktot, (uint64_t)Cout, 1, (uint64_t)Ktot * 2, (uint64_t)Ktot * Cout * 2, BLOCK_K, BLOCK_N, 1)) return (int)cudaErrorInvalidValue;
+    TcParams p{};
+    p.M = (int)(Ho * Wo); p.N = (int)Cout; p.K = (int)Cin; p.batch = 1;
+    p.tiles_x = (int)((Wo + bw - 1) / bw);
+    p.m_tiles = p.tiles_x * (int)((Ho + bh - 1) / bh);
+    p.n_tiles = (int)((Cout + BLOCK_N - 1) / BLOCK_N);
+    p.b_kmajor = 1;
+    p.taps = kh * kw; p.kw = kw; p.pad_top = pad_top; p.pad_left = pad_left; p.Wo = (int)Wo; p.Ho = (int)Ho; p.bw = (int)bw; p.bh = (int)bh;
+    p.k_blocks_per_tap = (int)((Cin + BLOCK_K - 1) / BLOCK_K);
+    p.C = (__half*)y; p.bias = (const __half*)bias; p.residual = (const __half*)residual; p.stride_c = 0;
+    return launch(ma, mb, p, st);
+}

@@ -1,0 +1,122 @@
+"""GPU parity tests for the hand-written kernels, called through the internal C ABI (include/onnxstream_b200_kernels.h)
+with torch only providing device memory.  Reference = fp64 math on the same fp16-rounded inputs; the tolerance for the
+fp16 tensor-core path is |err| <= 2^-9 * sum|a_i b_i| + 1 fp16 ulp of the result (fp32 accumulate, one final rounding)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+F16, F32 = 2, 3
+
+
+@pytest.fixture(scope="module")
+def K(engine_lib):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    lib = ctypes.CDLL(engine_lib)
+    vp, i64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    lib.osb_gemm.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, ci, ci, ci, vp]
+    lib.osb_conv2d.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, ci, ci, ci, i64, i64, ci, ci, vp]
+    lib.osb_tc_launch_count.restype = ctypes.c_uint64
+    lib.osb_launch_count_reset.restype = None
+    return lib
+
+
+def _stream():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check(out, ref, absref, what):
+    import torch
+    err = (out.double() - ref).abs()
+    tol = absref * 2.0 ** -9 + ref.abs() * 2.0 ** -10 + 1e-6
+    bad = (err > tol)
+    assert not bad.any(), f"{what}: {int(bad.sum())} / {bad.numel()} outside tolerance, max err {float(err.max()):.4g} (ref max {float(ref.abs().max()):.4g})"
+
+
+GEMM_CASES = [
+    # batch, M, N, K, b_transposed, bias, residual
+    (1, 256, 256, 128, 0, False, False),
+    (1, 256, 256, 128, 1, False, False),
+    (1, 128, 128, 64, 0, False, False),
+    (1, 300, 136, 72, 0, True, True),
+    (1, 300, 136, 72, 1, True, False),
+    (3, 200, 64, 40, 0, False, False),     # attention-like: small K, ragged M
+    (8, 4096, 40, 4096, 0, False, False) if False else (2, 512, 40, 512, 0, False, False),
+    (1, 4096, 320, 320, 0, True, True),
+    (1, 1024, 2560, 640, 0, True, False),
+    (1, 77, 640, 768, 0, False, False),
+]
+
+
+@pytest.mark.parametrize("case", GEMM_CASES)
+@pytest.mark.parametrize("impl", [1, 2])
+def test_gemm_f16(K, case, impl):
+    import torch
+    batch, M, N, Kd, bt, has_bias, has_res = case
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + Kd)
+    a = torch.randn(batch, M, Kd, device="cuda", generator=g).half()
+    b = (torch.randn(batch, N, Kd, device="cuda", generator=g) if bt else torch.randn(batch, Kd, N, device="cuda", generator=g)).half()
+    bias = torch.randn(N, device="cuda", generator=g).half() if has_bias else None
+    res = torch.randn(batch, M, N, device="cuda", generator=g).half() if has_res else None
+    c = torch.full((batch, M, N), float("nan"), device="cuda", dtype=torch.half)
+    K.osb_launch_count_reset()
+    rc = K.osb_gemm(a.data_ptr(), b.data_ptr(), c.data_ptr(), bias.data_ptr() if has_bias else None, res.data_ptr() if has_res else None,
+                    batch, M, N, Kd, M * Kd, N * Kd, M * N, bt, F16, impl, _stream())
+    assert rc == 0, f"osb_gemm rc={rc}"
+    torch.cuda.synchronize()
+    if impl == 2:
+        assert K.osb_tc_launch_count() >= 1
+    bd = b.double().transpose(1, 2) if bt else b.double()
+    ref = a.double() @ bd
+    absref = a.double().abs() @ bd.abs()
+    if has_bias:
+        ref = ref + bias.double(); absref = absref + bias.double().abs()
+    if has_res:
+        ref = ref + res.double(); absref = absref + res.double().abs()
+    _check(c, ref, absref, f"gemm {case} impl {impl}")
+
+
+CONV_CASES = [
+    # H, W, Cin, Cout, k, stride, pad, bias, residual
+    (16, 16, 64, 128, 3, 1, 1, True, False),
+    (16, 16, 64, 128, 1, 1, 0, True, True),
+    (8, 8, 128, 128, 3, 1, 1, True, False),
+    (64, 64, 320, 320, 3, 1, 1, True, True),
+    (32, 32, 96, 72, 3, 1, 1, False, False),      # ragged channels
+    (24, 40, 32, 40, 3, 1, 1, True, False),       # non power-of-two width
+    (256, 256, 32, 16, 3, 1, 1, True, False),     # wide image: one row segment per tile
+    (16, 16, 64, 64, 3, 2, 1, True, False),       # strided: CUDA-core path
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("impl", [1, 0])
+def test_conv_f16(K, case, impl):
+    import torch
+    import torch.nn.functional as Fn
+    H, W, Cin, Cout, k, s, pad, has_bias, has_res = case
+    g = torch.Generator(device="cuda").manual_seed(H * 5 + Cin)
+    x = torch.randn(H, W, Cin, device="cuda", generator=g).half()
+    w = (torch.randn(Cout, k, k, Cin, device="cuda", generator=g) / (k * k * Cin) ** 0.5).half()
+    bias = torch.randn(Cout, device="cuda", generator=g).half() if has_bias else None
+    Ho, Wo = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1
+    res = torch.randn(Ho, Wo, Cout, device="cuda", generator=g).half() if has_res else None
+    y = torch.full((Ho, Wo, Cout), float("nan"), device="cuda", dtype=torch.half)
+    rc = K.osb_conv2d(x.data_ptr(), w.data_ptr(), bias.data_ptr() if has_bias else None, res.data_ptr() if has_res else None, y.data_ptr(),
+                      H, W, Cin, Cout, k, k, s, pad, pad, Ho, Wo, F16, impl, _stream())
+    assert rc == 0, f"osb_conv2d rc={rc}"
+    torch.cuda.synchronize()
+    xn = x.double().permute(2, 0, 1)[None]
+    wn = w.double().permute(0, 3, 1, 2)
+    ref = Fn.conv2d(xn, wn, None, stride=s, padding=pad)[0].permute(1, 2, 0)
+    absref = Fn.conv2d(xn.abs(), wn.abs(), None, stride=s, padding=pad)[0].permute(1, 2, 0)
+    if has_bias:
+        ref = ref + bias.double(); absref = absref + bias.double().abs()
+    if has_res:
+        ref = ref + res.double(); absref = absref + res.double().abs()
+    _check(y, ref, absref, f"conv {case} impl {impl}")
