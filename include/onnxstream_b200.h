@@ -55,6 +55,7 @@ int   model_ext_get_tensor_type(ModelContext* obj, const char* name);           
  * [8] kernel launches, [9] tcgen05 launches, [10] steps executed, [11] ops fused away, [12] last run wall ms, [13] last run GPU ms,
  * [14] CUDA-graph replays.  Returns the number of fields available. */
 int   model_b200_get_stats(ModelContext* obj, double* out, int n);
+double model_b200_run_resident(ModelContext* obj, int steps);   /* replay the captured graph on device-resident inputs; CUDA-event ms, < 0 on error */
 int   model_b200_set_comm(ModelContext* obj, void* nccl_comm, int rank, int nranks);  /* weights: rank 0 uploads, NCCL broadcast to the rest */
 const char* model_b200_version(void);
 

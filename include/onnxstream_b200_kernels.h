@@ -117,6 +117,11 @@ int osb_fill(void* dst, int dtype, size_t n, float value, void* stream);
 /* 1 when the tcgen05/TMA GEMM path can take this problem (used by tests and the bench to assert the fast path ran). */
 int osb_gemm_tc_eligible(int64_t M, int64_t N, int64_t K, int dtype);
 
+/* Per-launch timing of the tcgen05 GEMM/conv kernel (CUDA events on the launching stream; eager mode only).
+ * osb_tc_profile(1) starts recording, osb_tc_profile_read fills {launches, total ms, total FLOPs, total algorithmic bytes}. */
+void osb_tc_profile(int enable);
+int osb_tc_profile_read(double* out4);
+
 /* Counters: number of kernel launches issued through this ABI since the last reset (bench.py's gpu_launches). */
 uint64_t osb_launch_count(void);
 void osb_launch_count_reset(void);

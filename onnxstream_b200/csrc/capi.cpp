@@ -125,8 +125,8 @@ void* model_get_tensor(ModelContext* obj, char* name)
     auto* r = (ReturnLayout*)malloc(sizeof(ReturnLayout));
     r->dims_num = t->shape.size();
     r->dims = t->shape.data();
-    r->data_num = t->f32.size();
-    r->data = t->f32.data();
+    r->data_num = t->count;
+    r->data = t->f32();
     return r;
 }
 
@@ -217,10 +217,10 @@ long long model_ext_get_tensor_i64(ModelContext* obj, const char* name, long lon
     for (auto& h : obj->E().tensors())
         if (h.name == name) {
             if (h.type != DType::i64) return -1;
-            for (size_t i = 0; i < h.i64.size() && (long long)i < cap; i++) dst[i] = h.i64[i];
+            for (size_t i = 0; i < h.count && (long long)i < cap; i++) dst[i] = h.i64()[i];
             *ndims = h.shape.size();
             for (size_t i = 0; i < h.shape.size() && i < 8; i++) dims[i] = h.shape[i];
-            return (long long)h.i64.size();
+            return (long long)h.count;
         }
     return -1;
 }
@@ -241,6 +241,12 @@ int model_b200_get_stats(ModelContext* obj, double* out, int n)
     int m = (int)(sizeof(v) / sizeof(v[0]));
     for (int i = 0; i < n && i < m; i++) out[i] = v[i];
     return m;
+}
+
+double model_b200_run_resident(ModelContext* obj, int steps)
+{
+    try { return obj->E().run_resident(steps); }
+    catch (const std::exception& e) { fprintf(stderr, "=== ERROR === %s\n", e.what()); return -1.0; }
 }
 
 int model_b200_set_comm(ModelContext* obj, void* nccl_comm, int rank, int nranks)

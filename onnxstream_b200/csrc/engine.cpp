@@ -42,6 +42,12 @@ const char* dtype_name(DType t)
     }
 }
 
+PinnedBuf::PinnedBuf(size_t n) : bytes(n)
+{
+    check_cuda(cudaHostAlloc(&ptr, std::max<size_t>(n, 16), cudaHostAllocDefault), "cudaHostAlloc(host tensor)");
+}
+PinnedBuf::~PinnedBuf() { if (ptr) cudaFreeHost(ptr); }
+
 // ================================================================================================================
 // DevicePool
 // ================================================================================================================

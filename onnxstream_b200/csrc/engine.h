@@ -138,12 +138,21 @@ struct EngineStats {
     int graph_replays = 0;
 };
 
+struct PinnedBuf {                    // page-locked host memory (cudaHostAlloc): H2D/D2H copies run at full PCIe rate
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    explicit PinnedBuf(size_t n);
+    ~PinnedBuf();
+};
+
 struct HostTensor {                   // what is left in the model's tensor list after run(): f32 NCHW or int64
     std::string name;
     DType type = DType::none;
     std::vector<size_t> shape;
-    std::vector<float> f32;
-    std::vector<int64_t> i64;
+    std::shared_ptr<PinnedBuf> buf;
+    size_t count = 0;
+    float* f32() const { return (float*)buf->ptr; }
+    int64_t* i64() const { return (int64_t*)buf->ptr; }
 };
 
 class Engine {
@@ -189,6 +198,9 @@ public:
     // inputs are copied to pinned host staging here and uploaded at the start of run()
     void* push_input(const std::string& name, DType type, const std::vector<size_t>& shape);  // returns host buffer to fill
     void run();
+    // Replays the captured CUDA graph `steps` times on the device-resident inputs of the last run (no H2D / D2H);
+    // returns the CUDA-event time in ms.  Requires b200_cuda_graph + b200_resident_weights and one completed run().
+    double run_resident(int steps);
     std::vector<HostTensor>& tensors() { return m_host_tensors; }   // inputs before run(), outputs after
     void clear_tensors();
 
@@ -222,7 +234,9 @@ private:
     int m_rank = 0, m_nranks = 1;
 
     void parse();
-    void run_eager();
+    void run_body(bool capturing);
+    bool try_replay();
+    void drop_graph();
     struct Impl;
     std::unique_ptr<Impl> m_impl;
 };

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
+#include <tuple>
 
 namespace osb {
 
@@ -75,6 +76,7 @@ struct Engine::Impl {
 
     DevPtr gn_stats;
     size_t cur_step = 0, cur_b = 0, cur_B = 1;
+    int runs_done = 0;
 
     // ------------------------------------------------------------------------------------------------------
     // helpers: allocation, conversion, layout
@@ -1685,6 +1687,7 @@ Engine::Engine(int device)
 Engine::~Engine()
 {
     if (m_stream) cudaStreamSynchronize(m_stream);
+    drop_graph();
     m_impl.reset();
     m_streamer.reset();
     if (m_stream) cudaStreamDestroy(m_stream);
@@ -1749,9 +1752,11 @@ void* Engine::push_input(const std::string& name, DType type, const std::vector<
     HostTensor t;
     t.name = name; t.type = type; t.shape = shape;
     size_t n = 1; for (auto d : shape) n *= d;
-    if (type == DType::f32) { t.f32.resize(n); m_host_tensors.push_back(std::move(t)); return m_host_tensors.back().f32.data(); }
-    if (type == DType::i64) { t.i64.resize(n); m_host_tensors.push_back(std::move(t)); return m_host_tensors.back().i64.data(); }
-    throw std::invalid_argument("Unsupported tensor data format.");
+    if (type != DType::f32 && type != DType::i64) throw std::invalid_argument("Unsupported tensor data format.");
+    t.count = n;
+    t.buf = std::make_shared<PinnedBuf>(n * dtype_size(type));
+    m_host_tensors.push_back(std::move(t));
+    return m_host_tensors.back().buf->ptr;
 }
 
 void Engine::clear_tensors() { m_host_tensors.clear(); }
@@ -1783,11 +1788,102 @@ void Engine::write_range_data(const char* filename)
     fclose(f);
 }
 
+// ---- CUDA graph state (one captured run, replayed while the inputs keep their names and shapes) ----
+struct GraphState {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    struct In { std::string name; std::vector<size_t> shape; DevPtr dev; size_t bytes; };
+    struct Out { std::string name; std::vector<size_t> shape; DevPtr dev; size_t count; };
+    std::vector<In> inputs;
+    std::vector<Out> outputs;
+    std::vector<DevPtr> keepalive;
+    bool ready = false;
+    bool failed = false;
+};
+static std::map<Engine*, GraphState> g_graphs;
+
+void Engine::drop_graph()
+{
+    auto it = g_graphs.find(this);
+    if (it == g_graphs.end()) return;
+    if (it->second.exec) cudaGraphExecDestroy(it->second.exec);
+    if (it->second.graph) cudaGraphDestroy(it->second.graph);
+    g_graphs.erase(it);
+}
+
+bool Engine::try_replay()
+{
+    auto it = g_graphs.find(this);
+    if (it == g_graphs.end() || !it->second.ready) return false;
+    GraphState& G = it->second;
+    // same inputs (names, shapes, order)?
+    std::vector<HostTensor*> fins;
+    for (auto& h : m_host_tensors) fins.push_back(&h);
+    if (fins.size() != G.inputs.size()) { drop_graph(); return false; }
+    for (size_t i = 0; i < fins.size(); i++)
+        if (fins[i]->type != DType::f32 || fins[i]->name != G.inputs[i].name || fins[i]->shape != G.inputs[i].shape) { drop_graph(); return false; }
+    auto t0 = std::chrono::high_resolution_clock::now();
+    cudaEvent_t ev0, ev1;
+    check_cuda(cudaEventCreate(&ev0), "cudaEventCreate");
+    check_cuda(cudaEventCreate(&ev1), "cudaEventCreate");
+    check_cuda(cudaEventRecord(ev0, m_stream), "cudaEventRecord");
+    m_stats.h2d_input_bytes = 0;
+    for (size_t i = 0; i < fins.size(); i++) {
+        check_cuda(cudaMemcpyAsync(G.inputs[i].dev->ptr, fins[i]->buf->ptr, G.inputs[i].bytes, cudaMemcpyHostToDevice, m_stream), "input H2D");
+        m_stats.h2d_input_bytes += G.inputs[i].bytes;
+    }
+    check_cuda(cudaGraphLaunch(G.exec, m_stream), "cudaGraphLaunch");
+    std::vector<HostTensor> outs;
+    m_stats.d2h_output_bytes = 0;
+    for (auto& o : G.outputs) {
+        HostTensor h;
+        h.name = o.name; h.type = DType::f32; h.shape = o.shape; h.count = o.count;
+        h.buf = std::make_shared<PinnedBuf>(o.count * 4);
+        check_cuda(cudaMemcpyAsync(h.buf->ptr, o.dev->ptr, o.count * 4, cudaMemcpyDeviceToHost, m_stream), "output D2H");
+        m_stats.d2h_output_bytes += o.count * 4;
+        outs.push_back(std::move(h));
+    }
+    check_cuda(cudaEventRecord(ev1, m_stream), "cudaEventRecord");
+    check_cuda(cudaStreamSynchronize(m_stream), "graph replay sync");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    m_host_tensors = std::move(outs);
+    m_stats.last_gpu_ms = ms;
+    m_stats.graph_replays++;
+    m_stats.weight_bytes_streamed = 0;
+    m_stats.last_run_ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
+    return true;
+}
+
+double Engine::run_resident(int steps)
+{
+    auto it = g_graphs.find(this);
+    if (it == g_graphs.end() || !it->second.ready)
+        throw std::runtime_error("run_resident: no captured graph (enable b200_cuda_graph + b200_resident_weights and call run() three times first)");
+    GraphState& G = it->second;
+    check_cuda(cudaSetDevice(m_device), "cudaSetDevice");
+    cudaEvent_t ev0, ev1;
+    check_cuda(cudaEventCreate(&ev0), "cudaEventCreate");
+    check_cuda(cudaEventCreate(&ev1), "cudaEventCreate");
+    check_cuda(cudaStreamSynchronize(m_stream), "sync");
+    check_cuda(cudaEventRecord(ev0, m_stream), "cudaEventRecord");
+    for (int i = 0; i < steps; i++) check_cuda(cudaGraphLaunch(G.exec, m_stream), "cudaGraphLaunch");
+    check_cuda(cudaEventRecord(ev1, m_stream), "cudaEventRecord");
+    check_cuda(cudaStreamSynchronize(m_stream), "sync");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    m_stats.graph_replays += steps;
+    return ms;
+}
+
 void Engine::run()
 {
     auto t0 = std::chrono::high_resolution_clock::now();
     check_cuda(cudaSetDevice(m_device), "cudaSetDevice");
     parse();
+    if (use_cuda_graph && try_replay()) return;
     Impl& I = *m_impl;
     osb_launch_count_reset();
 
@@ -1801,6 +1897,7 @@ void Engine::run()
         m_streamer = std::make_unique<WeightStreamer>(cap, !m_source->stable_pinned(), m_comm, m_rank, m_nranks);
         m_stats.weight_largest_node_bytes = I.largest_node;
         m_stats.weight_ring_bytes = m_streamer->capacity();
+        I.runs_done = 0;
     } else {
         m_first_run = false;
         m_source->on_restart();
@@ -1815,6 +1912,14 @@ void Engine::run()
     m_pool.reset_high_water();
     m_streamer->begin_run();
 
+    // Capture on the third run: run 1 fills the resident weight cache, run 2 warms every lazily-grown scratch buffer with
+    // the cache in place, run 3 records the graph (nothing allocates outside the pool any more).
+    bool has_i64_input = false;
+    for (auto& h : m_host_tensors) if (h.type == DType::i64) has_i64_input = true;
+    GraphState* G = nullptr;
+    bool capturing = use_cuda_graph && resident_weights && !has_i64_input && I.runs_done >= 2 && m_nranks == 1;
+    if (capturing) { auto& g = g_graphs[this]; if (g.failed) capturing = false; else G = &g; }
+
     cudaEvent_t ev0, ev1;
     check_cuda(cudaEventCreate(&ev0), "cudaEventCreate");
     check_cuda(cudaEventCreate(&ev1), "cudaEventCreate");
@@ -1822,64 +1927,117 @@ void Engine::run()
 
     // upload graph inputs (push_tensor semantics: same name pushed again => batch sibling, src/onnxstream.cpp:3040-3050)
     m_stats.h2d_input_bytes = 0;
-    {
-        std::vector<DevPtr> staging_keepalive;
-        for (auto& h : m_host_tensors) {
-            Tensor t;
-            t.name = h.name;
-            for (auto d : h.shape) t.shape.push_back((int64_t)d);
-            if (h.type == DType::i64) {
-                t.type = DType::i64;
-                t.i64 = std::make_shared<std::vector<int64_t>>(h.i64);
-            } else {
-                t.type = DType::f32;
-                t.dev = m_pool.alloc(h.f32.size() * 4);
-                check_cuda(cudaMemcpyAsync(t.dev->ptr, h.f32.data(), h.f32.size() * 4, cudaMemcpyHostToDevice, m_stream), "input H2D");
-                m_stats.h2d_input_bytes += h.f32.size() * 4;
-                if (use_fp16_arithmetic && !use_uint8_arithmetic && !use_uint8_qdq) t = I.convert(t, DType::f16);
-                t.name = h.name;
-            }
-            auto& v = I.store[h.name];
-            if (v.empty()) I.order.push_back(h.name);
-            v.push_back(std::move(t));
+    std::vector<std::pair<Tensor, bool>> uploaded;   // (device tensor, needs fp16 storage conversion)
+    for (auto& h : m_host_tensors) {
+        Tensor t;
+        t.name = h.name;
+        for (auto d : h.shape) t.shape.push_back((int64_t)d);
+        if (h.type == DType::i64) {
+            t.type = DType::i64;
+            t.i64 = std::make_shared<std::vector<int64_t>>(h.i64(), h.i64() + h.count);
+            uploaded.emplace_back(t, false);
+        } else {
+            t.type = DType::f32;
+            t.dev = m_pool.alloc(h.count * 4);
+            check_cuda(cudaMemcpyAsync(t.dev->ptr, h.buf->ptr, h.count * 4, cudaMemcpyHostToDevice, m_stream), "input H2D");
+            m_stats.h2d_input_bytes += h.count * 4;
+            if (G) G->inputs.push_back({ h.name, h.shape, t.dev, h.count * 4 });
+            uploaded.emplace_back(t, use_fp16_arithmetic && !use_uint8_arithmetic && !use_uint8_qdq);
         }
-        check_cuda(cudaStreamSynchronize(m_stream), "input upload sync");
     }
+    std::vector<HostTensor> pinned_inputs = std::move(m_host_tensors);   // keep the pinned sources alive until the copies ran
     m_host_tensors.clear();
 
-    for (size_t si = 0; si < I.steps.size(); si++) I.exec_step(si);
+    bool capture_open = false;
+    std::vector<std::tuple<std::string, std::vector<size_t>, Tensor>> finals;   // outputs as f32 plain device tensors
+    try {
+        if (capturing) {
+            check_cuda(cudaStreamSynchronize(m_stream), "pre-capture sync");
+            check_cuda(cudaStreamBeginCapture(m_stream, cudaStreamCaptureModeRelaxed), "cudaStreamBeginCapture");
+            capture_open = true;
+        }
+        for (auto& u : uploaded) {
+            Tensor t = u.first;
+            if (u.second) { t = I.convert(t, DType::f16); t.name = u.first.name; }
+            auto& v = I.store[t.name];
+            if (v.empty()) I.order.push_back(t.name);
+            v.push_back(std::move(t));
+        }
+        for (size_t si = 0; si < I.steps.size(); si++) I.exec_step(si);
+        m_streamer->end_run(m_stream);
 
-    m_streamer->end_run(m_stream);
+        // epilogue: everything still referenced becomes f32 NCHW (src/onnxstream.cpp:8217-8263)
+        for (auto& name : I.order) {
+            auto it = I.store.find(name);
+            if (it == I.store.end()) continue;
+            for (auto& t0_ : it->second) {
+                std::vector<size_t> shp;
+                for (auto d : t0_.shape) shp.push_back((size_t)d);
+                if (t0_.type == DType::i64) { finals.emplace_back(name, shp, t0_); continue; }
+                Tensor t = I.to_plain(t0_);
+                if (t.type == DType::f32 && !t.dev && t.dev_raw) { Tensor c = I.make(DType::f32, t.shape); check_cuda(cudaMemcpyAsync(c.mdata(), t.dev_raw, (size_t)t.numel() * 4, cudaMemcpyDeviceToDevice, m_stream), "copy"); t = c; }
+                t = I.convert(t, DType::f32);
+                if (t.dev.get() == t0_.dev.get() && capturing) {   // graph outputs need storage the graph owns exclusively
+                    Tensor c = I.make(DType::f32, t.shape);
+                    check_cuda(cudaMemcpyAsync(c.mdata(), t.data(), (size_t)t.numel() * 4, cudaMemcpyDeviceToDevice, m_stream), "copy");
+                    t = c;
+                }
+                finals.emplace_back(name, shp, t);
+            }
+        }
+        if (capturing) {
+            capture_open = false;
+            check_cuda(cudaStreamEndCapture(m_stream, &G->graph), "cudaStreamEndCapture");
+            check_cuda(cudaGraphInstantiate(&G->exec, G->graph, 0), "cudaGraphInstantiate");
+            for (auto& f : finals) if (std::get<2>(f).type != DType::i64) G->outputs.push_back({ std::get<0>(f), std::get<1>(f), std::get<2>(f).dev, (size_t)std::get<2>(f).numel() });
+            check_cuda(cudaGraphLaunch(G->exec, m_stream), "cudaGraphLaunch");   // capture does not execute: run it once now
+            G->ready = true;
+            m_pool.frozen = false;
+        }
+    } catch (...) {
+        if (capture_open) { cudaGraph_t junk = nullptr; cudaStreamEndCapture(m_stream, &junk); if (junk) cudaGraphDestroy(junk); }
+        if (capturing) { auto& g = g_graphs[this]; g.failed = true; g.inputs.clear(); g.outputs.clear(); }
+        I.store.clear(); I.order.clear();
+        cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+        if (capturing) {
+            // the op list is not capture-safe (host round trips): fall back to eager execution for good
+            cudaGetLastError();
+            m_host_tensors = std::move(pinned_inputs);
+            use_cuda_graph = false;
+            run();
+            return;
+        }
+        throw;
+    }
     check_cuda(cudaEventRecord(ev1, m_stream), "cudaEventRecord");
 
-    // epilogue: everything still referenced becomes f32 NCHW on the host (src/onnxstream.cpp:8217-8263)
     m_stats.d2h_output_bytes = 0;
-    for (auto& name : I.order) {
-        auto it = I.store.find(name);
-        if (it == I.store.end()) continue;
-        for (auto& t0_ : it->second) {
-            HostTensor h;
-            h.name = name;
-            for (auto d : t0_.shape) h.shape.push_back((size_t)d);
-            if (t0_.type == DType::i64) { h.type = DType::i64; h.i64 = *t0_.i64; }
-            else {
-                Tensor t = I.to_plain(t0_);
-                t = I.convert(t, DType::f32);
-                h.type = DType::f32;
-                h.f32.resize((size_t)t.numel());
-                check_cuda(cudaMemcpyAsync(h.f32.data(), t.data(), h.f32.size() * 4, cudaMemcpyDeviceToHost, m_stream), "output D2H");
-                check_cuda(cudaStreamSynchronize(m_stream), "output D2H sync");
-                m_stats.d2h_output_bytes += h.f32.size() * 4;
-            }
-            m_host_tensors.push_back(std::move(h));
+    for (auto& f : finals) {
+        HostTensor h;
+        h.name = std::get<0>(f);
+        h.shape = std::get<1>(f);
+        Tensor& t = std::get<2>(f);
+        h.count = (size_t)t.numel();
+        if (t.type == DType::i64) {
+            h.type = DType::i64;
+            h.buf = std::make_shared<PinnedBuf>(h.count * 8);
+            memcpy(h.buf->ptr, t.i64->data(), h.count * 8);
+        } else {
+            h.type = DType::f32;
+            h.buf = std::make_shared<PinnedBuf>(h.count * 4);
+            check_cuda(cudaMemcpyAsync(h.buf->ptr, t.data(), h.count * 4, cudaMemcpyDeviceToHost, m_stream), "output D2H");
+            m_stats.d2h_output_bytes += h.count * 4;
         }
+        m_host_tensors.push_back(std::move(h));
     }
     check_cuda(cudaStreamSynchronize(m_stream), "run sync");
     I.store.clear();
     I.order.clear();
+    finals.clear();
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, ev0, ev1);
+    if (!capturing) cudaEventElapsedTime(&ms, ev0, ev1);
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    I.runs_done++;
     m_stats.last_gpu_ms = ms;
     m_stats.kernel_launches = osb_launch_count();
     m_stats.tc_launches = osb_tc_launch_count();

@@ -19,6 +19,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <vector>
 
 namespace {
 
@@ -366,6 +367,11 @@ int num_sms()
     return n;
 }
 
+// optional per-launch timing (bench.py's roofline leg): CUDA events on the launching stream around every launch
+struct ProfRec { cudaEvent_t a, b; double flops, bytes; };
+bool g_prof = false;
+std::vector<ProfRec> g_prof_list;
+
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st)
 {
     static bool attr_set = false;
@@ -376,13 +382,45 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cuda
     }
     int total = p.m_tiles * p.n_tiles * p.batch;
     int grid = std::min(total, num_sms());
+    ProfRec rec{};
+    if (g_prof) {
+        cudaEventCreate(&rec.a); cudaEventCreate(&rec.b);
+        double M = p.M, N = p.N, Kt = (double)p.K * p.taps, B = p.batch;
+        rec.flops = 2.0 * M * N * Kt * B;
+        // algorithmic bytes: A once (conv: the input image once), B once, C once (+ residual / bias reads)
+        double a_bytes = (p.bh > 0 ? M * p.K : M * Kt) * 2.0 * B;
+        rec.bytes = a_bytes + N * Kt * 2.0 * (p.bh > 0 ? 1.0 : B) + M * N * 2.0 * B * (p.residual ? 2.0 : 1.0) + (p.bias ? N * 2.0 : 0.0);
+        cudaEventRecord(rec.a, st);
+    }
     tc_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, p);
+    if (g_prof) { cudaEventRecord(rec.b, st); g_prof_list.push_back(rec); }
     return launched(1);
 }
 
 inline uint32_t next_pow2(uint32_t v) { uint32_t r = 1; while (r < v) r <<= 1; return r; }
 
 }  // namespace
+
+extern "C" void osb_tc_profile(int enable)
+{
+    for (auto& r : g_prof_list) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof_list.clear();
+    g_prof = enable != 0;
+}
+
+// Sums over the launches recorded since osb_tc_profile(1): out = { launches, total ms, total flops, total algorithmic bytes }
+extern "C" int osb_tc_profile_read(double* out4)
+{
+    double ms = 0, fl = 0, by = 0;
+    for (auto& r : g_prof_list) {
+        if (cudaEventSynchronize(r.b) != cudaSuccess) return -1;
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) return -1;
+        ms += t; fl += r.flops; by += r.bytes;
+    }
+    out4[0] = (double)g_prof_list.size(); out4[1] = ms; out4[2] = fl; out4[3] = by;
+    return 0;
+}
 
 bool osb_tc_gemm_ok(int64_t M, int64_t N, int64_t K, int bt, const void* A, const void* B, const void* C, int64_t sa, int64_t sb, int64_t sc)
 {

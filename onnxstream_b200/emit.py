@@ -522,7 +522,7 @@ def emit_text_encoder(out_dir: Optional[str], cfg: CLIPConfig, wdtype: str = "fl
     pos = g.const(g.randn((1, T_, C), std=0.02))
     h = g.node("Add", [h, pos], [(1, T_, C)])
     mask = np.triu(np.full((T_, T_), -3.4028234663852886e+38, np.float32), k=1).reshape(1, 1, T_, T_)
-    mask_t = g.const(mask, quantizable=False, force_dtype="float32" if wdtype == "uint8" else None)
+    mask_t = g.const(mask, quantizable=False, force_dtype="float32")
     for _ in range(cfg.layers):
         n = g.layer_norm(h)
         q = g.node("Mul", [g.linear(n, C), g.scalar(1.0 / math.sqrt(d))], [(1, T_, C)])

@@ -1,8 +1,9 @@
 """Host-side Python mirror of OnnxStream's FFI surface (reference: src/exports.cpp:42-311, src/bindings.py).
 
 `Model` drives any shared library that exports the 16 ``model_*`` C entry points declared in
-``include/onnxstream_b200.h`` -- the B200 engine (``onnxstream_b200/csrc/libonnxstream_b200.so``) or, in the
-tests only, the reference itself compiled in place (``oracle/_ref/liboracle_ref.so``).  Method names,
+``include/onnxstream_b200.h`` -- the B200 engine (``onnxstream_b200/csrc/libonnxstream_b200.so``) by default; the
+test-suite points the same class at the reference compiled in place, so both sides of a parity test are driven
+identically.  This module never loads a checker library on its own.  Method names,
 argument meaning and error behaviour follow the reference's ``bindings.py`` so parity tests read the same on
 both libraries.  No torch types cross this boundary: numpy arrays in, numpy arrays out.
 """

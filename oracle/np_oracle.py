@@ -1,0 +1,231 @@
+"""oracle/np_oracle.py -- TEST INFRASTRUCTURE ONLY: numpy restatement of the reference's per-node semantics.
+
+An independent second oracle (SURVEY.md section 8c "Oracle plan (2)"): it interprets an OnnxStream model directory
+op by op in float64 (optionally rounding every node output to fp16, the reference's m_use_fp16_arithmetic storage
+rule) and is used to (a) arbitrate wherever oracle/_ref computed a result through oracle/xnn_shim.cpp rather than real
+XNNPACK (softmax, dynamic matmul, transpose, f16 Conv/FC), (b) generate the golden vectors under tests/golden/.
+Pinned by tests/test_cpu.py against oracle/_ref (the reference's own code run here) on every tiny architecture.
+
+Each handler cites the reference branch it restates (src/onnxstream.cpp).  Only `tests/`, `__graft_entry__.smoke()`
+and `bench.py`'s cpu_baseline leg may import this module; the product never does.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Dict, List, Optional
+
+import numpy as np
+
+try:
+    from scipy.special import erf as _erf
+except Exception:  # pragma: no cover
+    _erf = np.vectorize(math.erf)
+
+
+def _parse_tensor(s: str):
+    if not s:
+        return None
+    name, rest = s.split("(", 1)
+    rest = rest[:-1]
+    wtype, scale, zp = None, 0.0, 0
+    if ":" in rest:
+        wtype, shape = rest.split(":", 1)
+        if wtype.startswith("uint8["):
+            sc, z = wtype[6:-1].split(",")
+            scale, zp, wtype = float(sc), int(z), "uint8"
+    else:
+        shape = rest
+    dims = tuple(int(x) for x in shape.split(",") if x)
+    return dict(name=name, wtype=wtype, shape=dims, scale=scale, zp=zp)
+
+
+def parse_model(text: str):
+    """src/onnxstream.cpp:2445-2616."""
+    ops = []
+    for line in text.replace("\r", "\n").split("\n"):
+        if not line:
+            continue
+        sec = line.split("*")
+        name, typ = sec[0].split(":")
+        ins = [_parse_tensor(t) for t in sec[1][len("input:"):].split(";")]
+        outs = [_parse_tensor(t) for t in sec[2][len("output:"):].split(";")]
+        attrs = dict(kv.split(":") for kv in sec[3].split(";")) if len(sec) == 4 else {}
+        ops.append(dict(name=name, type=typ, inputs=ins, outputs=outs, attrs=attrs))
+    return ops
+
+
+_NP = {"float32": np.float32, "float16": np.float16, "int64": np.int64, "uint8": np.uint8}
+
+
+class NumpyOracle:
+    def __init__(self, model_dir: Optional[str] = None, text: Optional[str] = None, blobs: Optional[Dict[str, np.ndarray]] = None, fp16: bool = False):
+        self.dir = model_dir
+        self.text = text if text is not None else open(os.path.join(model_dir, "model.txt")).read()
+        self.blobs = blobs
+        self.fp16 = fp16
+        self.ops = parse_model(self.text)
+
+    # -- weights (src/onnxstream.cpp:2662-2760, 2885-2909) --
+    def _weight(self, t):
+        fn = t["name"]
+        shape = t["shape"]
+        if fn.endswith("_nchw.bin"):
+            fn = fn[:-len("_nchw.bin")] + "_nhwc.bin"
+            o, i, kh, kw = shape
+            shape = (o, kh, kw, i)
+        if self.blobs is not None:
+            a = np.asarray(self.blobs[fn]).reshape(shape)
+        else:
+            a = np.fromfile(os.path.join(self.dir, fn), dtype=_NP[t["wtype"]]).reshape(shape)
+        if t["wtype"] == "int64":
+            return a.astype(np.int64)
+        if t["wtype"] == "uint8":
+            a = (a.astype(np.float64) - t["zp"]) * np.float32(t["scale"]).astype(np.float64)
+        a = a.astype(np.float64)
+        return self._store(a)
+
+    def _store(self, a):
+        """Storage rounding: fp16 in fp16 mode, fp32 otherwise (values are carried as float64 between nodes)."""
+        if a.dtype == np.int64:
+            return a
+        return a.astype(np.float16).astype(np.float64) if self.fp16 else a.astype(np.float32).astype(np.float64)
+
+    def run(self, inputs: Dict[str, np.ndarray], extra_outputs=()) -> Dict[str, np.ndarray]:
+        env: Dict[str, np.ndarray] = {}
+        for k, v in inputs.items():
+            env[k] = v.astype(np.int64) if v.dtype == np.int64 else self._store(v.astype(np.float64))
+        refs: Dict[str, int] = {}
+        for op in self.ops:
+            for t in op["inputs"]:
+                if t and t["wtype"] is None:
+                    refs[t["name"]] = refs.get(t["name"], 0) + 1
+        for n in extra_outputs:
+            refs[n] = refs.get(n, 0) + 1
+        for op in self.ops:
+            xs = []
+            for t in op["inputs"]:
+                if t is None:
+                    xs.append(None)
+                elif t["wtype"] is not None:
+                    xs.append(self._weight(t))
+                else:
+                    xs.append(env[t["name"]])
+            ys = self._exec(op, xs)
+            if not isinstance(ys, (list, tuple)):
+                ys = [ys]
+            for t, y in zip(op["outputs"], ys):
+                assert tuple(y.shape) == tuple(t["shape"]), (op["type"], op["name"], y.shape, t["shape"])
+                env[t["name"]] = self._store(y)
+            for t in op["inputs"]:
+                if t and t["wtype"] is None:
+                    refs[t["name"]] -= 1
+                    if refs[t["name"]] == 0:
+                        del env[t["name"]]
+        return {k: (v if v.dtype == np.int64 else v.astype(np.float32)) for k, v in env.items()}
+
+    # -- per-op semantics --
+    def _exec(self, op, x):
+        t, a = op["type"], op["attrs"]
+        if t == "Conv":  # src/onnxstream.cpp:4494-4707, 1292-1534 (padding re-symmetrised from the sums)
+            inp, w = x[0], x[1]            # inp NCHW, w OHWI
+            b = x[2] if len(x) > 2 and x[2] is not None else None
+            pads = [int(v) for v in a["pads"].split(",")]
+            s = int(a["strides"].split(",")[0])
+            kh, kw = w.shape[1], w.shape[2]
+            ph, pw = pads[0] + pads[2], pads[1] + pads[3]
+            pt, pl = ph // 2, pw // 2
+            _, c, h, wd = inp.shape
+            ho, wo = (h + ph - kh) // s + 1, (wd + pw - kw) // s + 1
+            xp = np.zeros((c, h + ph, wd + pw))
+            xp[:, pt:pt + h, pl:pl + wd] = inp[0]
+            cols = np.empty((ho * wo, kh * kw * c))
+            k = 0
+            for ky in range(kh):
+                for kx in range(kw):
+                    patch = xp[:, ky:ky + s * (ho - 1) + 1:s, kx:kx + s * (wo - 1) + 1:s]   # [c, ho, wo]
+                    cols[:, k * c:(k + 1) * c] = patch.reshape(c, -1).T
+                    k += 1
+            y = cols @ w.reshape(w.shape[0], -1).T
+            if b is not None:
+                y = y + b
+            return y.T.reshape(1, w.shape[0], ho, wo)
+        if t == "MatMul":  # src/onnxstream.cpp:5669-5861
+            return np.matmul(x[0], x[1])
+        if t == "Gemm":  # src/onnxstream.cpp:4300-4375
+            return x[0] @ x[1] + x[2]
+        if t in ("Add", "Sub", "Mul", "Div"):  # src/onnxstream.cpp:5056-5175, 5394-5477, 3906-4000, 5605-5668
+            p, q = x
+            if p.dtype == np.int64 and q.dtype == np.int64:
+                if t == "Add": return p + q
+                if t == "Sub": return p - q
+                if t == "Mul": return (p.astype(np.float32) * q.astype(np.float32)).astype(np.int64)
+                return (p.astype(np.float32) / q.astype(np.float32)).astype(np.int64)
+            p, q = p.astype(np.float64), q.astype(np.float64)
+            if t == "Add": return p + q
+            if t == "Sub": return p - q
+            if t == "Mul": return p * q
+            return p / q
+        if t == "Sigmoid":  # src/onnxstream.cpp:4376-4493
+            return 1.0 / (1.0 + np.exp(-x[0]))
+        if t == "Erf": return _erf(x[0])
+        if t == "Sqrt": return np.sqrt(x[0])
+        if t == "Sin": return np.sin(x[0])
+        if t == "Cos": return np.cos(x[0])
+        if t == "Neg": return -x[0]
+        if t == "Pow": return np.power(x[0], float(np.asarray(x[1]).reshape(-1)[0]))  # src/onnxstream.cpp:5478-5604
+        if t == "Reshape":  # src/onnxstream.cpp:4708-4787
+            shp = [int(v) for v in x[1]]
+            shp = [x[0].shape[i] if v == 0 else v for i, v in enumerate(shp)]
+            return x[0].reshape(shp)
+        if t == "Unsqueeze":  # src/onnxstream.cpp:3859-3905
+            y = x[0]
+            rank = y.ndim + len(x[1])
+            for ax in sorted(int(v) % rank for v in x[1]):
+                y = np.expand_dims(y, ax)
+            return y
+        if t == "Squeeze":
+            return np.squeeze(x[0], tuple(int(v) for v in x[1])) if len(x) > 1 and x[1] is not None else np.squeeze(x[0])
+        if t == "Flatten":
+            ax = int(a.get("axis", 1))
+            return x[0].reshape(int(np.prod(x[0].shape[:ax])), -1)
+        if t == "Transpose":  # src/onnxstream.cpp:5176-5236
+            return np.transpose(x[0], [int(v) for v in a["perm"].split(",")])
+        if t == "Concat":  # src/onnxstream.cpp:4140-4299
+            return np.concatenate(x, axis=int(a["axis"]))
+        if t == "Split":
+            ax = int(a.get("axis", 0))
+            sizes = [int(v) for v in x[1]] if len(x) > 1 and x[1] is not None else [x[0].shape[ax] // len(op["outputs"])] * len(op["outputs"])
+            return np.split(x[0], np.cumsum(sizes)[:-1], axis=ax)
+        if t == "Slice":  # src/onnxstream.cpp:6499-6695
+            y = x[0]
+            starts, ends = x[1], x[2]
+            axes = x[3] if len(x) > 3 and x[3] is not None else np.arange(len(starts))
+            for s, e, ax in zip(starts, ends, axes):
+                idx = [slice(None)] * y.ndim
+                idx[int(ax)] = slice(int(s), int(e))
+                y = y[tuple(idx)]
+            return y
+        if t == "Resize":  # nearest / asymmetric / floor, src/onnxstream.cpp:6120-6315
+            sc = x[2]
+            sy, sx = float(sc[2]), float(sc[3])
+            h, w = x[0].shape[2], x[0].shape[3]
+            ho, wo = int(h * sy), int(w * sx)
+            yi = np.minimum((np.arange(ho) / sy).astype(np.int64), h - 1)
+            xi = np.minimum((np.arange(wo) / sx).astype(np.int64), w - 1)
+            return x[0][:, :, yi][:, :, :, xi]
+        if t == "Softmax":  # src/onnxstream.cpp:5862-5998
+            ax = int(a.get("axis", -1))
+            e = np.exp(x[0] - x[0].max(axis=ax, keepdims=True))
+            return e / e.sum(axis=ax, keepdims=True)
+        if t == "InstanceNormalization":  # src/onnxstream.cpp:4788-5055 (double statistics)
+            eps = float(a.get("epsilon", 1e-5))
+            v = x[0]
+            mean = v.mean(axis=2, keepdims=True)
+            var = ((v - mean) ** 2).mean(axis=2, keepdims=True)
+            return x[1].reshape(1, -1, 1) * (v - mean) / np.sqrt(var + eps) + x[2].reshape(1, -1, 1)
+        if t == "ReduceMean":  # src/onnxstream.cpp:5237-5393
+            return x[0].mean(axis=int(a["axes"]), keepdims=bool(int(a.get("keepdims", "1"))))
+        if t == "Gather":  # src/onnxstream.cpp:6316-6498
+            return np.take(x[0], x[1].astype(np.int64), axis=int(a.get("axis", 0)))
+        raise NotImplementedError(t)

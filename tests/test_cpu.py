@@ -1,0 +1,190 @@
+"""CPU-only suite (`-m "not gpu"`): the oracle against its pins, the host logic, and the C-ABI library surface.
+
+Pinning of the oracle: the reference ships no tests or golden vectors, so
+  (1) oracle/_ref = the reference's own sources compiled in place, i.e. outputs of the reference itself run here;
+  (2) oracle/np_oracle.py = an independent numpy restatement;
+(1) and (2) must agree on every tiny architecture, (2) must reproduce the committed golden vectors bit-for-bit, and
+(1) must match torch on a Conv -> GroupNorm -> SiLU chain (the check the survey used to validate the XNNPACK build).
+"""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+from onnxstream_b200 import emit
+from util import run_model, report
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+from np_oracle import NumpyOracle, parse_model  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def workdir():
+    with tempfile.TemporaryDirectory(prefix="osb200_c_") as d:
+        yield d
+
+
+def _archs(workdir, wdtype="float32"):
+    out = {}
+    cfg = emit.UNetConfig.tiny(8)
+    d = os.path.join(workdir, f"unet_{wdtype}") + "/"
+    emit.emit_unet(d, cfg, wdtype, seed=0)
+    out["unet"] = (d, emit.unet_inputs(cfg), "out_5F_sample")
+    cfgx = emit.UNetConfig.tiny(8, sdxl=True)
+    d = os.path.join(workdir, f"sdxl_{wdtype}") + "/"
+    emit.emit_unet(d, cfgx, wdtype, seed=3)
+    out["sdxl_unet"] = (d, emit.unet_inputs(cfgx), "out_5F_sample")
+    vc = emit.VAEConfig.tiny(8)
+    d = os.path.join(workdir, f"vae_{wdtype}") + "/"
+    emit.emit_vae_decoder(d, vc, wdtype)
+    out["vae"] = (d, {"input_2E_1": np.random.default_rng(5).standard_normal((1, 4, 8, 8)).astype(np.float32)}, "outsample")
+    cc = emit.CLIPConfig.tiny()
+    d = os.path.join(workdir, f"clip_{wdtype}") + "/"
+    emit.emit_text_encoder(d, cc, wdtype)
+    out["clip"] = (d, {"input_5F_ids": np.random.default_rng(6).integers(0, cc.vocab, (1, cc.tokens)).astype(np.int64)}, "last_5F_hidden_5F_state")
+    return out
+
+
+@pytest.mark.parametrize("arch", ["unet", "sdxl_unet", "vae", "clip"])
+def test_restatement_matches_reference_fp32(oracle_lib, workdir, arch):
+    d, inputs, out = _archs(workdir)[arch]
+    ref = run_model(oracle_lib, d, inputs, ())[0][out]
+    got = NumpyOracle(d).run(inputs)[out]
+    assert report(got, ref)["rel_to_max"] <= 5e-5
+
+
+def test_restatement_matches_reference_fp16(oracle_lib, workdir):
+    d, inputs, out = _archs(workdir, "float16")["unet"]
+    ref = run_model(oracle_lib, d, inputs, ("use_fp16_arithmetic", "fuse_ops_in_attention"))[0][out]
+    got = NumpyOracle(d, fp16=True).run(inputs)[out]
+    assert report(got, ref)["rel_to_max"] <= 1e-2    # both round every node output to fp16; XNNPACK f16 elementwise differs in the last bit
+
+
+def test_reference_matches_torch_conv_groupnorm_silu(oracle_lib, workdir):
+    import torch
+    import torch.nn.functional as F
+    g = emit.GraphBuilder(os.path.join(workdir, "cgs") + "/", "float32", seed=11, keep_in_memory=True)
+    x = g.input("x", (1, 16, 12, 12))
+    h = g.conv(x, 32, 3, stride=2, pad=1)
+    h = g.silu(g.group_norm(h, 8, 1e-5))
+    g.finish()
+    xin = np.random.default_rng(1).standard_normal((1, 16, 12, 12)).astype(np.float32)
+    ref = run_model(oracle_lib, g.out_dir, {"x": xin}, ())[0][h.name]
+    names = list(g.blobs)
+    w = torch.from_numpy(g.blobs[[n for n in names if n.endswith("_nhwc.bin")][0]][1]).permute(0, 3, 1, 2)
+    vecs = [torch.from_numpy(g.blobs[n][1]) for n in names if not n.endswith("_nhwc.bin") and g.blobs[n][0] == "float32"]
+    bias = vecs[0]
+    gamma, beta = vecs[-2].reshape(-1), vecs[-1].reshape(-1)
+    y = F.silu(F.group_norm(F.conv2d(torch.from_numpy(xin), w, bias, stride=2, padding=1), 8, gamma, beta, 1e-5)).numpy()
+    assert report(ref, y)["max_abs"] <= 2e-5
+
+
+def test_golden_vectors(oracle_lib):
+    """tests/golden/*.npz were produced by tests/golden/make_golden.py from oracle/_ref; the restatement and the reference
+    must both still reproduce them (guards the emitter, the oracle build and the restatement against silent drift)."""
+    files = sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+    assert files, "no golden fixtures committed"
+    sys.path.insert(0, GOLDEN)
+    import make_golden
+    for f in files:
+        z = np.load(os.path.join(GOLDEN, f))
+        case = f[:-4]
+        with tempfile.TemporaryDirectory() as d:
+            d = d + "/"
+            inputs, out_name, fp16 = make_golden.build_case(case, d)
+            opts = ("use_fp16_arithmetic", "fuse_ops_in_attention") if fp16 else ()
+            ref = run_model(oracle_lib, d, inputs, opts)[0][out_name]
+            assert report(ref, z["output"])["rel_to_max"] <= (2e-3 if fp16 else 1e-5), case
+            got = NumpyOracle(d, fp16=fp16).run(inputs)[out_name]
+            assert report(got, z["output"])["rel_to_max"] <= (1e-2 if fp16 else 5e-5), case
+
+
+def test_quantizer_rule():
+    """onnx2txt.ipynb cell 1 `quantize`: percentile range, zero point = floor(|lo| / scale), scalar special case."""
+    a = np.linspace(-1.0, 3.0, 10001).astype(np.float32)
+    q, scale, zp = emit.quantize_uint8(a)
+    lo, hi = np.sort(a)[10], np.sort(a)[-11]
+    assert abs(scale - (hi - lo) / 255.0) < 1e-7 and zp == int(abs(lo) / scale)
+    assert q.dtype == np.uint8 and q.min() == 0 and q.max() >= 254
+    q, scale, zp = emit.quantize_uint8(np.asarray(-0.5, np.float32))
+    assert (float(q) - zp) * scale == -0.5
+
+
+def test_parser_roundtrip(workdir):
+    d, inputs, out = _archs(workdir)["unet"]
+    ops = parse_model(open(d + "model.txt").read())
+    assert ops[-1]["outputs"][0]["name"] == out
+    conv = next(o for o in ops if o["type"] == "Conv")
+    assert conv["inputs"][1]["name"].endswith("_nchw.bin") and os.path.exists(d + conv["inputs"][1]["name"].replace("_nchw", "_nhwc"))
+
+
+def test_capi_exports_every_declared_symbol(engine_lib):
+    lib = ctypes.CDLL(engine_lib)
+    names = []
+    for h in ("onnxstream_b200.h", "onnxstream_b200_kernels.h"):
+        text = open(os.path.join(ROOT, "include", h)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names += re.findall(r"\b((?:model|osb)_[a-z0-9_]+)\s*\(", text)
+    assert len(set(names)) >= 40
+    missing = [n for n in sorted(set(names)) if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback(engine_lib):
+    """Without a CUDA device the library loads but model_new_2 must fail loudly -- there is no CPU path to fall back to."""
+    code = ("import ctypes,sys; l=ctypes.CDLL(%r); l.model_new_2.restype=ctypes.c_void_p; "
+            "h=l.model_new_2(0,b'nocache'); print('HANDLE', h)" % engine_lib)
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert "HANDLE None" in r.stdout, r.stdout + r.stderr
+    assert "no CUDA device" in r.stderr
+
+
+def test_product_does_not_import_oracle():
+    bad = []
+    for base, _, files in os.walk(os.path.join(ROOT, "onnxstream_b200")):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".h", ".cuh")):
+                t = open(os.path.join(base, f), errors="ignore").read()
+                if re.search(r"(import\s+np_oracle|from\s+oracle|oracle/_ref|liboracle_ref|xnn_shim)", t):
+                    bad.append(f)
+    assert not bad, bad
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from onnxstream_b200 import multi
+    ident = multi.exchange_unique_id(dist, rank, lambda: bytes(range(128)))
+    cfg = emit.UNetConfig.tiny(8)
+    inputs = multi.rank_inputs(cfg, rank)
+    agg = multi.aggregate_steps_per_sec(dist, world, steps=10, seconds=1.0 + rank)
+    q.put((rank, ident, float(inputs["sample"].sum()), agg))
+    dist.destroy_process_group()
+
+
+def test_multi_rank_host_logic_gloo():
+    """world_size-2 gloo run of the host-side N>1 logic bench.py uses: unique-id exchange, rank -> sample mapping,
+    max-over-ranks aggregation."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + os.getpid() % 1000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res[0][1] == res[1][1] == bytes(range(128))
+    assert res[0][2] != res[1][2]                       # rank r gets sample seed + r
+    assert res[0][3] == res[1][3] == pytest.approx(2 * 10 / 2.0)   # aggregate = world * steps / max(seconds)
