@@ -57,6 +57,7 @@ int   model_ext_get_tensor_type(ModelContext* obj, const char* name);           
 int   model_b200_get_stats(ModelContext* obj, double* out, int n);
 double model_b200_run_resident(ModelContext* obj, int steps);   /* replay the captured graph on device-resident inputs; CUDA-event ms, < 0 on error */
 int   model_b200_set_comm(ModelContext* obj, void* nccl_comm, int rank, int nranks);  /* weights: rank 0 uploads, NCCL broadcast to the rest */
+void  model_b200_profiler(int start);                          /* cudaProfilerStart / cudaProfilerStop */
 const char* model_b200_version(void);
 
 /* NCCL bootstrap helpers (the unique id travels over whatever out-of-band channel the host uses, e.g. torch.distributed). */

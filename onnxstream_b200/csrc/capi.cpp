@@ -8,6 +8,7 @@
 #include "engine_impl.h"
 #include "../../include/onnxstream_b200.h"
 
+#include <cuda_profiler_api.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -253,6 +254,12 @@ int model_b200_set_comm(ModelContext* obj, void* nccl_comm, int rank, int nranks
 {
     obj->E().set_comm((ncclComm*)nccl_comm, rank, nranks);
     return 0;
+}
+
+// cudaProfilerStart/Stop for `ncu --profile-from-start off` (profiles/ recipes)
+void model_b200_profiler(int start)
+{
+    if (start) cudaProfilerStart(); else cudaProfilerStop();
 }
 
 const char* model_b200_version() { return "onnxstream_b200 0.1 (sm_100a)"; }

@@ -332,8 +332,7 @@ cudaEvent_t WeightStreamer::get_event()
 
 void WeightStreamer::begin_run()
 {
-    m_live = 0;
-    m_streamed = 0;
+    m_streamed = 0;   // m_live keeps counting slots that are still queued from the previous run
 }
 
 // Reserve [off, off+bytes) in the ring.  Slots are FIFO in graph order; a slot can be overwritten once its consumer

@@ -186,6 +186,7 @@ public:
     bool keep_nhwc = true;           // keep conv trunks channel-last instead of transposing around every Conv
     int gemm_impl = 0;               // 0 auto, 1 force CUDA-core kernels, 2 force tcgen05
     double ring_factor = 1.0;        // weight ring capacity = ring_factor * largest node footprint
+    bool source_on_init_done = false;  // set by the C++ adapter when it already announced every weight to the provider
 
     void set_weight_source(std::unique_ptr<WeightSource> src);
     WeightSource* weight_source() { return m_source.get(); }

@@ -1892,7 +1892,7 @@ void Engine::run()
         I.build_plan();
         for (auto& kv : I.uses) m_refs_initial[kv.first] = kv.second;
         if (!m_source) m_source = make_disk_source(true);
-        for (auto& w : I.wplan) { const TensorRef& r = m_ops[w.op].in[w.in]; m_source->on_init(r.wtype, r.name, w.bytes); }
+        if (!source_on_init_done) for (auto& w : I.wplan) { const TensorRef& r = m_ops[w.op].in[w.in]; m_source->on_init(r.wtype, r.name, w.bytes); }
         size_t cap = (size_t)((double)I.largest_node * std::max(1.0, ring_factor)) + 4096;
         m_streamer = std::make_unique<WeightStreamer>(cap, !m_source->stable_pinned(), m_comm, m_rank, m_nranks);
         m_stats.weight_largest_node_bytes = I.largest_node;

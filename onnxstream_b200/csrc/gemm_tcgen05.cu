@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cstdio>
 #include <mutex>
 #include <vector>
 
@@ -43,6 +44,9 @@ struct TcParams {
     // conv geometry (taps == 1 for a plain GEMM)
     int taps, kw, pad_top, pad_left, Wo, Ho, bw, bh, tiles_x;
     int k_blocks_per_tap;
+    int stride;                  // conv stride (TMA traversal stride on W and H)
+    int split_k;                 // > 1: each tile's k-blocks are divided among split_k CTAs, fp32 partials go to `ws`
+    float* ws;                   // split-K workspace [split][batch][M][N] fp32
     // output
     __half* C;
     const __half* bias;
@@ -69,15 +73,21 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     uint32_t addr = smem_u32(bar);
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(addr), "r"(parity) : "memory");
+    uint32_t done = 0;
+    long long t0 = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) break;
+        // watchdog: a protocol bug must surface as a launch failure, never as a hung GPU (~2 s at 2 GHz)
+        long long now = clock64();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000LL) { printf("tc_gemm_kernel: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
 }
 
 __device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
@@ -189,20 +199,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
 
     const int tiles_per_batch = p.m_tiles * p.n_tiles;
-    const int total_tiles = tiles_per_batch * p.batch;
-    const int k_blocks = p.taps * p.k_blocks_per_tap;
+    const int total_tiles = tiles_per_batch * p.batch * p.split_k;
+    const int k_blocks_all = p.taps * p.k_blocks_per_tap;
+    const int kb_per_split = (k_blocks_all + p.split_k - 1) / p.split_k;   // host guarantees (split_k - 1) * kb_per_split < k_blocks_all
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                int b = tile / tiles_per_batch, r = tile % tiles_per_batch;
+                int sp = tile % p.split_k, t2 = tile / p.split_k;
+                int b = t2 / tiles_per_batch, r = t2 % tiles_per_batch;
                 int mt = r % p.m_tiles, nt = r / p.m_tiles;
                 int n0 = nt * BLOCK_N;
                 int y0 = 0, x0 = 0, m0 = mt * BLOCK_M;
                 if (p.taps > 1 || p.bh > 0) { y0 = (mt / p.tiles_x) * p.bh; x0 = (mt % p.tiles_x) * p.bw; }
-                for (int kb = 0; kb < k_blocks; kb++) {
+                int kb_lo = sp * kb_per_split, kb_hi = min(kb_lo + kb_per_split, k_blocks_all);
+                for (int kb = kb_lo; kb < kb_hi; kb++) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx(&full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
                     int tap = kb / p.k_blocks_per_tap, kc = (kb % p.k_blocks_per_tap) * BLOCK_K;
@@ -210,7 +223,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
                     if (p.bh > 0) {
                         int ky = tap / p.kw, kx = tap % p.kw;
-                        tma_load_3d(sa, &map_a, &full[stage], kc, x0 + kx - p.pad_left, y0 + ky - p.pad_top);
+                        tma_load_3d(sa, &map_a, &full[stage], kc, x0 * p.stride + kx - p.pad_left, y0 * p.stride + ky - p.pad_top);
                     } else {
                         tma_load_3d(sa, &map_a, &full[stage], kc, m0, b);
                     }
@@ -235,7 +248,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             __syncwarp();
             tc_fence_after();
             uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
-            for (int kb = 0; kb < k_blocks; kb++) {
+            int sp = tile % p.split_k;
+            int kb_lo = sp * kb_per_split, kb_hi = min(kb_lo + kb_per_split, k_blocks_all);
+            for (int kb = kb_lo; kb < kb_hi; kb++) {
                 if (lane == 0) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
@@ -250,10 +265,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         // B, MN-major SW128: two 64-column atoms 8192 B apart (LBO), 8-row k-groups 1024 B apart (SBO);
                         // K advances 16 rows = 2048 B
                         else bdesc = make_smem_desc(b_addr + k * (UMMA_K * 128), B_STAGE_BYTES / 2, 1024);
-                        umma_f16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_f16(tmem_d, adesc, bdesc, idesc, (kb != kb_lo || k != 0) ? 1u : 0u);
                     }
                     umma_commit(&empty[stage]);                       // frees the smem slot when these MMAs retire
-                    if (kb == k_blocks - 1) umma_commit(&acc_full[acc]);  // accumulator complete -> epilogue
+                    if (kb == kb_hi - 1) umma_commit(&acc_full[acc]);     // accumulator complete -> epilogue
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -265,7 +280,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int q = warp & 3;                 // TMEM lane quadrant this warp may access
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            int b = tile / tiles_per_batch, r = tile % tiles_per_batch;
+            int sp = tile % p.split_k, t2 = tile / p.split_k;
+            int b = t2 / tiles_per_batch, r = t2 % tiles_per_batch;
             int mt = r % p.m_tiles, nt = r / p.m_tiles;
             int n0 = nt * BLOCK_N;
             int row_in_tile = q * 32 + lane;
@@ -284,13 +300,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tc_fence_after();
             __half* crow = p.C + (long long)b * p.stride_c + out_row * p.N;
             const __half* rrow = p.residual ? p.residual + (long long)b * p.stride_c + out_row * p.N : nullptr;
+            float* wrow = p.split_k > 1 ? p.ws + (((long long)sp * p.batch + b) * p.M + out_row) * p.N : nullptr;
+            const bool vec_ok = (p.N & 7) == 0;
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N; c += 32) {
                 if (n0 + c >= p.N) break;       // warp-uniform
                 uint32_t v[32];
                 uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c);
                 tmem_ld_32x32b_x32(taddr, v);
-                if (row_ok) {
+                if (row_ok && wrow) {
+                    // split-K: raw fp32 partials; bias / residual / rounding happen in splitk_reduce_kernel
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        int n = n0 + c + j;
+                        if (n + 3 < p.N && (p.N & 3) == 0) *reinterpret_cast<uint4*>(wrow + n) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        else for (int t = 0; t < 4; t++) if (n + t < p.N) wrow[n + t] = __uint_as_float(v[j + t]);
+                    }
+                } else if (row_ok && !vec_ok) {
+                    for (int j = 0; j < 32; j++) {
+                        int n = n0 + c + j;
+                        if (n >= p.N) break;
+                        float f = __uint_as_float(v[j]);
+                        if (p.bias) f += __half2float(p.bias[n]);
+                        if (rrow) f += __half2float(rrow[n]);
+                        crow[n] = __float2half_rn(f);
+                    }
+                } else if (row_ok) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
                         int n = n0 + c + j;
@@ -329,7 +364,47 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
 }
 
+// split-K second pass: out[row][n] = fp16(sum_s ws[s][row][n] + bias[n] + residual[row][n]); rows = batch * M
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, __half* __restrict__ out, const __half* __restrict__ bias,
+                                     const __half* __restrict__ residual, long long rows, int N, int splits)
+{
+    long long total = rows * N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int s = 0; s < splits; s++) acc += ws[(long long)s * total + i];
+        if (bias) acc += __half2float(bias[i % N]);
+        if (residual) acc += __half2float(residual[i]);
+        out[i] = __float2half_rn(acc);
+    }
+}
+
 // ---- host side -------------------------------------------------------------------------------------------------
+float* g_ws = nullptr;
+size_t g_ws_bytes = 0;
+constexpr size_t WS_MAX = (size_t)96 << 20;
+
+// pick a split factor: fill the SMs when the tile count is small, keep >= 2 k-blocks per split, stay inside the workspace
+int choose_split(int tiles, int k_blocks, size_t out_elems, cudaStream_t st)
+{
+    if (tiles >= 100 || k_blocks < 4) return 1;
+    int split = 148 / tiles;
+    split = std::min(split, k_blocks / 2);
+    while (split > 1 && (size_t)split * out_elems * 4 > WS_MAX) split--;
+    if (split <= 1) return 1;
+    int kb_per = (k_blocks + split - 1) / split;
+    split = (k_blocks + kb_per - 1) / kb_per;          // no empty splits: every CTA must run at least one k-block
+    if (split <= 1) return 1;
+    size_t need = (size_t)split * out_elems * 4;
+    if (need > g_ws_bytes) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cs);
+        if (cs != cudaStreamCaptureStatusNone) return 1;   // never allocate inside a capture; warm-up runs size the workspace
+        if (g_ws) { cudaStreamSynchronize(st); cudaFree(g_ws); }
+        g_ws_bytes = std::max(need, (size_t)32 << 20);
+        if (cudaMalloc(&g_ws, g_ws_bytes) != cudaSuccess) { g_ws = nullptr; g_ws_bytes = 0; return 1; }
+    }
+    return split;
+}
 
 PFN_cuTensorMapEncodeTiled_v12000 get_encode()
 {
@@ -346,14 +421,14 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode()
 
 // rank-3 fp16 tensor map with 128B swizzle; dims/strides innermost first
 bool make_map(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes, uint64_t s2_bytes,
-              uint32_t b0, uint32_t b1, uint32_t b2)
+              uint32_t b0, uint32_t b1, uint32_t b2, uint32_t traversal_stride = 1)
 {
     auto enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[3] = { d0, d1, d2 };
     cuuint64_t strides[2] = { s1_bytes, s2_bytes };
     cuuint32_t box[3] = { b0, b1, b2 };
-    cuuint32_t estr[3] = { 1, 1, 1 };
+    cuuint32_t estr[3] = { 1, traversal_stride, traversal_stride };   // strided conv: every s-th pixel of the box span
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -380,7 +455,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cuda
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    int total = p.m_tiles * p.n_tiles * p.batch;
+    int total = p.m_tiles * p.n_tiles * p.batch * p.split_k;
     int grid = std::min(total, num_sms());
     ProfRec rec{};
     if (g_prof) {
@@ -393,8 +468,14 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cuda
         cudaEventRecord(rec.a, st);
     }
     tc_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, p);
+    if (p.split_k > 1) {
+        launched(1);
+        long long rows = (long long)p.batch * p.M;
+        int rgrid = (int)std::min<long long>((rows * p.N + 255) / 256, 148 * 8);
+        splitk_reduce_kernel<<<rgrid, 256, 0, st>>>(p.ws, p.C, p.bias, p.residual, rows, p.N, p.split_k);
+    }
     if (g_prof) { cudaEventRecord(rec.b, st); g_prof_list.push_back(rec); }
-    return launched(1);
+    return launched(p.split_k > 1 ? 0 : 1);
 }
 
 inline uint32_t next_pow2(uint32_t v) { uint32_t r = 1; while (r < v) r <<= 1; return r; }
@@ -424,8 +505,9 @@ extern "C" int osb_tc_profile_read(double* out4)
 
 bool osb_tc_gemm_ok(int64_t M, int64_t N, int64_t K, int bt, const void* A, const void* B, const void* C, int64_t sa, int64_t sb, int64_t sc)
 {
-    if (M < 32 || N < 8 || K < 8) return false;
-    if (N % 8 || K % 8) return false;
+    if (M < 32 || N < 1 || K < 8) return false;
+    if (K % 8) return false;
+    if (N % 8) { if (!bt || (sc % 8) || true) return false; }   // ragged N only through the conv entry (K-major B, scalar epilogue)
     if (M > (1 << 30) || N > (1 << 30) || K > (1 << 30)) return false;
     if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) return false;
     if ((sa % 8) || (sb % 8) || (sc % 8)) return false;
@@ -458,14 +540,17 @@ int osb_tc_gemm_launch(const void* A, const void* B, void* C, const void* bias, 
     p.b_kmajor = bt ? 1 : 0;
     p.taps = 1; p.kw = 1; p.bh = 0; p.bw = 0; p.tiles_x = 1;
     p.k_blocks_per_tap = (int)((K + BLOCK_K - 1) / BLOCK_K);
+    p.stride = 1;
     p.C = (__half*)C; p.bias = (const __half*)bias; p.residual = (const __half*)residual; p.stride_c = sc;
+    p.split_k = (sc == M * N || batch == 1) ? choose_split(p.m_tiles * p.n_tiles * p.batch, p.k_blocks_per_tap, (size_t)batch * M * N, st) : 1;
+    p.ws = g_ws;
     return launch(ma, mb, p, st);
 }
 
 bool osb_tc_conv_ok(int64_t H, int64_t W, int64_t Cin, int64_t Cout, int kh, int kw, int stride, const void* x, const void* w, const void* y)
 {
-    if (stride != 1) return false;           // strided convs: CUDA-core implicit GEMM (3 nodes in the UNet)
-    if (Cin % 8 || Cout % 8 || Cin < 16) return false;
+    if (stride < 1 || stride > 2) return false;
+    if (Cin % 8 || Cin < 16) return false;     // TMA needs 16-byte pixel strides; tiny-Cin stems stay on the CUDA-core kernel
     if (H * W < 64) return false;
     if (kh > 7 || kw > 7) return false;
     if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) return false;
@@ -475,11 +560,12 @@ bool osb_tc_conv_ok(int64_t H, int64_t W, int64_t Cin, int64_t Cout, int kh, int
 int osb_tc_conv_launch(const void* x, const void* w, const void* bias, const void* residual, void* y, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
                        int kh, int kw, int stride, int pad_top, int pad_left, int64_t Ho, int64_t Wo, cudaStream_t st)
 {
-    (void)stride;
     uint32_t bw = std::min<uint32_t>(128, next_pow2((uint32_t)Wo)), bh = 128 / bw;
     CUtensorMap ma, mb;
-    // A: NHWC input as (C, W, H); one box = bh rows x bw pixels x 64 channels, zero-filled outside the image
-    if (!make_map(&ma, x, (uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)Cin * 2, (uint64_t)W * Cin * 2, BLOCK_K, bw, bh)) return (int)cudaErrorInvalidValue;
+    // A: NHWC input as (C, W, H); one box = bh rows x bw pixels x 64 channels, zero-filled outside the image.  With a
+    // traversal stride s the box spans bw*s x bh*s input pixels and TMA delivers every s-th one.
+    if (!make_map(&ma, x, (uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)Cin * 2, (uint64_t)W * Cin * 2, BLOCK_K, bw * stride, bh * stride, (uint32_t)stride))
+        return (int)cudaErrorInvalidValue;
     // B: OHWI weights = [Cout][kh*kw*Cin], K-major
     int64_t Ktot = (int64_t)kh * kw * Cin;
     if (!make_map(&mb, w, (uint64_t)Ktot, (uint64_t)Cout, 1, (uint64_t)Ktot * 2, (uint64_t)Ktot * Cout * 2, BLOCK_K, BLOCK_N, 1)) return (int)cudaErrorInvalidValue;
@@ -491,6 +577,9 @@ int osb_tc_conv_launch(const void* x, const void* w, const void* bias, const voi
     p.b_kmajor = 1;
     p.taps = kh * kw; p.kw = kw; p.pad_top = pad_top; p.pad_left = pad_left; p.Wo = (int)Wo; p.Ho = (int)Ho; p.bw = (int)bw; p.bh = (int)bh;
     p.k_blocks_per_tap = (int)((Cin + BLOCK_K - 1) / BLOCK_K);
+    p.stride = stride;
     p.C = (__half*)y; p.bias = (const __half*)bias; p.residual = (const __half*)residual; p.stride_c = 0;
+    p.split_k = choose_split(p.m_tiles * p.n_tiles, p.taps * p.k_blocks_per_tap, (size_t)Ho * Wo * Cout, st);
+    p.ws = g_ws;
     return launch(ma, mb, p, st);
 }

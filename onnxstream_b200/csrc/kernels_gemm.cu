@@ -188,6 +188,66 @@ skinny_gemm_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restri
     }
 }
 
+// Skinny GEMM, B stored [K, N] (ONNX MatMul / Gemm weights), M <= 8: pure weight bandwidth.  The weight matrix is cut
+// into (256-column x k-slice) panels so that ~2 waves of CTAs stream it with 16-byte loads; partial sums are reduced in
+// shared memory, then added with fp32 atomics into a zeroed scratch row; a second tiny kernel applies bias / residual and
+// rounds to the storage type.  Reads every weight exactly once.
+template <typename T, int MAXM>
+__global__ void __launch_bounds__(128)
+gemv_panel_kernel(const T* __restrict__ A, const T* __restrict__ B, float* __restrict__ acc_out, int M, int N, int K, int k_per_cta)
+{
+    constexpr int VEC = 16 / sizeof(T);           // columns per thread
+    constexpr int COLS = 32 * VEC;                // columns per CTA
+    __shared__ float red[4][MAXM][COLS];
+    const int cg = threadIdx.x & 31, kl = threadIdx.x >> 5;       // 32 column groups x 4 k-lanes
+    const int n0 = blockIdx.x * COLS + cg * VEC;
+    const int k_lo = blockIdx.y * k_per_cta, k_hi = min(k_lo + k_per_cta, K);
+    float acc[MAXM][VEC];
+#pragma unroll
+    for (int m = 0; m < MAXM; m++)
+#pragma unroll
+        for (int v = 0; v < VEC; v++) acc[m][v] = 0.f;
+    if (n0 < N) {
+        for (int k = k_lo + kl; k < k_hi; k += 4) {
+            Vec<T, VEC> b = load_vec<T, VEC>(B + (int64_t)k * N + n0);
+#pragma unroll
+            for (int m = 0; m < MAXM; m++) {
+                if (m < M) {
+                    float a = to_float(A[(int64_t)m * K + k]);
+#pragma unroll
+                    for (int v = 0; v < VEC; v++) acc[m][v] += a * to_float(b.v[v]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < MAXM; m++)
+#pragma unroll
+        for (int v = 0; v < VEC; v++) red[kl][m][cg * VEC + v] = acc[m][v];
+    __syncthreads();
+    for (int i = threadIdx.x; i < M * COLS; i += 128) {
+        int m = i / COLS, c = i % COLS;
+        int n = blockIdx.x * COLS + c;
+        if (n >= N) continue;
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) v += red[j][m][c];
+        atomicAdd(&acc_out[(int64_t)m * N + n], v);
+    }
+}
+
+template <typename T>
+__global__ void gemv_finalize_kernel(const float* __restrict__ acc, T* __restrict__ C, const T* __restrict__ bias, const T* __restrict__ residual, int M, int N)
+{
+    int total = M * N;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        float v = acc[i];
+        if (bias) v += to_float(bias[i % N]);
+        if (residual) v += to_float(residual[i]);
+        C[i] = from_float<T>(v);
+    }
+}
+
 // ---- softmax with scale + additive mask (score tile of the attention decomposition) ---------------------------
 template <typename T>
 __global__ void softmax_scaled_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int64_t cols, float scale,
@@ -207,6 +267,43 @@ __global__ void softmax_scaled_kernel(const T* __restrict__ x, T* __restrict__ y
         float inv = 1.f / sum;
         for (int64_t c = threadIdx.x; c < cols; c += blockDim.x)
             yr[c] = from_float<T>(expf(to_float(xr[c]) * scale + (mr ? to_float(mr[c]) : 0.f) - mx) * inv);
+    }
+}
+
+// Same, one global read per element: the row is staged in shared memory as fp32 (cols <= 12288)
+template <typename T>
+__global__ void softmax_scaled_smem_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int cols, float scale,
+                                           const T* __restrict__ mask, int64_t mask_rows)
+{
+    extern __shared__ float row[];
+    __shared__ float red[32];
+    constexpr int VEC = 16 / sizeof(T);
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        const T* xr = x + r * cols;
+        const T* mr = mask ? mask + (r % mask_rows) * cols : nullptr;
+        T* yr = y + r * cols;
+        float mx = -INFINITY;
+        for (int c = threadIdx.x * VEC; c < cols; c += blockDim.x * VEC) {
+            Vec<T, VEC> v = load_vec<T, VEC>(xr + c);
+#pragma unroll
+            for (int k = 0; k < VEC; k++) {
+                float f = to_float(v.v[k]) * scale + (mr ? to_float(mr[c + k]) : 0.f);
+                row[c + k] = f;
+                mx = fmaxf(mx, f);
+            }
+        }
+        mx = block_reduce_max(mx, red);
+        float sum = 0.f;
+        for (int c = threadIdx.x; c < cols; c += blockDim.x) { float e = __expf(row[c] - mx); row[c] = e; sum += e; }
+        sum = block_reduce_sum(sum, red);
+        float inv = 1.f / sum;
+        for (int c = threadIdx.x * VEC; c < cols; c += blockDim.x * VEC) {
+            Vec<T, VEC> o;
+#pragma unroll
+            for (int k = 0; k < VEC; k++) o.v[k] = from_float<T>(row[c + k] * inv);
+            store_vec<T, VEC>(yr + c, o);
+        }
+        __syncthreads();
     }
 }
 
@@ -295,6 +392,34 @@ int osb_gemm(const void* A, const void* B, void* C, const void* bias, const void
     if (impl == 2 && !tc_ok) return (int)cudaErrorInvalidValue;
     if (tc_ok && impl != 1) return osb_tc_gemm_launch(A, B, C, bias, residual, batch, M, N, K, sa, sb, sc, bt, st);
     ConvGeom g{};
+    if (M <= 8 && batch == 1 && !bt && N % 8 == 0 && aligned16(B) && N >= 256 && K >= 64) {
+        // weight-bandwidth path
+        static float* scratch = nullptr; static size_t scratch_n = 0;
+        size_t need = (size_t)M * N;
+        if (need > scratch_n) {
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            cudaStreamIsCapturing(st, &cs);
+            if (cs != cudaStreamCaptureStatusNone) return (int)cudaErrorStreamCaptureUnsupported;
+            if (scratch) { cudaStreamSynchronize(st); cudaFree(scratch); }
+            scratch_n = std::max<size_t>(need, 1 << 20);
+            if (cudaMalloc(&scratch, scratch_n * 4) != cudaSuccess) { scratch = nullptr; scratch_n = 0; return (int)cudaErrorMemoryAllocation; }
+        }
+        cudaError_t e = cudaMemsetAsync(scratch, 0, need * 4, st);
+        if (e != cudaSuccess) return (int)e;
+        int vec = dtype == OSB_F16 ? 8 : 4, cols = 32 * vec;
+        int gx = (int)((N + cols - 1) / cols);
+        int gy = (int)max<int64_t>(1, min<int64_t>((K + 15) / 16, (592 + gx - 1) / gx));
+        int k_per = (int)((K + gy - 1) / gy);
+        gy = (int)((K + k_per - 1) / k_per);
+        dim3 grid(gx, gy);
+        if (dtype == OSB_F16) gemv_panel_kernel<__half, 8><<<grid, 128, 0, st>>>((const __half*)A, (const __half*)B, scratch, (int)M, (int)N, (int)K, k_per);
+        else gemv_panel_kernel<float, 8><<<grid, 128, 0, st>>>((const float*)A, (const float*)B, scratch, (int)M, (int)N, (int)K, k_per);
+        launched();
+        int fg = (int)min<int64_t>((M * N + 255) / 256, 148 * 4);
+        if (dtype == OSB_F16) gemv_finalize_kernel<__half><<<fg, 256, 0, st>>>(scratch, (__half*)C, (const __half*)bias, (const __half*)residual, (int)M, (int)N);
+        else gemv_finalize_kernel<float><<<fg, 256, 0, st>>>(scratch, (float*)C, (const float*)bias, (const float*)residual, (int)M, (int)N);
+        return launched();
+    }
     if (M <= 8 && batch == 1) {
         int grid = bt ? (int)min<int64_t>((N + 7) / 8, 148 * 8) : (int)((N + 63) / 64);
         if (dtype == OSB_F16) skinny_gemm_kernel<__half, 8><<<grid, 256, 0, st>>>((const __half*)A, (const __half*)B, (__half*)C, (const __half*)bias, (const __half*)residual, (int)M, (int)N, (int)K, bt);
@@ -351,6 +476,21 @@ int osb_softmax_scaled(const void* x, void* y, int dtype, int64_t rows, int64_t 
     int threads = cols >= 1024 ? 256 : (cols >= 256 ? 128 : 32);
     int grid = (int)min<int64_t>(rows, 148 * 16);
     if (mask_rows <= 0) mask_rows = 1;
+    int vecw = dtype == OSB_F16 ? 8 : 4;
+    if (cols >= 512 && cols <= 12288 && cols % vecw == 0 && aligned16(x) && aligned16(y)) {
+        size_t smem = (size_t)cols * sizeof(float);
+        grid = (int)min<int64_t>(rows, 148 * 4);
+        if (dtype == OSB_F16) {
+            static bool attr16 = false;
+            if (!attr16) { cudaFuncSetAttribute(softmax_scaled_smem_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 4); attr16 = true; }
+            softmax_scaled_smem_kernel<__half><<<grid, 256, smem, st>>>((const __half*)x, (__half*)y, rows, (int)cols, scale, (const __half*)mask, mask_rows);
+        } else if (dtype == OSB_F32) {
+            static bool attr32 = false;
+            if (!attr32) { cudaFuncSetAttribute(softmax_scaled_smem_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 4); attr32 = true; }
+            softmax_scaled_smem_kernel<float><<<grid, 256, smem, st>>>((const float*)x, (float*)y, rows, (int)cols, scale, (const float*)mask, mask_rows);
+        } else return (int)cudaErrorInvalidValue;
+        return launched();
+    }
     if (dtype == OSB_F16) softmax_scaled_kernel<__half><<<grid, threads, 0, st>>>((const __half*)x, (__half*)y, rows, cols, scale, (const __half*)mask, mask_rows);
     else if (dtype == OSB_F32) softmax_scaled_kernel<float><<<grid, threads, 0, st>>>((const float*)x, (float*)y, rows, cols, scale, (const float*)mask, mask_rows);
     else return (int)cudaErrorInvalidValue;

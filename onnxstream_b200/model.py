@@ -72,6 +72,8 @@ def load_library(path: str) -> ctypes.CDLL:
         "model_ext_push_tensor": ([vp, cp, cp, ui, ctypes.POINTER(ui), vp], None),
         "model_b200_get_stats": ([vp, ctypes.POINTER(ctypes.c_double), ctypes.c_int], ctypes.c_int),
         "model_b200_set_comm": ([vp, vp, ctypes.c_int, ctypes.c_int], ctypes.c_int),
+        "model_b200_run_resident": ([vp, ctypes.c_int], ctypes.c_double),
+        "osb_tc_profile": ([ctypes.c_int], None), "osb_tc_profile_read": ([ctypes.POINTER(ctypes.c_double)], ctypes.c_int),
         "osb_comm_unique_id": ([ctypes.c_char_p], ctypes.c_int), "osb_comm_init": ([ctypes.c_int, ctypes.c_int, ctypes.c_char_p], vp),
         "osb_comm_destroy": ([vp], None),
     }
@@ -86,7 +88,10 @@ def load_library(path: str) -> ctypes.CDLL:
 class Model:
     """One OnnxStream model instance behind the C ABI."""
 
-    def __init__(self, library_path: Optional[str] = None, threads_count: int = 0, weights_provider_name: str = "nocache"):
+    def __init__(self, library_path: Optional[str] = None, threads_count: int = 0, weights_provider_name: str = "nocache",
+                 plain_abi: bool = False):
+        """plain_abi=True restricts the wrapper to the reference's 16 entry points (no model_ext_* / model_b200_*)."""
+        self.plain_abi = plain_abi
         self.lib = load_library(library_path or ENGINE_LIB)
         self.h = self.lib.model_new_2(threads_count, weights_provider_name.encode())
         if not self.h:
@@ -157,7 +162,7 @@ class Model:
             raise OnnxStreamError("add_tensor: only float32 and int64 inputs are supported (src/exports.cpp:182-193)")
         array = np.ascontiguousarray(array)
         dims = (ctypes.c_uint * array.ndim)(*array.shape)
-        if hasattr(self.lib, "model_ext_push_tensor"):
+        if not self.plain_abi and hasattr(self.lib, "model_ext_push_tensor"):
             # Model::push_tensor semantics (works with use_fp16_arithmetic set, unlike the reference's model_add_tensor)
             self.lib.model_ext_push_tensor(self.h, t.encode(), name.encode(), array.ndim, dims, array.ctypes.data)
             return
@@ -210,6 +215,13 @@ class Model:
     STAT_FIELDS = ("weight_ring_bytes", "weight_peak_live_bytes", "weight_largest_node_bytes", "weight_bytes_streamed",
                    "weight_resident_bytes", "act_high_water_bytes", "h2d_input_bytes", "d2h_output_bytes", "kernel_launches",
                    "tc_launches", "steps_executed", "ops_fused_away", "last_run_ms", "last_gpu_ms", "graph_replays")
+
+    def run_resident(self, steps: int) -> float:
+        """B200 engine only: replay the captured CUDA graph `steps` times on device-resident inputs; returns CUDA-event ms."""
+        ms = self.lib.model_b200_run_resident(self.h, steps)
+        if ms < 0:
+            raise OnnxStreamError("model_b200_run_resident failed (no captured graph?)")
+        return ms
 
     def stats(self) -> Dict[str, float]:
         """B200 engine only: streaming / launch statistics of the last run (include/onnxstream_b200.h)."""

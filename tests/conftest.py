@@ -3,6 +3,8 @@ import sys
 
 import pytest
 
+os.environ.setdefault("OMP_NUM_THREADS", "4")   # the oracle's XNNPACK shim uses OpenMP; keep it from fanning out over 200 cores
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

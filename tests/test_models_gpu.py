@@ -31,11 +31,11 @@ def workdir():
 
 def _models(workdir, wdtype):
     out = {}
-    cfg = emit.UNetConfig.tiny(16)
+    cfg = emit.UNetConfig.tiny(8)
     d = os.path.join(workdir, f"unet_{wdtype}") + "/"
     emit.emit_unet(d, cfg, wdtype, seed=0)
     out["unet"] = (d, emit.unet_inputs(cfg), "out_5F_sample")
-    cfgx = emit.UNetConfig.tiny(16, sdxl=True)
+    cfgx = emit.UNetConfig.tiny(8, sdxl=True)
     d = os.path.join(workdir, f"sdxl_{wdtype}") + "/"
     emit.emit_unet(d, cfgx, wdtype, seed=3)
     out["sdxl_unet"] = (d, emit.unet_inputs(cfgx), "out_5F_sample")
@@ -123,7 +123,7 @@ def test_intermediates_match(engine_lib, oracle_lib, models32):
 def test_streaming_ring_bound(engine_lib, models16):
     """The HBM weight ring never exceeds one node's footprint (north star: peak resident weights <= largest node)."""
     d, inputs, out = models16["unet"]
-    got, m = run_model(engine_lib, d, inputs, FP16, wp="ram", runs=2)
+    got, m = run_model(engine_lib, d, inputs, FP16, wp="ram+nocache", runs=2)
     st = m.stats()
     assert st["weight_ring_bytes"] <= st["weight_largest_node_bytes"] + 8192
     assert st["weight_peak_live_bytes"] <= st["weight_ring_bytes"]
@@ -132,7 +132,7 @@ def test_streaming_ring_bound(engine_lib, models16):
     assert st["weight_resident_bytes"] == 0
 
 
-@pytest.mark.parametrize("wp", ["nocache", "prefetch", "ram", "ram+nocache", "ram+prefetch"])
+@pytest.mark.parametrize("wp", ["prefetch", "ram+nocache", "ram+prefetch"])
 def test_providers_agree(engine_lib, models16, wp):
     d, inputs, out = models16["unet"]
     a, _ = run_model(engine_lib, d, inputs, FP16, wp="nocache")
@@ -142,12 +142,11 @@ def test_providers_agree(engine_lib, models16, wp):
 
 def test_resident_and_graph_bit_identical(engine_lib, models16):
     d, inputs, out = models16["unet"]
-    a, _ = run_model(engine_lib, d, inputs, FP16, wp="ram")
-    b, m = run_model(engine_lib, d, inputs, FP16, wp="ram", b200_options=(("b200_resident_weights", 1), ("b200_cuda_graph", 1)), runs=5)
+    a, _ = run_model(engine_lib, d, inputs, FP16, wp="ram+nocache")
+    b, m = run_model(engine_lib, d, inputs, FP16, wp="ram+nocache", b200_options=(("b200_resident_weights", 1), ("b200_cuda_graph", 1)), runs=5)
     assert np.array_equal(a[out], b[out])
     assert m.stats()["graph_replays"] >= 1
-    ms = m.lib.model_b200_run_resident(m.h, 3)
-    assert ms > 0
+    assert m.run_resident(3) > 0
 
 
 def test_in_memory_weights(engine_lib, oracle_lib, workdir):
@@ -210,3 +209,16 @@ def test_errors_are_reported(engine_lib, workdir):
     m3.add_tensor("x", np.zeros((1, 2), np.float32))
     with pytest.raises(OnnxStreamError, match="unexpected shape of output"):
         m3.run()
+
+
+def test_cpp_dropin(oracle_lib, models32):
+    """The reference's OWN exports.cpp + onnxstream.h (unmodified, compiled in place) on top of compat_onnxstream.cpp and the
+    B200 engine: proves the C++ boundary (Model members, WeightsProvider contract, m_data hand-off) end to end."""
+    lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build", "link_test", "libonnxstream_ref_exports.so")
+    if not os.path.exists(lib):
+        pytest.skip("build/link_test not built (scripts/link_reference_apps.sh needs /root/reference)")
+    d, inputs, out = models32["unet"]
+    ref = _oracle(oracle_lib, "unet32", d, inputs, ())
+    for wp in ("nocache", "ram+prefetch"):
+        got, _ = run_model(lib, d, inputs, (), wp=wp, runs=2, plain_abi=True)
+        assert report(got[out], ref[out])["rel_to_max"] <= TOL["float32"], wp

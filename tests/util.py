@@ -5,8 +5,8 @@ import numpy as np
 from onnxstream_b200.model import Model
 
 
-def run_model(lib, model_dir, inputs, options=(), extra_outputs=(), wp="nocache", parts=None, ranges=None, upcast=(), b200_options=(), runs=1):
-    m = Model(lib, 0, wp)
+def run_model(lib, model_dir, inputs, options=(), extra_outputs=(), wp="nocache", parts=None, ranges=None, upcast=(), b200_options=(), runs=1, plain_abi=False):
+    m = Model(lib, 4, wp, plain_abi=plain_abi)   # 4 pthreadpool workers for the CPU oracle (0 = every core: slow on many-core hosts); the GPU engine ignores it
     for o in options:
         m.set_option(o, True)
     for name, val in b200_options:
@@ -29,7 +29,7 @@ def run_model(lib, model_dir, inputs, options=(), extra_outputs=(), wp="nocache"
         out = {}
         for n in m.get_all_tensor_names():
             t = m.get_tensor(n)
-            if t is None:
+            if t is None and not plain_abi:
                 t = m.get_tensor_i64(n)
             out[n] = t
     return out, m
