@@ -277,6 +277,11 @@ def main():
     step_api(mv, inputs)
     prof = (ctypes.c_double * 4)()
     rc = mv.lib.osb_tc_profile_read(prof)
+    if os.environ.get("OSB_TC_DUMP"):
+        buf = ctypes.create_string_buffer(1 << 20)
+        mv.lib.osb_tc_profile_dump.argtypes = [ctypes.c_char_p, ctypes.c_int]
+        nb = mv.lib.osb_tc_profile_dump(buf, len(buf))
+        open(os.environ["OSB_TC_DUMP"], "w").write(buf.raw[:max(nb, 0)].decode())
     mv.lib.osb_tc_profile(0)
     st_e = mv.stats()
     n_tc, tc_ms, tc_flops, tc_bytes = [float(x) for x in prof]

@@ -121,6 +121,11 @@ int osb_gemm_tc_eligible(int64_t M, int64_t N, int64_t K, int dtype);
  * osb_tc_profile(1) starts recording, osb_tc_profile_read fills {launches, total ms, total FLOPs, total algorithmic bytes}. */
 void osb_tc_profile(int enable);
 int osb_tc_profile_read(double* out4);
+int osb_tc_profile_dump(char* buf, int cap);   /* one line per launch: M N K taps batch split conv ms gflop */
+
+/* Programmatic dependent launch for every kernel of this library (default on). */
+int osb_pdl_enabled(void);
+void osb_set_pdl(int enable);
 
 /* Counters: number of kernel launches issued through this ABI since the last reset (bench.py's gpu_launches). */
 uint64_t osb_launch_count(void);

@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <algorithm>
+#include <utility>
 #include "../../include/onnxstream_b200_kernels.h"
 
 using std::min;
@@ -17,6 +18,29 @@ static inline int launched(int tensor_core = 0)
 {
     osb_count_launch(tensor_core);
     return (int)cudaGetLastError();
+}
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// Every kernel (a) signals at entry that the next kernel in the stream may be scheduled and (b) waits for its own
+// predecessor to complete before touching global memory.  With ~1000 short kernels per UNet step this hides the launch
+// latency and prologue of kernel i+1 behind the tail of kernel i (CUDA graphs keep the programmatic edges).
+__device__ __forceinline__ void osb_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void osb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void osb_pdl_prologue() { osb_pdl_trigger(); osb_pdl_wait(); }
+
+extern "C" int osb_pdl_enabled(void);
+
+template <typename... KArgs, typename... Args>
+static inline void osb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = osb_pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);   // errors surface through launched() / cudaGetLastError
 }
 
 static inline int grid_for(size_t work_items, int threads)

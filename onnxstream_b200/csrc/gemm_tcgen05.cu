@@ -47,6 +47,7 @@ struct TcParams {
     int stride;                  // conv stride (TMA traversal stride on W and H)
     int split_k;                 // > 1: each tile's k-blocks are divided among split_k CTAs, fp32 partials go to `ws`
     float* ws;                   // split-K workspace [split][batch][M][N] fp32
+    int* counters;               // split-K arrival counters, one per output tile (self-resetting)
     // output
     __half* C;
     const __half* bias;
@@ -165,6 +166,7 @@ __device__ __forceinline__ uint32_t make_idesc(int b_mn_major)
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p)
 {
+    osb_pdl_trigger();   // let the next kernel's CTAs be scheduled as ours drain; it waits for our completion before touching memory
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B swizzle atoms
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -176,6 +178,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t* acc_full = bars + 2 * STAGES;      // [ACC_STAGES]
     uint64_t* acc_empty = acc_full + ACC_STAGES; // [ACC_STAGES]
     uint32_t* tmem_slot = (uint32_t*)(acc_empty + ACC_STAGES);
+    volatile int* split_flag = (volatile int*)(tmem_slot + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -197,6 +200,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    osb_pdl_wait();      // everything above (barrier init, TMEM alloc, descriptor prefetch) overlapped the previous kernel's tail
 
     const int tiles_per_batch = p.m_tiles * p.n_tiles;
     const int total_tiles = tiles_per_batch * p.batch * p.split_k;
@@ -308,13 +312,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 uint32_t v[32];
                 uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c);
                 tmem_ld_32x32b_x32(taddr, v);
-                if (row_ok && wrow) {
-                    // split-K: raw fp32 partials; bias / residual / rounding happen in splitk_reduce_kernel
+                if (wrow) {
+                    // split-K: raw fp32 partials; the last CTA to arrive for this tile reduces them (below)
+                    if (row_ok) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        int n = n0 + c + j;
-                        if (n + 3 < p.N && (p.N & 3) == 0) *reinterpret_cast<uint4*>(wrow + n) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        else for (int t = 0; t < 4; t++) if (n + t < p.N) wrow[n + t] = __uint_as_float(v[j + t]);
+                        for (int j = 0; j < 32; j += 4) {
+                            int n = n0 + c + j;
+                            if (n + 3 < p.N && (p.N & 3) == 0) *reinterpret_cast<uint4*>(wrow + n) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            else for (int t = 0; t < 4; t++) if (n + t < p.N) wrow[n + t] = __uint_as_float(v[j + t]);
+                        }
                     }
                 } else if (row_ok && !vec_ok) {
                     for (int j = 0; j < 32; j++) {
@@ -353,6 +359,42 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tc_fence_before();
             mbar_arrive(&acc_empty[acc]);
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+            if (wrow && p.counters) {
+                // serial split-K reduction (kept for reference; the host currently prefers the parallel reduce kernel): publish the partials, count arrivals, the last CTA sums all splits in fp32,
+                // applies bias / residual and rounds once -- no separate reduce kernel, no extra launch.
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (warp == 2 && lane == 0) {
+                    int old = atomicAdd(&p.counters[t2], 1);
+                    *split_flag = (old == p.split_k - 1) ? 1 : 0;
+                    if (old == p.split_k - 1) p.counters[t2] = 0;      // re-arm for the next launch
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (*split_flag) {
+                    __threadfence();
+                    if (row_ok) {
+                        const long long plane = (long long)p.batch * p.M * p.N;
+                        const float* base = p.ws + ((long long)b * p.M + out_row) * p.N;
+                        for (int n = n0; n < n0 + BLOCK_N && n < p.N; n += 4) {
+                            float f[4] = { 0.f, 0.f, 0.f, 0.f };
+                            bool v4 = (n + 3 < p.N) && (p.N & 3) == 0;
+                            for (int sidx = 0; sidx < p.split_k; sidx++) {
+                                const float* src = base + sidx * plane + n;
+                                if (v4) { float4 t = __ldcg(reinterpret_cast<const float4*>(src)); f[0] += t.x; f[1] += t.y; f[2] += t.z; f[3] += t.w; }
+                                else for (int t = 0; t < 4; t++) if (n + t < p.N) f[t] += __ldcg(src + t);
+                            }
+                            for (int t = 0; t < 4; t++) {
+                                if (n + t >= p.N) break;
+                                float o = f[t];
+                                if (p.bias) o += __half2float(p.bias[n + t]);
+                                if (rrow) o += __half2float(rrow[n + t]);
+                                crow[n + t] = __float2half_rn(o);
+                            }
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");       // split_flag is reused by the next tile
+            }
         }
     }
 
@@ -368,19 +410,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, __half* __restrict__ out, const __half* __restrict__ bias,
                                      const __half* __restrict__ residual, long long rows, int N, int splits)
 {
-    long long total = rows * N;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        float acc = 0.f;
-        for (int s = 0; s < splits; s++) acc += ws[(long long)s * total + i];
-        if (bias) acc += __half2float(bias[i % N]);
-        if (residual) acc += __half2float(residual[i]);
-        out[i] = __float2half_rn(acc);
+    osb_pdl_prologue();
+    // N % 4 == 0: one float4 of every split plane per thread, fully coalesced
+    const long long total4 = rows * N / 4;
+    const long long plane4 = total4;
+    const float4* w4 = reinterpret_cast<const float4*>(ws);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        float4 a = w4[i];
+        for (int s = 1; s < splits; s++) { float4 t = w4[(long long)s * plane4 + i]; a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+        long long e = i * 4;
+        int n = (int)(e % N);
+        if (bias) { a.x += __half2float(bias[n]); a.y += __half2float(bias[n + 1]); a.z += __half2float(bias[n + 2]); a.w += __half2float(bias[n + 3]); }
+        if (residual) {
+            Vec<__half, 4> r = load_vec<__half, 4>(residual + e);
+            a.x += __half2float(r.v[0]); a.y += __half2float(r.v[1]); a.z += __half2float(r.v[2]); a.w += __half2float(r.v[3]);
+        }
+        Vec<__half, 4> o;
+        o.v[0] = __float2half_rn(a.x); o.v[1] = __float2half_rn(a.y); o.v[2] = __float2half_rn(a.z); o.v[3] = __float2half_rn(a.w);
+        store_vec<__half, 4>(out + e, o);
     }
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------
 float* g_ws = nullptr;
 size_t g_ws_bytes = 0;
+int* g_counters = nullptr;       // 1024 self-resetting tile counters
 constexpr size_t WS_MAX = (size_t)96 << 20;
 
 // pick a split factor: fill the SMs when the tile count is small, keep >= 2 k-blocks per split, stay inside the workspace
@@ -395,6 +449,13 @@ int choose_split(int tiles, int k_blocks, size_t out_elems, cudaStream_t st)
     split = (k_blocks + kb_per - 1) / kb_per;          // no empty splits: every CTA must run at least one k-block
     if (split <= 1) return 1;
     size_t need = (size_t)split * out_elems * 4;
+    if (!g_counters) {
+        cudaStreamCaptureStatus cs0 = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cs0);
+        if (cs0 != cudaStreamCaptureStatusNone) return 1;
+        if (cudaMalloc(&g_counters, 1024 * sizeof(int)) != cudaSuccess) { g_counters = nullptr; return 1; }
+        cudaMemset(g_counters, 0, 1024 * sizeof(int));
+    }
     if (need > g_ws_bytes) {
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(st, &cs);
@@ -443,7 +504,7 @@ int num_sms()
 }
 
 // optional per-launch timing (bench.py's roofline leg): CUDA events on the launching stream around every launch
-struct ProfRec { cudaEvent_t a, b; double flops, bytes; };
+struct ProfRec { cudaEvent_t a, b; double flops, bytes; int M, N, K, taps, batch, split, conv; };
 bool g_prof = false;
 std::vector<ProfRec> g_prof_list;
 
@@ -465,17 +526,20 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cuda
         // algorithmic bytes: A once (conv: the input image once), B once, C once (+ residual / bias reads)
         double a_bytes = (p.bh > 0 ? M * p.K : M * Kt) * 2.0 * B;
         rec.bytes = a_bytes + N * Kt * 2.0 * (p.bh > 0 ? 1.0 : B) + M * N * 2.0 * B * (p.residual ? 2.0 : 1.0) + (p.bias ? N * 2.0 : 0.0);
+        rec.M = p.M; rec.N = p.N; rec.K = p.K; rec.taps = p.taps; rec.batch = p.batch; rec.split = p.split_k; rec.conv = p.bh > 0;
         cudaEventRecord(rec.a, st);
     }
-    tc_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, p);
-    if (p.split_k > 1) {
+    osb_launch((tc_gemm_kernel), grid, NUM_THREADS, SMEM_BYTES, st, ma, mb, p);
+    if (p.split_k > 1 && !p.counters) {
         launched(1);
-        long long rows = (long long)p.batch * p.M;
-        int rgrid = (int)std::min<long long>((rows * p.N + 255) / 256, 148 * 8);
-        splitk_reduce_kernel<<<rgrid, 256, 0, st>>>(p.ws, p.C, p.bias, p.residual, rows, p.N, p.split_k);
+        long long total4 = (long long)p.batch * p.M * p.N / 4;
+        int rgrid = (int)std::min<long long>((total4 + 255) / 256, 148 * 8);
+        osb_launch((splitk_reduce_kernel), rgrid, 256, 0, st, (const float*)p.ws, p.C, p.bias, p.residual, (long long)p.batch * p.M, p.N, p.split_k);
+        if (g_prof) { cudaEventRecord(rec.b, st); g_prof_list.push_back(rec); }
+        return launched(0);
     }
     if (g_prof) { cudaEventRecord(rec.b, st); g_prof_list.push_back(rec); }
-    return launched(p.split_k > 1 ? 0 : 1);
+    return launched(1);
 }
 
 inline uint32_t next_pow2(uint32_t v) { uint32_t r = 1; while (r < v) r <<= 1; return r; }
@@ -501,6 +565,20 @@ extern "C" int osb_tc_profile_read(double* out4)
     }
     out4[0] = (double)g_prof_list.size(); out4[1] = ms; out4[2] = fl; out4[3] = by;
     return 0;
+}
+
+// One text line per recorded launch: "M N K taps batch split conv ms gflop"
+extern "C" int osb_tc_profile_dump(char* buf, int cap)
+{
+    int off = 0;
+    for (auto& r : g_prof_list) {
+        float t = 0.f;
+        if (cudaEventSynchronize(r.b) != cudaSuccess || cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) return -1;
+        int n = snprintf(buf + off, cap - off, "%d %d %d %d %d %d %d %.4f %.3f\n", r.M, r.N, r.K, r.taps, r.batch, r.split, r.conv, t, r.flops * 1e-9);
+        if (n < 0 || off + n >= cap) break;
+        off += n;
+    }
+    return off;
 }
 
 bool osb_tc_gemm_ok(int64_t M, int64_t N, int64_t K, int bt, const void* A, const void* B, const void* C, int64_t sa, int64_t sb, int64_t sc)
@@ -543,7 +621,7 @@ int osb_tc_gemm_launch(const void* A, const void* B, void* C, const void* bias, 
     p.stride = 1;
     p.C = (__half*)C; p.bias = (const __half*)bias; p.residual = (const __half*)residual; p.stride_c = sc;
     p.split_k = (sc == M * N || batch == 1) ? choose_split(p.m_tiles * p.n_tiles * p.batch, p.k_blocks_per_tap, (size_t)batch * M * N, st) : 1;
-    p.ws = g_ws;
+    p.ws = g_ws; p.counters = (p.N % 4) ? g_counters : nullptr;   // vectorised parallel reduce kernel needs N % 4 == 0
     return launch(ma, mb, p, st);
 }
 
@@ -580,6 +658,6 @@ int osb_tc_conv_launch(const void* x, const void* w, const void* bias, const voi
     p.stride = stride;
     p.C = (__half*)y; p.bias = (const __half*)bias; p.residual = (const __half*)residual; p.stride_c = 0;
     p.split_k = choose_split(p.m_tiles * p.n_tiles, p.taps * p.k_blocks_per_tap, (size_t)Ho * Wo * Cout, st);
-    p.ws = g_ws;
+    p.ws = g_ws; p.counters = (p.N % 4) ? g_counters : nullptr;   // vectorised parallel reduce kernel needs N % 4 == 0
     return launch(ma, mb, p, st);
 }

@@ -17,6 +17,7 @@ namespace {
 template <typename S, typename D>
 __global__ void convert_kernel(const S* __restrict__ src, D* __restrict__ dst, size_t n)
 {
+    osb_pdl_prologue();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         dst[i] = from_float<D>(to_float(src[i]));
 }
@@ -24,6 +25,7 @@ __global__ void convert_kernel(const S* __restrict__ src, D* __restrict__ dst, s
 template <typename D>
 __global__ void dequant_kernel(const uint8_t* __restrict__ src, D* __restrict__ dst, size_t n, float scale, int zp)
 {
+    osb_pdl_prologue();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         dst[i] = from_float<D>((float)((int)src[i] - zp) * scale);
 }
@@ -31,6 +33,7 @@ __global__ void dequant_kernel(const uint8_t* __restrict__ src, D* __restrict__ 
 template <typename S>
 __global__ void quant_kernel(const S* __restrict__ src, uint8_t* __restrict__ dst, size_t n, float scale, int zp)
 {
+    osb_pdl_prologue();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float q = rintf(to_float(src[i]) / scale) + (float)zp;
         dst[i] = (uint8_t)fminf(fmaxf(q, 0.f), 255.f);
@@ -39,6 +42,7 @@ __global__ void quant_kernel(const S* __restrict__ src, uint8_t* __restrict__ ds
 
 __global__ void i64_to_float_kernel(const int64_t* __restrict__ src, float* __restrict__ dst, size_t n)
 {
+    osb_pdl_prologue();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         dst[i] = (float)src[i];
 }
@@ -69,6 +73,7 @@ __device__ __forceinline__ float apply_unary(int op, float x, float alpha)
 template <typename T, int VEC>
 __global__ void unary_kernel(int op, const T* __restrict__ x, T* __restrict__ y, size_t n, float alpha)
 {
+    osb_pdl_prologue();
     size_t nvec = n / VEC;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
         Vec<T, VEC> v = load_vec<T, VEC>(x + i * VEC);
@@ -110,6 +115,7 @@ struct BinParams {
 template <typename T, int VEC>
 __global__ void binary_flat_kernel(int op, const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, size_t n, int a_scalar, int b_scalar)
 {
+    osb_pdl_prologue();
     float sa = a_scalar ? to_float(a[0]) : 0.f, sb = b_scalar ? to_float(b[0]) : 0.f;
     size_t nvec = n / VEC;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
@@ -131,6 +137,7 @@ template <typename T, int VEC>
 __global__ void binary_rowcol_kernel(int op, const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out,
                                      int64_t rows, int64_t cols, int b_per_row, int swap)
 {
+    osb_pdl_prologue();
     int64_t cvec = cols / VEC;
     int64_t total = rows * cvec;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -150,6 +157,7 @@ __global__ void binary_rowcol_kernel(int op, const T* __restrict__ a, const T* _
 template <typename T>
 __global__ void binary_generic_kernel(int op, const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, BinParams p, size_t n)
 {
+    osb_pdl_prologue();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         size_t rem = i;
         int64_t ao = 0, bo = 0;
@@ -182,6 +190,7 @@ struct CopyParams {
 template <typename T>
 __global__ void strided_copy_kernel(const T* __restrict__ in, T* __restrict__ out, CopyParams p, size_t n)
 {
+    osb_pdl_prologue();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         size_t rem = i;
         int64_t io = p.in_off, oo = p.out_off;
@@ -202,6 +211,7 @@ __global__ void strided_copy_kernel(const T* __restrict__ in, T* __restrict__ ou
 template <typename T>
 __global__ void transpose2d_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t rows, int64_t cols)
 {
+    osb_pdl_prologue();
     __shared__ T tile[32][33];
     int64_t b = blockIdx.z;
     const T* src = in + b * rows * cols;
@@ -225,6 +235,7 @@ __global__ void transpose2d_kernel(const T* __restrict__ in, T* __restrict__ out
 template <typename T>
 __global__ void softmax_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int64_t cols)
 {
+    osb_pdl_prologue();
     __shared__ float red[32];
     for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
         const T* xr = x + r * cols;
@@ -244,6 +255,7 @@ template <typename T>
 __global__ void layer_norm_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int64_t cols,
                                   const T* __restrict__ gamma, const T* __restrict__ beta, float eps)
 {
+    osb_pdl_prologue();
     __shared__ float red[32];
     for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
         const T* xr = x + r * cols;
@@ -267,6 +279,7 @@ __global__ void layer_norm_kernel(const T* __restrict__ x, T* __restrict__ y, in
 template <typename T>
 __global__ void reduce_mean_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int64_t cols)
 {
+    osb_pdl_prologue();
     __shared__ float red[32];
     for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
         const T* xr = x + r * cols;
@@ -285,6 +298,7 @@ __global__ void reduce_mean_kernel(const T* __restrict__ x, T* __restrict__ y, i
 template <typename T>
 __global__ void inorm_stats_kernel(const T* __restrict__ x, double* __restrict__ partial, int64_t n_per_c, int splits)
 {
+    osb_pdl_prologue();
     __shared__ double red[64];
     int64_t c = blockIdx.x;
     int s = blockIdx.y;
@@ -309,6 +323,7 @@ template <typename T>
 __global__ void inorm_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const double* __restrict__ partial, int64_t n_per_c, int splits,
                                    const T* __restrict__ scale, const T* __restrict__ bias, float eps)
 {
+    osb_pdl_prologue();
     int64_t c = blockIdx.x;
     double sum = 0.0, sq = 0.0;
     for (int s = 0; s < splits; s++) { sum += partial[(c * splits + s) * 2]; sq += partial[(c * splits + s) * 2 + 1]; }
@@ -335,6 +350,7 @@ __global__ void inorm_apply_kernel(const T* __restrict__ x, T* __restrict__ y, c
 template <typename T>
 __global__ void gn_stats_nhwc_kernel(const T* __restrict__ x, double* __restrict__ stats, int64_t C, int64_t HW, int groups, int64_t pix_per_cta)
 {
+    osb_pdl_prologue();
     extern __shared__ float sm[];  // 2 * groups
     for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) sm[i] = 0.f;
     __syncthreads();
@@ -351,9 +367,45 @@ __global__ void gn_stats_nhwc_kernel(const T* __restrict__ x, double* __restrict
     for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(&stats[i], (double)sm[i]);
 }
 
+// NHWC statistics, vectorised: a thread owns 8 consecutive channels (one 16-byte load per pixel) and walks down the
+// CTA's pixel strip; 256/(C/8) pixels are in flight per iteration.  Per-channel partials are folded into the 2*G group
+// bins with shared-memory atomics, then one double atomic per bin and CTA.
+template <typename T, int VEC>
+__global__ void gn_stats_nhwc_vec_kernel(const T* __restrict__ x, double* __restrict__ stats, int C, int64_t HW, int groups, int64_t pix_per_cta)
+{
+    osb_pdl_prologue();
+    extern __shared__ float sm[];  // 2 * groups
+    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    const int tpp = C / VEC;                        // threads per pixel
+    const int rows = blockDim.x / tpp;              // pixels in flight
+    const int cv = threadIdx.x % tpp, pr = threadIdx.x / tpp;
+    int64_t p0 = (int64_t)blockIdx.x * pix_per_cta, p1 = min(p0 + pix_per_cta, HW);
+    if (pr < rows) {
+        float s[VEC], q[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; k++) { s[k] = 0.f; q[k] = 0.f; }
+        for (int64_t p = p0 + pr; p < p1; p += rows) {
+            Vec<T, VEC> v = load_vec<T, VEC>(x + p * C + cv * VEC);
+#pragma unroll
+            for (int k = 0; k < VEC; k++) { float f = to_float(v.v[k]); s[k] += f; q[k] += f * f; }
+        }
+        const int cpg = C / groups;
+#pragma unroll
+        for (int k = 0; k < VEC; k++) {
+            int g = (cv * VEC + k) / cpg;
+            atomicAdd(&sm[2 * g], s[k]);
+            atomicAdd(&sm[2 * g + 1], q[k]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(&stats[i], (double)sm[i]);
+}
+
 template <typename T>
 __global__ void gn_stats_nchw_kernel(const T* __restrict__ x, double* __restrict__ stats, int64_t n_per_g, int splits)
 {
+    osb_pdl_prologue();
     __shared__ float red[32];
     int64_t g = blockIdx.x;
     int64_t chunk = (n_per_g + splits - 1) / splits;
@@ -370,6 +422,7 @@ template <typename T, int VEC>
 __global__ void gn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const double* __restrict__ stats, int nhwc, int64_t C, int64_t HW, int groups,
                                 const T* __restrict__ gamma, const T* __restrict__ beta, float eps, int silu)
 {
+    osb_pdl_prologue();
     int cpg = (int)(C / groups);
     double inv_n = 1.0 / (double)((int64_t)cpg * HW);
     size_t n = (size_t)C * HW, nvec = n / VEC;
@@ -400,6 +453,7 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, cons
 __global__ void gather_rows_kernel(const uint8_t* __restrict__ table, const int64_t* __restrict__ idx, uint8_t* __restrict__ out,
                                    int64_t n_idx, int64_t table_rows, int64_t row_bytes)
 {
+    osb_pdl_prologue();
     for (int64_t r = blockIdx.x; r < n_idx; r += gridDim.x) {
         int64_t src = idx[r];
         if (src < 0) src += table_rows;
@@ -416,6 +470,7 @@ __global__ void gather_rows_kernel(const uint8_t* __restrict__ table, const int6
 template <typename T>
 __global__ void fill_kernel(T* dst, size_t n, float v)
 {
+    osb_pdl_prologue();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = from_float<T>(v);
 }
 
@@ -448,9 +503,9 @@ static int binary_dispatch(int op, const T* a, const int64_t* as, const T* b, co
     bool a_scalar = all_zero(as, shape, ndim), b_scalar = all_zero(bs, shape, ndim);
     if ((a_contig || a_scalar) && (b_contig || b_scalar)) {
         if (al || (a_scalar && aligned16(b) && aligned16(out)) || (b_scalar && aligned16(a) && aligned16(out)))
-            binary_flat_kernel<T, VEC><<<grid_for(n / VEC + 1, 256), 256, 0, st>>>(op, a, b, out, n, a_scalar && !a_contig, b_scalar && !b_contig);
+            osb_launch((binary_flat_kernel<T, VEC>), grid_for(n / VEC + 1, 256), 256, 0, st, op, a, b, out, n, a_scalar && !a_contig, b_scalar && !b_contig);
         else
-            binary_flat_kernel<T, 1><<<grid_for(n, 256), 256, 0, st>>>(op, a, b, out, n, a_scalar && !a_contig, b_scalar && !b_contig);
+            osb_launch((binary_flat_kernel<T, 1>), grid_for(n, 256), 256, 0, st, op, a, b, out, n, a_scalar && !a_contig, b_scalar && !b_contig);
         return launched();
     }
     // one operand contiguous, the other varies only along the last dim (per-column) or is constant along it (per-row)
@@ -465,7 +520,7 @@ static int binary_dispatch(int op, const T* a, const int64_t* as, const T* b, co
         bool percol = (cols == 1 || ps[ndim - 1] == 1);
         for (int d = 0; d < ndim - 1 && percol; d++) if (shape[d] != 1 && ps[d] != 0) percol = false;
         if (percol && cols % VEC == 0 && aligned16(full) && aligned16(part) && aligned16(out)) {
-            binary_rowcol_kernel<T, VEC><<<grid_for((size_t)rows * (cols / VEC), 256), 256, 0, st>>>(op, full, part, out, rows, cols, 0, swap);
+            osb_launch((binary_rowcol_kernel<T, VEC>), grid_for((size_t)rows * (cols / VEC), 256), 256, 0, st, op, full, part, out, rows, cols, 0, swap);
             return launched();
         }
         // per-row: [R, 1] against [R, cols] where the partial operand is contiguous over the leading dims
@@ -474,7 +529,7 @@ static int binary_dispatch(int op, const T* a, const int64_t* as, const T* b, co
             int64_t s = 1;
             for (int d = ndim - 2; d >= 0; d--) { if (shape[d] != 1 && ps[d] != s) perrow = false; s *= shape[d]; }
             if (perrow && cols % VEC == 0 && aligned16(full) && aligned16(out)) {
-                binary_rowcol_kernel<T, VEC><<<grid_for((size_t)rows * (cols / VEC), 256), 256, 0, st>>>(op, full, part, out, rows, cols, 1, swap);
+                osb_launch((binary_rowcol_kernel<T, VEC>), grid_for((size_t)rows * (cols / VEC), 256), 256, 0, st, op, full, part, out, rows, cols, 1, swap);
                 return launched();
             }
         }
@@ -482,7 +537,7 @@ static int binary_dispatch(int op, const T* a, const int64_t* as, const T* b, co
     BinParams p;
     p.ndim = ndim;
     for (int d = 0; d < OSB_MAX_DIMS; d++) { p.shape[d] = d < ndim ? shape[d] : 1; p.as[d] = d < ndim ? as[d] : 0; p.bs[d] = d < ndim ? bs[d] : 0; }
-    binary_generic_kernel<T><<<grid_for(n, 256), 256, 0, st>>>(op, a, b, out, p, n);
+    osb_launch((binary_generic_kernel<T>), grid_for(n, 256), 256, 0, st, op, a, b, out, p, n);
     return launched();
 }
 
@@ -497,13 +552,13 @@ int osb_convert(const void* src, int sd, void* dst, int dd, size_t n, float scal
     if (n == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     int grid = grid_for(n, 256);
-    if (sd == OSB_F16 && dd == OSB_F32) convert_kernel<__half, float><<<grid, 256, 0, st>>>((const __half*)src, (float*)dst, n);
-    else if (sd == OSB_F32 && dd == OSB_F16) convert_kernel<float, __half><<<grid, 256, 0, st>>>((const float*)src, (__half*)dst, n);
-    else if (sd == OSB_U8 && dd == OSB_F32) dequant_kernel<float><<<grid, 256, 0, st>>>((const uint8_t*)src, (float*)dst, n, scale, zp);
-    else if (sd == OSB_U8 && dd == OSB_F16) dequant_kernel<__half><<<grid, 256, 0, st>>>((const uint8_t*)src, (__half*)dst, n, scale, zp);
-    else if (sd == OSB_F32 && dd == OSB_U8) quant_kernel<float><<<grid, 256, 0, st>>>((const float*)src, (uint8_t*)dst, n, scale, zp);
-    else if (sd == OSB_F16 && dd == OSB_U8) quant_kernel<__half><<<grid, 256, 0, st>>>((const __half*)src, (uint8_t*)dst, n, scale, zp);
-    else if (sd == OSB_I64 && dd == OSB_F32) i64_to_float_kernel<<<grid, 256, 0, st>>>((const int64_t*)src, (float*)dst, n);
+    if (sd == OSB_F16 && dd == OSB_F32) osb_launch((convert_kernel<__half, float>), grid, 256, 0, st, (const __half*)src, (float*)dst, n);
+    else if (sd == OSB_F32 && dd == OSB_F16) osb_launch((convert_kernel<float, __half>), grid, 256, 0, st, (const float*)src, (__half*)dst, n);
+    else if (sd == OSB_U8 && dd == OSB_F32) osb_launch((dequant_kernel<float>), grid, 256, 0, st, (const uint8_t*)src, (float*)dst, n, scale, zp);
+    else if (sd == OSB_U8 && dd == OSB_F16) osb_launch((dequant_kernel<__half>), grid, 256, 0, st, (const uint8_t*)src, (__half*)dst, n, scale, zp);
+    else if (sd == OSB_F32 && dd == OSB_U8) osb_launch((quant_kernel<float>), grid, 256, 0, st, (const float*)src, (uint8_t*)dst, n, scale, zp);
+    else if (sd == OSB_F16 && dd == OSB_U8) osb_launch((quant_kernel<__half>), grid, 256, 0, st, (const __half*)src, (uint8_t*)dst, n, scale, zp);
+    else if (sd == OSB_I64 && dd == OSB_F32) osb_launch((i64_to_float_kernel), grid, 256, 0, st, (const int64_t*)src, (float*)dst, n);
     else return (int)cudaErrorInvalidValue;
     return launched();
 }
@@ -514,11 +569,11 @@ int osb_unary(int op, const void* x, void* y, int dtype, size_t n, float alpha, 
     cudaStream_t st = (cudaStream_t)stream;
     bool al = aligned16(x) && aligned16(y);
     if (dtype == OSB_F16) {
-        if (al) unary_kernel<__half, 8><<<grid_for(n / 8 + 1, 256), 256, 0, st>>>(op, (const __half*)x, (__half*)y, n, alpha);
-        else unary_kernel<__half, 1><<<grid_for(n, 256), 256, 0, st>>>(op, (const __half*)x, (__half*)y, n, alpha);
+        if (al) osb_launch((unary_kernel<__half, 8>), grid_for(n / 8 + 1, 256), 256, 0, st, op, (const __half*)x, (__half*)y, n, alpha);
+        else osb_launch((unary_kernel<__half, 1>), grid_for(n, 256), 256, 0, st, op, (const __half*)x, (__half*)y, n, alpha);
     } else if (dtype == OSB_F32) {
-        if (al) unary_kernel<float, 4><<<grid_for(n / 4 + 1, 256), 256, 0, st>>>(op, (const float*)x, (float*)y, n, alpha);
-        else unary_kernel<float, 1><<<grid_for(n, 256), 256, 0, st>>>(op, (const float*)x, (float*)y, n, alpha);
+        if (al) osb_launch((unary_kernel<float, 4>), grid_for(n / 4 + 1, 256), 256, 0, st, op, (const float*)x, (float*)y, n, alpha);
+        else osb_launch((unary_kernel<float, 1>), grid_for(n, 256), 256, 0, st, op, (const float*)x, (float*)y, n, alpha);
     } else return (int)cudaErrorInvalidValue;
     return launched();
 }
@@ -566,11 +621,11 @@ int osb_strided_copy(const void* in, void* out, int elem_size, int ndim, const i
     }
     int grid = grid_for(n, 256);
     switch (es) {
-    case 1: strided_copy_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)in, (uint8_t*)out, p, n); break;
-    case 2: strided_copy_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)in, (uint16_t*)out, p, n); break;
-    case 4: strided_copy_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)in, (uint32_t*)out, p, n); break;
-    case 8: strided_copy_kernel<uint2><<<grid, 256, 0, st>>>((const uint2*)in, (uint2*)out, p, n); break;
-    case 16: strided_copy_kernel<uint4><<<grid, 256, 0, st>>>((const uint4*)in, (uint4*)out, p, n); break;
+    case 1: osb_launch((strided_copy_kernel<uint8_t>), grid, 256, 0, st, (const uint8_t*)in, (uint8_t*)out, p, n); break;
+    case 2: osb_launch((strided_copy_kernel<uint16_t>), grid, 256, 0, st, (const uint16_t*)in, (uint16_t*)out, p, n); break;
+    case 4: osb_launch((strided_copy_kernel<uint32_t>), grid, 256, 0, st, (const uint32_t*)in, (uint32_t*)out, p, n); break;
+    case 8: osb_launch((strided_copy_kernel<uint2>), grid, 256, 0, st, (const uint2*)in, (uint2*)out, p, n); break;
+    case 16: osb_launch((strided_copy_kernel<uint4>), grid, 256, 0, st, (const uint4*)in, (uint4*)out, p, n); break;
     default: return (int)cudaErrorInvalidValue;
     }
     return launched();
@@ -583,9 +638,9 @@ int osb_transpose2d(const void* in, void* out, int elem_size, int64_t batch, int
     dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)batch), block(32, 8);
     if (grid.y > 65535 || grid.z > 65535) return (int)cudaErrorInvalidValue;
     switch (elem_size) {
-    case 1: transpose2d_kernel<uint8_t><<<grid, block, 0, st>>>((const uint8_t*)in, (uint8_t*)out, rows, cols); break;
-    case 2: transpose2d_kernel<uint16_t><<<grid, block, 0, st>>>((const uint16_t*)in, (uint16_t*)out, rows, cols); break;
-    case 4: transpose2d_kernel<uint32_t><<<grid, block, 0, st>>>((const uint32_t*)in, (uint32_t*)out, rows, cols); break;
+    case 1: osb_launch((transpose2d_kernel<uint8_t>), grid, block, 0, st, (const uint8_t*)in, (uint8_t*)out, rows, cols); break;
+    case 2: osb_launch((transpose2d_kernel<uint16_t>), grid, block, 0, st, (const uint16_t*)in, (uint16_t*)out, rows, cols); break;
+    case 4: osb_launch((transpose2d_kernel<uint32_t>), grid, block, 0, st, (const uint32_t*)in, (uint32_t*)out, rows, cols); break;
     default: return (int)cudaErrorInvalidValue;
     }
     return launched();
@@ -597,8 +652,8 @@ int osb_softmax(const void* x, void* y, int dtype, int64_t rows, int64_t cols, v
     cudaStream_t st = (cudaStream_t)stream;
     int threads = cols >= 1024 ? 256 : (cols >= 256 ? 128 : 32);
     int grid = (int)min<int64_t>(rows, 148 * 16);
-    if (dtype == OSB_F16) softmax_kernel<__half><<<grid, threads, 0, st>>>((const __half*)x, (__half*)y, rows, cols);
-    else if (dtype == OSB_F32) softmax_kernel<float><<<grid, threads, 0, st>>>((const float*)x, (float*)y, rows, cols);
+    if (dtype == OSB_F16) osb_launch((softmax_kernel<__half>), grid, threads, 0, st, (const __half*)x, (__half*)y, rows, cols);
+    else if (dtype == OSB_F32) osb_launch((softmax_kernel<float>), grid, threads, 0, st, (const float*)x, (float*)y, rows, cols);
     else return (int)cudaErrorInvalidValue;
     return launched();
 }
@@ -609,8 +664,8 @@ int osb_layer_norm(const void* x, void* y, int dtype, int64_t rows, int64_t cols
     cudaStream_t st = (cudaStream_t)stream;
     int threads = cols >= 1024 ? 256 : (cols >= 256 ? 128 : 32);
     int grid = (int)min<int64_t>(rows, 148 * 16);
-    if (dtype == OSB_F16) layer_norm_kernel<__half><<<grid, threads, 0, st>>>((const __half*)x, (__half*)y, rows, cols, (const __half*)gamma, (const __half*)beta, eps);
-    else if (dtype == OSB_F32) layer_norm_kernel<float><<<grid, threads, 0, st>>>((const float*)x, (float*)y, rows, cols, (const float*)gamma, (const float*)beta, eps);
+    if (dtype == OSB_F16) osb_launch((layer_norm_kernel<__half>), grid, threads, 0, st, (const __half*)x, (__half*)y, rows, cols, (const __half*)gamma, (const __half*)beta, eps);
+    else if (dtype == OSB_F32) osb_launch((layer_norm_kernel<float>), grid, threads, 0, st, (const float*)x, (float*)y, rows, cols, (const float*)gamma, (const float*)beta, eps);
     else return (int)cudaErrorInvalidValue;
     return launched();
 }
@@ -621,8 +676,8 @@ int osb_reduce_mean(const void* x, void* y, int dtype, int64_t rows, int64_t col
     cudaStream_t st = (cudaStream_t)stream;
     int threads = cols >= 1024 ? 256 : (cols >= 256 ? 128 : 32);
     int grid = (int)min<int64_t>(rows, 148 * 16);
-    if (dtype == OSB_F16) reduce_mean_kernel<__half><<<grid, threads, 0, st>>>((const __half*)x, (__half*)y, rows, cols);
-    else if (dtype == OSB_F32) reduce_mean_kernel<float><<<grid, threads, 0, st>>>((const float*)x, (float*)y, rows, cols);
+    if (dtype == OSB_F16) osb_launch((reduce_mean_kernel<__half>), grid, threads, 0, st, (const __half*)x, (__half*)y, rows, cols);
+    else if (dtype == OSB_F32) osb_launch((reduce_mean_kernel<float>), grid, threads, 0, st, (const float*)x, (float*)y, rows, cols);
     else return (int)cudaErrorInvalidValue;
     return launched();
 }
@@ -650,11 +705,11 @@ int osb_instance_norm(const void* x, void* y, int dtype, int64_t channels, int64
     }
     dim3 grid((unsigned)channels, (unsigned)splits);
     if (dtype == OSB_F16) {
-        inorm_stats_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, g_inorm_partial, n_per_c, splits);
-        inorm_apply_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, (__half*)y, g_inorm_partial, n_per_c, splits, (const __half*)scale, (const __half*)bias, eps);
+        osb_launch((inorm_stats_kernel<__half>), grid, 256, 0, st, (const __half*)x, g_inorm_partial, n_per_c, splits);
+        osb_launch((inorm_apply_kernel<__half>), grid, 256, 0, st, (const __half*)x, (__half*)y, g_inorm_partial, n_per_c, splits, (const __half*)scale, (const __half*)bias, eps);
     } else if (dtype == OSB_F32) {
-        inorm_stats_kernel<float><<<grid, 256, 0, st>>>((const float*)x, g_inorm_partial, n_per_c, splits);
-        inorm_apply_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, g_inorm_partial, n_per_c, splits, (const float*)scale, (const float*)bias, eps);
+        osb_launch((inorm_stats_kernel<float>), grid, 256, 0, st, (const float*)x, g_inorm_partial, n_per_c, splits);
+        osb_launch((inorm_apply_kernel<float>), grid, 256, 0, st, (const float*)x, (float*)y, g_inorm_partial, n_per_c, splits, (const float*)scale, (const float*)bias, eps);
     } else return (int)cudaErrorInvalidValue;
     launched();
     return launched();
@@ -674,32 +729,43 @@ int osb_group_norm(const void* x, void* y, int dtype, int nhwc, int64_t C, int64
         int64_t ctas = min<int64_t>(HW, 148 * 4);
         int64_t ppc = (HW + ctas - 1) / ctas;
         ctas = (HW + ppc - 1) / ppc;
-        int threads = (int)min<int64_t>(1024, ((C + 31) / 32) * 32);
         size_t smem = sizeof(float) * 2 * groups;
-        if (dtype == OSB_F16) gn_stats_nhwc_kernel<__half><<<(unsigned)ctas, threads, smem, st>>>((const __half*)x, stats, C, HW, groups, ppc);
-        else if (dtype == OSB_F32) gn_stats_nhwc_kernel<float><<<(unsigned)ctas, threads, smem, st>>>((const float*)x, stats, C, HW, groups, ppc);
+        int vec = dtype == OSB_F16 ? 8 : 4;
+        if (C % vec == 0 && C / vec <= 256 && aligned16(x)) {
+            int64_t c2 = min<int64_t>(HW, 148 * 2);
+            int64_t ppc2 = (HW + c2 - 1) / c2;
+            c2 = (HW + ppc2 - 1) / ppc2;
+            if (dtype == OSB_F16) osb_launch((gn_stats_nhwc_vec_kernel<__half, 8>), (unsigned)c2, 256, smem, st, (const __half*)x, stats, (int)C, HW, groups, ppc2);
+            else if (dtype == OSB_F32) osb_launch((gn_stats_nhwc_vec_kernel<float, 4>), (unsigned)c2, 256, smem, st, (const float*)x, stats, (int)C, HW, groups, ppc2);
+            else return (int)cudaErrorInvalidValue;
+            goto stats_done;
+        }
+        int threads = (int)min<int64_t>(1024, ((C + 31) / 32) * 32);
+        if (dtype == OSB_F16) osb_launch((gn_stats_nhwc_kernel<__half>), (unsigned)ctas, threads, smem, st, (const __half*)x, stats, C, HW, groups, ppc);
+        else if (dtype == OSB_F32) osb_launch((gn_stats_nhwc_kernel<float>), (unsigned)ctas, threads, smem, st, (const float*)x, stats, C, HW, groups, ppc);
         else return (int)cudaErrorInvalidValue;
     } else {
         int64_t n_per_g = (C / groups) * HW;
         int splits = (int)max<int64_t>(1, min<int64_t>(64, (148 * 4 + groups - 1) / groups));
         while (splits > 1 && n_per_g / splits < 2048) splits--;
         dim3 grid((unsigned)groups, (unsigned)splits);
-        if (dtype == OSB_F16) gn_stats_nchw_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, stats, n_per_g, splits);
-        else if (dtype == OSB_F32) gn_stats_nchw_kernel<float><<<grid, 256, 0, st>>>((const float*)x, stats, n_per_g, splits);
+        if (dtype == OSB_F16) osb_launch((gn_stats_nchw_kernel<__half>), grid, 256, 0, st, (const __half*)x, stats, n_per_g, splits);
+        else if (dtype == OSB_F32) osb_launch((gn_stats_nchw_kernel<float>), grid, 256, 0, st, (const float*)x, stats, n_per_g, splits);
         else return (int)cudaErrorInvalidValue;
     }
+stats_done:
     launched();
     bool al = aligned16(x) && aligned16(y);
     if (dtype == OSB_F16) {
         if (al && n % 8 == 0 && (nhwc ? C % 8 == 0 : HW % 8 == 0))
-            gn_apply_kernel<__half, 8><<<grid_for(n / 8, 256), 256, 0, st>>>((const __half*)x, (__half*)y, stats, nhwc, C, HW, groups, (const __half*)gamma, (const __half*)beta, eps, fuse_silu);
+            osb_launch((gn_apply_kernel<__half, 8>), grid_for(n / 8, 256), 256, 0, st, (const __half*)x, (__half*)y, stats, nhwc, C, HW, groups, (const __half*)gamma, (const __half*)beta, eps, fuse_silu);
         else
-            gn_apply_kernel<__half, 1><<<grid_for(n, 256), 256, 0, st>>>((const __half*)x, (__half*)y, stats, nhwc, C, HW, groups, (const __half*)gamma, (const __half*)beta, eps, fuse_silu);
+            osb_launch((gn_apply_kernel<__half, 1>), grid_for(n, 256), 256, 0, st, (const __half*)x, (__half*)y, stats, nhwc, C, HW, groups, (const __half*)gamma, (const __half*)beta, eps, fuse_silu);
     } else {
         if (al && n % 4 == 0 && (nhwc ? C % 4 == 0 : HW % 4 == 0))
-            gn_apply_kernel<float, 4><<<grid_for(n / 4, 256), 256, 0, st>>>((const float*)x, (float*)y, stats, nhwc, C, HW, groups, (const float*)gamma, (const float*)beta, eps, fuse_silu);
+            osb_launch((gn_apply_kernel<float, 4>), grid_for(n / 4, 256), 256, 0, st, (const float*)x, (float*)y, stats, nhwc, C, HW, groups, (const float*)gamma, (const float*)beta, eps, fuse_silu);
         else
-            gn_apply_kernel<float, 1><<<grid_for(n, 256), 256, 0, st>>>((const float*)x, (float*)y, stats, nhwc, C, HW, groups, (const float*)gamma, (const float*)beta, eps, fuse_silu);
+            osb_launch((gn_apply_kernel<float, 1>), grid_for(n, 256), 256, 0, st, (const float*)x, (float*)y, stats, nhwc, C, HW, groups, (const float*)gamma, (const float*)beta, eps, fuse_silu);
     }
     return launched();
 }
@@ -708,7 +774,7 @@ int osb_gather_rows(const void* table, const int64_t* idx, void* out, int64_t n_
 {
     if (n_idx * row_bytes == 0) return 0;
     int threads = row_bytes >= 4096 ? 256 : 64;
-    gather_rows_kernel<<<(unsigned)min<int64_t>(n_idx, 148 * 8), threads, 0, (cudaStream_t)stream>>>((const uint8_t*)table, idx, (uint8_t*)out, n_idx, table_rows, row_bytes);
+    osb_launch((gather_rows_kernel), (unsigned)min<int64_t>(n_idx, 148 * 8), threads, 0, (cudaStream_t)stream, (const uint8_t*)table, idx, (uint8_t*)out, n_idx, table_rows, row_bytes);
     return launched();
 }
 
@@ -716,8 +782,8 @@ int osb_fill(void* dst, int dtype, size_t n, float value, void* stream)
 {
     if (n == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == OSB_F16) fill_kernel<__half><<<grid_for(n, 256), 256, 0, st>>>((__half*)dst, n, value);
-    else if (dtype == OSB_F32) fill_kernel<float><<<grid_for(n, 256), 256, 0, st>>>((float*)dst, n, value);
+    if (dtype == OSB_F16) osb_launch((fill_kernel<__half>), grid_for(n, 256), 256, 0, st, (__half*)dst, n, value);
+    else if (dtype == OSB_F32) osb_launch((fill_kernel<float>), grid_for(n, 256), 256, 0, st, (float*)dst, n, value);
     else return (int)cudaErrorInvalidValue;
     return launched();
 }

@@ -8,6 +8,7 @@
 // from the NHWC input (M = Ho*Wo, K = kh*kw*Cin in OHWI order, N = Cout, B = the OHWI weights read as [N, K]).
 
 #include "common.cuh"
+#include <cstdlib>
 
 // implemented in gemm_tcgen05.cu
 int osb_tc_gemm_launch(const void* A, const void* B, void* C, const void* bias, const void* residual,
@@ -35,6 +36,7 @@ igemm_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C
              int M, int N, int K, int64_t sa, int64_t sb, int64_t sc, int b_transposed, ConvGeom g,
              int zx, int zw, int zy, float requant)
 {
+    osb_pdl_prologue();
     using Acc = typename std::conditional<QU8, int, float>::type;
     __shared__ Acc As[BK][BM + 4];
     __shared__ Acc Bs[BK][BN + 4];
@@ -137,6 +139,7 @@ __global__ void __launch_bounds__(256)
 skinny_gemm_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C, const T* __restrict__ bias, const T* __restrict__ residual,
                    int M, int N, int K, int b_transposed)
 {
+    osb_pdl_prologue();
     // block handles 64 columns x all M rows; 256 threads = 4 k-slices x 64 columns (non-transposed B, coalesced over n)
     __shared__ float red[4][MAXM][64];
     if (!b_transposed) {
@@ -196,6 +199,7 @@ template <typename T, int MAXM>
 __global__ void __launch_bounds__(128)
 gemv_panel_kernel(const T* __restrict__ A, const T* __restrict__ B, float* __restrict__ acc_out, int M, int N, int K, int k_per_cta)
 {
+    osb_pdl_prologue();
     constexpr int VEC = 16 / sizeof(T);           // columns per thread
     constexpr int COLS = 32 * VEC;                // columns per CTA
     __shared__ float red[4][MAXM][COLS];
@@ -239,6 +243,7 @@ gemv_panel_kernel(const T* __restrict__ A, const T* __restrict__ B, float* __res
 template <typename T>
 __global__ void gemv_finalize_kernel(const float* __restrict__ acc, T* __restrict__ C, const T* __restrict__ bias, const T* __restrict__ residual, int M, int N)
 {
+    osb_pdl_prologue();
     int total = M * N;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         float v = acc[i];
@@ -253,6 +258,7 @@ template <typename T>
 __global__ void softmax_scaled_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int64_t cols, float scale,
                                       const T* __restrict__ mask, int64_t mask_rows)
 {
+    osb_pdl_prologue();
     __shared__ float red[32];
     for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
         const T* xr = x + r * cols;
@@ -275,6 +281,7 @@ template <typename T>
 __global__ void softmax_scaled_smem_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int cols, float scale,
                                            const T* __restrict__ mask, int64_t mask_rows)
 {
+    osb_pdl_prologue();
     extern __shared__ float row[];
     __shared__ float red[32];
     constexpr int VEC = 16 / sizeof(T);
@@ -313,6 +320,7 @@ __global__ void attention_rows_kernel(const T* __restrict__ q, const T* __restri
                                       T* __restrict__ out, int64_t heads, int64_t Tq, int64_t Tk, int d, int dv, float scale,
                                       int k_transposed, int64_t kv_group)
 {
+    osb_pdl_prologue();
     extern __shared__ float smem[];  // per warp: q row [d] + acc [dv] + p [32]
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     float* qs = smem + warp * (d + dv + 32);
@@ -367,8 +375,8 @@ int launch_igemm(const T* A, const T* B, T* C, const void* bias, const T* residu
 {
     dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)batch);
     if (grid.y > 65535 || grid.z > 65535) return (int)cudaErrorInvalidValue;
-    if (conv) igemm_kernel<T, true, false><<<grid, 256, 0, st>>>(A, B, C, bias, residual, (int)M, (int)N, (int)K, sa, sb, sc, bt, g, 0, 0, 0, 0.f);
-    else igemm_kernel<T, false, false><<<grid, 256, 0, st>>>(A, B, C, bias, residual, (int)M, (int)N, (int)K, sa, sb, sc, bt, g, 0, 0, 0, 0.f);
+    if (conv) osb_launch((igemm_kernel<T, true, false>), grid, 256, 0, st, A, B, C, bias, residual, (int)M, (int)N, (int)K, sa, sb, sc, bt, g, 0, 0, 0, 0.f);
+    else osb_launch((igemm_kernel<T, false, false>), grid, 256, 0, st, A, B, C, bias, residual, (int)M, (int)N, (int)K, sa, sb, sc, bt, g, 0, 0, 0, 0.f);
     return launched();
 }
 
@@ -412,18 +420,18 @@ int osb_gemm(const void* A, const void* B, void* C, const void* bias, const void
         int k_per = (int)((K + gy - 1) / gy);
         gy = (int)((K + k_per - 1) / k_per);
         dim3 grid(gx, gy);
-        if (dtype == OSB_F16) gemv_panel_kernel<__half, 8><<<grid, 128, 0, st>>>((const __half*)A, (const __half*)B, scratch, (int)M, (int)N, (int)K, k_per);
-        else gemv_panel_kernel<float, 8><<<grid, 128, 0, st>>>((const float*)A, (const float*)B, scratch, (int)M, (int)N, (int)K, k_per);
+        if (dtype == OSB_F16) osb_launch((gemv_panel_kernel<__half, 8>), grid, 128, 0, st, (const __half*)A, (const __half*)B, scratch, (int)M, (int)N, (int)K, k_per);
+        else osb_launch((gemv_panel_kernel<float, 8>), grid, 128, 0, st, (const float*)A, (const float*)B, scratch, (int)M, (int)N, (int)K, k_per);
         launched();
         int fg = (int)min<int64_t>((M * N + 255) / 256, 148 * 4);
-        if (dtype == OSB_F16) gemv_finalize_kernel<__half><<<fg, 256, 0, st>>>(scratch, (__half*)C, (const __half*)bias, (const __half*)residual, (int)M, (int)N);
-        else gemv_finalize_kernel<float><<<fg, 256, 0, st>>>(scratch, (float*)C, (const float*)bias, (const float*)residual, (int)M, (int)N);
+        if (dtype == OSB_F16) osb_launch((gemv_finalize_kernel<__half>), fg, 256, 0, st, scratch, (__half*)C, (const __half*)bias, (const __half*)residual, (int)M, (int)N);
+        else osb_launch((gemv_finalize_kernel<float>), fg, 256, 0, st, scratch, (float*)C, (const float*)bias, (const float*)residual, (int)M, (int)N);
         return launched();
     }
     if (M <= 8 && batch == 1) {
         int grid = bt ? (int)min<int64_t>((N + 7) / 8, 148 * 8) : (int)((N + 63) / 64);
-        if (dtype == OSB_F16) skinny_gemm_kernel<__half, 8><<<grid, 256, 0, st>>>((const __half*)A, (const __half*)B, (__half*)C, (const __half*)bias, (const __half*)residual, (int)M, (int)N, (int)K, bt);
-        else skinny_gemm_kernel<float, 8><<<grid, 256, 0, st>>>((const float*)A, (const float*)B, (float*)C, (const float*)bias, (const float*)residual, (int)M, (int)N, (int)K, bt);
+        if (dtype == OSB_F16) osb_launch((skinny_gemm_kernel<__half, 8>), grid, 256, 0, st, (const __half*)A, (const __half*)B, (__half*)C, (const __half*)bias, (const __half*)residual, (int)M, (int)N, (int)K, bt);
+        else osb_launch((skinny_gemm_kernel<float, 8>), grid, 256, 0, st, (const float*)A, (const float*)B, (float*)C, (const float*)bias, (const float*)residual, (int)M, (int)N, (int)K, bt);
         return launched();
     }
     if (dtype == OSB_F16) return launch_igemm<__half>((const __half*)A, (const __half*)B, (__half*)C, bias, (const __half*)residual, batch, M, N, K, sa, sb, sc, bt, false, g, st);
@@ -452,7 +460,7 @@ int osb_gemm_qu8(const uint8_t* A, const uint8_t* B, uint8_t* C, const int32_t* 
     ConvGeom g{};
     float requant = sx * sw / sy;
     dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), 1);
-    igemm_kernel<uint8_t, false, true><<<grid, 256, 0, (cudaStream_t)stream>>>(A, B, C, bias, nullptr, (int)M, (int)N, (int)K, 0, 0, 0, 0, g, zx, zw, zy, requant);
+    osb_launch((igemm_kernel<uint8_t, false, true>), grid, 256, 0, (cudaStream_t)stream, A, B, C, bias, nullptr, (int)M, (int)N, (int)K, 0, 0, 0, 0, g, zx, zw, zy, requant);
     return launched();
 }
 
@@ -465,7 +473,7 @@ int osb_conv2d_qu8(const uint8_t* x, const uint8_t* w, const int32_t* bias, uint
     int64_t M = Ho * Wo, N = Cout, K = (int64_t)kh * kw * Cin;
     float requant = sx * sw / sy;
     dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), 1);
-    igemm_kernel<uint8_t, true, true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, y, bias, nullptr, (int)M, (int)N, (int)K, 0, 0, 0, 1, g, zx, zw, zy, requant);
+    osb_launch((igemm_kernel<uint8_t, true, true>), grid, 256, 0, (cudaStream_t)stream, x, w, y, bias, nullptr, (int)M, (int)N, (int)K, 0, 0, 0, 1, g, zx, zw, zy, requant);
     return launched();
 }
 
@@ -483,16 +491,16 @@ int osb_softmax_scaled(const void* x, void* y, int dtype, int64_t rows, int64_t 
         if (dtype == OSB_F16) {
             static bool attr16 = false;
             if (!attr16) { cudaFuncSetAttribute(softmax_scaled_smem_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 4); attr16 = true; }
-            softmax_scaled_smem_kernel<__half><<<grid, 256, smem, st>>>((const __half*)x, (__half*)y, rows, (int)cols, scale, (const __half*)mask, mask_rows);
+            osb_launch((softmax_scaled_smem_kernel<__half>), grid, 256, smem, st, (const __half*)x, (__half*)y, rows, (int)cols, scale, (const __half*)mask, mask_rows);
         } else if (dtype == OSB_F32) {
             static bool attr32 = false;
             if (!attr32) { cudaFuncSetAttribute(softmax_scaled_smem_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 4); attr32 = true; }
-            softmax_scaled_smem_kernel<float><<<grid, 256, smem, st>>>((const float*)x, (float*)y, rows, (int)cols, scale, (const float*)mask, mask_rows);
+            osb_launch((softmax_scaled_smem_kernel<float>), grid, 256, smem, st, (const float*)x, (float*)y, rows, (int)cols, scale, (const float*)mask, mask_rows);
         } else return (int)cudaErrorInvalidValue;
         return launched();
     }
-    if (dtype == OSB_F16) softmax_scaled_kernel<__half><<<grid, threads, 0, st>>>((const __half*)x, (__half*)y, rows, cols, scale, (const __half*)mask, mask_rows);
-    else if (dtype == OSB_F32) softmax_scaled_kernel<float><<<grid, threads, 0, st>>>((const float*)x, (float*)y, rows, cols, scale, (const float*)mask, mask_rows);
+    if (dtype == OSB_F16) osb_launch((softmax_scaled_kernel<__half>), grid, threads, 0, st, (const __half*)x, (__half*)y, rows, cols, scale, (const __half*)mask, mask_rows);
+    else if (dtype == OSB_F32) osb_launch((softmax_scaled_kernel<float>), grid, threads, 0, st, (const float*)x, (float*)y, rows, cols, scale, (const float*)mask, mask_rows);
     else return (int)cudaErrorInvalidValue;
     return launched();
 }
@@ -507,13 +515,21 @@ int osb_attention(const void* q, const void* k, const void* v, const void* mask,
     size_t smem = (size_t)warps * (d + dv + 32) * sizeof(float);
     if (smem > 48 * 1024) return (int)cudaErrorInvalidValue;
     int grid = (int)min<int64_t>((heads * Tq + warps - 1) / warps, 148 * 8);
-    if (dtype == OSB_F16) attention_rows_kernel<__half><<<grid, warps * 32, smem, st>>>((const __half*)q, (const __half*)k, (const __half*)v, (const __half*)mask, (__half*)out, heads, Tq, Tk, (int)d, (int)dv, scale, k_transposed, kv_group);
-    else if (dtype == OSB_F32) attention_rows_kernel<float><<<grid, warps * 32, smem, st>>>((const float*)q, (const float*)k, (const float*)v, (const float*)mask, (float*)out, heads, Tq, Tk, (int)d, (int)dv, scale, k_transposed, kv_group);
+    if (dtype == OSB_F16) osb_launch((attention_rows_kernel<__half>), grid, warps * 32, smem, st, (const __half*)q, (const __half*)k, (const __half*)v, (const __half*)mask, (__half*)out, heads, Tq, Tk, (int)d, (int)dv, scale, k_transposed, kv_group);
+    else if (dtype == OSB_F32) osb_launch((attention_rows_kernel<float>), grid, warps * 32, smem, st, (const float*)q, (const float*)k, (const float*)v, (const float*)mask, (float*)out, heads, Tq, Tk, (int)d, (int)dv, scale, k_transposed, kv_group);
     else return (int)cudaErrorInvalidValue;
     return launched();
 }
 
 // ---- launch counters -----------------------------------------------------------------------------------------
+static int g_pdl = -1;
+int osb_pdl_enabled(void)
+{
+    // measured on B200: inside a CUDA graph PDL costs ~7% on this workload, so it is opt-in (OSB_PDL=1)
+    if (g_pdl < 0) { const char* e = getenv("OSB_PDL"); g_pdl = (e && e[0] == '1') ? 1 : 0; }
+    return g_pdl;
+}
+void osb_set_pdl(int enable) { g_pdl = enable ? 1 : 0; }
 static uint64_t g_launches = 0, g_tc_launches = 0;
 void osb_count_launch(int tensor_core) { g_launches++; if (tensor_core) g_tc_launches++; }
 uint64_t osb_launch_count(void) { return g_launches; }
