@@ -408,6 +408,21 @@ struct Engine::Impl {
         return with_scale ? 4 : 3;
     }
 
+    // Transpose(K) -> MatMul(Q, Kt) -> Div(s) -> Add(mask) -> Softmax(-1) -> MatMul(P, V)   (src/onnxstream.cpp:3643-3695)
+    size_t match_sdpa(size_t i) const
+    {
+        auto& ops = E.m_ops;
+        if (!E.use_scaled_dp_attn_op || E.use_uint8_arithmetic) return 0;
+        static const char* seq[] = { "Transpose", "MatMul", "Div", "Add", "Softmax", "MatMul" };
+        if (i + 5 >= ops.size()) return 0;
+        for (int k = 0; k < 6; k++) if (ops[i + k].type != seq[k]) return 0;
+        const OpDef &tr = ops[i], &mm0 = ops[i + 1], &dv = ops[i + 2], &ad = ops[i + 3], &sm = ops[i + 4], &mm1 = ops[i + 5];
+        if (tr.in.size() != 1 || mm0.in.size() != 2 || dv.in.size() != 2 || ad.in.size() != 2 || sm.in.size() != 1 || mm1.in.size() != 2) return 0;
+        if (sm.attrs.size() != 1 || sm.attrs[0].first != "axis" || sm.attrs[0].second != "-1") return 0;
+        if (!feeds(tr, mm0, 1) || !feeds(mm0, dv, 0) || !feeds(dv, ad, 0) || !feeds(ad, sm, 0) || !feeds(sm, mm1, 0)) return 0;
+        return 6;
+    }
+
     size_t match_groupnorm(size_t i, int& variant) const
     {
         auto& ops = E.m_ops;
@@ -548,7 +563,8 @@ struct Engine::Impl {
         while (i < ops.size()) {
             Step s; s.first = i; s.count = 1; s.kind = SK_SINGLE;
             int var = 0; size_t n;
-            if ((n = match_attention(i, var))) { s.kind = SK_ATTENTION; s.count = n; s.variant = var; }
+            if ((n = match_sdpa(i))) { s.kind = SK_SDPA; s.count = n; }
+            else if ((n = match_attention(i, var))) { s.kind = SK_ATTENTION; s.count = n; s.variant = var; }
             else if ((n = match_groupnorm(i, var))) { s.kind = SK_GROUPNORM; s.count = n; s.variant = var; }
             else if ((n = match_layernorm(i))) { s.kind = SK_LAYERNORM; s.count = n; }
             else if ((n = match_gelu(i, var))) { s.kind = SK_GELU; s.count = n; s.variant = var; }
@@ -611,6 +627,7 @@ struct Engine::Impl {
     void fused_gelu(const Step& s);
     void fused_silu(const Step& s);
     void fused_linear(const Step& s);
+    void fused_sdpa(const Step& s);
 
     Tensor binary(int bop, const Tensor& a, const Tensor& b);
     Tensor strided(const Tensor& x, const std::vector<int64_t>& out_shape, const std::vector<int64_t>& in_stride,
@@ -1503,6 +1520,37 @@ void Engine::Impl::fused_attention(const Step& s)
     push(mm1i, 0, out);
 }
 
+// ScaledDotProductAttention (src/onnxstream.cpp:7767-7882): q [B,Hq,Tq,D], k [B,Hkv,Tk,D], v [B,Hkv,Tk,Dv], scale 1/s,
+// additive mask [Tq,Tk] (or [1,1,Tq,Tk]); grouped KV heads supported.
+void Engine::Impl::fused_sdpa(const Step& s)
+{
+    size_t i = s.first;
+    const OpDef& op = E.m_ops[i];
+    Tensor q = to_plain(in(i + 1, 0)), k = to_plain(in(i, 0)), sc = in(i + 2, 1), m = to_plain(in(i + 3, 1)), v = to_plain(in(i + 5, 1));
+    if (q.shape.size() != 4) throw std::invalid_argument("ScaledDotProductAttention: invalid shape of query.");
+    if (k.shape.size() != 4) throw std::invalid_argument("ScaledDotProductAttention: invalid shape of key.");
+    if (v.shape.size() != 4) throw std::invalid_argument("ScaledDotProductAttention: invalid shape of value.");
+    if (!(m.shape.size() == 2 || (m.shape.size() == 4 && m.shape[0] == 1 && m.shape[1] == 1)))
+        throw std::invalid_argument("ScaledDotProductAttention: invalid shape of mask.");
+    int64_t B = q.shape[0], Hq = q.shape[1], Tq = q.shape[2], D = q.shape[3], Hkv = k.shape[1], Tk = k.shape[2], Dv = v.shape[3];
+    if (B != 1) throw std::invalid_argument("ScaledDotProductAttention: batch size != 1 (not implemented).");
+    if (k.shape[3] != D || v.shape[1] != Hkv || v.shape[2] != Tk || Hkv == 0 || Hq % Hkv) throw std::runtime_error("XnnPack::scaled_dot_product_attention: invalid size of key.");
+    if (m.numel() != Tq * Tk) throw std::runtime_error("XnnPack::scaled_dot_product_attention: invalid size of mask.");
+    float sval = scalar_of(sc, op);
+    float scale;
+    if (q.type == DType::f16) { sval = __half2float(__float2half_rn(sval)); scale = __half2float(__float2half_rn(1.0f / sval)); }   // fp16 path rounds the scale (cpp:7849-7866)
+    else scale = 1.0f / sval;
+    if (k.type != q.type) k = convert(k, q.type);
+    if (v.type != q.type) v = convert(v, q.type);
+    if (m.type != q.type) m = convert(m, q.type);
+    Tensor out = make(q.type, { B, Hq, Tq, Dv });
+    Tensor q3 = q, k3 = k, v3 = v;
+    q3.shape = { Hq, Tq, D }; k3.shape = { Hkv, Tk, D }; v3.shape = { Hkv, Tk, Dv };
+    Tensor o3 = out; o3.shape = { Hq, Tq, Dv };
+    attention_core(q3, k3, v3, scale, false, &m, Hq / Hkv, o3);
+    push(i + 5, 0, out);
+}
+
 void Engine::Impl::fused_groupnorm(const Step& s)
 {
     size_t i = s.first;
@@ -1648,6 +1696,7 @@ void Engine::Impl::exec_step(size_t si)
         case SK_GELU: fused_gelu(s); break;
         case SK_SILU: fused_silu(s); break;
         case SK_LINEAR: fused_linear(s); break;
+        case SK_SDPA: fused_sdpa(s); break;
         default: exec_single(s.first); break;
         }
     }

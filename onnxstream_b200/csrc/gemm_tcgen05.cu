@@ -40,6 +40,7 @@ struct TcParams {
     int M, N, K;                 // GEMM view of the problem (conv: M = Ho*Wo, K = Cin per tap)
     int batch;
     int m_tiles, n_tiles;
+    int bn;                      // N extent of a tile (64 / 80 / 96 / 128): chosen per problem to fill the 148 SMs
     int b_kmajor;                // 1: B is [N,K] row-major
     // conv geometry (taps == 1 for a plain GEMM)
     int taps, kw, pad_top, pad_left, Wo, Ho, bw, bh, tiles_x;
@@ -148,7 +149,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 }
 
 // instruction descriptor for kind::f16: fp16 x fp16 -> fp32, A K-major, B K- or MN-major
-__device__ __forceinline__ uint32_t make_idesc(int b_mn_major)
+__device__ __forceinline__ uint32_t make_idesc(int b_mn_major, int bn)
 {
     uint32_t d = 0;
     d |= 1u << 4;                              // c_format = F32
@@ -156,7 +157,7 @@ __device__ __forceinline__ uint32_t make_idesc(int b_mn_major)
     d |= 0u << 10;                             // b_format = F16
     d |= 0u << 15;                             // a_major  = K
     d |= (uint32_t)(b_mn_major ? 1 : 0) << 16; // b_major
-    d |= (uint32_t)(BLOCK_N >> 3) << 17;       // n_dim
+    d |= (uint32_t)(bn >> 3) << 17;            // n_dim
     d |= (uint32_t)(BLOCK_M >> 4) << 24;       // m_dim
     return d;
 }
@@ -215,13 +216,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 int sp = tile % p.split_k, t2 = tile / p.split_k;
                 int b = t2 / tiles_per_batch, r = t2 % tiles_per_batch;
                 int mt = r % p.m_tiles, nt = r / p.m_tiles;
-                int n0 = nt * BLOCK_N;
+                int n0 = nt * p.bn;
                 int y0 = 0, x0 = 0, m0 = mt * BLOCK_M;
                 if (p.taps > 1 || p.bh > 0) { y0 = (mt / p.tiles_x) * p.bh; x0 = (mt % p.tiles_x) * p.bw; }
                 int kb_lo = sp * kb_per_split, kb_hi = min(kb_lo + kb_per_split, k_blocks_all);
                 for (int kb = kb_lo; kb < kb_hi; kb++) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+                    mbar_expect_tx(&full[stage], A_STAGE_BYTES + (p.b_kmajor ? p.bn * (BLOCK_K * 2) : ((p.bn + 63) / 64) * (B_STAGE_BYTES / 2)));
                     int tap = kb / p.k_blocks_per_tap, kc = (kb % p.k_blocks_per_tap) * BLOCK_K;
                     uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
                     uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
@@ -236,7 +237,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         tma_load_3d(sb, &map_b, &full[stage], kglob, n0, b);
                     } else {
                         tma_load_3d(sb, &map_b, &full[stage], n0, kglob, b);
-                        tma_load_3d(sb + B_STAGE_BYTES / 2, &map_b, &full[stage], n0 + 64, kglob, b);
+                        if (p.bn > 64) tma_load_3d(sb + B_STAGE_BYTES / 2, &map_b, &full[stage], n0 + 64, kglob, b);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -244,7 +245,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        const uint32_t idesc = make_idesc(p.b_kmajor ? 0 : 1);
+        const uint32_t idesc = make_idesc(p.b_kmajor ? 0 : 1, p.bn);
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -287,7 +288,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             int sp = tile % p.split_k, t2 = tile / p.split_k;
             int b = t2 / tiles_per_batch, r = t2 % tiles_per_batch;
             int mt = r % p.m_tiles, nt = r / p.m_tiles;
-            int n0 = nt * BLOCK_N;
+            int n0 = nt * p.bn;
+            const int n_end = min(p.N, n0 + p.bn);
             int row_in_tile = q * 32 + lane;
             long long out_row;   // row index into C (conv: output pixel index)
             bool row_ok;
@@ -307,8 +309,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             float* wrow = p.split_k > 1 ? p.ws + (((long long)sp * p.batch + b) * p.M + out_row) * p.N : nullptr;
             const bool vec_ok = (p.N & 7) == 0;
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N; c += 32) {
-                if (n0 + c >= p.N) break;       // warp-uniform
+            for (int c = 0; c < p.bn; c += 32) {
+                if (n0 + c >= n_end) break;     // warp-uniform
                 uint32_t v[32];
                 uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c);
                 tmem_ld_32x32b_x32(taddr, v);
@@ -318,14 +320,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             int n = n0 + c + j;
-                            if (n + 3 < p.N && (p.N & 3) == 0) *reinterpret_cast<uint4*>(wrow + n) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                            else for (int t = 0; t < 4; t++) if (n + t < p.N) wrow[n + t] = __uint_as_float(v[j + t]);
+                            if (n + 3 < n_end && (p.N & 3) == 0) *reinterpret_cast<uint4*>(wrow + n) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            else for (int t = 0; t < 4; t++) if (n + t < n_end) wrow[n + t] = __uint_as_float(v[j + t]);
                         }
                     }
                 } else if (row_ok && !vec_ok) {
                     for (int j = 0; j < 32; j++) {
                         int n = n0 + c + j;
-                        if (n >= p.N) break;
+                        if (n >= n_end) break;
                         float f = __uint_as_float(v[j]);
                         if (p.bias) f += __half2float(p.bias[n]);
                         if (rrow) f += __half2float(rrow[n]);
@@ -335,7 +337,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
                         int n = n0 + c + j;
-                        if (n >= p.N) break;    // N % 8 == 0 is an eligibility requirement
+                        if (n >= n_end) break;  // N % 8 == 0 and bn % 16 == 0
                         float f[8];
 #pragma unroll
                         for (int t = 0; t < 8; t++) f[t] = __uint_as_float(v[j + t]);
@@ -375,7 +377,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (row_ok) {
                         const long long plane = (long long)p.batch * p.M * p.N;
                         const float* base = p.ws + ((long long)b * p.M + out_row) * p.N;
-                        for (int n = n0; n < n0 + BLOCK_N && n < p.N; n += 4) {
+                        for (int n = n0; n < n_end; n += 4) {
                             float f[4] = { 0.f, 0.f, 0.f, 0.f };
                             bool v4 = (n + 3 < p.N) && (p.N & 3) == 0;
                             for (int sidx = 0; sidx < p.split_k; sidx++) {
@@ -542,6 +544,22 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cuda
     return launched(1);
 }
 
+// Tile width: fewest waves over the 148 SMs, then least padded work (e.g. N = 320 at M = 4096: 80 -> 128 tiles in one wave
+// with no padding, instead of 96 tiles of 128 with 1/6 of every third tile wasted).
+int choose_bn(int64_t m_tiles, int64_t N, int64_t batch)
+{
+    static const int cand[] = { 128, 96, 80, 64 };
+    int best = 128; double best_cost = 1e30;
+    for (int bn : cand) {
+        if (bn > 64 && N <= 64) continue;
+        int64_t tiles = m_tiles * ((N + bn - 1) / bn) * batch;
+        double waves = (double)((tiles + 147) / 148);
+        double cost = waves * (bn + 24);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+    }
+    return best;
+}
+
 inline uint32_t next_pow2(uint32_t v) { uint32_t r = 1; while (r < v) r <<= 1; return r; }
 
 }  // namespace
@@ -609,12 +627,15 @@ int osb_tc_gemm_launch(const void* A, const void* B, void* C, const void* bias, 
         return 0;
     }
     if (!make_map(&ma, A, (uint64_t)K, (uint64_t)M, abatch, (uint64_t)K * 2, (uint64_t)(sa ? sa : M * K) * 2, BLOCK_K, BLOCK_M, 1)) return (int)cudaErrorInvalidValue;
-    bool okb = bt ? make_map(&mb, B, (uint64_t)K, (uint64_t)N, bbatch, (uint64_t)K * 2, (uint64_t)(sb ? sb : N * K) * 2, BLOCK_K, BLOCK_N, 1)
+    int64_t m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    int bn = choose_bn(m_tiles, N, batch);
+    bool okb = bt ? make_map(&mb, B, (uint64_t)K, (uint64_t)N, bbatch, (uint64_t)K * 2, (uint64_t)(sb ? sb : N * K) * 2, BLOCK_K, (uint32_t)bn, 1)
                   : make_map(&mb, B, (uint64_t)N, (uint64_t)K, bbatch, (uint64_t)N * 2, (uint64_t)(sb ? sb : N * K) * 2, 64, BLOCK_K, 1);
     if (!okb) return (int)cudaErrorInvalidValue;
     TcParams p{};
     p.M = (int)M; p.N = (int)N; p.K = (int)K; p.batch = (int)batch;
-    p.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M); p.n_tiles = (int)((N + BLOCK_N - 1) / BLOCK_N);
+    p.bn = bn;
+    p.m_tiles = (int)m_tiles; p.n_tiles = (int)((N + bn - 1) / bn);
     p.b_kmajor = bt ? 1 : 0;
     p.taps = 1; p.kw = 1; p.bh = 0; p.bw = 0; p.tiles_x = 1;
     p.k_blocks_per_tap = (int)((K + BLOCK_K - 1) / BLOCK_K);
@@ -646,12 +667,15 @@ int osb_tc_conv_launch(const void* x, const void* w, const void* bias, const voi
         return (int)cudaErrorInvalidValue;
     // B: OHWI weights = [Cout][kh*kw*Cin], K-major
     int64_t Ktot = (int64_t)kh * kw * Cin;
-    if (!make_map(&mb, w, (uint64_t)Ktot, (uint64_t)Cout, 1, (uint64_t)Ktot * 2, (uint64_t)Ktot * Cout * 2, BLOCK_K, BLOCK_N, 1)) return (int)cudaErrorInvalidValue;
+    int64_t tiles_x_ = (Wo + bw - 1) / bw, m_tiles_ = tiles_x_ * ((Ho + bh - 1) / bh);
+    int bn = choose_bn(m_tiles_, Cout, 1);
+    if (!make_map(&mb, w, (uint64_t)Ktot, (uint64_t)Cout, 1, (uint64_t)Ktot * 2, (uint64_t)Ktot * Cout * 2, BLOCK_K, (uint32_t)bn, 1)) return (int)cudaErrorInvalidValue;
     TcParams p{};
+    p.bn = bn;
     p.M = (int)(Ho * Wo); p.N = (int)Cout; p.K = (int)Cin; p.batch = 1;
     p.tiles_x = (int)((Wo + bw - 1) / bw);
     p.m_tiles = p.tiles_x * (int)((Ho + bh - 1) / bh);
-    p.n_tiles = (int)((Cout + BLOCK_N - 1) / BLOCK_N);
+    p.n_tiles = (int)((Cout + bn - 1) / bn);
     p.b_kmajor = 1;
     p.taps = kh * kw; p.kw = kw; p.pad_top = pad_top; p.pad_left = pad_left; p.Wo = (int)Wo; p.Ho = (int)Ho; p.bw = (int)bw; p.bh = (int)bh;
     p.k_blocks_per_tap = (int)((Cin + BLOCK_K - 1) / BLOCK_K);

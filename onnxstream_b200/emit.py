@@ -569,3 +569,112 @@ def unet_inputs(cfg: UNetConfig, seed: int = 0) -> Dict[str, np.ndarray]:
         d["text_5F_embeds"] = rng.standard_normal((1, cfg.text_embed_dim), dtype=np.float32)
         d["time_5F_ids"] = np.asarray([[px, px, 0, 0, px, px]], np.float32)
     return d
+
+
+@dataclass
+class LlamaConfig:
+    """TinyLlama-1.1B defaults; `tiny()` shrinks every dimension, topology unchanged."""
+    vocab: int = 32003
+    hidden: int = 2048
+    heads: int = 32
+    kv_heads: int = 4
+    head_dim: int = 64
+    mlp: int = 5632
+    layers: int = 22
+    past: int = 2047          # cached positions; the decode step adds one token
+    max_pos: int = 2048
+    eps: float = 1e-5
+
+    @staticmethod
+    def tiny() -> "LlamaConfig":
+        return LlamaConfig(vocab=50, hidden=64, heads=4, kv_heads=2, head_dim=16, mlp=128, layers=2, past=15, max_pos=32)
+
+
+def emit_llama_decode(out_dir: Optional[str], cfg: LlamaConfig, wdtype: str = "float32", seed: int = 4, keep_in_memory: bool = False) -> GraphBuilder:
+    """Llama-style single-token decode step with a KV cache, as llm.cpp drives it (src/llm.cpp:396-440): inputs
+    input_ids (1,1) int64, position_ids (1,1) int64, attention_mask (1,past+1) int64, pkv{2l},pkv{2l+1} (1,kv_heads,past,d);
+    outputs logits (1,1,vocab) and opkv* (the grown cache).  Attention uses the Transpose/MatMul/Div/Add/Softmax/MatMul
+    chain that the reference rewrites into ScaledDotProductAttention (src/onnxstream.cpp:3643-3695), with grouped KV heads.
+    RMSNorm ops carry `/input_layernorm/`, `/post_attention_layernorm/`, `/norm/` in their names so that m_requires_upcast can
+    keep them in fp32 (src/llm.cpp:385-389)."""
+    g = GraphBuilder(out_dir, wdtype, seed, keep_in_memory)
+    H, NH, KV, D, TT = cfg.hidden, cfg.heads, cfg.kv_heads, cfg.head_dim, cfg.past + 1
+    ids = g.input("input_5F_ids", (1, 1))
+    pos = g.input("position_5F_ids", (1, 1))
+    am = g.input("attention_5F_mask", (1, TT))
+    emb = g.const(g.randn((cfg.vocab, H), std=0.05))
+    h = g.node("Gather", [emb, ids], [(1, 1, H)], [("axis", "0")])
+    # rotary tables, gathered at position_ids
+    inv = 1.0 / (10000.0 ** (np.arange(0, D, 2, dtype=np.float64) / D))
+    fr = np.outer(np.arange(cfg.max_pos), inv)
+    tab = np.concatenate([fr, fr], axis=-1)
+    cos_t = g.const(np.cos(tab).astype(np.float32), quantizable=False)
+    sin_t = g.const(np.sin(tab).astype(np.float32), quantizable=False)
+    cos = g.node("Unsqueeze", [g.node("Gather", [cos_t, pos], [(1, 1, D)], [("axis", "0")]), g.i64([1])], [(1, 1, 1, D)])
+    sin = g.node("Unsqueeze", [g.node("Gather", [sin_t, pos], [(1, 1, D)], [("axis", "0")]), g.i64([1])], [(1, 1, 1, D)])
+    # additive mask from the int64 attention mask: (1 - m) * -65504 -> [1,1,1,T]
+    mf = g.node("Cast", [am], [(1, TT)], [("to", "1")])
+    mf = g.node("Sub", [g.scalar(1.0), mf], [(1, TT)])
+    mf = g.node("Mul", [mf, g.scalar(-65504.0)], [(1, TT)])
+    mf = g.node("Unsqueeze", [mf, g.i64([1])], [(1, 1, TT)])
+    mask = g.node("Unsqueeze", [mf, g.i64([2])], [(1, 1, 1, TT)])
+
+    def rms(x, tag):
+        p = g.node("Pow", [x, g.scalar(2.0)], [x.shape], name=g._uid(f"{tag}_Pow_"))
+        m = g.node("ReduceMean", [p], [x.shape[:-1] + (1,)], [("axes", "-1"), ("keepdims", "1")], name=g._uid(f"{tag}_ReduceMean_"))
+        a = g.node("Add", [m, g.scalar(cfg.eps)], [m.shape], name=g._uid(f"{tag}_Add_"))
+        s = g.node("Sqrt", [a], [m.shape], name=g._uid(f"{tag}_Sqrt_"))
+        r = g.node("Div", [g.scalar(1.0), s], [m.shape], name=g._uid(f"{tag}_Div_"))
+        n = g.node("Mul", [x, r], [x.shape], name=g._uid(f"{tag}_Mul_"))
+        return g.node("Mul", [g.const(g.randn((H,), std=0.02, mean=1.0)), n], [x.shape], name=g._uid(f"{tag}_Mul_"))
+
+    def rope(x, nh):
+        x1 = g.node("Slice", [x, g.i64([0]), g.i64([D // 2]), g.i64([3]), g.i64([1])], [(1, nh, 1, D // 2)])
+        x2 = g.node("Slice", [x, g.i64([D // 2]), g.i64([D]), g.i64([3]), g.i64([1])], [(1, nh, 1, D // 2)])
+        rot = g.node("Concat", [g.node("Neg", [x2], [x2.shape]), x1], [(1, nh, 1, D)], [("axis", "-1")])
+        return g.node("Add", [g.node("Mul", [x, cos], [x.shape]), g.node("Mul", [rot, sin], [x.shape])], [x.shape])
+
+    for l in range(cfg.layers):
+        pk = g.input(f"pkv{2 * l}", (1, KV, cfg.past, D))
+        pv = g.input(f"pkv{2 * l + 1}", (1, KV, cfg.past, D))
+        n = rms(h, f"_2F_model_2F_layers_2E_{l}_2F_input_5F_layernorm_2F_")
+        q = g.linear(n, NH * D, bias=False)
+        k = g.linear(n, KV * D, bias=False)
+        v = g.linear(n, KV * D, bias=False)
+        q = g.node("Transpose", [g.node("Reshape", [q, g.i64([1, 1, NH, D])], [(1, 1, NH, D)])], [(1, NH, 1, D)], [("perm", "0,2,1,3")])
+        k = g.node("Transpose", [g.node("Reshape", [k, g.i64([1, 1, KV, D])], [(1, 1, KV, D)])], [(1, KV, 1, D)], [("perm", "0,2,1,3")])
+        v = g.node("Transpose", [g.node("Reshape", [v, g.i64([1, 1, KV, D])], [(1, 1, KV, D)])], [(1, KV, 1, D)], [("perm", "0,2,1,3")])
+        q, k = rope(q, NH), rope(k, KV)
+        kc = g.node("Concat", [pk, k], [(1, KV, TT, D)], [("axis", "2")], out_names=[f"opkv{2 * l}"])
+        vc = g.node("Concat", [pv, v], [(1, KV, TT, D)], [("axis", "2")], out_names=[f"opkv{2 * l + 1}"])
+        g.mark_output(kc); g.mark_output(vc)
+        kt = g.node("Transpose", [kc], [(1, KV, D, TT)], [("perm", "0,1,3,2")])
+        s = g.node("MatMul", [q, kt], [(1, NH, 1, TT)])
+        s = g.node("Div", [s, g.scalar(math.sqrt(D))], [(1, NH, 1, TT)])
+        s = g.node("Add", [s, mask], [(1, NH, 1, TT)])
+        p = g.node("Softmax", [s], [(1, NH, 1, TT)], [("axis", "-1")])
+        o = g.node("MatMul", [p, vc], [(1, NH, 1, D)])
+        g.flops += 4 * NH * TT * D
+        o = g.node("Reshape", [g.node("Transpose", [o], [(1, 1, NH, D)], [("perm", "0,2,1,3")]), g.i64([1, 1, NH * D])], [(1, 1, NH * D)])
+        h = g.node("Add", [h, g.linear(o, H, bias=False)], [(1, 1, H)])
+        n = rms(h, f"_2F_model_2F_layers_2E_{l}_2F_post_5F_attention_5F_layernorm_2F_")
+        gate = g.silu(g.linear(n, cfg.mlp, bias=False))
+        up = g.linear(n, cfg.mlp, bias=False)
+        h = g.node("Add", [h, g.linear(g.node("Mul", [gate, up], [(1, 1, cfg.mlp)]), H, bias=False)], [(1, 1, H)])
+    n = rms(h, "_2F_model_2F_norm_2F_")
+    out = g.linear(n, cfg.vocab, bias=False)
+    g.lines[-1] = g.lines[-1].replace(out.text(), T("logits", out.shape).text())
+    g.mark_output(T("logits", out.shape))
+    g.finish()
+    return g
+
+
+def llama_inputs(cfg: LlamaConfig, seed: int = 0) -> Dict[str, np.ndarray]:
+    rng = np.random.default_rng(2000 + seed)
+    d = {"input_5F_ids": rng.integers(0, cfg.vocab, (1, 1)).astype(np.int64),
+         "position_5F_ids": np.asarray([[cfg.past]], np.int64),
+         "attention_5F_mask": np.ones((1, cfg.past + 1), np.int64)}
+    for l in range(cfg.layers):
+        d[f"pkv{2 * l}"] = rng.standard_normal((1, cfg.kv_heads, cfg.past, cfg.head_dim), dtype=np.float32)
+        d[f"pkv{2 * l + 1}"] = rng.standard_normal((1, cfg.kv_heads, cfg.past, cfg.head_dim), dtype=np.float32)
+    return d

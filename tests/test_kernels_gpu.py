@@ -131,3 +131,44 @@ def test_conv_f16(K, case, impl):
     if has_res:
         ref = ref + res.double(); absref = absref + res.double().abs()
     _check(y, ref, absref, f"conv {case} impl {impl}")
+
+
+def test_qu8_gemm_and_conv_bit_exact(K):
+    """W8A8 kernels against XNNPACK's fp32 requantisation, restated in numpy: acc = sum (x-zx)(w-zw) + bias;
+    y = clamp(lrintf(acc * (sx*sw/sy)) + zy, 0, 255) (verified bit-exact against xnn qu8 FC).  Bit-exact."""
+    import torch
+    vp, i64, ci, cf = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
+    K.osb_gemm_qu8.argtypes = [vp, vp, vp, vp, i64, i64, i64, ci, cf, ci, cf, ci, cf, vp]
+    K.osb_conv2d_qu8.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, ci, ci, ci, i64, i64, ci, cf, ci, cf, ci, cf, vp]
+    rng = np.random.default_rng(3)
+    zx, sx, zw, sw, zy, sy = 121, 0.031, 134, 0.0035, 117, 0.09
+    scale = np.float32(np.float32(np.float32(sx) * np.float32(sw)) / np.float32(sy))
+
+    def requant(acc):
+        f = (acc.astype(np.float32) * scale).astype(np.float32)
+        f = np.minimum(np.maximum(f, np.float32(0 - zy)), np.float32(255 - zy))
+        return (np.rint(f).astype(np.int32) + zy).astype(np.uint8)
+
+    M, N, Kd = 200, 136, 320
+    a = rng.integers(0, 256, (M, Kd), dtype=np.uint8); b = rng.integers(0, 256, (Kd, N), dtype=np.uint8)
+    bias = rng.integers(-2000, 2000, (N,), dtype=np.int32)
+    ref = requant((a.astype(np.int32) - zx) @ (b.astype(np.int32) - zw) + bias)
+    ta, tb, tbias = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), torch.from_numpy(bias).cuda()
+    tc = torch.zeros((M, N), dtype=torch.uint8, device="cuda")
+    assert K.osb_gemm_qu8(ta.data_ptr(), tb.data_ptr(), tc.data_ptr(), tbias.data_ptr(), M, N, Kd, zx, sx, zw, sw, zy, sy, _stream()) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(tc.cpu().numpy(), ref)
+
+    H = W = 12; Cin, Cout, k = 24, 40, 3
+    x = rng.integers(0, 256, (H, W, Cin), dtype=np.uint8); w = rng.integers(0, 256, (Cout, k, k, Cin), dtype=np.uint8)
+    xp = np.full((H + 2, W + 2, Cin), zx, np.int32); xp[1:-1, 1:-1] = x          # XNNPACK pads with the input zero point
+    acc = np.zeros((H, W, Cout), np.int64)
+    for ky in range(k):
+        for kx in range(k):
+            acc += (xp[ky:ky + H, kx:kx + W].astype(np.int64) - zx) @ (w[:, ky, kx].astype(np.int64) - zw).T
+    ref = requant(acc.astype(np.int32) + bias[:Cout])
+    tx, tw = torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda()
+    ty = torch.zeros((H, W, Cout), dtype=torch.uint8, device="cuda")
+    assert K.osb_conv2d_qu8(tx.data_ptr(), tw.data_ptr(), tbias.data_ptr(), ty.data_ptr(), H, W, Cin, Cout, k, k, 1, 1, 1, H, W, zx, sx, zw, sw, zy, sy, _stream()) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(ty.cpu().numpy(), ref)

@@ -222,3 +222,42 @@ def test_cpp_dropin(oracle_lib, models32):
     for wp in ("nocache", "ram+prefetch"):
         got, _ = run_model(lib, d, inputs, (), wp=wp, runs=2, plain_abi=True)
         assert report(got[out], ref[out])["rel_to_max"] <= TOL["float32"], wp
+
+
+UPCAST = ("_2F_input_5F_layernorm_2F_", "_2F_post_5F_attention_5F_layernorm_2F_", "_2F_norm_2F_")
+
+
+@pytest.mark.parametrize("mode", ["float32", "float16"])
+def test_llama_decode_parity(engine_lib, oracle_lib, workdir, mode):
+    """BASELINE config[4] hot path at toy size: Llama decode step with KV cache, grouped-KV ScaledDotProductAttention rewrite
+    (src/onnxstream.cpp:3643-3695, 7767-7882), int64 token / position inputs (Gather), rotary, RMSNorm kept in fp32 through
+    m_requires_upcast (src/llm.cpp:385-389).  logits and the grown KV cache are compared."""
+    cfg = emit.LlamaConfig.tiny()
+    d = os.path.join(workdir, f"llama_{mode}") + "/"
+    emit.emit_llama_decode(d, cfg, mode)
+    inputs = emit.llama_inputs(cfg)
+    opts = ("use_scaled_dp_attn_op",) + (("use_fp16_arithmetic",) if mode == "float16" else ())
+    kw = dict(extra_outputs=("opkv0", "opkv3"), upcast=UPCAST if mode == "float16" else ())
+    ref = run_model(oracle_lib, d, inputs, opts, **kw)[0]
+    got = run_model(engine_lib, d, inputs, opts, **kw)[0]
+    for n in ("logits", "opkv0", "opkv3"):
+        assert got[n].shape == ref[n].shape
+        assert report(got[n], ref[n])["rel_to_max"] <= TOL[mode], n
+    # shape / index path is bit-exact: the appended cache row position and the gathered embedding row
+    assert np.array_equal(got["opkv0"][:, :, :-1], ref["opkv0"][:, :, :-1]) or mode == "float16"
+
+
+@pytest.mark.parametrize("fp16", [False, True])
+def test_w8a32_parity(engine_lib, oracle_lib, workdir, fp16):
+    """BASELINE config[2] weight format at toy size: uint8 per-tensor asymmetric weights (onnx2txt percentile rule) streamed
+    as uint8 and dequantised on the device, fp32 (W8A32) or fp16 activations."""
+    cfg = emit.UNetConfig.tiny(8, sdxl=True)
+    d = os.path.join(workdir, "sdxl_u8") + "/"
+    emit.emit_unet(d, cfg, "uint8", seed=3)
+    inputs = emit.unet_inputs(cfg)
+    opts = FP16 if fp16 else ()
+    ref = run_model(oracle_lib, d, inputs, opts)[0]["out_5F_sample"]
+    got, m = run_model(engine_lib, d, inputs, opts, wp="ram+nocache", runs=2)
+    assert report(got["out_5F_sample"], ref)["rel_to_max"] <= (TOL["float16"] if fp16 else TOL["float32"])
+    u8 = sum(os.path.getsize(os.path.join(d, f)) for f in os.listdir(d) if f.endswith(".bin"))
+    assert abs(m.stats()["weight_bytes_streamed"] - u8) <= 8 * 4096      # uint8 bytes cross PCIe, not their fp32 expansion
