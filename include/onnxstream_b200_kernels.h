@@ -54,6 +54,8 @@ int osb_softmax(const void* x, void* y, int dtype, int64_t rows, int64_t cols, v
 /* Softmax over the last axis of (x * scale + mask[row % mask_rows]): the Mul + Softmax pair of the attention pattern
  * (src/onnxstream.cpp:6837-6887) and the mask add of the SDPA pattern; mask may be NULL. */
 int osb_softmax_scaled(const void* x, void* y, int dtype, int64_t rows, int64_t cols, float scale, const void* mask, int64_t mask_rows, void* stream);
+/* rows stored `ld` elements apart (ld >= cols, ld <= 256 when ld != cols); pad columns of y are zero-filled */
+int osb_softmax_scaled_ld(const void* x, void* y, int dtype, int64_t rows, int64_t cols, int64_t ld, float scale, const void* mask, int64_t mask_rows, void* stream);
 
 /* InstanceNormalization on [1, C, N] contiguous (src/onnxstream.cpp:4788-5055): two-pass mean/variance per channel
  * (the reference accumulates in double), y = scale[c] * (x - mean) / sqrt(var + eps) + bias[c]. scale/bias in `dtype`. */
@@ -86,6 +88,13 @@ int osb_gather_rows(const void* table, const int64_t* idx, void* out, int64_t n_
 int osb_gemm(const void* A, const void* B, void* C, const void* bias, const void* residual,
              int64_t batch, int64_t M, int64_t N, int64_t K,
              int64_t stride_a, int64_t stride_b, int64_t stride_c, int b_transposed, int dtype, int impl, void* stream);
+
+/* Same with explicit leading dimensions (elements between consecutive rows of A, B, C): lets the attention GEMMs read the
+ * per-head slices of a [T, heads*d] projection in place -- the Reshape/Transpose/Reshape head split and merge of the exported
+ * graph costs no copy -- and write O straight into the merged [T, heads*d] layout. */
+int osb_gemm_ld(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, const void* bias, const void* residual,
+                int64_t batch, int64_t M, int64_t N, int64_t K, int64_t stride_a, int64_t stride_b, int64_t stride_c,
+                int b_transposed, int dtype, int impl, void* stream);
 
 /* 2-D convolution, batch 1, groups 1, dilation 1: XnnPack::convolution (src/onnxstream.cpp:1292-1534).
  * x NHWC [H,W,Cin], w OHWI [Cout,kh,kw,Cin], bias [Cout] or NULL, y NHWC [Ho,Wo,Cout]; optional residual (same shape

@@ -37,7 +37,7 @@ std::vector<int64_t> parse_ints(const std::string& s)
 
 [[noreturn]] void fail(const OpDef& op, const std::string& msg) { throw std::invalid_argument(op.type + ": " + msg); }
 
-enum StepKind { SK_SINGLE = 0, SK_ATTENTION, SK_GROUPNORM, SK_LAYERNORM, SK_GELU, SK_SILU, SK_LINEAR, SK_SDPA };
+enum StepKind { SK_SINGLE = 0, SK_ATTENTION, SK_GROUPNORM, SK_LAYERNORM, SK_GELU, SK_SILU, SK_LINEAR, SK_SDPA, SK_MHA };
 
 struct Step {
     StepKind kind = SK_SINGLE;
@@ -408,6 +408,45 @@ struct Engine::Impl {
         return with_scale ? 4 : 3;
     }
 
+    // Whole multi-head attention of the diffusers export: three bias-free projections, the
+    // Reshape/Transpose/Reshape head split of each (K additionally pre-transposed), MatMul-Mul-Softmax-MatMul, and the head
+    // merge -- 20 ops.  Executed as 3 projection GEMMs + strided per-head GEMMs reading the projections in place.
+    size_t match_mha(size_t i) const
+    {
+        auto& ops = E.m_ops;
+        if (!E.fuse_nodes || E.use_uint8_arithmetic || E.use_uint8_qdq) return 0;
+        static const char* seq[20] = { "MatMul", "Reshape", "Transpose", "Reshape", "MatMul", "Reshape", "Transpose", "Reshape", "Transpose",
+                                       "MatMul", "Reshape", "Transpose", "Reshape", "MatMul", "Mul", "Softmax", "MatMul", "Reshape", "Transpose", "Reshape" };
+        if (i + 19 >= ops.size()) return 0;
+        for (int k = 0; k < 20; k++) if (ops[i + k].type != seq[k] || ops[i + k].out.size() != 1 || upcast_op(ops[i + k])) return 0;
+        auto lin = [&](const OpDef& o) { return o.in.size() == 2 && o.in[0].present && o.in[0].wtype == DType::none && is_float_weight(o.in[1]) && o.in[1].shape.size() == 2 && o.in[0].shape.size() == 3 && o.in[0].shape[0] == 1; };
+        if (!lin(ops[i]) || !lin(ops[i + 4]) || !lin(ops[i + 9])) return 0;
+        auto perm = [&](const OpDef& o, const char* p) { auto a = o.attr("perm"); return a && *a == p && o.in.size() == 1; };
+        if (!perm(ops[i + 2], "0,2,1,3") || !perm(ops[i + 6], "0,2,1,3") || !perm(ops[i + 11], "0,2,1,3") || !perm(ops[i + 18], "0,2,1,3") || !perm(ops[i + 8], "0,2,1")) return 0;
+        // chains
+        if (!feeds(ops[i], ops[i + 1], 0) || !feeds(ops[i + 1], ops[i + 2], 0) || !feeds(ops[i + 2], ops[i + 3], 0)) return 0;
+        if (!feeds(ops[i + 4], ops[i + 5], 0) || !feeds(ops[i + 5], ops[i + 6], 0) || !feeds(ops[i + 6], ops[i + 7], 0) || !feeds(ops[i + 7], ops[i + 8], 0)) return 0;
+        if (!feeds(ops[i + 9], ops[i + 10], 0) || !feeds(ops[i + 10], ops[i + 11], 0) || !feeds(ops[i + 11], ops[i + 12], 0)) return 0;
+        if (ops[i + 13].in.size() != 2 || !feeds(ops[i + 3], ops[i + 13], 0) || !feeds(ops[i + 8], ops[i + 13], 1)) return 0;
+        if (ops[i + 14].in.size() != 2 || !feeds(ops[i + 13], ops[i + 14], 0) || !is_scalar_weight(ops[i + 14].in[1])) return 0;
+        auto& sm = ops[i + 15];
+        if (sm.in.size() != 1 || !feeds(ops[i + 14], sm, 0) || sm.attrs.size() != 1 || sm.attrs[0].first != "axis" || sm.attrs[0].second != "-1") return 0;
+        if (ops[i + 16].in.size() != 2 || !feeds(sm, ops[i + 16], 0) || !feeds(ops[i + 12], ops[i + 16], 1)) return 0;
+        if (!feeds(ops[i + 16], ops[i + 17], 0) || !feeds(ops[i + 17], ops[i + 18], 0) || !feeds(ops[i + 18], ops[i + 19], 0)) return 0;
+        // shapes
+        auto& qs = ops[i + 3].out[0].shape; auto& kts = ops[i + 8].out[0].shape; auto& vs = ops[i + 12].out[0].shape; auto& os = ops[i + 19].out[0].shape;
+        auto& q4 = ops[i + 1].out[0].shape; auto& k4 = ops[i + 5].out[0].shape; auto& v4 = ops[i + 10].out[0].shape; auto& o4 = ops[i + 17].out[0].shape;
+        if (qs.size() != 3 || kts.size() != 3 || vs.size() != 3 || os.size() != 3 || q4.size() != 4 || k4.size() != 4 || v4.size() != 4 || o4.size() != 4) return 0;
+        int64_t h = qs[0], T = qs[1], d = qs[2], Tk = kts[2];
+        if (kts[0] != h || kts[1] != d || vs[0] != h || vs[1] != Tk || vs[2] != d || d % 8) return 0;
+        int64_t C = h * d;
+        if (ops[i].out[0].shape != std::vector<int64_t>{ 1, T, C } || ops[i + 4].out[0].shape != std::vector<int64_t>{ 1, Tk, C } || ops[i + 9].out[0].shape != std::vector<int64_t>{ 1, Tk, C }) return 0;
+        if (q4 != std::vector<int64_t>{ 1, T, h, d } || k4 != std::vector<int64_t>{ 1, Tk, h, d } || v4 != std::vector<int64_t>{ 1, Tk, h, d } || o4 != std::vector<int64_t>{ 1, h, T, d }) return 0;
+        if (os != std::vector<int64_t>{ 1, T, C }) return 0;
+        for (int k : { 1, 3, 5, 7, 10, 12, 17, 19 }) if (ops[i + k].in.size() != 2 || ops[i + k].in[1].wtype != DType::i64) return 0;
+        return 20;
+    }
+
     // Transpose(K) -> MatMul(Q, Kt) -> Div(s) -> Add(mask) -> Softmax(-1) -> MatMul(P, V)   (src/onnxstream.cpp:3643-3695)
     size_t match_sdpa(size_t i) const
     {
@@ -563,7 +602,8 @@ struct Engine::Impl {
         while (i < ops.size()) {
             Step s; s.first = i; s.count = 1; s.kind = SK_SINGLE;
             int var = 0; size_t n;
-            if ((n = match_sdpa(i))) { s.kind = SK_SDPA; s.count = n; }
+            if ((n = match_mha(i))) { s.kind = SK_MHA; s.count = n; }
+            else if ((n = match_sdpa(i))) { s.kind = SK_SDPA; s.count = n; }
             else if ((n = match_attention(i, var))) { s.kind = SK_ATTENTION; s.count = n; s.variant = var; }
             else if ((n = match_groupnorm(i, var))) { s.kind = SK_GROUPNORM; s.count = n; s.variant = var; }
             else if ((n = match_layernorm(i))) { s.kind = SK_LAYERNORM; s.count = n; }
@@ -628,6 +668,7 @@ struct Engine::Impl {
     void fused_silu(const Step& s);
     void fused_linear(const Step& s);
     void fused_sdpa(const Step& s);
+    void fused_mha(const Step& s);
 
     Tensor binary(int bop, const Tensor& a, const Tensor& b);
     Tensor strided(const Tensor& x, const std::vector<int64_t>& out_shape, const std::vector<int64_t>& in_stride,
@@ -1520,6 +1561,58 @@ void Engine::Impl::fused_attention(const Step& s)
     push(mm1i, 0, out);
 }
 
+// Multi-head attention block (see match_mha).  Per-op semantics are those of the MatMul / Reshape / Transpose /
+// AttentionFusedOps branches (src/onnxstream.cpp:5669-5861, 4708-4787, 5176-5236, 6696-6929); the head split and merge
+// become leading-dimension arithmetic on the projection buffers instead of copies.
+void Engine::Impl::fused_mha(const Step& s)
+{
+    size_t i = s.first;
+    const OpDef& op = E.m_ops[i];
+    Tensor x = to_plain(in(i, 0)), xk = to_plain(in(i + 4, 0)), xv = to_plain(in(i + 9, 0));
+    Tensor wq = in(i, 1), wk = in(i + 4, 1), wv = in(i + 9, 1);
+    for (size_t k : { (size_t)1, (size_t)3, (size_t)5, (size_t)7, (size_t)10, (size_t)12, (size_t)17, (size_t)19 }) (void)in(i + k, 1);   // shape constants: validated statically
+    DType ty = x.type;
+    if (ty != DType::f16 && ty != DType::f32) fail(op, "wrong data type of input 0.");
+    if (xk.type != ty) xk = convert(xk, ty);
+    if (xv.type != ty) xv = convert(xv, ty);
+    if (wq.type != ty) wq = convert(wq, ty);
+    if (wk.type != ty) wk = convert(wk, ty);
+    if (wv.type != ty) wv = convert(wv, ty);
+    auto& qs = E.m_ops[i + 3].out[0].shape; auto& kts = E.m_ops[i + 8].out[0].shape;
+    int64_t h = qs[0], T = qs[1], d = qs[2], Tk = kts[2], C = h * d;
+    int64_t Tkp = (Tk + 7) & ~(int64_t)7;
+    size_t es = dtype_size(ty);
+    float scale = scalar_of(in(i + 14, 1), E.m_ops[i + 14]);
+    if (ty == DType::f16) scale = __half2float(__float2half_rn(scale));
+    if (x.shape[2] != wq.shape[0] || xk.shape[2] != wk.shape[0] || xv.shape[2] != wv.shape[0]) throw std::runtime_error("XnnPack::matrix_multiply_fp32: invalid shape of inputs.");
+
+    Tensor ql = make(ty, { T, C }), kl = make(ty, { Tkp, C }), vl = make(ty, { Tkp, C }), out = make(ty, { 1, T, C });
+    if (Tkp != Tk) {   // zero pad rows: they are read as extra (null) keys / values by the padded GEMMs
+        ck(cudaMemsetAsync((char*)kl.mdata() + Tk * C * es, 0, (Tkp - Tk) * C * es, st), "cudaMemsetAsync");
+        ck(cudaMemsetAsync((char*)vl.mdata() + Tk * C * es, 0, (Tkp - Tk) * C * es, st), "cudaMemsetAsync");
+    }
+    ck(osb_gemm(x.data(), wq.data(), ql.mdata(), nullptr, nullptr, 1, T, C, x.shape[2], 0, 0, 0, 0, K(ty), E.gemm_impl, st), "osb_gemm(q)");
+    ck(osb_gemm(xk.data(), wk.data(), kl.mdata(), nullptr, nullptr, 1, Tk, C, xk.shape[2], 0, 0, 0, 0, K(ty), E.gemm_impl, st), "osb_gemm(k)");
+    ck(osb_gemm(xv.data(), wv.data(), vl.mdata(), nullptr, nullptr, 1, Tk, C, xv.shape[2], 0, 0, 0, 0, K(ty), E.gemm_impl, st), "osb_gemm(v)");
+
+    int64_t per_head = T * Tkp * (int64_t)es;
+    int64_t hc = std::max<int64_t>(1, std::min<int64_t>(h, ((int64_t)512 << 20) / std::max<int64_t>(per_head, 1)));
+    for (int64_t h0 = 0; h0 < h; h0 += hc) {
+        int64_t nh = std::min(hc, h - h0);
+        Tensor S = make(ty, { nh, T, Tkp });
+        const char* qp = (const char*)ql.data() + h0 * d * es;
+        const char* kp = (const char*)kl.data() + h0 * d * es;
+        const char* vp = (const char*)vl.data() + h0 * d * es;
+        char* op_ = (char*)out.mdata() + h0 * d * es;
+        // S[h] = Q[h] (T x d, rows C apart) * K[h]^T (K stored [Tkp x d], rows C apart => "B transposed")
+        ck(osb_gemm_ld(qp, C, kp, C, S.mdata(), Tkp, nullptr, nullptr, nh, T, Tkp, d, d, d, T * Tkp, 1, K(ty), E.gemm_impl, st), "osb_gemm_ld(QK)");
+        ck(osb_softmax_scaled_ld(S.data(), S.mdata(), K(ty), nh * T, Tk, Tkp, scale, nullptr, 1, st), "osb_softmax_scaled_ld");
+        // O[:, h*d:(h+1)*d] = P[h] (T x Tkp) * V[h] (Tkp x d, rows C apart), written in place into the merged [T, C] layout
+        ck(osb_gemm_ld(S.data(), Tkp, vp, C, op_, C, nullptr, nullptr, nh, T, d, Tkp, T * Tkp, d, d, 0, K(ty), E.gemm_impl, st), "osb_gemm_ld(PV)");
+    }
+    push(i + 19, 0, out);
+}
+
 // ScaledDotProductAttention (src/onnxstream.cpp:7767-7882): q [B,Hq,Tq,D], k [B,Hkv,Tk,D], v [B,Hkv,Tk,Dv], scale 1/s,
 // additive mask [Tq,Tk] (or [1,1,Tq,Tk]); grouped KV heads supported.
 void Engine::Impl::fused_sdpa(const Step& s)
@@ -1697,6 +1790,7 @@ void Engine::Impl::exec_step(size_t si)
         case SK_SILU: fused_silu(s); break;
         case SK_LINEAR: fused_linear(s); break;
         case SK_SDPA: fused_sdpa(s); break;
+        case SK_MHA: fused_mha(s); break;
         default: exec_single(s.first); break;
         }
     }

@@ -42,6 +42,7 @@ struct TcParams {
     int m_tiles, n_tiles;
     int bn;                      // N extent of a tile (64 / 80 / 96 / 128): chosen per problem to fill the 148 SMs
     int b_kmajor;                // 1: B is [N,K] row-major
+    int a_swap, b_swap;          // tensor map has (batch, row) order swapped because the batch stride is the smaller one (per-head views)
     // conv geometry (taps == 1 for a plain GEMM)
     int taps, kw, pad_top, pad_left, Wo, Ho, bw, bh, tiles_x;
     int k_blocks_per_tap;
@@ -54,6 +55,7 @@ struct TcParams {
     const __half* bias;
     const __half* residual;
     long long stride_c;          // elements between batches
+    long long ldc;               // elements between output rows (== N for a dense C)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------
@@ -230,14 +232,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         int ky = tap / p.kw, kx = tap % p.kw;
                         tma_load_3d(sa, &map_a, &full[stage], kc, x0 * p.stride + kx - p.pad_left, y0 * p.stride + ky - p.pad_top);
                     } else {
-                        tma_load_3d(sa, &map_a, &full[stage], kc, m0, b);
+                        if (p.a_swap) tma_load_3d(sa, &map_a, &full[stage], kc, b, m0); else tma_load_3d(sa, &map_a, &full[stage], kc, m0, b);
                     }
                     int kglob = tap * p.K + kc;   // K index into B (conv: taps are concatenated along K)
                     if (p.b_kmajor) {
-                        tma_load_3d(sb, &map_b, &full[stage], kglob, n0, b);
+                        if (p.b_swap) tma_load_3d(sb, &map_b, &full[stage], kglob, b, n0); else tma_load_3d(sb, &map_b, &full[stage], kglob, n0, b);
                     } else {
-                        tma_load_3d(sb, &map_b, &full[stage], n0, kglob, b);
-                        if (p.bn > 64) tma_load_3d(sb + B_STAGE_BYTES / 2, &map_b, &full[stage], n0 + 64, kglob, b);
+                        if (p.b_swap) {
+                            tma_load_3d(sb, &map_b, &full[stage], n0, b, kglob);
+                            if (p.bn > 64) tma_load_3d(sb + B_STAGE_BYTES / 2, &map_b, &full[stage], n0 + 64, b, kglob);
+                        } else {
+                            tma_load_3d(sb, &map_b, &full[stage], n0, kglob, b);
+                            if (p.bn > 64) tma_load_3d(sb + B_STAGE_BYTES / 2, &map_b, &full[stage], n0 + 64, kglob, b);
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -304,8 +311,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
-            __half* crow = p.C + (long long)b * p.stride_c + out_row * p.N;
-            const __half* rrow = p.residual ? p.residual + (long long)b * p.stride_c + out_row * p.N : nullptr;
+            __half* crow = p.C + (long long)b * p.stride_c + out_row * p.ldc;
+            const __half* rrow = p.residual ? p.residual + (long long)b * p.stride_c + out_row * p.ldc : nullptr;
             float* wrow = p.split_k > 1 ? p.ws + (((long long)sp * p.batch + b) * p.M + out_row) * p.N : nullptr;
             const bool vec_ok = (p.N & 7) == 0;
 #pragma unroll 1
@@ -498,6 +505,19 @@ bool make_map(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint
     return r == CUDA_SUCCESS;
 }
 
+// rank-3 map over (inner, row, batch) that keeps the global strides ascending: when the batch stride is the smaller one
+// (per-head slices of a [T, heads*d] buffer) the two outer dimensions are swapped and *swapped is set.
+bool make_map_rb(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t row_stride_bytes, uint64_t batch_stride_bytes,
+                 uint32_t box_inner, uint32_t box_rows, int* swapped)
+{
+    if (batch > 1 && batch_stride_bytes < row_stride_bytes) {
+        *swapped = 1;
+        return make_map(map, base, inner, batch, rows, batch_stride_bytes, row_stride_bytes, box_inner, 1, box_rows);
+    }
+    *swapped = 0;
+    return make_map(map, base, inner, rows, batch, row_stride_bytes, batch_stride_bytes, box_inner, box_rows, 1);
+}
+
 int num_sms()
 {
     static int n = 0;
@@ -599,11 +619,13 @@ extern "C" int osb_tc_profile_dump(char* buf, int cap)
     return off;
 }
 
-bool osb_tc_gemm_ok(int64_t M, int64_t N, int64_t K, int bt, const void* A, const void* B, const void* C, int64_t sa, int64_t sb, int64_t sc)
+bool osb_tc_gemm_ok(int64_t M, int64_t N, int64_t K, int bt, const void* A, const void* B, const void* C, int64_t sa, int64_t sb, int64_t sc,
+                    int64_t lda, int64_t ldb, int64_t ldc)
 {
+    if ((lda % 8) || (ldb % 8) || (ldc % 8)) return false;
     if (M < 32 || N < 1 || K < 8) return false;
     if (K % 8) return false;
-    if (N % 8) { if (!bt || (sc % 8) || true) return false; }   // ragged N only through the conv entry (K-major B, scalar epilogue)
+    if (N % 8) return false;   // ragged N only through the conv entry (K-major B, scalar epilogue)
     if (M > (1 << 30) || N > (1 << 30) || K > (1 << 30)) return false;
     if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) return false;
     if ((sa % 8) || (sb % 8) || (sc % 8)) return false;
@@ -612,8 +634,11 @@ bool osb_tc_gemm_ok(int64_t M, int64_t N, int64_t K, int bt, const void* A, cons
 }
 
 int osb_tc_gemm_launch(const void* A, const void* B, void* C, const void* bias, const void* residual, int64_t batch, int64_t M, int64_t N, int64_t K,
-                       int64_t sa, int64_t sb, int64_t sc, int bt, cudaStream_t st)
+                       int64_t sa, int64_t sb, int64_t sc, int bt, cudaStream_t st, int64_t lda, int64_t ldb, int64_t ldc)
 {
+    if (lda <= 0) lda = K;
+    if (ldb <= 0) ldb = bt ? K : N;
+    if (ldc <= 0) ldc = N;
     CUtensorMap ma, mb;
     // A: [batch][M][K]; a shared operand (stride 0) is presented as batch extent 1 and the batch coordinate ignored
     uint64_t abatch = sa ? (uint64_t)batch : 1, bbatch = sb ? (uint64_t)batch : 1;
@@ -621,27 +646,29 @@ int osb_tc_gemm_launch(const void* A, const void* B, void* C, const void* bias, 
         // shared operands across the batch: fold the batch into per-batch launches (rare: 2-D weights with n > 1)
         for (int64_t i = 0; i < batch; i++) {
             int r = osb_tc_gemm_launch((const __half*)A + i * sa, (const __half*)B + i * sb, (__half*)C + i * sc, bias,
-                                       residual ? (const __half*)residual + i * sc : nullptr, 1, M, N, K, M * K, bt ? N * K : K * N, sc, bt, st);
+                                       residual ? (const __half*)residual + i * sc : nullptr, 1, M, N, K, M * lda, bt ? N * ldb : K * ldb, sc, bt, st, lda, ldb, ldc);
             if (r) return r;
         }
         return 0;
     }
-    if (!make_map(&ma, A, (uint64_t)K, (uint64_t)M, abatch, (uint64_t)K * 2, (uint64_t)(sa ? sa : M * K) * 2, BLOCK_K, BLOCK_M, 1)) return (int)cudaErrorInvalidValue;
+    int a_swap = 0, b_swap = 0;
+    if (!make_map_rb(&ma, A, (uint64_t)K, (uint64_t)M, abatch, (uint64_t)lda * 2, (uint64_t)(sa ? sa : M * lda) * 2, BLOCK_K, BLOCK_M, &a_swap)) return (int)cudaErrorInvalidValue;
     int64_t m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
     int bn = choose_bn(m_tiles, N, batch);
-    bool okb = bt ? make_map(&mb, B, (uint64_t)K, (uint64_t)N, bbatch, (uint64_t)K * 2, (uint64_t)(sb ? sb : N * K) * 2, BLOCK_K, (uint32_t)bn, 1)
-                  : make_map(&mb, B, (uint64_t)N, (uint64_t)K, bbatch, (uint64_t)N * 2, (uint64_t)(sb ? sb : N * K) * 2, 64, BLOCK_K, 1);
+    bool okb = bt ? make_map_rb(&mb, B, (uint64_t)K, (uint64_t)N, bbatch, (uint64_t)ldb * 2, (uint64_t)(sb ? sb : N * ldb) * 2, BLOCK_K, (uint32_t)bn, &b_swap)
+                  : make_map_rb(&mb, B, (uint64_t)N, (uint64_t)K, bbatch, (uint64_t)ldb * 2, (uint64_t)(sb ? sb : K * ldb) * 2, 64, BLOCK_K, &b_swap);
     if (!okb) return (int)cudaErrorInvalidValue;
     TcParams p{};
     p.M = (int)M; p.N = (int)N; p.K = (int)K; p.batch = (int)batch;
     p.bn = bn;
     p.m_tiles = (int)m_tiles; p.n_tiles = (int)((N + bn - 1) / bn);
     p.b_kmajor = bt ? 1 : 0;
+    p.a_swap = a_swap; p.b_swap = b_swap;
     p.taps = 1; p.kw = 1; p.bh = 0; p.bw = 0; p.tiles_x = 1;
     p.k_blocks_per_tap = (int)((K + BLOCK_K - 1) / BLOCK_K);
     p.stride = 1;
-    p.C = (__half*)C; p.bias = (const __half*)bias; p.residual = (const __half*)residual; p.stride_c = sc;
-    p.split_k = (sc == M * N || batch == 1) ? choose_split(p.m_tiles * p.n_tiles * p.batch, p.k_blocks_per_tap, (size_t)batch * M * N, st) : 1;
+    p.C = (__half*)C; p.bias = (const __half*)bias; p.residual = (const __half*)residual; p.stride_c = sc; p.ldc = ldc;
+    p.split_k = (ldc == N && (sc == M * N || batch == 1)) ? choose_split(p.m_tiles * p.n_tiles * p.batch, p.k_blocks_per_tap, (size_t)batch * M * N, st) : 1;
     p.ws = g_ws; p.counters = (p.N % 4) ? g_counters : nullptr;   // vectorised parallel reduce kernel needs N % 4 == 0
     return launch(ma, mb, p, st);
 }
@@ -680,7 +707,7 @@ int osb_tc_conv_launch(const void* x, const void* w, const void* bias, const voi
     p.taps = kh * kw; p.kw = kw; p.pad_top = pad_top; p.pad_left = pad_left; p.Wo = (int)Wo; p.Ho = (int)Ho; p.bw = (int)bw; p.bh = (int)bh;
     p.k_blocks_per_tap = (int)((Cin + BLOCK_K - 1) / BLOCK_K);
     p.stride = stride;
-    p.C = (__half*)y; p.bias = (const __half*)bias; p.residual = (const __half*)residual; p.stride_c = 0;
+    p.C = (__half*)y; p.bias = (const __half*)bias; p.residual = (const __half*)residual; p.stride_c = 0; p.ldc = Cout;
     p.split_k = choose_split(p.m_tiles * p.n_tiles, p.taps * p.k_blocks_per_tap, (size_t)Ho * Wo * Cout, st);
     p.ws = g_ws; p.counters = (p.N % 4) ? g_counters : nullptr;   // vectorised parallel reduce kernel needs N % 4 == 0
     return launch(ma, mb, p, st);

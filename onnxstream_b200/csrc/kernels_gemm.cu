@@ -13,11 +13,12 @@
 // implemented in gemm_tcgen05.cu
 int osb_tc_gemm_launch(const void* A, const void* B, void* C, const void* bias, const void* residual,
                        int64_t batch, int64_t M, int64_t N, int64_t K, int64_t sa, int64_t sb, int64_t sc,
-                       int b_transposed, cudaStream_t st);
+                       int b_transposed, cudaStream_t st, int64_t lda, int64_t ldb, int64_t ldc);
 int osb_tc_conv_launch(const void* x, const void* w, const void* bias, const void* residual, void* y,
                        int64_t H, int64_t W, int64_t Cin, int64_t Cout, int kh, int kw, int stride, int pad_top, int pad_left,
                        int64_t Ho, int64_t Wo, cudaStream_t st);
-bool osb_tc_gemm_ok(int64_t M, int64_t N, int64_t K, int b_transposed, const void* A, const void* B, const void* C, int64_t sa, int64_t sb, int64_t sc);
+bool osb_tc_gemm_ok(int64_t M, int64_t N, int64_t K, int b_transposed, const void* A, const void* B, const void* C, int64_t sa, int64_t sb, int64_t sc,
+                    int64_t lda, int64_t ldb, int64_t ldc);
 bool osb_tc_conv_ok(int64_t H, int64_t W, int64_t Cin, int64_t Cout, int kh, int kw, int stride, const void* x, const void* w, const void* y);
 
 namespace {
@@ -34,8 +35,11 @@ __global__ void __launch_bounds__(256)
 igemm_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C,
              const void* __restrict__ bias, const T* __restrict__ residual,
              int M, int N, int K, int64_t sa, int64_t sb, int64_t sc, int b_transposed, ConvGeom g,
-             int zx, int zw, int zy, float requant)
+             int zx, int zw, int zy, float requant, int lda, int ldb, int ldc)
 {
+    if (lda <= 0) lda = K;
+    if (ldb <= 0) ldb = b_transposed ? K : N;
+    if (ldc <= 0) ldc = N;
     osb_pdl_prologue();
     using Acc = typename std::conditional<QU8, int, float>::type;
     __shared__ Acc As[BK][BM + 4];
@@ -74,7 +78,7 @@ igemm_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C
                         if (QU8) v = (Acc)((int)raw - zx); else v = (Acc)to_float(raw);
                     }
                 } else {
-                    T raw = A[(int64_t)m * K + k];
+                    T raw = A[(int64_t)m * lda + k];
                     if (QU8) v = (Acc)((int)raw - zx); else v = (Acc)to_float(raw);
                 }
             }
@@ -85,7 +89,7 @@ igemm_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C
             int kk = k0 + bk, n = n0 + bn;
             Acc w = 0;
             if (kk < K && n < N) {
-                T raw = b_transposed ? B[(int64_t)n * K + kk] : B[(int64_t)kk * N + n];
+                T raw = b_transposed ? B[(int64_t)n * ldb + kk] : B[(int64_t)kk * ldb + n];
                 if (QU8) w = (Acc)((int)raw - zw); else w = (Acc)to_float(raw);
             }
             Bs[bk][bn] = w;
@@ -121,12 +125,12 @@ igemm_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C
                 scaled = fmaxf(scaled, (float)(0 - zy));
                 scaled = fminf(scaled, (float)(255 - zy));
                 int q = (int)lrintf(scaled) + zy;
-                C[(int64_t)m * N + n] = (uint8_t)q;
+                C[(int64_t)m * ldc + n] = (uint8_t)q;
             } else {
                 float v = acc[i][j];
                 if (bias) v += to_float(((const T*)bias)[n]);
-                if (residual) v += to_float(residual[(int64_t)m * N + n]);
-                C[(int64_t)m * N + n] = from_float<T>(v);
+                if (residual) v += to_float(residual[(int64_t)m * ldc + n]);
+                C[(int64_t)m * ldc + n] = from_float<T>(v);
             }
         }
     }
@@ -276,6 +280,37 @@ __global__ void softmax_scaled_kernel(const T* __restrict__ x, T* __restrict__ y
     }
 }
 
+// Short rows (cross-attention: 77 keys): one warp per row, values kept in registers (cols <= 256), row stride `ld`,
+// pad columns [cols, ld) zero-filled so the tile can feed a GEMM whose K is padded to a multiple of 8.
+template <typename T>
+__global__ void softmax_scaled_warp_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int cols, int ld, float scale,
+                                           const T* __restrict__ mask, int64_t mask_rows)
+{
+    osb_pdl_prologue();
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int64_t r = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * wpb) {
+        const T* xr = x + r * ld;
+        const T* mr = mask ? mask + (r % mask_rows) * cols : nullptr;
+        T* yr = y + r * ld;
+        float v[8];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            int c = lane + 32 * j;
+            v[j] = c < cols ? to_float(xr[c]) * scale + (mr ? to_float(mr[c]) : 0.f) : -INFINITY;
+            mx = fmaxf(mx, v[j]);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { v[j] = (lane + 32 * j) < cols ? __expf(v[j] - mx) : 0.f; sum += v[j]; }
+        sum = warp_sum(sum);
+        float inv = 1.f / sum;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { int c = lane + 32 * j; if (c < ld) yr[c] = from_float<T>(v[j] * inv); }
+    }
+}
+
 // Same, one global read per element: the row is staged in shared memory as fp32 (cols <= 12288)
 template <typename T>
 __global__ void softmax_scaled_smem_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int cols, float scale,
@@ -371,12 +406,12 @@ __global__ void attention_rows_kernel(const T* __restrict__ q, const T* __restri
 
 template <typename T>
 int launch_igemm(const T* A, const T* B, T* C, const void* bias, const T* residual, int64_t batch, int64_t M, int64_t N, int64_t K,
-                 int64_t sa, int64_t sb, int64_t sc, int bt, bool conv, ConvGeom g, cudaStream_t st)
+                 int64_t sa, int64_t sb, int64_t sc, int bt, bool conv, ConvGeom g, cudaStream_t st, int64_t lda = 0, int64_t ldb = 0, int64_t ldc = 0)
 {
     dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)batch);
     if (grid.y > 65535 || grid.z > 65535) return (int)cudaErrorInvalidValue;
-    if (conv) osb_launch((igemm_kernel<T, true, false>), grid, 256, 0, st, A, B, C, bias, residual, (int)M, (int)N, (int)K, sa, sb, sc, bt, g, 0, 0, 0, 0.f);
-    else osb_launch((igemm_kernel<T, false, false>), grid, 256, 0, st, A, B, C, bias, residual, (int)M, (int)N, (int)K, sa, sb, sc, bt, g, 0, 0, 0, 0.f);
+    if (conv) osb_launch((igemm_kernel<T, true, false>), grid, 256, 0, st, A, B, C, bias, residual, (int)M, (int)N, (int)K, sa, sb, sc, bt, g, 0, 0, 0, 0.f, 0, 0, 0);
+    else osb_launch((igemm_kernel<T, false, false>), grid, 256, 0, st, A, B, C, bias, residual, (int)M, (int)N, (int)K, sa, sb, sc, bt, g, 0, 0, 0, 0.f, (int)lda, (int)ldb, (int)ldc);
     return launched();
 }
 
@@ -386,21 +421,28 @@ extern "C" {
 
 int osb_gemm_tc_eligible(int64_t M, int64_t N, int64_t K, int dtype)
 {
-    return dtype == OSB_F16 && osb_tc_gemm_ok(M, N, K, 0, nullptr, nullptr, nullptr, 0, 0, 0) ? 1 : 0;
+    return dtype == OSB_F16 && osb_tc_gemm_ok(M, N, K, 0, nullptr, nullptr, nullptr, 0, 0, 0, K, N, N) ? 1 : 0;
 }
 
 int osb_gemm(const void* A, const void* B, void* C, const void* bias, const void* residual, int64_t batch, int64_t M, int64_t N, int64_t K,
              int64_t sa, int64_t sb, int64_t sc, int bt, int dtype, int impl, void* stream)
 {
+    return osb_gemm_ld(A, K, B, bt ? K : N, C, N, bias, residual, batch, M, N, K, sa, sb, sc, bt, dtype, impl, stream);
+}
+
+int osb_gemm_ld(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, const void* bias, const void* residual,
+                int64_t batch, int64_t M, int64_t N, int64_t K, int64_t sa, int64_t sb, int64_t sc, int bt, int dtype, int impl, void* stream)
+{
+    const bool dense = lda == K && ldb == (bt ? K : N) && ldc == N;
     if (batch * M * N == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype != OSB_F16 && dtype != OSB_F32) return (int)cudaErrorInvalidValue;
     if (K == 0) return (int)cudaErrorInvalidValue;
-    bool tc_ok = dtype == OSB_F16 && osb_tc_gemm_ok(M, N, K, bt, A, B, C, sa, sb, sc);
+    bool tc_ok = dtype == OSB_F16 && osb_tc_gemm_ok(M, N, K, bt, A, B, C, sa, sb, sc, lda, ldb, ldc);
     if (impl == 2 && !tc_ok) return (int)cudaErrorInvalidValue;
-    if (tc_ok && impl != 1) return osb_tc_gemm_launch(A, B, C, bias, residual, batch, M, N, K, sa, sb, sc, bt, st);
+    if (tc_ok && impl != 1) return osb_tc_gemm_launch(A, B, C, bias, residual, batch, M, N, K, sa, sb, sc, bt, st, lda, ldb, ldc);
     ConvGeom g{};
-    if (M <= 8 && batch == 1 && !bt && N % 8 == 0 && aligned16(B) && N >= 256 && K >= 64) {
+    if (dense && M <= 8 && batch == 1 && !bt && N % 8 == 0 && aligned16(B) && N >= 256 && K >= 64) {
         // weight-bandwidth path
         static float* scratch = nullptr; static size_t scratch_n = 0;
         size_t need = (size_t)M * N;
@@ -428,14 +470,14 @@ int osb_gemm(const void* A, const void* B, void* C, const void* bias, const void
         else osb_launch((gemv_finalize_kernel<float>), fg, 256, 0, st, scratch, (float*)C, (const float*)bias, (const float*)residual, (int)M, (int)N);
         return launched();
     }
-    if (M <= 8 && batch == 1) {
+    if (dense && M <= 8 && batch == 1) {
         int grid = bt ? (int)min<int64_t>((N + 7) / 8, 148 * 8) : (int)((N + 63) / 64);
         if (dtype == OSB_F16) osb_launch((skinny_gemm_kernel<__half, 8>), grid, 256, 0, st, (const __half*)A, (const __half*)B, (__half*)C, (const __half*)bias, (const __half*)residual, (int)M, (int)N, (int)K, bt);
         else osb_launch((skinny_gemm_kernel<float, 8>), grid, 256, 0, st, (const float*)A, (const float*)B, (float*)C, (const float*)bias, (const float*)residual, (int)M, (int)N, (int)K, bt);
         return launched();
     }
-    if (dtype == OSB_F16) return launch_igemm<__half>((const __half*)A, (const __half*)B, (__half*)C, bias, (const __half*)residual, batch, M, N, K, sa, sb, sc, bt, false, g, st);
-    return launch_igemm<float>((const float*)A, (const float*)B, (float*)C, bias, (const float*)residual, batch, M, N, K, sa, sb, sc, bt, false, g, st);
+    if (dtype == OSB_F16) return launch_igemm<__half>((const __half*)A, (const __half*)B, (__half*)C, bias, (const __half*)residual, batch, M, N, K, sa, sb, sc, bt, false, g, st, lda, ldb, ldc);
+    return launch_igemm<float>((const float*)A, (const float*)B, (float*)C, bias, (const float*)residual, batch, M, N, K, sa, sb, sc, bt, false, g, st, lda, ldb, ldc);
 }
 
 int osb_conv2d(const void* x, const void* w, const void* bias, const void* residual, void* y, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
@@ -460,7 +502,7 @@ int osb_gemm_qu8(const uint8_t* A, const uint8_t* B, uint8_t* C, const int32_t* 
     ConvGeom g{};
     float requant = sx * sw / sy;
     dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), 1);
-    osb_launch((igemm_kernel<uint8_t, false, true>), grid, 256, 0, (cudaStream_t)stream, A, B, C, bias, nullptr, (int)M, (int)N, (int)K, 0, 0, 0, 0, g, zx, zw, zy, requant);
+    osb_launch((igemm_kernel<uint8_t, false, true>), grid, 256, 0, (cudaStream_t)stream, A, B, C, bias, nullptr, (int)M, (int)N, (int)K, 0, 0, 0, 0, g, zx, zw, zy, requant, 0, 0, 0);
     return launched();
 }
 
@@ -473,11 +515,17 @@ int osb_conv2d_qu8(const uint8_t* x, const uint8_t* w, const int32_t* bias, uint
     int64_t M = Ho * Wo, N = Cout, K = (int64_t)kh * kw * Cin;
     float requant = sx * sw / sy;
     dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), 1);
-    osb_launch((igemm_kernel<uint8_t, true, true>), grid, 256, 0, (cudaStream_t)stream, x, w, y, bias, nullptr, (int)M, (int)N, (int)K, 0, 0, 0, 1, g, zx, zw, zy, requant);
+    osb_launch((igemm_kernel<uint8_t, true, true>), grid, 256, 0, (cudaStream_t)stream, x, w, y, bias, nullptr, (int)M, (int)N, (int)K, 0, 0, 0, 1, g, zx, zw, zy, requant, 0, 0, 0);
     return launched();
 }
 
 int osb_softmax_scaled(const void* x, void* y, int dtype, int64_t rows, int64_t cols, float scale, const void* mask, int64_t mask_rows, void* stream)
+{
+    return osb_softmax_scaled_ld(x, y, dtype, rows, cols, cols, scale, mask, mask_rows, stream);
+}
+
+// rows of `cols` valid elements stored `ld` apart; the pad columns [cols, ld) of y are zero-filled (they feed a padded GEMM K)
+int osb_softmax_scaled_ld(const void* x, void* y, int dtype, int64_t rows, int64_t cols, int64_t ld, float scale, const void* mask, int64_t mask_rows, void* stream)
 {
     if (rows * cols == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
@@ -485,6 +533,14 @@ int osb_softmax_scaled(const void* x, void* y, int dtype, int64_t rows, int64_t 
     int grid = (int)min<int64_t>(rows, 148 * 16);
     if (mask_rows <= 0) mask_rows = 1;
     int vecw = dtype == OSB_F16 ? 8 : 4;
+    if (ld <= 256 && cols <= ld) {
+        grid = (int)min<int64_t>((rows + 7) / 8, 148 * 8);
+        if (dtype == OSB_F16) osb_launch((softmax_scaled_warp_kernel<__half>), grid, 256, 0, st, (const __half*)x, (__half*)y, rows, (int)cols, (int)ld, scale, (const __half*)mask, mask_rows);
+        else if (dtype == OSB_F32) osb_launch((softmax_scaled_warp_kernel<float>), grid, 256, 0, st, (const float*)x, (float*)y, rows, (int)cols, (int)ld, scale, (const float*)mask, mask_rows);
+        else return (int)cudaErrorInvalidValue;
+        return launched();
+    }
+    if (ld != cols) return (int)cudaErrorInvalidValue;   // padded rows are only needed (and supported) for short rows
     if (cols >= 512 && cols <= 12288 && cols % vecw == 0 && aligned16(x) && aligned16(y)) {
         size_t smem = (size_t)cols * sizeof(float);
         grid = (int)min<int64_t>(rows, 148 * 4);

@@ -172,3 +172,37 @@ def test_qu8_gemm_and_conv_bit_exact(K):
     assert K.osb_conv2d_qu8(tx.data_ptr(), tw.data_ptr(), tbias.data_ptr(), ty.data_ptr(), H, W, Cin, Cout, k, k, 1, 1, 1, H, W, zx, sx, zw, sw, zy, sy, _stream()) == 0
     torch.cuda.synchronize()
     assert np.array_equal(ty.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("T,Tk,h,d", [(256, 256, 4, 40), (192, 77, 8, 40), (64, 64, 2, 160)])
+def test_gemm_head_views(K, impl, T, Tk, h, d):
+    """osb_gemm_ld on per-head slices of [T, h*d] projections (the fused multi-head-attention step): S = Q_h K_h^T with a padded
+    leading dimension, then O[:, h*d:(h+1)*d] = P_h V_h written in place into the merged layout."""
+    import torch
+    vp, i64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    K.osb_gemm_ld.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i64, i64, i64, i64, i64, i64, i64, ci, ci, ci, vp]
+    C = h * d
+    Tkp = (Tk + 7) // 8 * 8
+    g = torch.Generator(device="cuda").manual_seed(T + Tk)
+    q = torch.randn(T, C, device="cuda", generator=g).half()
+    k = torch.zeros(Tkp, C, device="cuda", dtype=torch.half); k[:Tk] = torch.randn(Tk, C, device="cuda", generator=g).half()
+    v = torch.zeros(Tkp, C, device="cuda", dtype=torch.half); v[:Tk] = torch.randn(Tk, C, device="cuda", generator=g).half()
+    S = torch.full((h, T, Tkp), float("nan"), device="cuda", dtype=torch.half)
+    rc = K.osb_gemm_ld(q.data_ptr(), C, k.data_ptr(), C, S.data_ptr(), Tkp, None, None, h, T, Tkp, d, d, d, T * Tkp, 1, F16, impl, _stream())
+    assert rc == 0
+    torch.cuda.synchronize()
+    qh = q.double().view(T, h, d).permute(1, 0, 2)
+    kh = k.double().view(Tkp, h, d).permute(1, 0, 2)
+    ref = qh @ kh.transpose(1, 2)
+    _check(S, ref, qh.abs() @ kh.abs().transpose(1, 2), "QK head views")
+    P = torch.softmax(S.float(), dim=-1).half()
+    P[:, :, Tk:] = 0
+    O = torch.full((T, C), float("nan"), device="cuda", dtype=torch.half)
+    rc = K.osb_gemm_ld(P.data_ptr(), Tkp, v.data_ptr(), C, O.data_ptr(), C, None, None, h, T, d, Tkp, T * Tkp, d, d, 0, F16, impl, _stream())
+    assert rc == 0
+    torch.cuda.synchronize()
+    vh = v.double().view(Tkp, h, d).permute(1, 0, 2)
+    ref = (P.double() @ vh).permute(1, 0, 2).reshape(T, C)
+    absref = (P.double().abs() @ vh.abs()).permute(1, 0, 2).reshape(T, C)
+    _check(O, ref, absref, "PV head views")
