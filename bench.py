@@ -35,6 +35,16 @@ if WORLD > 1 and "OSB_KEEP_VISIBLE" not in os.environ:
     devs = vis.split(",") if vis else [str(i) for i in range(64)]
     os.environ["CUDA_VISIBLE_DEVICES"] = devs[LOCAL_RANK]
 
+# The contract is ONE JSON line on stdout: native libraries (NCCL prints its version banner) must not pollute it, so
+# fd 1 points at stderr while the bench runs and the line is written to the saved descriptor at the end.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit_line(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
 import numpy as np  # noqa: E402
 
 from onnxstream_b200 import emit  # noqa: E402
@@ -205,7 +215,7 @@ def run_reference(args):
     if RANK != 0:
         return
     if not os.path.exists(ORACLE_LIB):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/liboracle_ref.so missing (built from /root/reference by __graft_entry__.build())"}))
+        emit_line({"impl": "reference", "unavailable": "oracle/_ref/liboracle_ref.so missing (built from /root/reference by __graft_entry__.build())"})
         return
     # calibrate on a small prefix, then size the per-step sample so that (K+W) steps take ~150 s
     m, f0, _ = cpu_sample(d, inputs, 0.03, "cal")
@@ -230,7 +240,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit_line(line)
 
 
 def main():
@@ -260,12 +270,11 @@ def main():
         out_v = step_api(mv, inputs)
     st_v = mv.stats()
     launches_per_step = int(st_v["kernel_launches"])
+    clocks = ClockSampler(); clocks.start()      # sampled from the warm-up through both timed regions (value and e2e)
     mv.run_resident(args.warmup)
-    clocks = ClockSampler(); clocks.start()
     dist_barrier(dist)
     gpu_ms = mv.run_resident(args.steps)
     dist_barrier(dist)
-    clk = clocks.stop()
     gpu_ms = dist_max(dist, gpu_ms)
     ms_per_step = gpu_ms / args.steps
     value = WORLD * 1000.0 / ms_per_step
@@ -314,6 +323,7 @@ def main():
         out_e = step_api(me, inputs)
     dist_barrier(dist)
     e2e_s = dist_max(dist, time.perf_counter() - t0)
+    clk = clocks.stop()
     st = me.stats()
     e2e_value = WORLD * args.steps / e2e_s
     h2d = int(st["weight_bytes_streamed"] + st["h2d_input_bytes"])
@@ -346,7 +356,7 @@ def main():
         except Exception as e:   # the baseline must never take the bench down
             line["cpu_baseline"] = {"value": None, "unit": "steps/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
     if RANK == 0:
-        print(json.dumps(line))
+        emit_line(line)
     if dist is not None:
         dist.destroy_process_group()
 
