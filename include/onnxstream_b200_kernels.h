@@ -112,6 +112,13 @@ int osb_attention(const void* q, const void* k, const void* v, const void* mask,
                   int64_t heads, int64_t Tq, int64_t Tk, int64_t d, int64_t dv, float scale, int k_transposed,
                   int64_t kv_group, int dtype, void* stream);
 
+/* Fused flash-style multi-head attention on tcgen05 (fp16, d <= 64): q [T, heads*d] / k, v [Tk, heads*d] are read in place
+ * from the projection buffers (row strides ld*), out [T, heads*d] is written in the merged layout; the score tile lives in TMEM.
+ * Covers the MatMul/Mul/Softmax/MatMul pattern plus the head split / merge around it (src/onnxstream.cpp:3576-3633, 6696-6929). */
+int osb_flash_attention_ok(int64_t T, int64_t Tk, int64_t d, int dtype);
+int osb_flash_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out, int64_t ldo,
+                        int64_t heads, int64_t T, int64_t Tk, int64_t d, float scale, void* stream);
+
 /* qu8 GEMM / conv with XNNPACK's requantisation (bit-exact target):
  * acc = sum (x - zx)(w - zw) + bias_i32; y = clamp(lrintf(acc * (sx*sw/sy)) + zy, 0, 255). */
 int osb_gemm_qu8(const uint8_t* A, const uint8_t* B, uint8_t* C, const int32_t* bias, int64_t M, int64_t N, int64_t K,

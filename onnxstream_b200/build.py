@@ -17,7 +17,7 @@ LIB = os.path.join(CSRC, "libonnxstream_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = os.environ.get("OSB_CXX", "/usr/bin/g++")
 
-CU_SOURCES = ["kernels_basic.cu", "kernels_gemm.cu", "gemm_tcgen05.cu"]
+CU_SOURCES = ["kernels_basic.cu", "kernels_gemm.cu", "gemm_tcgen05.cu", "attention_tcgen05.cu"]
 CPP_SOURCES = ["engine.cpp", "engine_run.cpp", "capi.cpp", "comm.cpp"]
 HEADERS = ["common.cuh", "engine.h", "engine_impl.h", "../../include/onnxstream_b200_kernels.h", "../../include/onnxstream_b200.h"]
 

@@ -1,0 +1,381 @@
+// attention_tcgen05.cu -- fused flash-style attention for sm_100a: softmax(Q K^T * scale) V in ONE kernel, score tile
+// in TMEM, never in HBM.  Replaces the reference's sliced AttentionFusedOps loop (src/onnxstream.cpp:6696-6929: per head and
+// per Q-slice a MatMul, a Mul, a Softmax and a MatMul, each through XNNPACK with the [Tq/parts, Tk] score tile round-tripping
+// through two aux buffers, src/onnxstream.cpp:6798-6799).
+//
+// One CTA per (head, 128-query tile), 192 threads:
+//   warp 0      TMA producer: Q tile once, then a (K tile, V tile) pair per 128 keys into a 2-stage ring
+//   warp 1      MMA issuer: S[j] = Q K_j^T (tcgen05.mma, 128x128x64, S double-buffered in TMEM) and O += P_j V_j (128x64x128)
+//   warps 2..5  softmax: thread r owns query row r -- tcgen05.ld its S row, online max / sum in fp32 (exp2 with the scale
+//               folded in), rescales its O row in TMEM when the running max moves (tcgen05.ld / tcgen05.st), writes P as fp16
+//               into 128B-swizzled shared memory (the A operand of the second MMA), finally O / sum -> fp16 -> global
+// Q, K, V are read in place from the [T, heads*d] projection buffers through strided tensor maps and O is written in the
+// merged [T, heads*d] layout, so the exported graph's head split / merge costs nothing.  d <= 64, d % 8 == 0.
+
+#include "common.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cstdio>
+#include <mutex>
+
+namespace {
+
+constexpr int BQ = 128;                 // queries per CTA
+constexpr int BKV = 128;                // keys per tile
+constexpr int BD = 64;                  // head dim padded to one 128-byte swizzle row
+constexpr int KV_STAGES = 2;
+constexpr int Q_BYTES = BQ * BD * 2;    // 16 KiB
+constexpr int K_BYTES = BKV * BD * 2;   // 16 KiB
+constexpr int V_BYTES = BKV * BD * 2;   // 16 KiB (128 key rows x 64 columns)
+constexpr int P_BYTES = BQ * BKV * 2;   // 32 KiB (two 64-key k-blocks)
+constexpr int FA_SMEM = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + P_BYTES + 1024 + 256;
+constexpr int FA_THREADS = 192;
+constexpr int TMEM_COLS_FA = 512;       // S0 [0,128) S1 [128,256) O [256,320)
+constexpr int O_COL = 256;
+
+struct FaParams {
+    int T, Tk, d, heads;
+    int q_tiles, kv_tiles;
+    float scale_log2;        // scale * log2(e)
+    __half* out;             // [T, ldo] merged layout, head h at column h*d
+    long long ldo;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t addr = smem_u32(bar), done = 0;
+    long long t0 = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) break;
+        long long now = clock64();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000LL) { printf("flash_attention_kernel: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
+    }
+}
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr),
+          "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ uint32_t idesc_f16(int n, int b_mn_major)
+{
+    return (1u << 4) | ((uint32_t)(b_mn_major ? 1 : 0) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(FA_THREADS, 1)
+flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                       const FaParams p)
+{
+    osb_pdl_trigger();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + Q_BYTES;
+    uint8_t* sV = sK + KV_STAGES * K_BYTES;
+    uint8_t* sP = sV + KV_STAGES * V_BYTES;
+    uint64_t* bars = (uint64_t*)(sP + P_BYTES);
+    uint64_t* q_full = bars;                 // [1]
+    uint64_t* kv_full = bars + 1;            // [2]
+    uint64_t* kv_empty = bars + 3;           // [2]
+    uint64_t* s_full = bars + 5;             // [2]
+    uint64_t* s_empty = bars + 7;            // [2]
+    uint64_t* p_full = bars + 9;             // [1]
+    uint64_t* pv_done = bars + 10;           // [1]
+    uint32_t* tmem_slot = (uint32_t*)(bars + 11);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, head = blockIdx.y;
+    const int q0 = qt * BQ;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; i++) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 128); }
+        mbar_init(p_full, 128);
+        mbar_init(pv_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS_FA) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    osb_pdl_wait();
+
+    const int n_kv = p.kv_tiles;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(q_full, Q_BYTES);
+            tma_load_3d(sQ, &map_q, q_full, 0, head, q0);
+            for (int j = 0; j < n_kv; j++) {
+                int st = j & 1;
+                mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+                mbar_expect_tx(&kv_full[st], K_BYTES + V_BYTES);
+                tma_load_3d(sK + st * K_BYTES, &map_k, &kv_full[st], 0, head, j * BKV);
+                tma_load_3d(sV + st * V_BYTES, &map_v, &kv_full[st], 0, head, j * BKV);
+                tma_load_3d(sV + st * V_BYTES + V_BYTES / 2, &map_v, &kv_full[st], 0, head, j * BKV + 64);
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc_s = idesc_f16(BKV, 0);     // S = Q K^T: A K-major, B K-major, N = 128 keys
+        const uint32_t idesc_o = idesc_f16(BD, 1);      // O += P V : A K-major (P), B MN-major (V rows = keys), N = 64
+        if (lane == 0) {
+            mbar_wait(q_full, 0);
+            tc_fence_after();
+        }
+        __syncwarp();
+        const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+        for (int j = 0; j <= n_kv; j++) {
+            if (lane == 0) {
+                if (j < n_kv) {
+                    int st = j & 1;
+                    mbar_wait(&kv_full[st], (j >> 1) & 1);
+                    mbar_wait(&s_empty[st], ((j >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    uint32_t k_addr = smem_u32(sK + st * K_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BD / 16; k++)
+                        umma_f16(tmem_base + (uint32_t)(st * BKV), smem_desc(q_addr + k * 32, 16, 1024), smem_desc(k_addr + k * 32, 16, 1024), idesc_s, k != 0);
+                    umma_commit(&s_full[st]);
+                }
+                if (j >= 1) {
+                    int jj = j - 1, st = jj & 1;
+                    mbar_wait(p_full, jj & 1);
+                    tc_fence_after();
+                    uint32_t v_addr = smem_u32(sV + st * V_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BKV / 16; k++) {
+                        // P: two 64-key k-blocks 16 KiB apart, 32 B per 16-key step inside a block; V: 16 key rows = 2048 B per step
+                        uint64_t adesc = smem_desc(p_addr + (k >> 2) * (P_BYTES / 2) + (k & 3) * 32, 16, 1024);
+                        uint64_t bdesc = smem_desc(v_addr + k * 2048, V_BYTES, 1024);
+                        umma_f16(tmem_base + O_COL, adesc, bdesc, idesc_o, (jj != 0 || k != 0) ? 1u : 0u);
+                    }
+                    umma_commit(&kv_empty[st]);
+                    umma_commit(pv_done);
+                }
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== softmax / correction / epilogue (warps 2..5): thread = query row =====================
+        const int qd = warp & 3;
+        const int row = qd * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int j = 0; j < n_kv; j++) {
+            int st = j & 1;
+            mbar_wait(&s_full[st], (j >> 1) & 1);
+            tc_fence_after();
+            const uint32_t s_addr = tmem_base + lane_addr + (uint32_t)(st * BKV);
+            const int key0 = j * BKV;
+            // pass 1: tile max of this row (keys beyond Tk are padding: K rows were zero-filled by TMA)
+            float mt = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < BKV; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(s_addr + c, v);
+#pragma unroll
+                for (int t = 0; t < 32; t++) if (key0 + c + t < p.Tk) mt = fmaxf(mt, __uint_as_float(v[t]));
+            }
+            float m_new = fmaxf(m_run, mt * p.scale_log2);
+            float alpha = exp2f(m_run - m_new);          // 0 on the first tile (m_run = -inf)
+            // pass 2: p = 2^(s*scale*log2e - m_new), packed to fp16 in registers
+            uint32_t pk[64];
+            float lsum = 0.f;
+#pragma unroll
+            for (int c = 0; c < BKV; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(s_addr + c, v);
+#pragma unroll
+                for (int t = 0; t < 32; t += 2) {
+                    float p0 = (key0 + c + t < p.Tk) ? exp2f(__uint_as_float(v[t]) * p.scale_log2 - m_new) : 0.f;
+                    float p1 = (key0 + c + t + 1 < p.Tk) ? exp2f(__uint_as_float(v[t + 1]) * p.scale_log2 - m_new) : 0.f;
+                    __half2 h2 = __floats2half2_rn(p0, p1);
+                    // the sum uses the rounded values that the second MMA will actually see
+                    lsum += __low2float(h2) + __high2float(h2);
+                    pk[(c + t) >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&s_empty[st]);                   // S[st] may be overwritten by QK^T of tile j+2
+            l_run = l_run * alpha + lsum;
+            m_run = m_new;
+            if (j > 0) {
+                // PV of the previous tile must have retired: O is stable and the P buffer is free
+                mbar_wait(pv_done, (j - 1) & 1);
+                tc_fence_after();
+                // rescale this row of O
+#pragma unroll 1
+                for (int c = 0; c < BD; c += 32) {
+                    uint32_t o[32];
+                    tmem_ld32(tmem_base + lane_addr + O_COL + c, o);
+#pragma unroll
+                    for (int t = 0; t < 32; t++) o[t] = __float_as_uint(__uint_as_float(o[t]) * alpha);
+                    tmem_st32(tmem_base + lane_addr + O_COL + c, o);
+                }
+            }
+            // P row -> shared memory, K-major SWIZZLE_128B: k-block kb = key/64, 16-byte chunk index XOR (row % 8)
+            {
+                uint8_t* prow = sP + row * 128;
+#pragma unroll
+                for (int ch = 0; ch < 16; ch++) {
+                    int kb = ch >> 3, c8 = ch & 7;
+                    uint4 val = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+                    *reinterpret_cast<uint4*>(prow + kb * (P_BYTES / 2) + ((c8 ^ (row & 7)) << 4)) = val;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the async proxy (UMMA)
+            tc_fence_before();
+            mbar_arrive(p_full);
+        }
+        // epilogue: O / l -> fp16 -> out[q, head*d + c]
+        mbar_wait(pv_done, (n_kv - 1) & 1);
+        tc_fence_after();
+        const int qrow = q0 + row;
+        const float inv = 1.f / l_run;
+        __half* orow = p.out + (long long)qrow * p.ldo + (long long)head * p.d;
+#pragma unroll 1
+        for (int c = 0; c < BD; c += 32) {
+            if (c >= p.d) break;
+            uint32_t o[32];
+            tmem_ld32(tmem_base + lane_addr + O_COL + c, o);
+            if (qrow < p.T) {
+#pragma unroll
+                for (int t = 0; t < 32; t += 8) {
+                    if (c + t >= p.d) break;       // d % 8 == 0
+                    Vec<__half, 8> w;
+#pragma unroll
+                    for (int u = 0; u < 8; u++) w.v[u] = __float2half_rn(__uint_as_float(o[t + u]) * inv);
+                    store_vec<__half, 8>(orow + c + t, w);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS_FA) : "memory");
+    }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 fa_encode()
+{
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+    });
+    return fn;
+}
+
+// [rows, heads*d] projection viewed as (d, heads, rows): strides (d*2, ld*2) bytes; box (64, 1, box_rows)
+bool head_map(CUtensorMap* map, const void* base, int d, int heads, int64_t rows, int64_t ld, uint32_t box_rows)
+{
+    auto enc = fa_encode();
+    if (!enc) return false;
+    cuuint64_t dims[3] = { (cuuint64_t)d, (cuuint64_t)heads, (cuuint64_t)rows };
+    cuuint64_t strides[2] = { (cuuint64_t)d * 2, (cuuint64_t)ld * 2 };
+    cuuint32_t box[3] = { 64, 1, box_rows };
+    cuuint32_t estr[3] = { 1, 1, 1 };
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" int osb_flash_attention_ok(int64_t T, int64_t Tk, int64_t d, int dtype)
+{
+    return dtype == OSB_F16 && d >= 8 && d <= 64 && d % 8 == 0 && T >= 64 && Tk >= 1 && fa_encode() != nullptr;
+}
+
+// q [T, heads*d] (row stride ldq), k / v [Tk, heads*d] (row strides ldk / ldv), out [T, heads*d] (row stride ldo); fp16.
+extern "C" int osb_flash_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out, int64_t ldo,
+                                   int64_t heads, int64_t T, int64_t Tk, int64_t d, float scale, void* stream)
+{
+    if (heads * T == 0) return 0;
+    if (d > 64 || d % 8 || (ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return (int)cudaErrorInvalidValue;
+    if ((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) & 15) != 0) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUtensorMap mq, mk, mv;
+    if (!head_map(&mq, q, (int)d, (int)heads, T, ldq, BQ)) return (int)cudaErrorInvalidValue;
+    if (!head_map(&mk, k, (int)d, (int)heads, Tk, ldk, BKV)) return (int)cudaErrorInvalidValue;
+    if (!head_map(&mv, v, (int)d, (int)heads, Tk, ldv, 64)) return (int)cudaErrorInvalidValue;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(flash_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    FaParams p{};
+    p.T = (int)T; p.Tk = (int)Tk; p.d = (int)d; p.heads = (int)heads;
+    p.q_tiles = (int)((T + BQ - 1) / BQ); p.kv_tiles = (int)((Tk + BKV - 1) / BKV);
+    p.scale_log2 = scale * 1.4426950408889634f;
+    p.out = (__half*)out; p.ldo = ldo;
+    dim3 grid((unsigned)p.q_tiles, (unsigned)heads);
+    osb_launch((flash_attention_kernel), grid, FA_THREADS, (size_t)FA_SMEM, st, mq, mk, mv, p);
+    return launched(1);
+}

@@ -167,6 +167,7 @@ void model_set_option(ModelContext* obj, char* name, unsigned int value)
     else if (!strcmp(name, "b200_fuse_nodes")) e.fuse_nodes = v;
     else if (!strcmp(name, "b200_keep_nhwc")) e.keep_nhwc = v;
     else if (!strcmp(name, "b200_gemm_impl")) e.gemm_impl = (int)value;
+    else if (!strcmp(name, "b200_flash_attention")) e.flash_attention = v;
     else if (!strcmp(name, "b200_ring_factor_x100")) e.ring_factor = value / 100.0;
     else set = false;
     if (!set) {

@@ -185,6 +185,7 @@ public:
     bool fuse_nodes = true;          // GroupNorm/LayerNorm/GELU/SiLU/bias/residual fusions
     bool keep_nhwc = true;           // keep conv trunks channel-last instead of transposing around every Conv
     int gemm_impl = 0;               // 0 auto, 1 force CUDA-core kernels, 2 force tcgen05
+    bool flash_attention = true;     // fused tcgen05 attention for d <= 64 (else two GEMMs around a softmax)
     double ring_factor = 1.0;        // weight ring capacity = ring_factor * largest node footprint
     bool source_on_init_done = false;  // set by the C++ adapter when it already announced every weight to the provider
 

@@ -1595,6 +1595,12 @@ void Engine::Impl::fused_mha(const Step& s)
     ck(osb_gemm(xk.data(), wk.data(), kl.mdata(), nullptr, nullptr, 1, Tk, C, xk.shape[2], 0, 0, 0, 0, K(ty), E.gemm_impl, st), "osb_gemm(k)");
     ck(osb_gemm(xv.data(), wv.data(), vl.mdata(), nullptr, nullptr, 1, Tk, C, xv.shape[2], 0, 0, 0, 0, K(ty), E.gemm_impl, st), "osb_gemm(v)");
 
+    if (E.flash_attention && E.gemm_impl != 1 && osb_flash_attention_ok(T, Tk, d, K(ty))) {
+        // one kernel: QK^T -> online softmax -> PV with the score tile in TMEM
+        ck(osb_flash_attention(ql.data(), C, kl.data(), C, vl.data(), C, out.mdata(), C, h, T, Tk, d, scale, st), "osb_flash_attention");
+        push(i + 19, 0, out);
+        return;
+    }
     int64_t per_head = T * Tkp * (int64_t)es;
     int64_t hc = std::max<int64_t>(1, std::min<int64_t>(h, ((int64_t)512 << 20) / std::max<int64_t>(per_head, 1)));
     for (int64_t h0 = 0; h0 < h; h0 += hc) {

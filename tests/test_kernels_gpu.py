@@ -206,3 +206,30 @@ def test_gemm_head_views(K, impl, T, Tk, h, d):
     ref = (P.double() @ vh).permute(1, 0, 2).reshape(T, C)
     absref = (P.double().abs() @ vh.abs()).permute(1, 0, 2).reshape(T, C)
     _check(O, ref, absref, "PV head views")
+
+
+@pytest.mark.parametrize("T,Tk,h,d", [(128, 128, 1, 64), (256, 384, 2, 40), (200, 77, 4, 40), (4096, 4096, 8, 40), (1024, 1024, 10, 64)])
+def test_flash_attention(K, T, Tk, h, d):
+    """Fused tcgen05 attention against softmax(QK^T s)V in fp64 on the fp16-rounded operands.  Tolerance: P is rounded to
+    fp16 before the second MMA (as the reference's fp16 softmax output is), so |err| <= 2^-9 * sum|p_i v_i| + 2^-10 |ref|."""
+    import torch
+    vp, i64, cf = ctypes.c_void_p, ctypes.c_int64, ctypes.c_float
+    K.osb_flash_attention.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i64, i64, i64, i64, cf, vp]
+    C = h * d
+    g = torch.Generator(device="cuda").manual_seed(T * 3 + Tk)
+    q = torch.randn(T, C, device="cuda", generator=g).half()
+    k = torch.randn(Tk, C, device="cuda", generator=g).half()
+    v = torch.randn(Tk, C, device="cuda", generator=g).half()
+    o = torch.full((T, C), float("nan"), device="cuda", dtype=torch.half)
+    scale = 1.0 / d ** 0.5
+    rc = K.osb_flash_attention(q.data_ptr(), C, k.data_ptr(), C, v.data_ptr(), C, o.data_ptr(), C, h, T, Tk, d, scale, _stream())
+    assert rc == 0
+    torch.cuda.synchronize()
+    qh = q.double().view(T, h, d).permute(1, 0, 2); kh = k.double().view(Tk, h, d).permute(1, 0, 2); vh = v.double().view(Tk, h, d).permute(1, 0, 2)
+    P = torch.softmax(qh @ kh.transpose(1, 2) * scale, dim=-1)
+    ref = (P @ vh).permute(1, 0, 2).reshape(T, C)
+    absref = (P @ vh.abs()).permute(1, 0, 2).reshape(T, C)
+    err = (o.double() - ref).abs()
+    tol = absref * 2.0 ** -8 + ref.abs() * 2.0 ** -9 + 1e-4
+    assert not torch.isnan(o).any()
+    assert not (err > tol).any(), f"max err {float(err.max()):.4g}, ref max {float(ref.abs().max()):.4g}, bad {(err > tol).sum().item()}"
