@@ -51,6 +51,8 @@ from onnxstream_b200 import emit  # noqa: E402
 from onnxstream_b200.model import Model, ENGINE_LIB  # noqa: E402
 
 ORACLE_LIB = os.path.join(ROOT, "oracle", "_ref", "liboracle_ref.so")
+REF_THREADS = min(os.cpu_count() or 1, 32)
+os.environ.setdefault("OMP_NUM_THREADS", str(REF_THREADS))
 METRIC = "SD1.5 UNet 512x512 bs=1 denoise steps/s (one UNet Model::run per step)"
 
 
@@ -202,7 +204,9 @@ def cpu_sample(d, inputs, frac, tag):
         n, acc = len(lf), total
     fn = d + f"model_prefix_{tag}.txt"
     open(fn, "w").write("\n".join(l for l, _ in lf[:n]) + "\n")
-    m = Model(ORACLE_LIB, 0, "nocache")
+    # XNNPACK's pthreadpool with one worker per core is far slower than a moderate pool on many-core hosts (measured: 128
+    # workers -> 295 s per UNet run on the GPU box, vs 38 s with 8 on an 8-core host), so the reference gets min(cores, 32).
+    m = Model(ORACLE_LIB, REF_THREADS, "nocache")
     m.set_option("fuse_ops_in_attention", True)   # fp16 weights, fp32 arithmetic: the reference's --rpi mode (src/sd.cpp:1636-1638)
     m.read_file(fn)
     return m, acc / total, n
@@ -211,7 +215,7 @@ def cpu_sample(d, inputs, frac, tag):
 def run_reference(args):
     d, cfg, meta = ensure_model(args.workload)
     inputs = emit.unet_inputs(cfg)
-    cores = os.cpu_count()
+    cores = REF_THREADS
     if RANK != 0:
         return
     if not os.path.exists(ORACLE_LIB):
@@ -351,7 +355,7 @@ def main():
             frac = 0.15
             m, f, nops = cpu_sample(d, inputs, frac, "cpu")
             t = time.time(); step_api(m, inputs, "nonexistent"); dt = time.time() - t
-            line["cpu_baseline"] = {"value": f / dt, "unit": "steps/s", "cores": os.cpu_count(), "kind": "reference",
+            line["cpu_baseline"] = {"value": f / dt, "unit": "steps/s", "cores": REF_THREADS, "host_cores": os.cpu_count(), "kind": "reference",
                                     "sample": f"first {nops} of {meta['ops']} graph ops ({100 * f:.1f}% of the UNet's Conv/MatMul FLOPs) through the reference's Model::run (fp16 weights, fp32 XNNPACK arithmetic), {dt:.1f} s, extrapolated to a full UNet run"}
         except Exception as e:   # the baseline must never take the bench down
             line["cpu_baseline"] = {"value": None, "unit": "steps/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}

@@ -60,6 +60,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
                     print(out)
     if jobs or force or not os.path.exists(LIB):
         _run([NVCC, "-shared", "-o", LIB] + objs + ["-cudart", "static", "-ccbin", CXX, "-Xlinker", "--no-undefined", "-ldl", "-lpthread"])
+    # keep the C++ drop-in link test (reference apps + compat_onnxstream.cpp) in step with the engine ABI
+    link_script = os.path.join(os.path.dirname(HERE), "scripts", "link_reference_apps.sh")
+    compat_obj = os.path.join(os.path.dirname(HERE), "build", "link_test", "compat.o")
+    if os.path.isdir("/root/reference/src") and os.path.exists(link_script) and _newer(hdrs + [os.path.join(CSRC, "compat_onnxstream.cpp"), LIB], compat_obj):
+        r = subprocess.run(["bash", link_script], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link test (reference apps against the B200 engine) failed:\n" + r.stdout[-3000:])
     return LIB
 
 

@@ -84,6 +84,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// issue only: several loads can be in flight before one tcgen05.wait::ld
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32])
 {
     asm volatile(
@@ -228,33 +243,29 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             tc_fence_after();
             const uint32_t s_addr = tmem_base + lane_addr + (uint32_t)(st * BKV);
             const int key0 = j * BKV;
-            // pass 1: tile max of this row (keys beyond Tk are padding: K rows were zero-filled by TMA)
+            // one TMEM pass: the whole 128-key row of S into registers (4 loads in flight, one wait)
+            uint32_t sv[128];
+            tmem_ld32_nowait(s_addr, sv);
+            tmem_ld32_nowait(s_addr + 32, sv + 32);
+            tmem_ld32_nowait(s_addr + 64, sv + 64);
+            tmem_ld32_nowait(s_addr + 96, sv + 96);
+            tmem_ld_wait();
+            const bool tail = key0 + BKV > p.Tk;          // only the last tile has padding keys (K rows zero-filled by TMA)
             float mt = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < BKV; c += 32) {
-                uint32_t v[32];
-                tmem_ld32(s_addr + c, v);
 #pragma unroll
-                for (int t = 0; t < 32; t++) if (key0 + c + t < p.Tk) mt = fmaxf(mt, __uint_as_float(v[t]));
-            }
+            for (int t = 0; t < 128; t++) if (!tail || key0 + t < p.Tk) mt = fmaxf(mt, __uint_as_float(sv[t]));
             float m_new = fmaxf(m_run, mt * p.scale_log2);
             float alpha = exp2f(m_run - m_new);          // 0 on the first tile (m_run = -inf)
-            // pass 2: p = 2^(s*scale*log2e - m_new), packed to fp16 in registers
+            // p = 2^(s*scale*log2e - m_new), packed to fp16 in registers (the S registers die as P is produced)
             uint32_t pk[64];
             float lsum = 0.f;
 #pragma unroll
-            for (int c = 0; c < BKV; c += 32) {
-                uint32_t v[32];
-                tmem_ld32(s_addr + c, v);
-#pragma unroll
-                for (int t = 0; t < 32; t += 2) {
-                    float p0 = (key0 + c + t < p.Tk) ? exp2f(__uint_as_float(v[t]) * p.scale_log2 - m_new) : 0.f;
-                    float p1 = (key0 + c + t + 1 < p.Tk) ? exp2f(__uint_as_float(v[t + 1]) * p.scale_log2 - m_new) : 0.f;
-                    __half2 h2 = __floats2half2_rn(p0, p1);
-                    // the sum uses the rounded values that the second MMA will actually see
-                    lsum += __low2float(h2) + __high2float(h2);
-                    pk[(c + t) >> 1] = *reinterpret_cast<uint32_t*>(&h2);
-                }
+            for (int t = 0; t < 128; t += 2) {
+                float p0 = (!tail || key0 + t < p.Tk) ? exp2f(__uint_as_float(sv[t]) * p.scale_log2 - m_new) : 0.f;
+                float p1 = (!tail || key0 + t + 1 < p.Tk) ? exp2f(__uint_as_float(sv[t + 1]) * p.scale_log2 - m_new) : 0.f;
+                __half2 h2 = __floats2half2_rn(p0, p1);
+                lsum += __low2float(h2) + __high2float(h2);   // the sum uses the rounded values the second MMA will see
+                pk[t >> 1] = *reinterpret_cast<uint32_t*>(&h2);
             }
             tc_fence_before();
             mbar_arrive(&s_empty[st]);                   // S[st] may be overwritten by QK^T of tile j+2
@@ -264,7 +275,8 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 // PV of the previous tile must have retired: O is stable and the P buffer is free
                 mbar_wait(pv_done, (j - 1) & 1);
                 tc_fence_after();
-                // rescale this row of O
+                // rescale this row of O -- skipped when no row of the warp moved its maximum (the common case after a few tiles)
+                if (__any_sync(0xffffffffu, alpha != 1.f))
 #pragma unroll 1
                 for (int c = 0; c < BD; c += 32) {
                     uint32_t o[32];

@@ -19,10 +19,12 @@ struct cpuinfo_x86_isa cpuinfo_isa = { 0 };
 EOC
 gcc -c "$OUT/cpuinfo_stub.c" -o "$OUT/cpuinfo_stub.o"
 FLAGS="-std=c++20 -O1 -fPIC -fcoroutines -I$REF -I$TORCH/include -I/usr/local/cuda/include"
+# compat.o depends on the engine headers: always rebuilt (a stale one is an ABI mismatch against libonnxstream_b200.so);
+# the reference's own translation units only change with the reference, so they are compiled once.
 $CXX $FLAGS -c "$ROOT/onnxstream_b200/csrc/compat_onnxstream.cpp" -I"$ROOT/onnxstream_b200/csrc" -o "$OUT/compat.o"
-$CXX $FLAGS -c "$REF/sd.cpp" -o "$OUT/sd.o"
-$CXX $FLAGS -c "$REF/llm.cpp" -o "$OUT/llm.o"
-$CXX $FLAGS -c "$REF/exports.cpp" -o "$OUT/exports.o"
+[ "$OUT/sd.o" -nt "$REF/sd.cpp" ] || $CXX $FLAGS -c "$REF/sd.cpp" -o "$OUT/sd.o"
+[ "$OUT/llm.o" -nt "$REF/llm.cpp" ] || $CXX $FLAGS -c "$REF/llm.cpp" -o "$OUT/llm.o" 2>/dev/null
+[ "$OUT/exports.o" -nt "$REF/exports.cpp" ] || $CXX $FLAGS -c "$REF/exports.cpp" -o "$OUT/exports.o"
 LIB="$ROOT/onnxstream_b200/csrc/libonnxstream_b200.so"
 $CXX -o "$OUT/sd" "$OUT/sd.o" "$OUT/compat.o" "$OUT/cpuinfo_stub.o" "$LIB" -Wl,-rpath,"$(dirname $LIB)" -lpthread
 $CXX -o "$OUT/llm" "$OUT/llm.o" "$OUT/compat.o" "$LIB" -Wl,-rpath,"$(dirname $LIB)" -lpthread
