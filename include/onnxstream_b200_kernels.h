@@ -64,7 +64,8 @@ int osb_instance_norm(const void* x, void* y, int dtype, int64_t channels, int64
 
 /* Fused GroupNorm (+SiLU): the Reshape/InstanceNormalization/Reshape/Mul/Add[/Sigmoid/Mul] chain of the diffusers export
  *  in one pass pair. x is [1,C,H,W] in NCHW (nhwc=0) or NHWC (nhwc=1) physical order; gamma/beta [C].
- * `stats` is caller-provided device scratch of 2*groups doubles (sum, sum of squares per group). */
+ * `stats` is caller-provided device scratch of 2048 bytes, zero-initialised once by the caller (the single-launch NHWC path keeps
+ * its region self-cleaning; the two-pass path clears its own region per call). */
 int osb_group_norm(const void* x, void* y, int dtype, int nhwc, int64_t C, int64_t HW, int groups,
                    const void* gamma, const void* beta, float eps, int fuse_silu, void* stats, void* stream);
 

@@ -37,7 +37,7 @@ std::vector<int64_t> parse_ints(const std::string& s)
 
 [[noreturn]] void fail(const OpDef& op, const std::string& msg) { throw std::invalid_argument(op.type + ": " + msg); }
 
-enum StepKind { SK_SINGLE = 0, SK_ATTENTION, SK_GROUPNORM, SK_LAYERNORM, SK_GELU, SK_SILU, SK_LINEAR, SK_SDPA, SK_MHA };
+enum StepKind { SK_SINGLE = 0, SK_ATTENTION, SK_GROUPNORM, SK_LAYERNORM, SK_GELU, SK_SILU, SK_LINEAR, SK_SDPA, SK_MHA, SK_CONV_ADD };
 
 struct Step {
     StepKind kind = SK_SINGLE;
@@ -561,6 +561,23 @@ struct Engine::Impl {
         return 2;
     }
 
+    // Conv -> Add(conv_out, other) with `other` an activation of the same shape: residual add in the conv epilogue
+    // (resnet `x + conv2(...)`, transformer `proj_out(...) + residual`)
+    size_t match_conv_add(size_t i, int& variant) const
+    {
+        auto& ops = E.m_ops;
+        if (!E.fuse_nodes || E.use_uint8_arithmetic || E.use_uint8_qdq) return 0;
+        if (i + 1 >= ops.size() || ops[i].type != "Conv" || ops[i + 1].type != "Add") return 0;
+        const OpDef &cv = ops[i], &ad = ops[i + 1];
+        if (cv.out.size() != 1 || ad.in.size() != 2 || upcast_op(cv) || upcast_op(ad)) return 0;
+        for (int k = 0; k < 2; k++)
+            if (feeds(cv, ad, k) && ad.in[1 - k].present && ad.in[1 - k].wtype == DType::none && ad.in[1 - k].shape == cv.out[0].shape && cv.out[0].shape.size() == 4) {
+                variant = 1 - k;   // index of the residual operand
+                return 2;
+            }
+        return 0;
+    }
+
     // MatMul(x, W[K,N]) -> Add(bias[N], y) [-> Add(y, residual)]
     size_t match_linear(size_t i, int& variant) const
     {
@@ -610,6 +627,7 @@ struct Engine::Impl {
             else if ((n = match_gelu(i, var))) { s.kind = SK_GELU; s.count = n; s.variant = var; }
             else if ((n = match_silu(i))) { s.kind = SK_SILU; s.count = n; }
             else if ((n = match_linear(i, var))) { s.kind = SK_LINEAR; s.count = n; s.variant = var; }
+            else if ((n = match_conv_add(i, var))) { s.kind = SK_CONV_ADD; s.count = n; s.variant = var; }
             steps.push_back(s);
             i += s.count;
         }
@@ -645,7 +663,7 @@ struct Engine::Impl {
                     order.erase(std::remove(order.begin(), order.end(), o.name), order.end());
                 }
     }
-    void op_conv(size_t oi);
+    void op_conv(size_t oi, const Tensor* residual = nullptr, size_t out_op = (size_t)-1);
     void op_matmul(size_t oi, const Tensor* bias = nullptr, const Tensor* residual = nullptr, size_t out_op = (size_t)-1);
     void op_gemm(size_t oi);
     void op_binary(size_t oi, int bop);
@@ -783,7 +801,7 @@ Tensor Engine::Impl::binary(int bop, const Tensor& a_in, const Tensor& b_in)
 // ================================================================================================================
 
 // Conv (src/onnxstream.cpp:4494-4707 -> XnnPack::convolution 1292-1534)
-void Engine::Impl::op_conv(size_t oi)
+void Engine::Impl::op_conv(size_t oi, const Tensor* residual, size_t out_op)
 {
     const OpDef& op = E.m_ops[oi];
     if (op.in.size() != 3 && op.in.size() != 2) fail(op, "wrong number of inputs.");
@@ -863,12 +881,19 @@ void Engine::Impl::op_conv(size_t oi)
         if (w.type != x.type) w = convert(w, x.type);
         if (has_b && b.type != x.type) b = convert(b, x.type);
         y = make(x.type, { 1, Cout, Ho, Wo }, Layout::nhwc);
-        ck(osb_conv2d(x.data(), w.data(), has_b ? b.data() : nullptr, nullptr, y.mdata(), H, W, Cin, Cout, kh, kw, stride, pad_top, pad_left, Ho, Wo,
+        Tensor rr;
+        if (residual) {
+            rr = *residual;
+            if (rr.shape.size() == 3) rr.shape.push_back(1);
+            rr = to_nhwc(rr);
+            if (rr.type != x.type) rr = convert(rr, x.type);
+        }
+        ck(osb_conv2d(x.data(), w.data(), has_b ? b.data() : nullptr, residual ? rr.data() : nullptr, y.mdata(), H, W, Cin, Cout, kh, kw, stride, pad_top, pad_left, Ho, Wo,
                       K(x.type), E.gemm_impl, st), "osb_conv2d");
     }
     if (is1d) y.shape.pop_back();
     if (!E.keep_nhwc || is1d) { Tensor t = y; if (is1d) { t.shape.push_back(1); } t = to_plain(t); if (is1d) t.shape.pop_back(); y = t; }
-    push(oi, 0, y);
+    push(out_op == (size_t)-1 ? oi : out_op, 0, y);
 }
 
 // MatMul (src/onnxstream.cpp:5669-5861 -> XnnPack::matrix_multiply 1035-1215); optional fused bias / residual epilogue
@@ -1672,7 +1697,7 @@ void Engine::Impl::fused_groupnorm(const Step& s)
     if (x.type != DType::f16 && x.type != DType::f32) fail(inrm, "wrong data type of input.");
     if (gamma.type != x.type) gamma = convert(gamma, x.type);
     if (beta.type != x.type) beta = convert(beta, x.type);
-    if (!gn_stats) gn_stats = E.m_pool.alloc(2 * 64 * sizeof(double));
+    if (!gn_stats) { gn_stats = E.m_pool.alloc(2048); ck(cudaMemsetAsync(gn_stats->ptr, 0, 2048, st), "cudaMemsetAsync(gn scratch)"); }
     Tensor y = make(x.type, x.shape, x.layout);
     ck(osb_group_norm(x.data(), y.mdata(), K(x.type), x.layout == Layout::nhwc ? 1 : 0, C, HW, G, gamma.data(), beta.data(), eps, s.variant == 1 ? 1 : 0,
                       gn_stats->ptr, st), "osb_group_norm");
@@ -1797,6 +1822,7 @@ void Engine::Impl::exec_step(size_t si)
         case SK_LINEAR: fused_linear(s); break;
         case SK_SDPA: fused_sdpa(s); break;
         case SK_MHA: fused_mha(s); break;
+        case SK_CONV_ADD: { Tensor res = in(s.first + 1, (size_t)s.variant); op_conv(s.first, &res, s.first + 1); break; }
         default: exec_single(s.first); break;
         }
     }

@@ -19,6 +19,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -28,12 +29,13 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 128;
 constexpr int BLOCK_K = 64;            // 64 fp16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 6;
+constexpr int STAGES_DEEP = 6;          // long K loops: one CTA per SM, deep TMA ring
+constexpr int STAGES_SHORT = 3;         // short K loops: half the shared memory so two CTAs share an SM and hide each other's prologue / epilogue
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;   // 256
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
 constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;  // 16 KiB
-constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int smem_bytes_for(int stages) { return stages * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/; }
 constexpr int NUM_THREADS = 192;       // 6 warps
 
 struct TcParams {
@@ -47,6 +49,7 @@ struct TcParams {
     int taps, kw, pad_top, pad_left, Wo, Ho, bw, bh, tiles_x;
     int k_blocks_per_tap;
     int stride;                  // conv stride (TMA traversal stride on W and H)
+    int short_k;                 // host hint: few k-blocks per CTA -> 3-stage ring, two CTAs per SM
     int split_k;                 // > 1: each tile's k-blocks are divided among split_k CTAs, fp32 partials go to `ws`
     float* ws;                   // split-K workspace [split][batch][M][N] fp32
     int* counters;               // split-K arrival counters, one per output tile (self-resetting)
@@ -166,7 +169,8 @@ __device__ __forceinline__ uint32_t make_idesc(int b_mn_major, int bn)
 
 // ---- the kernel -----------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, STAGES <= STAGES_SHORT ? 2 : 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p)
 {
     osb_pdl_trigger();   // let the next kernel's CTAs be scheduled as ours drain; it waits for our completion before touching memory
@@ -369,40 +373,58 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_arrive(&acc_empty[acc]);
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             if (wrow && p.counters) {
-                // serial split-K reduction (kept for reference; the host currently prefers the parallel reduce kernel): publish the partials, count arrivals, the last CTA sums all splits in fp32,
-                // applies bias / residual and rounds once -- no separate reduce kernel, no extra launch.
+                // Parallel in-kernel split-K reduction (no second launch).  All split_k CTAs of a tile are co-resident (the host
+                // keeps tiles * split_k <= resident CTA slots), so they can rendezvous on a counter: publish partials -> arrive ->
+                // wait for everyone -> each CTA reduces its own slice of the tile's rows in fp32, adds bias / residual, rounds once.
                 __threadfence();
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (warp == 2 && lane == 0) {
-                    int old = atomicAdd(&p.counters[t2], 1);
-                    *split_flag = (old == p.split_k - 1) ? 1 : 0;
-                    if (old == p.split_k - 1) p.counters[t2] = 0;      // re-arm for the next launch
+                    atomicAdd(&p.counters[2 * t2], 1);
+                    long long t0 = clock64();
+                    while (true) {
+                        int seen;
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.counters + 2 * t2) : "memory");
+                        if (seen >= p.split_k) break;
+                        if (clock64() - t0 > 4000000000LL) { printf("tc_gemm_kernel: split-K rendezvous timed out (block %d)\n", blockIdx.x); __trap(); }
+                    }
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (*split_flag) {
-                    __threadfence();
-                    if (row_ok) {
-                        const long long plane = (long long)p.batch * p.M * p.N;
-                        const float* base = p.ws + ((long long)b * p.M + out_row) * p.N;
-                        for (int n = n0; n < n_end; n += 4) {
-                            float f[4] = { 0.f, 0.f, 0.f, 0.f };
-                            bool v4 = (n + 3 < p.N) && (p.N & 3) == 0;
-                            for (int sidx = 0; sidx < p.split_k; sidx++) {
-                                const float* src = base + sidx * plane + n;
-                                if (v4) { float4 t = __ldcg(reinterpret_cast<const float4*>(src)); f[0] += t.x; f[1] += t.y; f[2] += t.z; f[3] += t.w; }
-                                else for (int t = 0; t < 4; t++) if (n + t < p.N) f[t] += __ldcg(src + t);
+                __threadfence();
+                {
+                    const int rows_per = (BLOCK_M + p.split_k - 1) / p.split_k;
+                    const int r_lo = sp * rows_per, r_hi = min(r_lo + rows_per, BLOCK_M);
+                    const long long plane = (long long)p.batch * p.M * p.N;
+                    const int nvec = (n_end - n0) >> 2;      // N % 4 == 0 (host guarantees it on this path)
+                    for (int rr = r_lo + q; rr < r_hi; rr += 4) {   // one tile row per epilogue warp and pass; lanes sweep the columns
+                        long long orow_idx; bool ok;
+                        if (p.bh > 0) {
+                            int y = (mt / p.tiles_x) * p.bh + rr / p.bw, x = (mt % p.tiles_x) * p.bw + rr % p.bw;
+                            ok = y < p.Ho && x < p.Wo; orow_idx = (long long)y * p.Wo + x;
+                        } else { int m = mt * BLOCK_M + rr; ok = m < p.M; orow_idx = m; }
+                        if (!ok) continue;
+                        const float* src0 = p.ws + ((long long)b * p.M + orow_idx) * p.N;
+                        __half* dst = p.C + (long long)b * p.stride_c + orow_idx * p.ldc;
+                        const __half* res = p.residual ? p.residual + (long long)b * p.stride_c + orow_idx * p.ldc : nullptr;
+                        for (int v = lane; v < nvec; v += 32) {
+                            int n = n0 + (v << 2);
+                            float4 a = __ldcg(reinterpret_cast<const float4*>(src0 + n));
+                            for (int sidx = 1; sidx < p.split_k; sidx++) {
+                                float4 t = __ldcg(reinterpret_cast<const float4*>(src0 + sidx * plane + n));
+                                a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
                             }
-                            for (int t = 0; t < 4; t++) {
-                                if (n + t >= p.N) break;
-                                float o = f[t];
-                                if (p.bias) o += __half2float(p.bias[n + t]);
-                                if (rrow) o += __half2float(rrow[n + t]);
-                                crow[n + t] = __float2half_rn(o);
-                            }
+                            if (p.bias) { a.x += __half2float(p.bias[n]); a.y += __half2float(p.bias[n + 1]); a.z += __half2float(p.bias[n + 2]); a.w += __half2float(p.bias[n + 3]); }
+                            if (res) { Vec<__half, 4> r4 = load_vec<__half, 4>(res + n); a.x += __half2float(r4.v[0]); a.y += __half2float(r4.v[1]); a.z += __half2float(r4.v[2]); a.w += __half2float(r4.v[3]); }
+                            Vec<__half, 4> o4;
+                            o4.v[0] = __float2half_rn(a.x); o4.v[1] = __float2half_rn(a.y); o4.v[2] = __float2half_rn(a.z); o4.v[3] = __float2half_rn(a.w);
+                            store_vec<__half, 4>(dst + n, o4);
                         }
                     }
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");       // split_flag is reused by the next tile
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (warp == 2 && lane == 0) {
+                    int done = atomicAdd(&p.counters[2 * t2 + 1], 1);
+                    if (done == p.split_k - 1) { p.counters[2 * t2] = 0; p.counters[2 * t2 + 1] = 0; __threadfence(); }   // re-arm for the next launch
+                }
             }
         }
     }
@@ -443,7 +465,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, __half* __res
 // ---- host side -------------------------------------------------------------------------------------------------
 float* g_ws = nullptr;
 size_t g_ws_bytes = 0;
-int* g_counters = nullptr;       // 1024 self-resetting tile counters
+int* g_counters = nullptr;       // self-resetting (arrive, done) counter pairs, one pair per output tile
 constexpr size_t WS_MAX = (size_t)96 << 20;
 
 // pick a split factor: fill the SMs when the tile count is small, keep >= 2 k-blocks per split, stay inside the workspace
@@ -462,8 +484,8 @@ int choose_split(int tiles, int k_blocks, size_t out_elems, cudaStream_t st)
         cudaStreamCaptureStatus cs0 = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(st, &cs0);
         if (cs0 != cudaStreamCaptureStatusNone) return 1;
-        if (cudaMalloc(&g_counters, 1024 * sizeof(int)) != cudaSuccess) { g_counters = nullptr; return 1; }
-        cudaMemset(g_counters, 0, 1024 * sizeof(int));
+        if (cudaMalloc(&g_counters, 4096 * sizeof(int)) != cudaSuccess) { g_counters = nullptr; return 1; }
+        cudaMemset(g_counters, 0, 4096 * sizeof(int));
     }
     if (need > g_ws_bytes) {
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -530,16 +552,36 @@ struct ProfRec { cudaEvent_t a, b; double flops, bytes; int M, N, K, taps, batch
 bool g_prof = false;
 std::vector<ProfRec> g_prof_list;
 
+// Few k-blocks per CTA => latency-bound: prefer the 3-stage variant (2 CTAs / SM).  OSB_TC_SHORT=0 disables it (A/B runs).
+int short_k_hint(int k_blocks, int split)
+{
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("OSB_TC_SHORT"); enabled = (e && e[0] == '0') ? 0 : 1; }
+    int per_cta = (k_blocks + split - 1) / std::max(split, 1);
+    return enabled && per_cta <= 12 ? 1 : 0;
+}
+
+bool inkernel_reduce()
+{
+    static int v = -1;
+    // measured on B200 (SD1.5 UNet step): the rendezvous costs more than the 4 us reduce kernel it saves (9.17 vs 8.00 ms per
+    // step), so the separate vectorised reduce kernel is the default; OSB_TC_INKERNEL_REDUCE=1 selects the in-kernel variant.
+    if (v < 0) { const char* e = getenv("OSB_TC_INKERNEL_REDUCE"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<STAGES_DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(STAGES_DEEP));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<STAGES_SHORT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(STAGES_SHORT));
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
     int total = p.m_tiles * p.n_tiles * p.batch * p.split_k;
-    int grid = std::min(total, num_sms());
+    const bool short_k = p.short_k != 0;
+    int grid = std::min(total, num_sms() * (short_k ? 2 : 1));
     ProfRec rec{};
     if (g_prof) {
         cudaEventCreate(&rec.a); cudaEventCreate(&rec.b);
@@ -551,7 +593,8 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cuda
         rec.M = p.M; rec.N = p.N; rec.K = p.K; rec.taps = p.taps; rec.batch = p.batch; rec.split = p.split_k; rec.conv = p.bh > 0;
         cudaEventRecord(rec.a, st);
     }
-    osb_launch((tc_gemm_kernel), grid, NUM_THREADS, SMEM_BYTES, st, ma, mb, p);
+    if (short_k) osb_launch((tc_gemm_kernel<STAGES_SHORT>), grid, NUM_THREADS, (size_t)smem_bytes_for(STAGES_SHORT), st, ma, mb, p);
+    else osb_launch((tc_gemm_kernel<STAGES_DEEP>), grid, NUM_THREADS, (size_t)smem_bytes_for(STAGES_DEEP), st, ma, mb, p);
     if (p.split_k > 1 && !p.counters) {
         launched(1);
         long long total4 = (long long)p.batch * p.M * p.N / 4;
@@ -669,7 +712,10 @@ int osb_tc_gemm_launch(const void* A, const void* B, void* C, const void* bias, 
     p.stride = 1;
     p.C = (__half*)C; p.bias = (const __half*)bias; p.residual = (const __half*)residual; p.stride_c = sc; p.ldc = ldc;
     p.split_k = (ldc == N && (sc == M * N || batch == 1)) ? choose_split(p.m_tiles * p.n_tiles * p.batch, p.k_blocks_per_tap, (size_t)batch * M * N, st) : 1;
-    p.ws = g_ws; p.counters = (p.N % 4) ? g_counters : nullptr;   // vectorised parallel reduce kernel needs N % 4 == 0
+    p.ws = g_ws;
+    // in-kernel rendezvous reduction needs every CTA resident at once and float4-aligned rows; otherwise the reduce kernel runs
+    p.counters = (p.split_k > 1 && p.N % 4 == 0 && p.ldc % 4 == 0 && (long long)p.m_tiles * p.n_tiles * p.batch * p.split_k <= num_sms() && inkernel_reduce()) ? g_counters : nullptr;
+    p.short_k = short_k_hint(p.taps * p.k_blocks_per_tap, p.split_k);
     return launch(ma, mb, p, st);
 }
 
@@ -709,6 +755,9 @@ int osb_tc_conv_launch(const void* x, const void* w, const void* bias, const voi
     p.stride = stride;
     p.C = (__half*)y; p.bias = (const __half*)bias; p.residual = (const __half*)residual; p.stride_c = 0; p.ldc = Cout;
     p.split_k = choose_split(p.m_tiles * p.n_tiles, p.taps * p.k_blocks_per_tap, (size_t)Ho * Wo * Cout, st);
-    p.ws = g_ws; p.counters = (p.N % 4) ? g_counters : nullptr;   // vectorised parallel reduce kernel needs N % 4 == 0
+    p.ws = g_ws;
+    // in-kernel rendezvous reduction needs every CTA resident at once and float4-aligned rows; otherwise the reduce kernel runs
+    p.counters = (p.split_k > 1 && p.N % 4 == 0 && p.ldc % 4 == 0 && (long long)p.m_tiles * p.n_tiles * p.batch * p.split_k <= num_sms() && inkernel_reduce()) ? g_counters : nullptr;
+    p.short_k = short_k_hint(p.taps * p.k_blocks_per_tap, p.split_k);
     return launch(ma, mb, p, st);
 }

@@ -7,6 +7,8 @@
 // multiple of the SM count, fp32 math on fp16 storage, every tensor read once and written once.
 
 #include "common.cuh"
+#include <cstdio>
+#include <cstdlib>
 
 namespace {
 
@@ -402,6 +404,96 @@ __global__ void gn_stats_nhwc_vec_kernel(const T* __restrict__ x, double* __rest
     for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(&stats[i], (double)sm[i]);
 }
 
+// GroupNorm(+SiLU) on NHWC in ONE launch: statistics -> grid rendezvous -> apply.  All CTAs are co-resident (grid <= 2 per
+// SM), so after publishing its partial sums every CTA waits on an arrival counter and then normalises its own pixel strip,
+// which is still L2-resident.  The scratch (2*G doubles + 2 counters) is zero on entry and the last CTA out re-zeroes it, so
+// a CUDA graph needs a single node per GroupNorm instead of memset + 2 kernels.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256, 2)
+gn_fused_nhwc_kernel(const T* __restrict__ x, T* __restrict__ y, double* __restrict__ stats, int* __restrict__ counters,
+                     int C, int64_t HW, int groups, int64_t pix_per_cta, const T* __restrict__ gamma, const T* __restrict__ beta, float eps, int silu)
+{
+    osb_pdl_prologue();
+    extern __shared__ float sm[];  // 2 * groups partials, then 2 * groups (mean, rstd)
+    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    const int tpp = C / VEC;
+    const int rows = blockDim.x / tpp;
+    const int cv = threadIdx.x % tpp, pr = threadIdx.x / tpp;
+    const int cpg = C / groups;
+    int64_t p0 = (int64_t)blockIdx.x * pix_per_cta, p1 = min(p0 + pix_per_cta, HW);
+    if (pr < rows) {
+        float s[VEC], q[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; k++) { s[k] = 0.f; q[k] = 0.f; }
+        for (int64_t p = p0 + pr; p < p1; p += rows) {
+            Vec<T, VEC> v = load_vec<T, VEC>(x + p * C + cv * VEC);
+#pragma unroll
+            for (int k = 0; k < VEC; k++) { float f = to_float(v.v[k]); s[k] += f; q[k] += f * f; }
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; k++) {
+            int g = (cv * VEC + k) / cpg;
+            atomicAdd(&sm[2 * g], s[k]);
+            atomicAdd(&sm[2 * g + 1], q[k]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(&stats[i], (double)sm[i]);
+    // ---- grid rendezvous ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(&counters[0], 1);
+        long long t0 = clock64();
+        while (true) {
+            int seen;
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(counters) : "memory");
+            if (seen >= (int)gridDim.x) break;
+            if (clock64() - t0 > 4000000000LL) { printf("gn_fused_nhwc_kernel: rendezvous timed out (block %d)\n", blockIdx.x); __trap(); }
+        }
+    }
+    __syncthreads();
+    __threadfence();
+    // ---- per-group mean / rstd into shared memory ----
+    const double inv_n = 1.0 / (double)((int64_t)cpg * HW);
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        double mean = __ldcg(&stats[2 * g]) * inv_n;
+        double var = __ldcg(&stats[2 * g + 1]) * inv_n - mean * mean;
+        sm[2 * g] = (float)mean;
+        sm[2 * g + 1] = rsqrtf(fmaxf((float)var, 0.f) + eps);
+    }
+    __syncthreads();
+    if (pr < rows) {
+        float gm[VEC], bt[VEC], mu[VEC], rs[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; k++) {
+            int c = cv * VEC + k, g = c / cpg;
+            gm[k] = gamma ? to_float(gamma[c]) : 1.f; bt[k] = beta ? to_float(beta[c]) : 0.f; mu[k] = sm[2 * g]; rs[k] = sm[2 * g + 1];
+        }
+        for (int64_t p = p0 + pr; p < p1; p += rows) {
+            Vec<T, VEC> v = load_vec<T, VEC>(x + p * C + cv * VEC);
+#pragma unroll
+            for (int k = 0; k < VEC; k++) {
+                float o = (to_float(v.v[k]) - mu[k]) * rs[k] * gm[k] + bt[k];
+                if (silu) o = o / (1.f + __expf(-o));
+                v.v[k] = from_float<T>(o);
+            }
+            store_vec<T, VEC>(y + p * C + cv * VEC, v);
+        }
+    }
+    // ---- last CTA out re-zeroes the scratch for the next launch ----
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int done = atomicAdd(&counters[1], 1);
+        if (done == (int)gridDim.x - 1) {
+            for (int i = 0; i < 2 * groups; i++) stats[i] = 0.0;
+            counters[0] = 0; counters[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
 template <typename T>
 __global__ void gn_stats_nchw_kernel(const T* __restrict__ x, double* __restrict__ stats, int64_t n_per_g, int splits)
 {
@@ -722,6 +814,24 @@ int osb_group_norm(const void* x, void* y, int dtype, int nhwc, int64_t C, int64
     if (C * HW == 0) return 0;
     if (C % groups) return (int)cudaErrorInvalidValue;
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        // single-launch path: NHWC, vectorisable channel count, scratch layout [0,1024) two-pass stats | [1024,1920) fused stats
+        // (zero-initialised by the caller, self-cleaning) | [1920,1928) rendezvous counters
+        int vec = dtype == OSB_F16 ? 8 : 4;
+        static int fused_ok = -1;
+        if (fused_ok < 0) { const char* e = getenv("OSB_GN_FUSED"); fused_ok = (e && e[0] == '0') ? 0 : 1; }
+        if (fused_ok && nhwc && groups <= 48 && C % vec == 0 && C / vec <= 256 && aligned16(x) && aligned16(y) && (dtype == OSB_F16 || dtype == OSB_F32)) {
+            double* fstats = (double*)((char*)stats_ + 1024);
+            int* counters = (int*)((char*)stats_ + 1920);
+            int64_t c2 = std::min<int64_t>(HW, 148 * 2);
+            int64_t ppc2 = (HW + c2 - 1) / c2;
+            c2 = (HW + ppc2 - 1) / ppc2;
+            size_t smem = sizeof(float) * 2 * groups;
+            if (dtype == OSB_F16) osb_launch((gn_fused_nhwc_kernel<__half, 8>), (unsigned)c2, 256, smem, st, (const __half*)x, (__half*)y, fstats, counters, (int)C, HW, groups, ppc2, (const __half*)gamma, (const __half*)beta, eps, fuse_silu);
+            else osb_launch((gn_fused_nhwc_kernel<float, 4>), (unsigned)c2, 256, smem, st, (const float*)x, (float*)y, fstats, counters, (int)C, HW, groups, ppc2, (const float*)gamma, (const float*)beta, eps, fuse_silu);
+            return launched();
+        }
+    }
     cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups, st);
     if (e != cudaSuccess) return (int)e;
     size_t n = (size_t)C * HW;
