@@ -258,17 +258,37 @@ public:
 class RamSource : public WeightSource {
 public:
     explicit RamSource(std::unique_ptr<WeightSource> inner) : m_inner(std::move(inner)) {}
-    ~RamSource() override { for (auto& kv : m_blobs) cudaFreeHost(kv.second.ptr); }
+    ~RamSource() override { for (auto& c : m_chunks) cudaFreeHost(c.base); }
     struct Blob { void* ptr; size_t bytes; };
     std::unordered_map<std::string, Blob> m_blobs;
     std::unique_ptr<WeightSource> m_inner;
 
+    // Blobs are bump-allocated, 256-byte aligned, from large pinned chunks in the order they are first requested (= graph
+    // order).  A node's weights therefore sit back to back in host memory with exactly the layout the HBM ring gives them, and
+    // the streamer can move a whole node with ONE cudaMemcpyAsync (and one NCCL broadcast) instead of one per blob.
+    struct Chunk { char* base; size_t cap, used; };
+    std::vector<Chunk> m_chunks;
+
+    void* arena_alloc(size_t bytes)
+    {
+        size_t need = (std::max<size_t>(bytes, 16) + 255) & ~(size_t)255;
+        if (m_chunks.empty() || m_chunks.back().used + need > m_chunks.back().cap) {
+            size_t cap = std::max<size_t>(need, (size_t)128 << 20);
+            void* p = nullptr;
+            check_cuda(cudaHostAlloc(&p, cap, cudaHostAllocDefault), "cudaHostAlloc(weights)");
+            m_chunks.push_back({ (char*)p, cap, 0 });
+        }
+        Chunk& c = m_chunks.back();
+        void* p = c.base + c.used;
+        c.used += need;
+        return p;
+    }
+
     void* add(const std::string& name, size_t bytes)
     {
         auto it = m_blobs.find(name);
-        if (it != m_blobs.end()) { cudaFreeHost(it->second.ptr); m_blobs.erase(it); }
-        void* p = nullptr;
-        check_cuda(cudaHostAlloc(&p, std::max<size_t>(bytes, 16), cudaHostAllocDefault), "cudaHostAlloc(weights)");
+        if (it != m_blobs.end() && it->second.bytes >= bytes) { it->second.bytes = bytes; return it->second.ptr; }
+        void* p = arena_alloc(bytes);
         m_blobs[name] = { p, bytes };
         return p;
     }
@@ -387,13 +407,27 @@ WeightStreamer::Slot* WeightStreamer::stage(WeightSource& src, const std::vector
         b.bytes = r.bytes;
         // every rank reads the host bytes (small constants are evaluated on the host); only the root uploads them
         b.host = src.fetch(r.name, r.type, r.bytes, m_host ? (char*)m_host + cur : nullptr);
-        if (r.bytes && r.type != DType::i64) {
-            if (do_h2d) check_cuda(cudaMemcpyAsync(b.dev, b.host, r.bytes, cudaMemcpyHostToDevice, m_copy), "cudaMemcpyAsync(weights H2D)");
-            if (m_nranks > 1) nccl_broadcast(b.dev, r.bytes);
-            m_streamed += r.bytes;
-        }
         s.blobs.push_back(b);
         cur += (r.bytes + 255) & ~(size_t)255;
+    }
+    // one transfer per node when the host copies are laid out exactly like the ring slot (pinned arena of the "ram" sources,
+    // or the pinned mirror of the disk sources); otherwise one per blob
+    bool contiguous = !s.blobs.empty();
+    for (size_t k = 0; k + 1 < s.blobs.size() && contiguous; k++)
+        contiguous = (const char*)s.blobs[k + 1].host == (const char*)s.blobs[k].host + ((s.blobs[k].bytes + 255) & ~(size_t)255);
+    if (contiguous) {
+        size_t span = ((const char*)s.blobs.back().host - (const char*)s.blobs.front().host) + s.blobs.back().bytes;
+        if (do_h2d) check_cuda(cudaMemcpyAsync(s.blobs.front().dev, s.blobs.front().host, span, cudaMemcpyHostToDevice, m_copy), "cudaMemcpyAsync(node H2D)");
+        if (m_nranks > 1) nccl_broadcast(s.blobs.front().dev, span);
+        for (size_t k = 0; k < node.size(); k++) if (node[k].type != DType::i64) m_streamed += node[k].bytes;
+    } else {
+        for (size_t k = 0; k < node.size(); k++) {
+            const Blob& b = s.blobs[k];
+            if (!b.bytes || node[k].type == DType::i64) continue;
+            if (do_h2d) check_cuda(cudaMemcpyAsync(b.dev, b.host, b.bytes, cudaMemcpyHostToDevice, m_copy), "cudaMemcpyAsync(weights H2D)");
+            if (m_nranks > 1) nccl_broadcast(b.dev, b.bytes);
+            m_streamed += b.bytes;
+        }
     }
     check_cuda(cudaEventRecord(s.ready, m_copy), "cudaEventRecord(ready)");
     m_live += s.bytes;
