@@ -54,6 +54,10 @@ GEMM_CASES = [
     (1, 256, 1280, 2560, 0, True, True),     # split-K, MN-major B
     (1, 1, 1280, 1280, 0, True, False),      # time-embedding Gemm: weight-bandwidth GEMV
     (1, 4, 5632, 2048, 0, False, False),
+    (1, 64, 32, 32, 0, True, False),         # VAE toy attention projections / score GEMMs
+    (1, 64, 64, 32, 1, False, False),
+    (1, 64, 32, 64, 0, False, True),
+    (1, 1024, 16, 16, 0, True, False),
 ]
 
 
@@ -102,6 +106,13 @@ CONV_CASES = [
     (8, 8, 1280, 1280, 3, 1, 1, True, True),      # weight-bound 8x8 level, split-K
     (64, 64, 320, 4, 3, 1, 1, True, False),       # conv_out: ragged Cout, scalar epilogue
     (64, 64, 4, 320, 3, 1, 1, True, False),       # conv_in: tiny Cin stays on the CUDA-core kernel
+    (8, 8, 32, 32, 3, 1, 1, True, True),          # VAE-decoder toy shapes: narrow channels
+    (16, 16, 32, 32, 3, 1, 1, True, False),
+    (32, 32, 32, 16, 3, 1, 1, True, False),
+    (32, 32, 16, 16, 3, 1, 1, True, True),
+    (32, 32, 16, 3, 3, 1, 1, True, False),
+    (32, 32, 32, 16, 1, 1, 0, True, True),
+    (16, 16, 24, 40, 3, 1, 1, False, False),
 ]
 
 
