@@ -64,6 +64,13 @@ __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, 
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// one lane of a converged warp, chosen by the hardware: ptxas knows the guarded region runs on exactly one lane
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xffffffff;\n\tselp.u32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -178,58 +185,68 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 
     const int n_kv = p.kv_tiles;
 
+    // Producer and MMA warps run warp-uniform control flow and issue from elect.sync-guarded regions: inside an `if (lane == 0)`
+    // region ptxas wraps every UTCHMMA / UTMALDG in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop (measured: the issue loop, not
+    // the tensor pipe or the loads, bounded the kernel).
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(q_full, Q_BYTES);
             tma_load_3d(sQ, &map_q, q_full, 0, head, q0);
-            for (int j = 0; j < n_kv; j++) {
-                int st = j & 1;
-                mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        }
+        __syncwarp();
+        for (int j = 0; j < n_kv; j++) {
+            const int st = j & 1;
+            mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+            if (elect_one()) {
                 mbar_expect_tx(&kv_full[st], K_BYTES + V_BYTES);
                 tma_load_3d(sK + st * K_BYTES, &map_k, &kv_full[st], 0, head, j * BKV);
                 tma_load_3d(sV + st * V_BYTES, &map_v, &kv_full[st], 0, head, j * BKV);
                 tma_load_3d(sV + st * V_BYTES + V_BYTES / 2, &map_v, &kv_full[st], 0, head, j * BKV + 64);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
         const uint32_t idesc_s = idesc_f16(BKV, 0);     // S = Q K^T: A K-major, B K-major, N = 128 keys
         const uint32_t idesc_o = idesc_f16(BD, 1);      // O += P V : A K-major (P), B MN-major (V rows = keys), N = 64
-        if (lane == 0) {
-            mbar_wait(q_full, 0);
-            tc_fence_after();
-        }
-        __syncwarp();
-        const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+        mbar_wait(q_full, 0);
+        tc_fence_after();
+        // descriptor templates; only the 14-bit start-address field (16-byte units) moves
+        const uint64_t qdesc0 = smem_desc(smem_u32(sQ), 16, 1024);
+        const uint64_t kdesc0 = smem_desc(smem_u32(sK), 16, 1024);
+        const uint64_t pdesc0 = smem_desc(smem_u32(sP), 16, 1024);
+        const uint64_t vdesc0 = smem_desc(smem_u32(sV), V_BYTES, 1024);
         for (int j = 0; j <= n_kv; j++) {
-            if (lane == 0) {
-                if (j < n_kv) {
-                    int st = j & 1;
-                    mbar_wait(&kv_full[st], (j >> 1) & 1);
-                    mbar_wait(&s_empty[st], ((j >> 1) & 1) ^ 1);
-                    tc_fence_after();
-                    uint32_t k_addr = smem_u32(sK + st * K_BYTES);
+            if (j < n_kv) {
+                const int st = j & 1;
+                mbar_wait(&kv_full[st], (j >> 1) & 1);
+                mbar_wait(&s_empty[st], ((j >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint64_t kdesc = kdesc0 + (uint64_t)(st * (K_BYTES >> 4));
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BD / 16; k++)
-                        umma_f16(tmem_base + (uint32_t)(st * BKV), smem_desc(q_addr + k * 32, 16, 1024), smem_desc(k_addr + k * 32, 16, 1024), idesc_s, k != 0);
+                        umma_f16(tmem_base + (uint32_t)(st * BKV), qdesc0 + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k != 0);
                     umma_commit(&s_full[st]);
                 }
-                if (j >= 1) {
-                    int jj = j - 1, st = jj & 1;
-                    mbar_wait(p_full, jj & 1);
-                    tc_fence_after();
-                    uint32_t v_addr = smem_u32(sV + st * V_BYTES);
+                __syncwarp();
+            }
+            if (j >= 1) {
+                const int jj = j - 1, st = jj & 1;
+                mbar_wait(p_full, jj & 1);
+                tc_fence_after();
+                const uint64_t vdesc = vdesc0 + (uint64_t)(st * (V_BYTES >> 4));
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BKV / 16; k++) {
                         // P: two 64-key k-blocks 16 KiB apart, 32 B per 16-key step inside a block; V: 16 key rows = 2048 B per step
-                        uint64_t adesc = smem_desc(p_addr + (k >> 2) * (P_BYTES / 2) + (k & 3) * 32, 16, 1024);
-                        uint64_t bdesc = smem_desc(v_addr + k * 2048, V_BYTES, 1024);
-                        umma_f16(tmem_base + O_COL, adesc, bdesc, idesc_o, (jj != 0 || k != 0) ? 1u : 0u);
+                        umma_f16(tmem_base + O_COL, pdesc0 + (uint64_t)(((k >> 2) * (P_BYTES / 2) + (k & 3) * 32) >> 4), vdesc + (uint64_t)(k * (2048 >> 4)),
+                                 idesc_o, (jj != 0 || k != 0) ? 1u : 0u);
                     }
                     umma_commit(&kv_empty[st]);
                     umma_commit(pv_done);
                 }
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else {
         // ===================== softmax / correction / epilogue (warps 2..5): thread = query row =====================

@@ -108,6 +108,22 @@ __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, 
                  ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
+// The producer / MMA warps run WARP-UNIFORM control flow and issue from an elect.sync-guarded region.  (Inside an
+// `if (lane == 0)` region ptxas cannot keep the operands of UTCHMMA / UTMALDG in uniform registers and wraps every one of them
+// in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop: ~1000 issue cycles per k-block, measured with ncu source sampling.)
+__device__ __forceinline__ void tma_load_3d_s(uint32_t smem_addr, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_addr), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// one lane of a converged warp, chosen by the hardware (elect.sync): ptxas knows the guarded region runs on exactly one lane
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xffffffff;\n\tselp.u32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -215,8 +231,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int kb_per_split = (k_blocks_all + p.split_k - 1) / p.split_k;   // host guarantees (split_k - 1) * kb_per_split < k_blocks_all
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (warp-uniform control flow, leader-predicated issue) =====================
+        {
+            const uint32_t sa0 = smem_u32(smem_a), sb0 = smem_u32(smem_b);
+            const uint32_t tx_bytes = A_STAGE_BYTES + (p.b_kmajor ? p.bn * (BLOCK_K * 2) : ((p.bn + 63) / 64) * (B_STAGE_BYTES / 2));
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int sp = tile % p.split_k, t2 = tile / p.split_k;
@@ -226,65 +244,70 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 int y0 = 0, x0 = 0, m0 = mt * BLOCK_M;
                 if (p.taps > 1 || p.bh > 0) { y0 = (mt / p.tiles_x) * p.bh; x0 = (mt % p.tiles_x) * p.bw; }
                 int kb_lo = sp * kb_per_split, kb_hi = min(kb_lo + kb_per_split, k_blocks_all);
+                // (tap, channel block) walk incrementally: no divisions inside the k loop
+                int tap = kb_lo / p.k_blocks_per_tap, kcb = kb_lo % p.k_blocks_per_tap;
+                int ky = tap / p.kw, kx = tap % p.kw;
+                const int ax = x0 * p.stride - p.pad_left, ay = y0 * p.stride - p.pad_top;
                 for (int kb = kb_lo; kb < kb_hi; kb++) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], A_STAGE_BYTES + (p.b_kmajor ? p.bn * (BLOCK_K * 2) : ((p.bn + 63) / 64) * (B_STAGE_BYTES / 2)));
-                    int tap = kb / p.k_blocks_per_tap, kc = (kb % p.k_blocks_per_tap) * BLOCK_K;
-                    uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
-                    uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
-                    if (p.bh > 0) {
-                        int ky = tap / p.kw, kx = tap % p.kw;
-                        tma_load_3d(sa, &map_a, &full[stage], kc, x0 * p.stride + kx - p.pad_left, y0 * p.stride + ky - p.pad_top);
-                    } else {
-                        if (p.a_swap) tma_load_3d(sa, &map_a, &full[stage], kc, b, m0); else tma_load_3d(sa, &map_a, &full[stage], kc, m0, b);
-                    }
-                    int kglob = tap * p.K + kc;   // K index into B (conv: taps are concatenated along K)
-                    if (p.b_kmajor) {
-                        if (p.b_swap) tma_load_3d(sb, &map_b, &full[stage], kglob, b, n0); else tma_load_3d(sb, &map_b, &full[stage], kglob, n0, b);
-                    } else {
-                        if (p.b_swap) {
-                            tma_load_3d(sb, &map_b, &full[stage], n0, b, kglob);
-                            if (p.bn > 64) tma_load_3d(sb + B_STAGE_BYTES / 2, &map_b, &full[stage], n0 + 64, b, kglob);
+                    if (elect_one()) {
+                        mbar_expect_tx(&full[stage], tx_bytes);
+                        const int kc = kcb * BLOCK_K;
+                        const uint32_t sa = sa0 + stage * A_STAGE_BYTES;
+                        const uint32_t sb = sb0 + stage * B_STAGE_BYTES;
+                        if (p.bh > 0) tma_load_3d_s(sa, &map_a, &full[stage], kc, ax + kx, ay + ky);
+                        else if (p.a_swap) tma_load_3d_s(sa, &map_a, &full[stage], kc, b, m0);
+                        else tma_load_3d_s(sa, &map_a, &full[stage], kc, m0, b);
+                        const int kglob = tap * p.K + kc;   // K index into B (conv: taps are concatenated along K)
+                        if (p.b_kmajor) {
+                            if (p.b_swap) tma_load_3d_s(sb, &map_b, &full[stage], kglob, b, n0);
+                            else tma_load_3d_s(sb, &map_b, &full[stage], kglob, n0, b);
                         } else {
-                            tma_load_3d(sb, &map_b, &full[stage], n0, kglob, b);
-                            if (p.bn > 64) tma_load_3d(sb + B_STAGE_BYTES / 2, &map_b, &full[stage], n0 + 64, kglob, b);
+                            if (p.b_swap) {
+                                tma_load_3d_s(sb, &map_b, &full[stage], n0, b, kglob);
+                                if (p.bn > 64) tma_load_3d_s(sb + B_STAGE_BYTES / 2, &map_b, &full[stage], n0 + 64, b, kglob);
+                            } else {
+                                tma_load_3d_s(sb, &map_b, &full[stage], n0, kglob, b);
+                                if (p.bn > 64) tma_load_3d_s(sb + B_STAGE_BYTES / 2, &map_b, &full[stage], n0 + 64, kglob, b);
+                            }
                         }
                     }
+                    __syncwarp();
+                    if (++kcb == p.k_blocks_per_tap) { kcb = 0; tap++; if (++kx == p.kw) { kx = 0; ky++; } }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+        // ===================== MMA issuer (warp-uniform control flow, leader-predicated issue) =====================
         const uint32_t idesc = make_idesc(p.b_kmajor ? 0 : 1, p.bn);
+        // Descriptor templates: everything but the 14-bit start address is loop-invariant.
+        //   A, K-major SW128: 8-row groups 1024 B apart; K advances 32 B inside the swizzle row.
+        //   B, K-major: same.  B, MN-major SW128: two 64-column atoms 8192 B apart (LBO), 8-row k-groups 1024 B apart (SBO);
+        //   K advances 16 rows = 2048 B.
+        const uint64_t adesc0 = make_smem_desc(smem_u32(smem_a), 16, 1024);
+        const uint64_t bdesc0 = p.b_kmajor ? make_smem_desc(smem_u32(smem_b), 16, 1024) : make_smem_desc(smem_u32(smem_b), B_STAGE_BYTES / 2, 1024);
+        const uint32_t b_kstep = p.b_kmajor ? (UMMA_K * 2) >> 4 : (UMMA_K * 128) >> 4;   // descriptor address units (16 B)
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            if (lane == 0) mbar_wait(&acc_empty[acc], acc_phase ^ 1);
-            __syncwarp();
+            mbar_wait(&acc_empty[acc], acc_phase ^ 1);
             tc_fence_after();
-            uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
-            int sp = tile % p.split_k;
-            int kb_lo = sp * kb_per_split, kb_hi = min(kb_lo + kb_per_split, k_blocks_all);
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+            const int sp = tile % p.split_k;
+            const int kb_lo = sp * kb_per_split, kb_hi = min(kb_lo + kb_per_split, k_blocks_all);
             for (int kb = kb_lo; kb < kb_hi; kb++) {
-                if (lane == 0) {
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
-                    uint32_t a_addr = smem_u32(smem_a + stage * A_STAGE_BYTES);
-                    uint32_t b_addr = smem_u32(smem_b + stage * B_STAGE_BYTES);
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint64_t adesc = adesc0 + (uint64_t)(stage * (A_STAGE_BYTES >> 4));
+                const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (B_STAGE_BYTES >> 4));
+                if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
-                        // A, K-major SW128: 8-row groups 1024 B apart; K advances 32 B inside the swizzle row
-                        uint64_t adesc = make_smem_desc(a_addr + k * (UMMA_K * 2), 16, 1024);
-                        uint64_t bdesc;
-                        if (p.b_kmajor) bdesc = make_smem_desc(b_addr + k * (UMMA_K * 2), 16, 1024);
-                        // B, MN-major SW128: two 64-column atoms 8192 B apart (LBO), 8-row k-groups 1024 B apart (SBO);
-                        // K advances 16 rows = 2048 B
-                        else bdesc = make_smem_desc(b_addr + k * (UMMA_K * 128), B_STAGE_BYTES / 2, 1024);
-                        umma_f16(tmem_d, adesc, bdesc, idesc, (kb != kb_lo || k != 0) ? 1u : 0u);
-                    }
-                    umma_commit(&empty[stage]);                       // frees the smem slot when these MMAs retire
-                    if (kb == kb_hi - 1) umma_commit(&acc_full[acc]);     // accumulator complete -> epilogue
+                    for (int k = 0; k < BLOCK_K / UMMA_K; k++)
+                        umma_f16(tmem_d, adesc + (uint64_t)(k * ((UMMA_K * 2) >> 4)), bdesc + (uint64_t)(k * b_kstep), idesc,
+                                 (kb != kb_lo || k != 0) ? 1u : 0u);
+                    umma_commit(&empty[stage]);                          // frees the smem slot when these MMAs retire
+                    if (kb == kb_hi - 1) umma_commit(&acc_full[acc]);    // accumulator complete -> epilogue
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -471,8 +494,11 @@ constexpr size_t WS_MAX = (size_t)96 << 20;
 // pick a split factor: fill the SMs when the tile count is small, keep >= 2 k-blocks per split, stay inside the workspace
 int choose_split(int tiles, int k_blocks, size_t out_elems, cudaStream_t st)
 {
-    if (tiles >= 100 || k_blocks < 4) return 1;
-    int split = 148 / tiles;
+    static const int forced = [] { const char* e = getenv("OSB_TC_SPLIT"); return e ? atoi(e) : 0; }();   // tuning experiments only
+    // measured over every tc shape of the SD 1.5 UNet (r01 sweep): below ~32 k-blocks the second launch (the reduce) costs more
+    // than the idle SMs do
+    if ((tiles >= 100 && forced <= 0) || k_blocks < 4 || (k_blocks < 32 && forced <= 0)) return 1;
+    int split = forced > 0 ? forced : 148 / tiles;
     split = std::min(split, k_blocks / 2);
     while (split > 1 && (size_t)split * out_elems * 4 > WS_MAX) split--;
     if (split <= 1) return 1;
@@ -609,18 +635,23 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cuda
 
 // Tile width: fewest waves over the 148 SMs, then least padded work (e.g. N = 320 at M = 4096: 80 -> 128 tiles in one wave
 // with no padding, instead of 96 tiles of 128 with 1/6 of every third tile wasted).
+int env_int(const char* name)
+{
+    const char* e = getenv(name);
+    return e ? atoi(e) : 0;
+}
+
 int choose_bn(int64_t m_tiles, int64_t N, int64_t batch)
 {
-    static const int cand[] = { 128, 96, 80, 64 };
-    int best = 128; double best_cost = 1e30;
-    for (int bn : cand) {
-        if (bn > 64 && N <= 64) continue;
-        int64_t tiles = m_tiles * ((N + bn - 1) / bn) * batch;
-        double waves = (double)((tiles + 147) / 148);
-        double cost = waves * (bn + 24);
-        if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
-    }
-    return best;
+    static const int forced = env_int("OSB_TC_BN");     // tuning experiments only
+    if (forced == 128 || forced == 96 || forced == 80 || forced == 64) return (N <= 64 && forced > 64) ? 64 : forced;
+    // Measured (r01): the mainloop is bound by L2->SM bytes per k-block, (128 + bn) * 128 B, so the widest tile wins whenever the
+    // K loop is long; split-K (not a narrower tile) supplies parallelism.  Narrow tiles only where N itself is narrow.
+    (void)m_tiles; (void)batch;
+    if (N <= 64) return 64;
+    if (N <= 80) return 80;
+    if (N <= 96) return 96;
+    return 128;
 }
 
 inline uint32_t next_pow2(uint32_t v) { uint32_t r = 1; while (r < v) r <<= 1; return r; }
