@@ -69,6 +69,10 @@ int osb_instance_norm(const void* x, void* y, int dtype, int64_t channels, int64
 int osb_group_norm(const void* x, void* y, int dtype, int nhwc, int64_t C, int64_t HW, int groups,
                    const void* gamma, const void* beta, float eps, int fuse_silu, void* stats, void* stream);
 
+/* GEGLU feed-forward gate: x [rows, 2*inner] -> y [rows, inner], y = x[:, :inner] * gelu_erf(x[:, inner:]).  One pass for the
+ * Slice, Slice, Div, Erf, Add, Mul, Mul, Mul group (src/onnxstream.cpp Slice 6499-6652, Erf 1950-2100, binary ops 1666-1949). */
+int osb_geglu(const void* x, void* y, int dtype, int64_t rows, int64_t inner, void* stream);
+
 /* Fused LayerNorm over the last axis (ReduceMean,Sub,Pow,ReduceMean,Add,Sqrt,Div,Mul,Add chain; src/onnxstream.cpp
  * 5237-5393 et al.).  gamma/beta may be NULL. */
 int osb_layer_norm(const void* x, void* y, int dtype, int64_t rows, int64_t cols, const void* gamma, const void* beta,
@@ -89,6 +93,12 @@ int osb_gather_rows(const void* table, const int64_t* idx, void* out, int64_t n_
 int osb_gemm(const void* A, const void* B, void* C, const void* bias, const void* residual,
              int64_t batch, int64_t M, int64_t N, int64_t K,
              int64_t stride_a, int64_t stride_b, int64_t stride_c, int b_transposed, int dtype, int impl, void* stream);
+
+/* `groups` (1..3) GEMMs C_g = A * B_g sharing A [M,K] and the shape, dense operands, no bias: one tcgen05 launch when the
+ * problem qualifies (the q/k/v MatMuls of an attention block, src/onnxstream.cpp:4343-4664 run three times), else `groups`
+ * ordinary launches. */
+int osb_gemm_grouped(const void* A, const void* const* B, void* const* C, int groups, int64_t M, int64_t N, int64_t K,
+                     int b_transposed, int dtype, int impl, void* stream);
 
 /* Same with explicit leading dimensions (elements between consecutive rows of A, B, C): lets the attention GEMMs read the
  * per-head slices of a [T, heads*d] projection in place -- the Reshape/Transpose/Reshape head split and merge of the exported

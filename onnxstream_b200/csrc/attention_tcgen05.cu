@@ -64,6 +64,14 @@ __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, 
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// 2^x on the SFU, flush-to-zero: one MUFU.EX2 (exp2f() adds a range check and two scaling multiplies for denormal results,
+// which a probability that is about to be rounded to fp16 does not need).  ex2(-inf) = +0.
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 // one lane of a converged warp, chosen by the hardware: ptxas knows the guarded region runs on exactly one lane
 __device__ __forceinline__ bool elect_one()
 {
@@ -268,22 +276,42 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             tmem_ld32_nowait(s_addr + 96, sv + 96);
             tmem_ld_wait();
             const bool tail = key0 + BKV > p.Tk;          // only the last tile has padding keys (K rows zero-filled by TMA)
+            // Two uniform code paths: the full-tile path carries no per-element predicates (measured: the predicated single path
+            // spent ~20 issue slots per score, the SFU needs 8).
             float mt = -INFINITY;
+            if (!tail) {
 #pragma unroll
-            for (int t = 0; t < 128; t++) if (!tail || key0 + t < p.Tk) mt = fmaxf(mt, __uint_as_float(sv[t]));
-            float m_new = fmaxf(m_run, mt * p.scale_log2);
-            float alpha = exp2f(m_run - m_new);          // 0 on the first tile (m_run = -inf)
-            // p = 2^(s*scale*log2e - m_new), packed to fp16 in registers (the S registers die as P is produced)
-            uint32_t pk[64];
-            float lsum = 0.f;
+                for (int t = 0; t < 128; t++) mt = fmaxf(mt, __uint_as_float(sv[t]));
+            } else {
 #pragma unroll
-            for (int t = 0; t < 128; t += 2) {
-                float p0 = (!tail || key0 + t < p.Tk) ? exp2f(__uint_as_float(sv[t]) * p.scale_log2 - m_new) : 0.f;
-                float p1 = (!tail || key0 + t + 1 < p.Tk) ? exp2f(__uint_as_float(sv[t + 1]) * p.scale_log2 - m_new) : 0.f;
-                __half2 h2 = __floats2half2_rn(p0, p1);
-                lsum += __low2float(h2) + __high2float(h2);   // the sum uses the rounded values the second MMA will see
-                pk[t >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+                for (int t = 0; t < 128; t++) if (key0 + t < p.Tk) mt = fmaxf(mt, __uint_as_float(sv[t]));
             }
+            const float m_new = fmaxf(m_run, mt * p.scale_log2);      // scale_log2 > 0
+            const float alpha = ex2_approx(m_run - m_new);            // 0 on the first tile (m_run = -inf)
+            const float neg_m = -m_new;
+            // p = 2^(s*scale*log2e - m_new): one FFMA + one MUFU.EX2 per score, packed to fp16 as produced
+            uint32_t pk[64];
+            float lsum0 = 0.f, lsum1 = 0.f;
+            if (!tail) {
+#pragma unroll
+                for (int t = 0; t < 128; t += 2) {
+                    float p0 = ex2_approx(fmaf(__uint_as_float(sv[t]), p.scale_log2, neg_m));
+                    float p1 = ex2_approx(fmaf(__uint_as_float(sv[t + 1]), p.scale_log2, neg_m));
+                    lsum0 += p0; lsum1 += p1;
+                    __half2 h2 = __floats2half2_rn(p0, p1);
+                    pk[t >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < 128; t += 2) {
+                    float p0 = key0 + t < p.Tk ? ex2_approx(fmaf(__uint_as_float(sv[t]), p.scale_log2, neg_m)) : 0.f;
+                    float p1 = key0 + t + 1 < p.Tk ? ex2_approx(fmaf(__uint_as_float(sv[t + 1]), p.scale_log2, neg_m)) : 0.f;
+                    lsum0 += p0; lsum1 += p1;
+                    __half2 h2 = __floats2half2_rn(p0, p1);
+                    pk[t >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+            }
+            const float lsum = lsum0 + lsum1;
             tc_fence_before();
             mbar_arrive(&s_empty[st]);                   // S[st] may be overwritten by QK^T of tile j+2
             l_run = l_run * alpha + lsum;
@@ -305,12 +333,12 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             }
             // P row -> shared memory, K-major SWIZZLE_128B: k-block kb = key/64, 16-byte chunk index XOR (row % 8)
             {
-                uint8_t* prow = sP + row * 128;
+                const uint32_t prow = smem_u32(sP) + row * 128;
 #pragma unroll
                 for (int ch = 0; ch < 16; ch++) {
                     int kb = ch >> 3, c8 = ch & 7;
-                    uint4 val = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
-                    *reinterpret_cast<uint4*>(prow + kb * (P_BYTES / 2) + ((c8 ^ (row & 7)) << 4)) = val;
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + kb * (P_BYTES / 2) + ((c8 ^ (row & 7)) << 4)),
+                                 "r"(pk[ch * 4]), "r"(pk[ch * 4 + 1]), "r"(pk[ch * 4 + 2]), "r"(pk[ch * 4 + 3]) : "memory");
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the async proxy (UMMA)

@@ -37,7 +37,7 @@ std::vector<int64_t> parse_ints(const std::string& s)
 
 [[noreturn]] void fail(const OpDef& op, const std::string& msg) { throw std::invalid_argument(op.type + ": " + msg); }
 
-enum StepKind { SK_SINGLE = 0, SK_ATTENTION, SK_GROUPNORM, SK_LAYERNORM, SK_GELU, SK_SILU, SK_LINEAR, SK_SDPA, SK_MHA, SK_CONV_ADD };
+enum StepKind { SK_SINGLE = 0, SK_ATTENTION, SK_GROUPNORM, SK_LAYERNORM, SK_GELU, SK_SILU, SK_LINEAR, SK_SDPA, SK_MHA, SK_CONV_ADD, SK_GEGLU };
 
 struct Step {
     StepKind kind = SK_SINGLE;
@@ -550,6 +550,30 @@ struct Engine::Impl {
         return 5;
     }
 
+    // GEGLU gate: Slice(x, 0:inner), Slice(x, inner:2*inner) on the last axis, gelu_erf of the second, Mul -- one kernel, no
+    // materialised halves.  The slice bounds are int64 weights, so they are verified when the step executes (fused_geglu falls
+    // back to the op-by-op path if they are not the two halves).
+    size_t match_geglu(size_t i) const
+    {
+        auto& ops = E.m_ops;
+        if (!E.fuse_nodes || E.use_uint8_arithmetic || E.use_uint8_qdq) return 0;
+        if (i + 7 >= ops.size() || ops[i].type != "Slice" || ops[i + 1].type != "Slice") return 0;
+        const OpDef &s0 = ops[i], &s1 = ops[i + 1];
+        if (s0.in.size() != 5 || s1.in.size() != 5 || s0.out.size() != 1 || s1.out.size() != 1) return 0;
+        if (s0.in[0].wtype != DType::none || s1.in[0].wtype != DType::none || s0.in[0].name != s1.in[0].name) return 0;
+        for (int k = 1; k < 5; k++) if (!s0.in[k].present || s0.in[k].wtype != DType::i64 || !s1.in[k].present || s1.in[k].wtype != DType::i64) return 0;
+        if (s0.out[0].shape != s1.out[0].shape || s0.out[0].shape.empty()) return 0;
+        for (auto& name : E.extra_outputs) if (name == s0.out[0].name || name == s1.out[0].name) return 0;
+        int var = 0;
+        if (match_gelu(i + 2, var) != 6 || var != 1) return 0;
+        const OpDef &dv = ops[i + 2], &m0 = ops[i + 5], &gm = ops[i + 7];
+        // gate half: read by Div and by the first Mul of the chain, nothing else; value half: read by the last Mul only
+        auto u1 = uses.find(s1.out[0].name), u0 = uses.find(s0.out[0].name);
+        if (u1 == uses.end() || u1->second != 2 || u0 == uses.end() || u0->second != 1) return 0;
+        if (dv.in[0].name != s1.out[0].name || m0.in[0].name != s1.out[0].name || gm.in[0].name != s0.out[0].name) return 0;
+        return 8;
+    }
+
     size_t match_silu(size_t i) const
     {
         auto& ops = E.m_ops;
@@ -624,6 +648,7 @@ struct Engine::Impl {
             else if ((n = match_attention(i, var))) { s.kind = SK_ATTENTION; s.count = n; s.variant = var; }
             else if ((n = match_groupnorm(i, var))) { s.kind = SK_GROUPNORM; s.count = n; s.variant = var; }
             else if ((n = match_layernorm(i))) { s.kind = SK_LAYERNORM; s.count = n; }
+            else if ((n = match_geglu(i))) { s.kind = SK_GEGLU; s.count = n; }
             else if ((n = match_gelu(i, var))) { s.kind = SK_GELU; s.count = n; s.variant = var; }
             else if ((n = match_silu(i))) { s.kind = SK_SILU; s.count = n; }
             else if ((n = match_linear(i, var))) { s.kind = SK_LINEAR; s.count = n; s.variant = var; }
@@ -683,6 +708,7 @@ struct Engine::Impl {
     void fused_groupnorm(const Step& s);
     void fused_layernorm(const Step& s);
     void fused_gelu(const Step& s);
+    void fused_geglu(const Step& s);
     void fused_silu(const Step& s);
     void fused_linear(const Step& s);
     void fused_sdpa(const Step& s);
@@ -1611,16 +1637,34 @@ void Engine::Impl::fused_mha(const Step& s)
     if (ty == DType::f16) scale = __half2float(__float2half_rn(scale));
     if (x.shape[2] != wq.shape[0] || xk.shape[2] != wk.shape[0] || xv.shape[2] != wv.shape[0]) throw std::runtime_error("XnnPack::matrix_multiply_fp32: invalid shape of inputs.");
 
-    Tensor ql = make(ty, { T, C }), kl = make(ty, { Tkp, C }), vl = make(ty, { Tkp, C }), out = make(ty, { 1, T, C });
-    if (Tkp != Tk) {   // zero pad rows: they are read as extra (null) keys / values by the padded GEMMs
-        ck(cudaMemsetAsync((char*)kl.mdata() + Tk * C * es, 0, (Tkp - Tk) * C * es, st), "cudaMemsetAsync");
-        ck(cudaMemsetAsync((char*)vl.mdata() + Tk * C * es, 0, (Tkp - Tk) * C * es, st), "cudaMemsetAsync");
+    const bool use_flash = E.flash_attention && E.gemm_impl != 1 && osb_flash_attention_ok(T, Tk, d, K(ty));
+    // the flash kernel reads K / V through tensor maps of exactly Tk rows (rows beyond are zero-filled by TMA): no padding needed
+    const int64_t Tka = use_flash ? Tk : Tkp;
+    Tensor ql = make(ty, { T, C }), kl = make(ty, { Tka, C }), vl = make(ty, { Tka, C }), out = make(ty, { 1, T, C });
+    if (Tka != Tk) {   // zero pad rows: they are read as extra (null) keys / values by the padded GEMMs
+        ck(cudaMemsetAsync((char*)kl.mdata() + Tk * C * es, 0, (Tka - Tk) * C * es, st), "cudaMemsetAsync");
+        ck(cudaMemsetAsync((char*)vl.mdata() + Tk * C * es, 0, (Tka - Tk) * C * es, st), "cudaMemsetAsync");
     }
-    ck(osb_gemm(x.data(), wq.data(), ql.mdata(), nullptr, nullptr, 1, T, C, x.shape[2], 0, 0, 0, 0, K(ty), E.gemm_impl, st), "osb_gemm(q)");
-    ck(osb_gemm(xk.data(), wk.data(), kl.mdata(), nullptr, nullptr, 1, Tk, C, xk.shape[2], 0, 0, 0, 0, K(ty), E.gemm_impl, st), "osb_gemm(k)");
-    ck(osb_gemm(xv.data(), wv.data(), vl.mdata(), nullptr, nullptr, 1, Tk, C, xv.shape[2], 0, 0, 0, 0, K(ty), E.gemm_impl, st), "osb_gemm(v)");
+    // projections: the ones that share their input run as one grouped launch (self-attention: q, k, v; cross-attention: k, v)
+    const bool kv_same = xk.data() == xv.data() && xk.shape == xv.shape && wk.shape == wv.shape;
+    const bool qkv_same = kv_same && x.data() == xk.data() && x.shape == xk.shape && wq.shape == wk.shape && T == Tk;
+    if (qkv_same) {
+        const void* Bs[3] = { wq.data(), wk.data(), wv.data() };
+        void* Cs[3] = { ql.mdata(), kl.mdata(), vl.mdata() };
+        ck(osb_gemm_grouped(x.data(), Bs, Cs, 3, T, C, x.shape[2], 0, K(ty), E.gemm_impl, st), "osb_gemm_grouped(qkv)");
+    } else {
+        ck(osb_gemm(x.data(), wq.data(), ql.mdata(), nullptr, nullptr, 1, T, C, x.shape[2], 0, 0, 0, 0, K(ty), E.gemm_impl, st), "osb_gemm(q)");
+        if (kv_same) {
+            const void* Bs[2] = { wk.data(), wv.data() };
+            void* Cs[2] = { kl.mdata(), vl.mdata() };
+            ck(osb_gemm_grouped(xk.data(), Bs, Cs, 2, Tk, C, xk.shape[2], 0, K(ty), E.gemm_impl, st), "osb_gemm_grouped(kv)");
+        } else {
+            ck(osb_gemm(xk.data(), wk.data(), kl.mdata(), nullptr, nullptr, 1, Tk, C, xk.shape[2], 0, 0, 0, 0, K(ty), E.gemm_impl, st), "osb_gemm(k)");
+            ck(osb_gemm(xv.data(), wv.data(), vl.mdata(), nullptr, nullptr, 1, Tk, C, xv.shape[2], 0, 0, 0, 0, K(ty), E.gemm_impl, st), "osb_gemm(v)");
+        }
+    }
 
-    if (E.flash_attention && E.gemm_impl != 1 && osb_flash_attention_ok(T, Tk, d, K(ty))) {
+    if (use_flash) {
         // one kernel: QK^T -> online softmax -> PV with the score tile in TMEM
         ck(osb_flash_attention(ql.data(), C, kl.data(), C, vl.data(), C, out.mdata(), C, h, T, Tk, d, scale, st), "osb_flash_attention");
         push(i + 19, 0, out);
@@ -1737,6 +1781,36 @@ void Engine::Impl::fused_gelu(const Step& s)
     }
 }
 
+void Engine::Impl::fused_geglu(const Step& s)
+{
+    size_t i = s.first;
+    Tensor x = in(i, 0);
+    auto whole = [&](size_t oi, int64_t lo, int64_t hi) {
+        Tensor st_ = in(oi, 1), en = in(oi, 2), ax = in(oi, 3), sp = in(oi, 4);
+        if (!st_.i64 || !en.i64 || !ax.i64 || !sp.i64 || st_.i64->size() != 1 || en.i64->size() != 1 || ax.i64->size() != 1 || sp.i64->size() != 1) return false;
+        int64_t a = (*ax.i64)[0], n = x.shape.empty() ? 0 : x.shape.back();
+        if (a < 0) a += (int64_t)x.shape.size();
+        int64_t b = (*st_.i64)[0], e = (*en.i64)[0];
+        if (b < 0) b += n; if (e < 0) e += n;
+        e = std::min(e, n);
+        return a == (int64_t)x.shape.size() - 1 && (*sp.i64)[0] == 1 && b == lo && e == hi;
+    };
+    int64_t n2 = x.shape.empty() ? 0 : x.shape.back(), inner = n2 / 2;
+    float c0 = scalar_of(in(i + 2, 1), E.m_ops[i + 2]), c1 = scalar_of(in(i + 4, 1), E.m_ops[i + 4]), c2 = scalar_of(in(i + 6, 1), E.m_ops[i + 6]);
+    bool ok = (x.type == DType::f16 || x.type == DType::f32) && x.layout == Layout::plain && n2 >= 2 && n2 % 2 == 0 &&
+              whole(i, 0, inner) && whole(i + 1, inner, n2) && std::fabs(c0 - 1.41421356f) <= 1e-3f && c1 == 1.f && c2 == 0.5f;
+    if (!ok) {
+        // not the two halves (or an unexpected constant): run the group with the ordinary handlers
+        Step a = s; a.kind = SK_SINGLE;
+        exec_unfused(a);
+        return;
+    }
+    std::vector<int64_t> os = x.shape; os.back() = inner;
+    Tensor y = make(x.type, os);
+    ck(osb_geglu(x.data(), y.mdata(), K(x.type), x.numel() / n2, inner, st), "osb_geglu");
+    push(i + 7, 0, y);
+}
+
 void Engine::Impl::fused_silu(const Step& s)
 {
     Tensor x = in(s.first, 0);
@@ -1818,6 +1892,7 @@ void Engine::Impl::exec_step(size_t si)
         case SK_GROUPNORM: fused_groupnorm(s); break;
         case SK_LAYERNORM: fused_layernorm(s); break;
         case SK_GELU: fused_gelu(s); break;
+        case SK_GEGLU: fused_geglu(s); break;
         case SK_SILU: fused_silu(s); break;
         case SK_LINEAR: fused_linear(s); break;
         case SK_SDPA: fused_sdpa(s); break;

@@ -53,6 +53,10 @@ struct TcParams {
     int split_k;                 // > 1: each tile's k-blocks are divided among split_k CTAs, fp32 partials go to `ws`
     float* ws;                   // split-K workspace [split][batch][M][N] fp32
     int* counters;               // split-K arrival counters, one per output tile (self-resetting)
+    // grouped launch (groups > 1): `batch` problems share A and the shape; problem g has its own B map (map_b, map_b1, map_b2) and output
+    int groups;
+    __half* C1;
+    __half* C2;
     // output
     __half* C;
     const __half* bias;
@@ -187,7 +191,8 @@ __device__ __forceinline__ uint32_t make_idesc(int b_mn_major, int bn)
 
 template <int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, STAGES <= STAGES_SHORT ? 2 : 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_b1,
+               const __grid_constant__ CUtensorMap map_b2, const TcParams p)
 {
     osb_pdl_trigger();   // let the next kernel's CTAs be scheduled as ours drain; it waits for our completion before touching memory
     extern __shared__ uint8_t smem_raw[];
@@ -243,6 +248,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 int n0 = nt * p.bn;
                 int y0 = 0, x0 = 0, m0 = mt * BLOCK_M;
                 if (p.taps > 1 || p.bh > 0) { y0 = (mt / p.tiles_x) * p.bh; x0 = (mt % p.tiles_x) * p.bw; }
+                // grouped launch: the batch index selects the B map; every operand is addressed at batch coordinate 0
+                const CUtensorMap* mbp = &map_b;
+                if (p.groups > 1) { if (b == 1) mbp = &map_b1; else if (b == 2) mbp = &map_b2; b = 0; }
                 int kb_lo = sp * kb_per_split, kb_hi = min(kb_lo + kb_per_split, k_blocks_all);
                 // (tap, channel block) walk incrementally: no divisions inside the k loop
                 int tap = kb_lo / p.k_blocks_per_tap, kcb = kb_lo % p.k_blocks_per_tap;
@@ -260,15 +268,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         else tma_load_3d_s(sa, &map_a, &full[stage], kc, m0, b);
                         const int kglob = tap * p.K + kc;   // K index into B (conv: taps are concatenated along K)
                         if (p.b_kmajor) {
-                            if (p.b_swap) tma_load_3d_s(sb, &map_b, &full[stage], kglob, b, n0);
-                            else tma_load_3d_s(sb, &map_b, &full[stage], kglob, n0, b);
+                            if (p.b_swap) tma_load_3d_s(sb, mbp, &full[stage], kglob, b, n0);
+                            else tma_load_3d_s(sb, mbp, &full[stage], kglob, n0, b);
                         } else {
                             if (p.b_swap) {
-                                tma_load_3d_s(sb, &map_b, &full[stage], n0, b, kglob);
-                                if (p.bn > 64) tma_load_3d_s(sb + B_STAGE_BYTES / 2, &map_b, &full[stage], n0 + 64, b, kglob);
+                                tma_load_3d_s(sb, mbp, &full[stage], n0, b, kglob);
+                                if (p.bn > 64) tma_load_3d_s(sb + B_STAGE_BYTES / 2, mbp, &full[stage], n0 + 64, b, kglob);
                             } else {
-                                tma_load_3d_s(sb, &map_b, &full[stage], n0, kglob, b);
-                                if (p.bn > 64) tma_load_3d_s(sb + B_STAGE_BYTES / 2, &map_b, &full[stage], n0 + 64, kglob, b);
+                                tma_load_3d_s(sb, mbp, &full[stage], n0, kglob, b);
+                                if (p.bn > 64) tma_load_3d_s(sb + B_STAGE_BYTES / 2, mbp, &full[stage], n0 + 64, kglob, b);
                             }
                         }
                     }
@@ -338,7 +346,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
-            __half* crow = p.C + (long long)b * p.stride_c + out_row * p.ldc;
+            __half* cbase = p.C;
+            if (p.groups > 1) cbase = b == 0 ? p.C : (b == 1 ? p.C1 : p.C2);    // stride_c == 0 in a grouped launch
+            __half* crow = cbase + (long long)b * p.stride_c + out_row * p.ldc;
             const __half* rrow = p.residual ? p.residual + (long long)b * p.stride_c + out_row * p.ldc : nullptr;
             float* wrow = p.split_k > 1 ? p.ws + (((long long)sp * p.batch + b) * p.M + out_row) * p.N : nullptr;
             const bool vec_ok = (p.N & 7) == 0;
@@ -596,8 +606,10 @@ bool inkernel_reduce()
     return v == 1;
 }
 
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st)
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st, const CUtensorMap* mb1p = nullptr, const CUtensorMap* mb2p = nullptr)
 {
+    const CUtensorMap& mb1 = mb1p ? *mb1p : mb;
+    const CUtensorMap& mb2 = mb2p ? *mb2p : mb;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<STAGES_DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(STAGES_DEEP));
@@ -619,8 +631,8 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cuda
         rec.M = p.M; rec.N = p.N; rec.K = p.K; rec.taps = p.taps; rec.batch = p.batch; rec.split = p.split_k; rec.conv = p.bh > 0;
         cudaEventRecord(rec.a, st);
     }
-    if (short_k) osb_launch((tc_gemm_kernel<STAGES_SHORT>), grid, NUM_THREADS, (size_t)smem_bytes_for(STAGES_SHORT), st, ma, mb, p);
-    else osb_launch((tc_gemm_kernel<STAGES_DEEP>), grid, NUM_THREADS, (size_t)smem_bytes_for(STAGES_DEEP), st, ma, mb, p);
+    if (short_k) osb_launch((tc_gemm_kernel<STAGES_SHORT>), grid, NUM_THREADS, (size_t)smem_bytes_for(STAGES_SHORT), st, ma, mb, mb1, mb2, p);
+    else osb_launch((tc_gemm_kernel<STAGES_DEEP>), grid, NUM_THREADS, (size_t)smem_bytes_for(STAGES_DEEP), st, ma, mb, mb1, mb2, p);
     if (p.split_k > 1 && !p.counters) {
         launched(1);
         long long total4 = (long long)p.batch * p.M * p.N / 4;
@@ -748,6 +760,40 @@ int osb_tc_gemm_launch(const void* A, const void* B, void* C, const void* bias, 
     p.counters = (p.split_k > 1 && p.N % 4 == 0 && p.ldc % 4 == 0 && (long long)p.m_tiles * p.n_tiles * p.batch * p.split_k <= num_sms() && inkernel_reduce()) ? g_counters : nullptr;
     p.short_k = short_k_hint(p.taps * p.k_blocks_per_tap, p.split_k);
     return launch(ma, mb, p, st);
+}
+
+// `groups` (2 or 3) GEMMs C_g = A * B_g that share A and the shape, in ONE launch (the q/k/v projections of an attention block):
+// three times the tiles per launch, one dependency instead of three.  No bias / residual / split-K.
+int osb_tc_gemm_grouped_launch(const void* A, const void* const* B, void* const* C, int groups, int64_t M, int64_t N, int64_t K, int bt, cudaStream_t st,
+                               int64_t lda, int64_t ldb, int64_t ldc)
+{
+    if (groups < 2 || groups > 3) return (int)cudaErrorInvalidValue;
+    CUtensorMap ma, mb[3];
+    int a_swap = 0, b_swap = 0;
+    if (!make_map_rb(&ma, A, (uint64_t)K, (uint64_t)M, 1, (uint64_t)lda * 2, (uint64_t)(M * lda) * 2, BLOCK_K, BLOCK_M, &a_swap)) return (int)cudaErrorInvalidValue;
+    int64_t m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    int bn = choose_bn(m_tiles, N, groups);
+    for (int g = 0; g < groups; g++) {
+        int sw = 0;
+        bool ok = bt ? make_map_rb(&mb[g], B[g], (uint64_t)K, (uint64_t)N, 1, (uint64_t)ldb * 2, (uint64_t)(N * ldb) * 2, BLOCK_K, (uint32_t)bn, &sw)
+                     : make_map_rb(&mb[g], B[g], (uint64_t)N, (uint64_t)K, 1, (uint64_t)ldb * 2, (uint64_t)(K * ldb) * 2, 64, BLOCK_K, &sw);
+        if (!ok || (g > 0 && sw != b_swap)) return (int)cudaErrorInvalidValue;
+        b_swap = sw;
+    }
+    TcParams p{};
+    p.M = (int)M; p.N = (int)N; p.K = (int)K; p.batch = groups; p.groups = groups;
+    p.bn = bn;
+    p.m_tiles = (int)m_tiles; p.n_tiles = (int)((N + bn - 1) / bn);
+    p.b_kmajor = bt ? 1 : 0;
+    p.a_swap = a_swap; p.b_swap = b_swap;
+    p.taps = 1; p.kw = 1; p.bh = 0; p.bw = 0; p.tiles_x = 1;
+    p.k_blocks_per_tap = (int)((K + BLOCK_K - 1) / BLOCK_K);
+    p.stride = 1;
+    p.C = (__half*)C[0]; p.C1 = (__half*)C[1]; p.C2 = (__half*)(groups > 2 ? C[2] : C[1]);
+    p.bias = nullptr; p.residual = nullptr; p.stride_c = 0; p.ldc = ldc;
+    p.split_k = 1; p.ws = g_ws; p.counters = nullptr;
+    p.short_k = short_k_hint(p.taps * p.k_blocks_per_tap, 1);
+    return launch(ma, mb[0], p, st, &mb[1], groups > 2 ? &mb[2] : &mb[1]);
 }
 
 bool osb_tc_conv_ok(int64_t H, int64_t W, int64_t Cin, int64_t Cout, int kh, int kw, int stride, const void* x, const void* w, const void* y)

@@ -156,6 +156,23 @@ __global__ void binary_rowcol_kernel(int op, const T* __restrict__ a, const T* _
     }
 }
 
+// GEGLU: x is [rows, 2*inner]; out[r, c] = x[r, c] * gelu_erf(x[r, inner + c]) -- the two Slices, the Erf chain and the Mul of
+// the feed-forward gate in one pass (same arithmetic as OSB_BIN_MUL_GELU on materialised halves)
+template <typename T, int VEC>
+__global__ void geglu_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t rows, int64_t inner)
+{
+    osb_pdl_prologue();
+    int64_t cvec = inner / VEC;
+    int64_t total = rows * cvec;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / cvec, c = (i % cvec) * VEC;
+        Vec<T, VEC> va = load_vec<T, VEC>(x + r * 2 * inner + c), vb = load_vec<T, VEC>(x + r * 2 * inner + inner + c), vo;
+#pragma unroll
+        for (int k = 0; k < VEC; k++) vo.v[k] = from_float<T>(apply_binary(OSB_BIN_MUL_GELU, to_float(va.v[k]), to_float(vb.v[k])));
+        store_vec<T, VEC>(out + r * inner + c, vo);
+    }
+}
+
 template <typename T>
 __global__ void binary_generic_kernel(int op, const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, BinParams p, size_t n)
 {
@@ -274,6 +291,54 @@ __global__ void layer_norm_kernel(const T* __restrict__ x, T* __restrict__ y, in
             if (gamma) o *= to_float(gamma[c]);
             if (beta) o += to_float(beta[c]);
             yr[c] = from_float<T>(o);
+        }
+    }
+}
+
+// LayerNorm, one warp per row, the row held in registers (cols <= 64 * LN_MAX_ITERS, cols even): one global read, shuffle
+// reductions only, same two-pass mean / variance arithmetic as the block kernel above.
+constexpr int LN_MAX_ITERS = 20;
+template <typename T>
+__global__ void __launch_bounds__(128)
+layer_norm_warp_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int cols,
+                       const T* __restrict__ gamma, const T* __restrict__ beta, float eps)
+{
+    osb_pdl_prologue();
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const T* xr = x + r * cols;
+    T* yr = y + r * cols;
+    float v[2 * LN_MAX_ITERS];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_ITERS; i++) {
+        int c = lane * 2 + i * 64;
+        if (c < cols) {
+            Vec<T, 2> t = load_vec<T, 2>(xr + c);
+            v[2 * i] = to_float(t.v[0]); v[2 * i + 1] = to_float(t.v[1]);
+            s += v[2 * i] + v[2 * i + 1];
+        } else { v[2 * i] = 0.f; v[2 * i + 1] = 0.f; }
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)cols;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_ITERS; i++) {
+        int c = lane * 2 + i * 64;
+        if (c < cols) { float d0 = v[2 * i] - mean, d1 = v[2 * i + 1] - mean; q += d0 * d0 + d1 * d1; }
+    }
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = 1.f / sqrtf(q / (float)cols + eps);
+#pragma unroll
+    for (int i = 0; i < LN_MAX_ITERS; i++) {
+        int c = lane * 2 + i * 64;
+        if (c < cols) {
+            float o0 = (v[2 * i] - mean) * rstd, o1 = (v[2 * i + 1] - mean) * rstd;
+            if (gamma) { Vec<T, 2> g = load_vec<T, 2>(gamma + c); o0 *= to_float(g.v[0]); o1 *= to_float(g.v[1]); }
+            if (beta) { Vec<T, 2> b = load_vec<T, 2>(beta + c); o0 += to_float(b.v[0]); o1 += to_float(b.v[1]); }
+            Vec<T, 2> w; w.v[0] = from_float<T>(o0); w.v[1] = from_float<T>(o1);
+            store_vec<T, 2>(yr + c, w);
         }
     }
 }
@@ -431,12 +496,18 @@ gn_fused_nhwc_kernel(const T* __restrict__ x, T* __restrict__ y, double* __restr
 #pragma unroll
             for (int k = 0; k < VEC; k++) { float f = to_float(v.v[k]); s[k] += f; q[k] += f * f; }
         }
+        // combine the channels of this vector that fall into the same group in registers first: 2 (not 2 * VEC) shared atomics
+        // per group touched -- the contended shared atomics were the longest phase of the kernel
+        int g_cur = (cv * VEC) / cpg;
+        float gs = 0.f, gq = 0.f;
 #pragma unroll
         for (int k = 0; k < VEC; k++) {
             int g = (cv * VEC + k) / cpg;
-            atomicAdd(&sm[2 * g], s[k]);
-            atomicAdd(&sm[2 * g + 1], q[k]);
+            if (g != g_cur) { atomicAdd(&sm[2 * g_cur], gs); atomicAdd(&sm[2 * g_cur + 1], gq); g_cur = g; gs = 0.f; gq = 0.f; }
+            gs += s[k]; gq += q[k];
         }
+        atomicAdd(&sm[2 * g_cur], gs);
+        atomicAdd(&sm[2 * g_cur + 1], gq);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(&stats[i], (double)sm[i]);
@@ -670,6 +741,21 @@ int osb_unary(int op, const void* x, void* y, int dtype, size_t n, float alpha, 
     return launched();
 }
 
+int osb_geglu(const void* x, void* y, int dtype, int64_t rows, int64_t inner, void* stream)
+{
+    if (rows * inner == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    bool al = aligned16(x) && aligned16(y);
+    if (dtype == OSB_F16) {
+        if (al && inner % 8 == 0) osb_launch((geglu_kernel<__half, 8>), grid_for((size_t)rows * (inner / 8), 256), 256, 0, st, (const __half*)x, (__half*)y, rows, inner);
+        else osb_launch((geglu_kernel<__half, 1>), grid_for((size_t)rows * inner, 256), 256, 0, st, (const __half*)x, (__half*)y, rows, inner);
+    } else if (dtype == OSB_F32) {
+        if (al && inner % 4 == 0) osb_launch((geglu_kernel<float, 4>), grid_for((size_t)rows * (inner / 4), 256), 256, 0, st, (const float*)x, (float*)y, rows, inner);
+        else osb_launch((geglu_kernel<float, 1>), grid_for((size_t)rows * inner, 256), 256, 0, st, (const float*)x, (float*)y, rows, inner);
+    } else return (int)cudaErrorInvalidValue;
+    return launched();
+}
+
 int osb_binary(int op, const void* a, const int64_t* as, const void* b, const int64_t* bs, void* out, const int64_t* shape, int ndim, int dtype, void* stream)
 {
     if (ndim < 1 || ndim > OSB_MAX_DIMS) return (int)cudaErrorInvalidValue;
@@ -754,6 +840,14 @@ int osb_layer_norm(const void* x, void* y, int dtype, int64_t rows, int64_t cols
 {
     if (rows * cols == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    const int esz = dtype == OSB_F16 ? 2 : 4;
+    auto al = [&](const void* p) { return p == nullptr || ((uintptr_t)p % (2 * esz)) == 0; };
+    if ((cols % 2) == 0 && cols <= 64 * LN_MAX_ITERS && rows >= 64 && al(x) && al(y) && al(gamma) && al(beta) && (dtype == OSB_F16 || dtype == OSB_F32)) {
+        unsigned grid_w = (unsigned)((rows + 3) / 4);
+        if (dtype == OSB_F16) osb_launch((layer_norm_warp_kernel<__half>), grid_w, 128, 0, st, (const __half*)x, (__half*)y, rows, (int)cols, (const __half*)gamma, (const __half*)beta, eps);
+        else osb_launch((layer_norm_warp_kernel<float>), grid_w, 128, 0, st, (const float*)x, (float*)y, rows, (int)cols, (const float*)gamma, (const float*)beta, eps);
+        return launched();
+    }
     int threads = cols >= 1024 ? 256 : (cols >= 256 ? 128 : 32);
     int grid = (int)min<int64_t>(rows, 148 * 16);
     if (dtype == OSB_F16) osb_launch((layer_norm_kernel<__half>), grid, threads, 0, st, (const __half*)x, (__half*)y, rows, cols, (const __half*)gamma, (const __half*)beta, eps);

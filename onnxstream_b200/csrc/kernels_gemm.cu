@@ -17,6 +17,8 @@ int osb_tc_gemm_launch(const void* A, const void* B, void* C, const void* bias, 
 int osb_tc_conv_launch(const void* x, const void* w, const void* bias, const void* residual, void* y,
                        int64_t H, int64_t W, int64_t Cin, int64_t Cout, int kh, int kw, int stride, int pad_top, int pad_left,
                        int64_t Ho, int64_t Wo, cudaStream_t st);
+int osb_tc_gemm_grouped_launch(const void* A, const void* const* B, void* const* C, int groups, int64_t M, int64_t N, int64_t K, int bt, cudaStream_t st,
+                               int64_t lda, int64_t ldb, int64_t ldc);
 bool osb_tc_gemm_ok(int64_t M, int64_t N, int64_t K, int b_transposed, const void* A, const void* B, const void* C, int64_t sa, int64_t sb, int64_t sc,
                     int64_t lda, int64_t ldb, int64_t ldc);
 bool osb_tc_conv_ok(int64_t H, int64_t W, int64_t Cin, int64_t Cout, int kh, int kw, int stride, const void* x, const void* w, const void* y);
@@ -422,6 +424,22 @@ extern "C" {
 int osb_gemm_tc_eligible(int64_t M, int64_t N, int64_t K, int dtype)
 {
     return dtype == OSB_F16 && osb_tc_gemm_ok(M, N, K, 0, nullptr, nullptr, nullptr, 0, 0, 0, K, N, N) ? 1 : 0;
+}
+
+int osb_gemm_grouped(const void* A, const void* const* B, void* const* C, int groups, int64_t M, int64_t N, int64_t K, int bt, int dtype, int impl, void* stream)
+{
+    if (groups < 1 || groups > 3) return (int)cudaErrorInvalidValue;
+    if (M * N == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t lda = K, ldb = bt ? K : N, ldc = N;
+    bool tc_ok = groups >= 2 && dtype == OSB_F16 && impl != 1;
+    for (int g = 0; g < groups && tc_ok; g++) tc_ok = osb_tc_gemm_ok(M, N, K, bt, A, B[g], C[g], 0, 0, 0, lda, ldb, ldc);
+    if (tc_ok) return osb_tc_gemm_grouped_launch(A, B, C, groups, M, N, K, bt, st, lda, ldb, ldc);
+    for (int g = 0; g < groups; g++) {
+        int r = osb_gemm(A, B[g], C[g], nullptr, nullptr, 1, M, N, K, 0, 0, 0, bt, dtype, impl, stream);
+        if (r) return r;
+    }
+    return 0;
 }
 
 int osb_gemm(const void* A, const void* B, void* C, const void* bias, const void* residual, int64_t batch, int64_t M, int64_t N, int64_t K,

@@ -244,3 +244,98 @@ def test_flash_attention(K, T, Tk, h, d):
     tol = absref * 2.0 ** -8 + ref.abs() * 2.0 ** -9 + 1e-4
     assert not torch.isnan(o).any()
     assert not (err > tol).any(), f"max err {float(err.max()):.4g}, ref max {float(ref.abs().max()):.4g}, bad {(err > tol).sum().item()}"
+
+
+@pytest.mark.parametrize("dtype", [F16, F32])
+@pytest.mark.parametrize("rows,cols", [(4096, 320), (1024, 640), (256, 1280), (77, 768), (64, 1282), (33, 7), (5, 2048)])
+def test_layer_norm(K, dtype, rows, cols):
+    """Warp-per-row (register-resident) and block-per-row LayerNorm against fp64 math on the same inputs."""
+    import torch
+    torch.manual_seed(rows * 31 + cols)
+    td = torch.float16 if dtype == F16 else torch.float32
+    x = (torch.randn(rows, cols, device="cuda") * 3 + 0.5).to(td)
+    g = torch.randn(cols, device="cuda").to(td)
+    b = torch.randn(cols, device="cuda").to(td)
+    y = torch.full((rows, cols), float("nan"), device="cuda", dtype=td)
+    vp, i64, ci, cf = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
+    K.osb_layer_norm.argtypes = [vp, vp, ci, i64, i64, vp, vp, cf, vp]
+    rc = K.osb_layer_norm(x.data_ptr(), y.data_ptr(), dtype, rows, cols, g.data_ptr(), b.data_ptr(), 1e-5, _stream())
+    torch.cuda.synchronize()
+    assert rc == 0
+    xd = x.double()
+    ref = (xd - xd.mean(1, keepdim=True)) / torch.sqrt(xd.var(1, unbiased=False, keepdim=True) + 1e-5) * g.double() + b.double()
+    tol = (2.0 ** -10 if dtype == F16 else 2.0 ** -20) * (ref.abs() + 4.0)
+    err = (y.double() - ref).abs()
+    assert not (err > tol).any(), f"max err {float(err.max()):.4g}"
+
+
+@pytest.mark.parametrize("dtype", [F16, F32])
+@pytest.mark.parametrize("C,HW,silu", [(320, 4096, 1), (640, 1024, 1), (1280, 64, 0), (2560, 256, 1), (960, 4096, 1), (32, 256, 0)])
+def test_group_norm_nhwc(K, dtype, C, HW, silu):
+    """GroupNorm(32) (+SiLU) on NHWC activations: single-launch rendezvous kernel / two-pass fallback vs fp64 math."""
+    import torch
+    torch.manual_seed(C + HW)
+    td = torch.float16 if dtype == F16 else torch.float32
+    x = (torch.randn(HW, C, device="cuda") * 2 + 0.25).to(td)
+    g = torch.randn(C, device="cuda").to(td)
+    b = torch.randn(C, device="cuda").to(td)
+    y = torch.full((HW, C), float("nan"), device="cuda", dtype=td)
+    scratch = torch.zeros(2048, device="cuda", dtype=torch.uint8)
+    vp, i64, ci, cf = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
+    K.osb_group_norm.argtypes = [vp, vp, ci, ci, i64, i64, ci, vp, vp, cf, ci, vp, vp]
+    for _ in range(2):     # second launch checks that the kernel re-armed its scratch
+        rc = K.osb_group_norm(x.data_ptr(), y.data_ptr(), dtype, 1, C, HW, 32, g.data_ptr(), b.data_ptr(), 1e-5, silu, scratch.data_ptr(), _stream())
+        assert rc == 0
+    torch.cuda.synchronize()
+    xd = x.double().view(HW, 32, C // 32)
+    mean = xd.mean(dim=(0, 2), keepdim=True)
+    var = xd.var(dim=(0, 2), unbiased=False, keepdim=True)
+    ref = ((xd - mean) / torch.sqrt(var + 1e-5)).view(HW, C) * g.double() + b.double()
+    if silu:
+        ref = ref * torch.sigmoid(ref)
+    tol = (2.0 ** -9 if dtype == F16 else 2.0 ** -18) * (ref.abs() + 4.0)
+    err = (y.double() - ref).abs()
+    assert not (err > tol).any(), f"max err {float(err.max()):.4g}"
+
+
+@pytest.mark.parametrize("groups,M,N,Kd", [(3, 4096, 320, 320), (3, 1024, 640, 640), (2, 77, 1280, 768), (3, 256, 1280, 1280), (2, 64, 1280, 1280), (3, 200, 136, 72)])
+def test_gemm_grouped(K, groups, M, N, Kd):
+    """q/k/v projections as one grouped tcgen05 launch: every member must equal its stand-alone GEMM reference."""
+    import torch
+    torch.manual_seed(M + N + Kd)
+    a = torch.randn(M, Kd, device="cuda").half()
+    bs = [torch.randn(Kd, N, device="cuda").half() for _ in range(groups)]
+    cs = [torch.full((M, N), float("nan"), device="cuda", dtype=torch.half) for _ in range(groups)]
+    vp, i64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    K.osb_gemm_grouped.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ci, i64, i64, i64, ci, ci, ci, vp]
+    B = (vp * groups)(*[b.data_ptr() for b in bs])
+    C = (vp * groups)(*[c.data_ptr() for c in cs])
+    K.osb_launch_count_reset()
+    rc = K.osb_gemm_grouped(a.data_ptr(), B, C, groups, M, N, Kd, 0, F16, 0, _stream())
+    torch.cuda.synchronize()
+    assert rc == 0
+    if N % 8 == 0 and Kd % 8 == 0 and M >= 32:
+        assert K.osb_tc_launch_count() == 1, "expected ONE tcgen05 launch for the whole group"
+    for g in range(groups):
+        ref = a.double() @ bs[g].double()
+        absref = a.double().abs() @ bs[g].double().abs()
+        _check(cs[g], ref, absref, f"grouped gemm member {g}")
+
+
+@pytest.mark.parametrize("dtype", [F16, F32])
+@pytest.mark.parametrize("rows,inner", [(4096, 1280), (256, 5120), (77, 12), (5, 7)])
+def test_geglu(K, dtype, rows, inner):
+    import torch
+    torch.manual_seed(rows + inner)
+    td = torch.float16 if dtype == F16 else torch.float32
+    x = (torch.randn(rows, 2 * inner, device="cuda") * 2).to(td)
+    y = torch.full((rows, inner), float("nan"), device="cuda", dtype=td)
+    vp, i64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    K.osb_geglu.argtypes = [vp, vp, ci, i64, i64, vp]
+    assert K.osb_geglu(x.data_ptr(), y.data_ptr(), dtype, rows, inner, _stream()) == 0
+    torch.cuda.synchronize()
+    xd = x.double()
+    gate = xd[:, inner:]
+    ref = xd[:, :inner] * (0.5 * gate * (1.0 + torch.erf(gate / 2.0 ** 0.5)))
+    tol = (2.0 ** -10 if dtype == F16 else 2.0 ** -20) * (ref.abs() + 1.0)
+    assert not ((y.double() - ref).abs() > tol).any()
