@@ -244,5 +244,6 @@ private:
 };
 
 void check_cuda(int err, const char* what);
+void* pinned_alloc(size_t bytes, const char* what);   // page-locked host memory on the NUMA node local to the current device
 
 }  // namespace osb
