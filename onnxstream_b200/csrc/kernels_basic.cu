@@ -295,10 +295,11 @@ __global__ void layer_norm_kernel(const T* __restrict__ x, T* __restrict__ y, in
     }
 }
 
-// LayerNorm, one warp per row, the row held in registers (cols <= 64 * LN_MAX_ITERS, cols even): one global read, shuffle
-// reductions only, same two-pass mean / variance arithmetic as the block kernel above.
+// LayerNorm, one warp per row, the row held in registers (cols <= 64 * ITERS, cols even): one global read, shuffle reductions
+// only, same two-pass mean / variance arithmetic as the block kernel above.  Every load of a phase is issued before the first
+// use (a load inside an `if (c < cols) { ...accumulate... }` body serialises the row on memory latency -- measured 2x slower).
 constexpr int LN_MAX_ITERS = 20;
-template <typename T>
+template <typename T, int ITERS>
 __global__ void __launch_bounds__(128)
 layer_norm_warp_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int cols,
                        const T* __restrict__ gamma, const T* __restrict__ beta, float eps)
@@ -309,37 +310,43 @@ layer_norm_warp_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows,
     if (r >= rows) return;
     const T* xr = x + r * cols;
     T* yr = y + r * cols;
-    float v[2 * LN_MAX_ITERS];
+    Vec<T, 2> raw[ITERS], gr[ITERS], br[ITERS];
+#pragma unroll
+    for (int i = 0; i < ITERS; i++) {
+        int c = lane * 2 + i * 64;
+        raw[i].v[0] = from_float<T>(0.f); raw[i].v[1] = from_float<T>(0.f);
+        if (c < cols) raw[i] = load_vec<T, 2>(xr + c);
+    }
+#pragma unroll
+    for (int i = 0; i < ITERS; i++) {
+        int c = lane * 2 + i * 64;
+        gr[i].v[0] = from_float<T>(1.f); gr[i].v[1] = from_float<T>(1.f);
+        br[i].v[0] = from_float<T>(0.f); br[i].v[1] = from_float<T>(0.f);
+        if (gamma && c < cols) gr[i] = load_vec<T, 2>(gamma + c);
+        if (beta && c < cols) br[i] = load_vec<T, 2>(beta + c);
+    }
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_ITERS; i++) {
-        int c = lane * 2 + i * 64;
-        if (c < cols) {
-            Vec<T, 2> t = load_vec<T, 2>(xr + c);
-            v[2 * i] = to_float(t.v[0]); v[2 * i + 1] = to_float(t.v[1]);
-            s += v[2 * i] + v[2 * i + 1];
-        } else { v[2 * i] = 0.f; v[2 * i + 1] = 0.f; }
-    }
+    for (int i = 0; i < ITERS; i++) s += to_float(raw[i].v[0]) + to_float(raw[i].v[1]);   // padding lanes hold zeros
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mean = s / (float)cols;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_ITERS; i++) {
+    for (int i = 0; i < ITERS; i++) {
         int c = lane * 2 + i * 64;
-        if (c < cols) { float d0 = v[2 * i] - mean, d1 = v[2 * i + 1] - mean; q += d0 * d0 + d1 * d1; }
+        float d0 = to_float(raw[i].v[0]) - mean, d1 = to_float(raw[i].v[1]) - mean;
+        q += c < cols ? d0 * d0 + d1 * d1 : 0.f;
     }
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rstd = 1.f / sqrtf(q / (float)cols + eps);
 #pragma unroll
-    for (int i = 0; i < LN_MAX_ITERS; i++) {
+    for (int i = 0; i < ITERS; i++) {
         int c = lane * 2 + i * 64;
-        if (c < cols) {
-            float o0 = (v[2 * i] - mean) * rstd, o1 = (v[2 * i + 1] - mean) * rstd;
-            if (gamma) { Vec<T, 2> g = load_vec<T, 2>(gamma + c); o0 *= to_float(g.v[0]); o1 *= to_float(g.v[1]); }
-            if (beta) { Vec<T, 2> b = load_vec<T, 2>(beta + c); o0 += to_float(b.v[0]); o1 += to_float(b.v[1]); }
-            Vec<T, 2> w; w.v[0] = from_float<T>(o0); w.v[1] = from_float<T>(o1);
-            store_vec<T, 2>(yr + c, w);
-        }
+        float o0 = (to_float(raw[i].v[0]) - mean) * rstd, o1 = (to_float(raw[i].v[1]) - mean) * rstd;
+        if (gamma) { o0 *= to_float(gr[i].v[0]); o1 *= to_float(gr[i].v[1]); }
+        if (beta) { o0 += to_float(br[i].v[0]); o1 += to_float(br[i].v[1]); }
+        Vec<T, 2> w; w.v[0] = from_float<T>(o0); w.v[1] = from_float<T>(o1);
+        if (c < cols) store_vec<T, 2>(yr + c, w);
     }
 }
 
@@ -844,8 +851,10 @@ int osb_layer_norm(const void* x, void* y, int dtype, int64_t rows, int64_t cols
     auto al = [&](const void* p) { return p == nullptr || ((uintptr_t)p % (2 * esz)) == 0; };
     if ((cols % 2) == 0 && cols <= 64 * LN_MAX_ITERS && rows >= 64 && al(x) && al(y) && al(gamma) && al(beta) && (dtype == OSB_F16 || dtype == OSB_F32)) {
         unsigned grid_w = (unsigned)((rows + 3) / 4);
-        if (dtype == OSB_F16) osb_launch((layer_norm_warp_kernel<__half>), grid_w, 128, 0, st, (const __half*)x, (__half*)y, rows, (int)cols, (const __half*)gamma, (const __half*)beta, eps);
-        else osb_launch((layer_norm_warp_kernel<float>), grid_w, 128, 0, st, (const float*)x, (float*)y, rows, (int)cols, (const float*)gamma, (const float*)beta, eps);
+#define OSB_LN_LAUNCH(T_, IT_) osb_launch((layer_norm_warp_kernel<T_, IT_>), grid_w, 128, 0, st, (const T_*)x, (T_*)y, rows, (int)cols, (const T_*)gamma, (const T_*)beta, eps)
+        if (dtype == OSB_F16) { if (cols <= 320) OSB_LN_LAUNCH(__half, 5); else if (cols <= 640) OSB_LN_LAUNCH(__half, 10); else OSB_LN_LAUNCH(__half, LN_MAX_ITERS); }
+        else { if (cols <= 320) OSB_LN_LAUNCH(float, 5); else if (cols <= 640) OSB_LN_LAUNCH(float, 10); else OSB_LN_LAUNCH(float, LN_MAX_ITERS); }
+#undef OSB_LN_LAUNCH
         return launched();
     }
     int threads = cols >= 1024 ? 256 : (cols >= 256 ? 128 : 32);

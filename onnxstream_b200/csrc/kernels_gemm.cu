@@ -203,7 +203,8 @@ skinny_gemm_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restri
 // rounds to the storage type.  Reads every weight exactly once.
 template <typename T, int MAXM>
 __global__ void __launch_bounds__(128)
-gemv_panel_kernel(const T* __restrict__ A, const T* __restrict__ B, float* __restrict__ acc_out, int M, int N, int K, int k_per_cta)
+gemv_panel_kernel(const T* __restrict__ A, const T* __restrict__ B, float* __restrict__ acc_out, int M, int N, int K, int k_per_cta,
+                  int* __restrict__ counters, T* __restrict__ C, const T* __restrict__ bias, const T* __restrict__ residual)
 {
     osb_pdl_prologue();
     constexpr int VEC = 16 / sizeof(T);           // columns per thread
@@ -244,19 +245,27 @@ gemv_panel_kernel(const T* __restrict__ A, const T* __restrict__ B, float* __res
         for (int j = 0; j < 4; j++) v += red[j][m][c];
         atomicAdd(&acc_out[(int64_t)m * N + n], v);
     }
-}
-
-template <typename T>
-__global__ void gemv_finalize_kernel(const float* __restrict__ acc, T* __restrict__ C, const T* __restrict__ bias, const T* __restrict__ residual, int M, int N)
-{
-    osb_pdl_prologue();
-    int total = M * N;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        float v = acc[i];
-        if (bias) v += to_float(bias[i % N]);
-        if (residual) v += to_float(residual[i]);
-        C[i] = from_float<T>(v);
+    // The last K-slice CTA of this column panel to arrive finishes the panel: fp32 sums (+ bias, + residual) -> one rounding ->
+    // C, and re-arms the scratch (zero sums, zero counter) for the next launch.  One graph node per GEMV instead of
+    // memset + panel + finalize.
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(&counters[blockIdx.x], 1) == (int)gridDim.y - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < M * COLS; i += 128) {
+        int m = i / COLS, c = i % COLS;
+        int n = blockIdx.x * COLS + c;
+        if (n >= N) continue;
+        float v = __ldcg(&acc_out[(int64_t)m * N + n]);
+        acc_out[(int64_t)m * N + n] = 0.f;
+        if (bias) v += to_float(bias[n]);
+        if (residual) v += to_float(residual[(int64_t)m * N + n]);
+        C[(int64_t)m * N + n] = from_float<T>(v);
     }
+    if (threadIdx.x == 0) counters[blockIdx.x] = 0;
 }
 
 // ---- softmax with scale + additive mask (score tile of the attention decomposition) ---------------------------
@@ -462,8 +471,11 @@ int osb_gemm_ld(const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
     ConvGeom g{};
     if (dense && M <= 8 && batch == 1 && !bt && N % 8 == 0 && aligned16(B) && N >= 256 && K >= 64) {
         // weight-bandwidth path
+        // scratch: fp32 sums [M][N] followed by one arrival counter per column panel; zeroed when allocated, re-armed by the kernel
         static float* scratch = nullptr; static size_t scratch_n = 0;
-        size_t need = (size_t)M * N;
+        int vec = dtype == OSB_F16 ? 8 : 4, cols = 32 * vec;
+        int gx = (int)((N + cols - 1) / cols);
+        size_t need = (size_t)M * N + (size_t)gx;
         if (need > scratch_n) {
             cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
             cudaStreamIsCapturing(st, &cs);
@@ -471,21 +483,19 @@ int osb_gemm_ld(const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
             if (scratch) { cudaStreamSynchronize(st); cudaFree(scratch); }
             scratch_n = std::max<size_t>(need, 1 << 20);
             if (cudaMalloc(&scratch, scratch_n * 4) != cudaSuccess) { scratch = nullptr; scratch_n = 0; return (int)cudaErrorMemoryAllocation; }
+            if (cudaMemsetAsync(scratch, 0, scratch_n * 4, st) != cudaSuccess) return (int)cudaErrorUnknown;
         }
-        cudaError_t e = cudaMemsetAsync(scratch, 0, need * 4, st);
-        if (e != cudaSuccess) return (int)e;
-        int vec = dtype == OSB_F16 ? 8 : 4, cols = 32 * vec;
-        int gx = (int)((N + cols - 1) / cols);
+        // counters live at a fixed offset (end of the buffer) so that a different N never aliases un-armed sums
+        int* counters = (int*)(scratch + scratch_n) - 4096;
+        if (gx > 4096 || (size_t)M * N > scratch_n - 4096) return (int)cudaErrorInvalidValue;
         int gy = (int)max<int64_t>(1, min<int64_t>((K + 15) / 16, (592 + gx - 1) / gx));
         int k_per = (int)((K + gy - 1) / gy);
         gy = (int)((K + k_per - 1) / k_per);
         dim3 grid(gx, gy);
-        if (dtype == OSB_F16) osb_launch((gemv_panel_kernel<__half, 8>), grid, 128, 0, st, (const __half*)A, (const __half*)B, scratch, (int)M, (int)N, (int)K, k_per);
-        else osb_launch((gemv_panel_kernel<float, 8>), grid, 128, 0, st, (const float*)A, (const float*)B, scratch, (int)M, (int)N, (int)K, k_per);
-        launched();
-        int fg = (int)min<int64_t>((M * N + 255) / 256, 148 * 4);
-        if (dtype == OSB_F16) osb_launch((gemv_finalize_kernel<__half>), fg, 256, 0, st, scratch, (__half*)C, (const __half*)bias, (const __half*)residual, (int)M, (int)N);
-        else osb_launch((gemv_finalize_kernel<float>), fg, 256, 0, st, scratch, (float*)C, (const float*)bias, (const float*)residual, (int)M, (int)N);
+        if (dtype == OSB_F16) osb_launch((gemv_panel_kernel<__half, 8>), grid, 128, 0, st, (const __half*)A, (const __half*)B, scratch, (int)M, (int)N, (int)K, k_per,
+                                         counters, (__half*)C, (const __half*)bias, (const __half*)residual);
+        else osb_launch((gemv_panel_kernel<float, 8>), grid, 128, 0, st, (const float*)A, (const float*)B, scratch, (int)M, (int)N, (int)K, k_per,
+                        counters, (float*)C, (const float*)bias, (const float*)residual);
         return launched();
     }
     if (dense && M <= 8 && batch == 1) {
