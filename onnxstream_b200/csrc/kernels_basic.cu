@@ -481,7 +481,7 @@ __global__ void gn_stats_nhwc_vec_kernel(const T* __restrict__ x, double* __rest
 // which is still L2-resident.  The scratch (2*G doubles + 2 counters) is zero on entry and the last CTA out re-zeroes it, so
 // a CUDA graph needs a single node per GroupNorm instead of memset + 2 kernels.
 template <typename T, int VEC>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(512, 1)
 gn_fused_nhwc_kernel(const T* __restrict__ x, T* __restrict__ y, double* __restrict__ stats, int* __restrict__ counters,
                      int C, int64_t HW, int groups, int64_t pix_per_cta, const T* __restrict__ gamma, const T* __restrict__ beta, float eps, int silu)
 {
@@ -923,15 +923,19 @@ int osb_group_norm(const void* x, void* y, int dtype, int nhwc, int64_t C, int64
         int vec = dtype == OSB_F16 ? 8 : 4;
         static int fused_ok = -1;
         if (fused_ok < 0) { const char* e = getenv("OSB_GN_FUSED"); fused_ok = (e && e[0] == '0') ? 0 : 1; }
-        if (fused_ok && nhwc && groups <= 48 && C % vec == 0 && C / vec <= 256 && aligned16(x) && aligned16(y) && (dtype == OSB_F16 || dtype == OSB_F32)) {
+        if (fused_ok && nhwc && groups <= 48 && C % vec == 0 && C / vec <= 512 && aligned16(x) && aligned16(y) && (dtype == OSB_F16 || dtype == OSB_F32)) {
             double* fstats = (double*)((char*)stats_ + 1024);
             int* counters = (int*)((char*)stats_ + 1920);
-            int64_t c2 = std::min<int64_t>(HW, 148 * 2);
+            // one CTA per SM by default (every CTA must be co-resident for the rendezvous; fewer CTAs = fewer same-address atomics)
+            static const int cta_cap = [] { const char* e = getenv("OSB_GN_CTAS"); int v = e ? atoi(e) : 0; return v > 0 ? v : 148; }();
+            int threads = C / vec <= 256 ? 256 : 512;
+            // co-residency bound: 512-thread CTAs are only guaranteed one slot per SM, 256-thread CTAs two
+            int64_t c2 = std::min<int64_t>(HW, std::min(cta_cap, threads == 512 ? 148 : 296));
             int64_t ppc2 = (HW + c2 - 1) / c2;
             c2 = (HW + ppc2 - 1) / ppc2;
             size_t smem = sizeof(float) * 2 * groups;
-            if (dtype == OSB_F16) osb_launch((gn_fused_nhwc_kernel<__half, 8>), (unsigned)c2, 256, smem, st, (const __half*)x, (__half*)y, fstats, counters, (int)C, HW, groups, ppc2, (const __half*)gamma, (const __half*)beta, eps, fuse_silu);
-            else osb_launch((gn_fused_nhwc_kernel<float, 4>), (unsigned)c2, 256, smem, st, (const float*)x, (float*)y, fstats, counters, (int)C, HW, groups, ppc2, (const float*)gamma, (const float*)beta, eps, fuse_silu);
+            if (dtype == OSB_F16) osb_launch((gn_fused_nhwc_kernel<__half, 8>), (unsigned)c2, threads, smem, st, (const __half*)x, (__half*)y, fstats, counters, (int)C, HW, groups, ppc2, (const __half*)gamma, (const __half*)beta, eps, fuse_silu);
+            else osb_launch((gn_fused_nhwc_kernel<float, 4>), (unsigned)c2, threads, smem, st, (const float*)x, (float*)y, fstats, counters, (int)C, HW, groups, ppc2, (const float*)gamma, (const float*)beta, eps, fuse_silu);
             return launched();
         }
     }
