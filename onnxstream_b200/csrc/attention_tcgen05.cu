@@ -28,8 +28,9 @@ constexpr int Q_BYTES = BQ * BD * 2;    // 16 KiB
 constexpr int K_BYTES = BKV * BD * 2;   // 16 KiB
 constexpr int V_BYTES = BKV * BD * 2;   // 16 KiB (128 key rows x 64 columns)
 constexpr int P_BYTES = BQ * BKV * 2;   // 32 KiB (two 64-key k-blocks)
-constexpr int FA_SMEM = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + P_BYTES + 1024 + 256;
-constexpr int FA_THREADS = 192;
+constexpr int XCHG_BYTES = 2 * 2 * BQ * 4;   // half-row maxima / sums exchanged between the two warps of a row quadrant (double-buffered)
+constexpr int FA_SMEM = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + P_BYTES + 1024 + 256 + XCHG_BYTES;
+constexpr int FA_THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 softmax (two per TMEM lane quadrant)
 constexpr int TMEM_COLS_FA = 512;       // S0 [0,128) S1 [128,256) O [256,320)
 constexpr int O_COL = 256;
 
@@ -164,6 +165,7 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     uint64_t* p_full = bars + 9;             // [1]
     uint64_t* pv_done = bars + 10;           // [1]
     uint32_t* tmem_slot = (uint32_t*)(bars + 11);
+    float* xchg = (float*)((uint8_t*)bars + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, head = blockIdx.y;
@@ -176,8 +178,8 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     }
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
-        for (int i = 0; i < 2; i++) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 128); }
-        mbar_init(p_full, 128);
+        for (int i = 0; i < 2; i++) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 256); }
+        mbar_init(p_full, 256);
         mbar_init(pv_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -257,44 +259,53 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             }
         }
     } else {
-        // ===================== softmax / correction / epilogue (warps 2..5): thread = query row =====================
+        // ===================== softmax / correction / epilogue (warps 2..9) =====================
+        // Two warps per TMEM lane quadrant: warp w and w + 4 own the same 32 query rows and split the 128 keys of a tile (and the
+        // 64 columns of O) in halves, so every SM sub-partition has two softmax warps to interleave (one warp alone left the SFU
+        // idle while it waited on TMEM loads / fences).  Per tile the pair exchanges its half-row maxima through shared memory
+        // (one 64-thread named barrier); the row sums stay per half (same running maximum) and are added once at the end.
         const int qd = warp & 3;
+        const int half = (warp - 2) >> 2;             // 0: keys [0,64) of the tile, O columns [0,32); 1: the other halves
         const int row = qd * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+        const int bar_id = 1 + qd;                    // named barrier of this pair (0 is __syncthreads)
         float m_run = -INFINITY, l_run = 0.f;
         for (int j = 0; j < n_kv; j++) {
             int st = j & 1;
             mbar_wait(&s_full[st], (j >> 1) & 1);
             tc_fence_after();
-            const uint32_t s_addr = tmem_base + lane_addr + (uint32_t)(st * BKV);
-            const int key0 = j * BKV;
-            // one TMEM pass: the whole 128-key row of S into registers (4 loads in flight, one wait)
-            uint32_t sv[128];
+            const uint32_t s_addr = tmem_base + lane_addr + (uint32_t)(st * BKV + half * 64);
+            const int key0 = j * BKV + half * 64;
+            uint32_t sv[64];
             tmem_ld32_nowait(s_addr, sv);
             tmem_ld32_nowait(s_addr + 32, sv + 32);
-            tmem_ld32_nowait(s_addr + 64, sv + 64);
-            tmem_ld32_nowait(s_addr + 96, sv + 96);
             tmem_ld_wait();
-            const bool tail = key0 + BKV > p.Tk;          // only the last tile has padding keys (K rows zero-filled by TMA)
+            const bool tail = key0 + 64 > p.Tk;           // only the last tile has padding keys (K rows zero-filled by TMA)
             // Two uniform code paths: the full-tile path carries no per-element predicates (measured: the predicated single path
             // spent ~20 issue slots per score, the SFU needs 8).
             float mt = -INFINITY;
             if (!tail) {
 #pragma unroll
-                for (int t = 0; t < 128; t++) mt = fmaxf(mt, __uint_as_float(sv[t]));
+                for (int t = 0; t < 64; t++) mt = fmaxf(mt, __uint_as_float(sv[t]));
             } else {
 #pragma unroll
-                for (int t = 0; t < 128; t++) if (key0 + t < p.Tk) mt = fmaxf(mt, __uint_as_float(sv[t]));
+                for (int t = 0; t < 64; t++) if (key0 + t < p.Tk) mt = fmaxf(mt, __uint_as_float(sv[t]));
             }
+            // exchange the half-row maxima (double-buffered by tile parity: one barrier per tile is enough)
+            float* xw = xchg + ((j & 1) * 2 + half) * BQ;
+            float* xr = xchg + ((j & 1) * 2 + (half ^ 1)) * BQ;
+            xw[row] = mt;
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            mt = fmaxf(mt, xr[row]);
             const float m_new = fmaxf(m_run, mt * p.scale_log2);      // scale_log2 > 0
             const float alpha = ex2_approx(m_run - m_new);            // 0 on the first tile (m_run = -inf)
             const float neg_m = -m_new;
             // p = 2^(s*scale*log2e - m_new): one FFMA + one MUFU.EX2 per score, packed to fp16 as produced
-            uint32_t pk[64];
+            uint32_t pk[32];
             float lsum0 = 0.f, lsum1 = 0.f;
             if (!tail) {
 #pragma unroll
-                for (int t = 0; t < 128; t += 2) {
+                for (int t = 0; t < 64; t += 2) {
                     float p0 = ex2_approx(fmaf(__uint_as_float(sv[t]), p.scale_log2, neg_m));
                     float p1 = ex2_approx(fmaf(__uint_as_float(sv[t + 1]), p.scale_log2, neg_m));
                     lsum0 += p0; lsum1 += p1;
@@ -303,7 +314,7 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 }
             } else {
 #pragma unroll
-                for (int t = 0; t < 128; t += 2) {
+                for (int t = 0; t < 64; t += 2) {
                     float p0 = key0 + t < p.Tk ? ex2_approx(fmaf(__uint_as_float(sv[t]), p.scale_log2, neg_m)) : 0.f;
                     float p1 = key0 + t + 1 < p.Tk ? ex2_approx(fmaf(__uint_as_float(sv[t + 1]), p.scale_log2, neg_m)) : 0.f;
                     lsum0 += p0; lsum1 += p1;
@@ -314,46 +325,50 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             const float lsum = lsum0 + lsum1;
             tc_fence_before();
             mbar_arrive(&s_empty[st]);                   // S[st] may be overwritten by QK^T of tile j+2
-            l_run = l_run * alpha + lsum;
+            l_run = l_run * alpha + lsum;                // partial sum over this warp's key halves
             m_run = m_new;
             if (j > 0) {
                 // PV of the previous tile must have retired: O is stable and the P buffer is free
                 mbar_wait(pv_done, (j - 1) & 1);
                 tc_fence_after();
-                // rescale this row of O -- skipped when no row of the warp moved its maximum (the common case after a few tiles)
-                if (__any_sync(0xffffffffu, alpha != 1.f))
-#pragma unroll 1
-                for (int c = 0; c < BD; c += 32) {
+                // rescale this warp's 32 columns of O -- skipped when no row of the warp moved its maximum (the common case after a
+                // few tiles; both warps of a pair see the same alpha)
+                if (__any_sync(0xffffffffu, alpha != 1.f)) {
                     uint32_t o[32];
-                    tmem_ld32(tmem_base + lane_addr + O_COL + c, o);
+                    tmem_ld32(tmem_base + lane_addr + O_COL + half * 32, o);
 #pragma unroll
                     for (int t = 0; t < 32; t++) o[t] = __float_as_uint(__uint_as_float(o[t]) * alpha);
-                    tmem_st32(tmem_base + lane_addr + O_COL + c, o);
+                    tmem_st32(tmem_base + lane_addr + O_COL + half * 32, o);
                 }
             }
-            // P row -> shared memory, K-major SWIZZLE_128B: k-block kb = key/64, 16-byte chunk index XOR (row % 8)
+            // P half-row -> shared memory, K-major SWIZZLE_128B: k-block = this warp's key half, 16-byte chunk index XOR (row % 8)
             {
-                const uint32_t prow = smem_u32(sP) + row * 128;
+                const uint32_t prow = smem_u32(sP) + row * 128 + half * (P_BYTES / 2);
 #pragma unroll
-                for (int ch = 0; ch < 16; ch++) {
-                    int kb = ch >> 3, c8 = ch & 7;
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + kb * (P_BYTES / 2) + ((c8 ^ (row & 7)) << 4)),
-                                 "r"(pk[ch * 4]), "r"(pk[ch * 4 + 1]), "r"(pk[ch * 4 + 2]), "r"(pk[ch * 4 + 3]) : "memory");
+                for (int c8 = 0; c8 < 8; c8++) {
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + ((c8 ^ (row & 7)) << 4)),
+                                 "r"(pk[c8 * 4]), "r"(pk[c8 * 4 + 1]), "r"(pk[c8 * 4 + 2]), "r"(pk[c8 * 4 + 3]) : "memory");
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the async proxy (UMMA)
             tc_fence_before();
             mbar_arrive(p_full);
         }
-        // epilogue: O / l -> fp16 -> out[q, head*d + c]
+        // epilogue: O / l -> fp16 -> out[q, head*d + c]; l = sum of the pair's partial sums (same running maximum)
+        {
+            float* xw = xchg + ((n_kv & 1) * 2 + half) * BQ;
+            float* xr = xchg + ((n_kv & 1) * 2 + (half ^ 1)) * BQ;
+            xw[row] = l_run;
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            l_run += xr[row];
+        }
         mbar_wait(pv_done, (n_kv - 1) & 1);
         tc_fence_after();
         const int qrow = q0 + row;
         const float inv = 1.f / l_run;
         __half* orow = p.out + (long long)qrow * p.ldo + (long long)head * p.d;
-#pragma unroll 1
-        for (int c = 0; c < BD; c += 32) {
-            if (c >= p.d) break;
+        const int c = half * 32;
+        if (c < p.d) {
             uint32_t o[32];
             tmem_ld32(tmem_base + lane_addr + O_COL + c, o);
             if (qrow < p.T) {

@@ -219,7 +219,7 @@ def test_gemm_head_views(K, impl, T, Tk, h, d):
     _check(O, ref, absref, "PV head views")
 
 
-@pytest.mark.parametrize("T,Tk,h,d", [(128, 128, 1, 64), (256, 384, 2, 40), (200, 77, 4, 40), (4096, 4096, 8, 40), (1024, 1024, 10, 64)])
+@pytest.mark.parametrize("T,Tk,h,d", [(128, 128, 1, 64), (256, 384, 2, 40), (200, 77, 4, 40), (64, 30, 2, 32), (300, 200, 3, 64), (4096, 4096, 8, 40), (1024, 1024, 10, 64)])
 def test_flash_attention(K, T, Tk, h, d):
     """Fused tcgen05 attention against softmax(QK^T s)V in fp64 on the fp16-rounded operands.  Tolerance: P is rounded to
     fp16 before the second MMA (as the reference's fp16 softmax output is), so |err| <= 2^-9 * sum|p_i v_i| + 2^-10 |ref|."""
