@@ -29,7 +29,7 @@ constexpr int K_BYTES = BKV * BD * 2;   // 16 KiB
 constexpr int V_BYTES = BKV * BD * 2;   // 16 KiB (128 key rows x 64 columns)
 constexpr int P_BYTES = BQ * BKV * 2;   // 32 KiB (two 64-key k-blocks)
 constexpr int XCHG_BYTES = 2 * 2 * BQ * 4;   // half-row maxima / sums exchanged between the two warps of a row quadrant (double-buffered)
-constexpr int FA_SMEM = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + P_BYTES + 1024 + 256 + XCHG_BYTES;
+constexpr int FA_SMEM = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + 2 * P_BYTES + 1024 + 256 + XCHG_BYTES;
 constexpr int FA_THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 softmax (two per TMEM lane quadrant)
 constexpr int TMEM_COLS_FA = 512;       // S0 [0,128) S1 [128,256) O [256,320)
 constexpr int O_COL = 256;
@@ -156,15 +156,15 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     uint8_t* sK = sQ + Q_BYTES;
     uint8_t* sV = sK + KV_STAGES * K_BYTES;
     uint8_t* sP = sV + KV_STAGES * V_BYTES;
-    uint64_t* bars = (uint64_t*)(sP + P_BYTES);
+    uint64_t* bars = (uint64_t*)(sP + 2 * P_BYTES);   // P is double-buffered: softmax of tile j+1 never waits for the PV MMA of tile j
     uint64_t* q_full = bars;                 // [1]
     uint64_t* kv_full = bars + 1;            // [2]
     uint64_t* kv_empty = bars + 3;           // [2]
     uint64_t* s_full = bars + 5;             // [2]
     uint64_t* s_empty = bars + 7;            // [2]
-    uint64_t* p_full = bars + 9;             // [1]
-    uint64_t* pv_done = bars + 10;           // [1]
-    uint32_t* tmem_slot = (uint32_t*)(bars + 11);
+    uint64_t* p_full = bars + 9;             // [2]
+    uint64_t* pv_done = bars + 11;           // [2]
+    uint32_t* tmem_slot = (uint32_t*)(bars + 13);
     float* xchg = (float*)((uint8_t*)bars + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -178,9 +178,7 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     }
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
-        for (int i = 0; i < 2; i++) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 256); }
-        mbar_init(p_full, 256);
-        mbar_init(pv_done, 1);
+        for (int i = 0; i < 2; i++) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 256); mbar_init(&p_full[i], 256); mbar_init(&pv_done[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -242,18 +240,19 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             }
             if (j >= 1) {
                 const int jj = j - 1, st = jj & 1;
-                mbar_wait(p_full, jj & 1);
+                mbar_wait(&p_full[st], (jj >> 1) & 1);
                 tc_fence_after();
                 const uint64_t vdesc = vdesc0 + (uint64_t)(st * (V_BYTES >> 4));
+                const uint64_t pdesc = pdesc0 + (uint64_t)(st * (P_BYTES >> 4));
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BKV / 16; k++) {
                         // P: two 64-key k-blocks 16 KiB apart, 32 B per 16-key step inside a block; V: 16 key rows = 2048 B per step
-                        umma_f16(tmem_base + O_COL, pdesc0 + (uint64_t)(((k >> 2) * (P_BYTES / 2) + (k & 3) * 32) >> 4), vdesc + (uint64_t)(k * (2048 >> 4)),
+                        umma_f16(tmem_base + O_COL, pdesc + (uint64_t)(((k >> 2) * (P_BYTES / 2) + (k & 3) * 32) >> 4), vdesc + (uint64_t)(k * (2048 >> 4)),
                                  idesc_o, (jj != 0 || k != 0) ? 1u : 0u);
                     }
                     umma_commit(&kv_empty[st]);
-                    umma_commit(pv_done);
+                    umma_commit(&pv_done[st]);
                 }
                 __syncwarp();
             }
@@ -327,23 +326,23 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             mbar_arrive(&s_empty[st]);                   // S[st] may be overwritten by QK^T of tile j+2
             l_run = l_run * alpha + lsum;                // partial sum over this warp's key halves
             m_run = m_new;
-            if (j > 0) {
-                // PV of the previous tile must have retired: O is stable and the P buffer is free
-                mbar_wait(pv_done, (j - 1) & 1);
+            // O may only be rescaled once PV(j-1) has retired; the P buffer of this parity is free once PV(j-2) has (the tensor pipe
+            // retires in order).  Rescaling is skipped when no row of the warp moved its maximum -- the common case after a few
+            // tiles, and then the softmax of tile j never waits for the MMA of tile j-1 (both warps of a pair see the same alpha).
+            if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+                mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
                 tc_fence_after();
-                // rescale this warp's 32 columns of O -- skipped when no row of the warp moved its maximum (the common case after a
-                // few tiles; both warps of a pair see the same alpha)
-                if (__any_sync(0xffffffffu, alpha != 1.f)) {
-                    uint32_t o[32];
-                    tmem_ld32(tmem_base + lane_addr + O_COL + half * 32, o);
+                uint32_t o[32];
+                tmem_ld32(tmem_base + lane_addr + O_COL + half * 32, o);
 #pragma unroll
-                    for (int t = 0; t < 32; t++) o[t] = __float_as_uint(__uint_as_float(o[t]) * alpha);
-                    tmem_st32(tmem_base + lane_addr + O_COL + half * 32, o);
-                }
+                for (int t = 0; t < 32; t++) o[t] = __float_as_uint(__uint_as_float(o[t]) * alpha);
+                tmem_st32(tmem_base + lane_addr + O_COL + half * 32, o);
+            } else if (j > 1) {
+                mbar_wait(&pv_done[j & 1], ((j - 2) >> 1) & 1);
             }
             // P half-row -> shared memory, K-major SWIZZLE_128B: k-block = this warp's key half, 16-byte chunk index XOR (row % 8)
             {
-                const uint32_t prow = smem_u32(sP) + row * 128 + half * (P_BYTES / 2);
+                const uint32_t prow = smem_u32(sP) + st * P_BYTES + row * 128 + half * (P_BYTES / 2);
 #pragma unroll
                 for (int c8 = 0; c8 < 8; c8++) {
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + ((c8 ^ (row & 7)) << 4)),
@@ -352,7 +351,7 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the async proxy (UMMA)
             tc_fence_before();
-            mbar_arrive(p_full);
+            mbar_arrive(&p_full[st]);
         }
         // epilogue: O / l -> fp16 -> out[q, head*d + c]; l = sum of the pair's partial sums (same running maximum)
         {
@@ -362,7 +361,7 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
             l_run += xr[row];
         }
-        mbar_wait(pv_done, (n_kv - 1) & 1);
+        mbar_wait(&pv_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
         tc_fence_after();
         const int qrow = q0 + row;
         const float inv = 1.f / l_run;
