@@ -23,7 +23,7 @@ namespace {
 constexpr int BQ = 128;                 // queries per CTA
 constexpr int BKV = 128;                // keys per tile
 constexpr int BD = 64;                  // head dim padded to one 128-byte swizzle row
-constexpr int KV_STAGES = 2;
+constexpr int KV_STAGES = 4;            // K/V ring: a stage is freed by PV(j) and needed again by QK(j + KV_STAGES); with 2 stages the TMA round trip was exposed on every tile
 constexpr int Q_BYTES = BQ * BD * 2;    // 16 KiB
 constexpr int K_BYTES = BKV * BD * 2;   // 16 KiB
 constexpr int V_BYTES = BKV * BD * 2;   // 16 KiB (128 key rows x 64 columns)
@@ -158,13 +158,13 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     uint8_t* sP = sV + KV_STAGES * V_BYTES;
     uint64_t* bars = (uint64_t*)(sP + 2 * P_BYTES);   // P is double-buffered: softmax of tile j+1 never waits for the PV MMA of tile j
     uint64_t* q_full = bars;                 // [1]
-    uint64_t* kv_full = bars + 1;            // [2]
-    uint64_t* kv_empty = bars + 3;           // [2]
-    uint64_t* s_full = bars + 5;             // [2]
-    uint64_t* s_empty = bars + 7;            // [2]
-    uint64_t* p_full = bars + 9;             // [2]
-    uint64_t* pv_done = bars + 11;           // [2]
-    uint32_t* tmem_slot = (uint32_t*)(bars + 13);
+    uint64_t* kv_full = bars + 1;                      // [KV_STAGES]
+    uint64_t* kv_empty = kv_full + KV_STAGES;          // [KV_STAGES]
+    uint64_t* s_full = kv_empty + KV_STAGES;           // [2]
+    uint64_t* s_empty = s_full + 2;                    // [2]
+    uint64_t* p_full = s_empty + 2;                    // [2]
+    uint64_t* pv_done = p_full + 2;                    // [2]
+    uint32_t* tmem_slot = (uint32_t*)(pv_done + 2);
     float* xchg = (float*)((uint8_t*)bars + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -178,7 +178,8 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     }
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
-        for (int i = 0; i < 2; i++) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 256); mbar_init(&p_full[i], 256); mbar_init(&pv_done[i], 1); }
+        for (int i = 0; i < KV_STAGES; i++) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 256); mbar_init(&p_full[i], 256); mbar_init(&pv_done[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -203,8 +204,8 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         }
         __syncwarp();
         for (int j = 0; j < n_kv; j++) {
-            const int st = j & 1;
-            mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+            const int st = j % KV_STAGES;
+            mbar_wait(&kv_empty[st], ((j / KV_STAGES) & 1) ^ 1);
             if (elect_one()) {
                 mbar_expect_tx(&kv_full[st], K_BYTES + V_BYTES);
                 tma_load_3d(sK + st * K_BYTES, &map_k, &kv_full[st], 0, head, j * BKV);
@@ -225,11 +226,11 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const uint64_t vdesc0 = smem_desc(smem_u32(sV), V_BYTES, 1024);
         for (int j = 0; j <= n_kv; j++) {
             if (j < n_kv) {
-                const int st = j & 1;
-                mbar_wait(&kv_full[st], (j >> 1) & 1);
+                const int st = j & 1, ks = j % KV_STAGES;
+                mbar_wait(&kv_full[ks], (j / KV_STAGES) & 1);
                 mbar_wait(&s_empty[st], ((j >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint64_t kdesc = kdesc0 + (uint64_t)(st * (K_BYTES >> 4));
+                const uint64_t kdesc = kdesc0 + (uint64_t)(ks * (K_BYTES >> 4));
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BD / 16; k++)
@@ -242,7 +243,8 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 const int jj = j - 1, st = jj & 1;
                 mbar_wait(&p_full[st], (jj >> 1) & 1);
                 tc_fence_after();
-                const uint64_t vdesc = vdesc0 + (uint64_t)(st * (V_BYTES >> 4));
+                const int ks = jj % KV_STAGES;
+                const uint64_t vdesc = vdesc0 + (uint64_t)(ks * (V_BYTES >> 4));
                 const uint64_t pdesc = pdesc0 + (uint64_t)(st * (P_BYTES >> 4));
                 if (elect_one()) {
 #pragma unroll
@@ -251,7 +253,7 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         umma_f16(tmem_base + O_COL, pdesc + (uint64_t)(((k >> 2) * (P_BYTES / 2) + (k & 3) * 32) >> 4), vdesc + (uint64_t)(k * (2048 >> 4)),
                                  idesc_o, (jj != 0 || k != 0) ? 1u : 0u);
                     }
-                    umma_commit(&kv_empty[st]);
+                    umma_commit(&kv_empty[ks]);
                     umma_commit(&pv_done[st]);
                 }
                 __syncwarp();
