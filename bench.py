@@ -303,6 +303,14 @@ def main():
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
                 "peak_source": peak_src, "launches": int(n_tc), "kernel_ms_per_step": tc_ms, "flops_per_step": tc_flops,
                 "algorithmic_bytes_per_step": tc_bytes, "share_of_step": tc_ms / ms_per_step if ms_per_step else None, "traffic": None}
+    # DRAM traffic of the same kernel from the committed ncu pass (profiles/r01_tc_traffic.json, made by scripts/ncu_traffic.py):
+    # per launch, like `achieved`; the algorithmic bytes per launch stand beside it
+    tpath = os.path.join(ROOT, "profiles", "r01_tc_traffic.json")
+    if os.path.exists(tpath) and n_tc:
+        tj = json.load(open(tpath))
+        roofline["traffic"] = tj.get("dram_bytes_per_launch")
+        roofline["traffic_unit"] = "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, %d launches of one step)" % tj.get("launches", 0)
+        roofline["algorithmic_bytes_per_launch"] = tc_bytes / n_tc
     del mv
 
     # ---------------- e2e arm: host buffers through the C ABI, weights streamed every step ----------------

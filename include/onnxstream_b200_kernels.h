@@ -138,6 +138,14 @@ int osb_conv2d_qu8(const uint8_t* x, const uint8_t* w, const int32_t* bias, uint
                    int64_t H, int64_t W, int64_t Cin, int64_t Cout, int kh, int kw, int stride, int pad_top, int pad_left,
                    int64_t Ho, int64_t Wo, int zx, float sx, int zw, float sw, int zy, float sy, void* stream);
 
+/* ScatterND with full-rank indices (src/onnxstream.cpp:7939-8074): out[pos[i]] = updates[i] for 2- or 4-byte elements; `pos`
+ * = host-linearised, range-checked positions, on the device. */
+int osb_scatter_elems(void* out, const int64_t* pos, const void* updates, int64_t n, int elem_size, void* stream);
+
+/* MaxPool, NHWC, dilation 1, ceil_mode 0 (XnnPack::maxpool_nhwc, src/onnxstream.cpp:1537-1664; branch 8075-8143). */
+int osb_maxpool_nhwc(const void* x, void* y, int dtype, int64_t H, int64_t W, int64_t C, int kh, int kw, int stride, int pad_top,
+                     int pad_left, int64_t Ho, int64_t Wo, void* stream);
+
 /* Fill `n` bytes-worth of elements with a constant (ConstantOfShape, src/onnxstream.cpp:7543-7588). */
 int osb_fill(void* dst, int dtype, size_t n, float value, void* stream);
 

@@ -5,6 +5,8 @@
 // and every handler enqueues CUDA kernels on the compute stream; int64 tensors (shape arithmetic) stay on the host
 // and are evaluated with the reference's own integer semantics, bit-exactly.
 #include "engine_impl.h"
+
+#include <limits>
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -1552,6 +1554,117 @@ void Engine::Impl::op_misc_host(size_t oi)
             for (size_t i = 0; i < nd; i++) is[i] = xs[i] == 1 ? 0 : cs[i];
             push(oi, 0, strided(x, os, is, nullptr, 0));
         }
+    } else if (op.type == "ArgMax") {
+        // src/onnxstream.cpp:6930-7002: int64 (1, D) input, last axis, keepdims 0, first maximum wins
+        if (op.in.size() != 1) fail(op, "wrong number of inputs.");
+        if (op.out.size() != 1) fail(op, "wrong number of outputs.");
+        int axis = 0, keepdims = 1, select_last = 0;
+        for (auto& a : op.attrs) {
+            if (a.first == "axis") axis = std::stoi(a.second);
+            else if (a.first == "keepdims") keepdims = std::stoi(a.second);
+            else if (a.first == "select_last_index") select_last = std::stoi(a.second);
+            else fail(op, "unrecognized attribute: " + a.first + ".");
+        }
+        Tensor x = in(oi, 0);
+        if (axis < 0) axis += (int)x.shape.size();
+        if (axis < 0 || axis >= (int)x.shape.size()) fail(op, "invalid axis attribute.");
+        if (axis != (int)x.shape.size() - 1) fail(op, "argmax supported on last axis only (not implemented).");
+        if (keepdims) fail(op, "keepdims must be 0 (not implemented).");
+        if (select_last) fail(op, "select_last_index must be 0 (not implemented).");
+        if (x.shape.size() != 2 || x.shape[0] != 1) fail(op, "shape of input must be (1,D) (not implemented).");
+        if (x.type != DType::i64) fail(op, "wrong data type of input (not implemented).");
+        int64_t best = std::numeric_limits<int64_t>::min(), arg = 0;
+        for (int64_t i = 0; i < (int64_t)x.i64->size(); i++) if ((*x.i64)[i] > best) { best = (*x.i64)[i]; arg = i; }
+        push(oi, 0, mk_i64({ arg }, { 1 }));
+    } else if (op.type == "Trilu") {
+        // src/onnxstream.cpp:7883-7938: upper triangle of a 2-D float tensor, out[y][x] = x - k >= y ? in[y][x] : 0
+        if (op.in.size() != 2) fail(op, "wrong number of inputs.");
+        if (op.out.size() != 1) fail(op, "wrong number of outputs.");
+        std::string upper = "1";
+        for (auto& a : op.attrs) { if (a.first == "upper") upper = a.second; else fail(op, "unrecognized attribute (not implemented)."); }
+        if (upper != "1") fail(op, "'upper' must be 1 (not implemented).");
+        Tensor x = to_plain(in(oi, 0)), kt = in(oi, 1);
+        if (x.type != DType::f32 && x.type != DType::f16) fail(op, "wrong data type of input.");
+        if (kt.type != DType::i64) fail(op, "wrong data type of k.");
+        if (x.shape.size() != 2) fail(op, "input must be 2D (not implemented).");
+        if (!kt.shape.empty()) fail(op, "second input (k) must be a scalar (not implemented).");
+        // masks are tiny (causal-mask construction): evaluate on the host, exactly, in the storage type
+        const int64_t h = x.shape[0], w = x.shape[1], k = (*kt.i64)[0];
+        const size_t es = dtype_size(x.type);
+        std::vector<uint8_t> hv((size_t)x.numel() * es);
+        ck(cudaMemcpyAsync(hv.data(), x.data(), hv.size(), cudaMemcpyDeviceToHost, st), "trilu D2H");
+        ck(cudaStreamSynchronize(st), "sync");
+        for (int64_t yy = 0; yy < h; yy++)
+            for (int64_t xx = 0; xx < w; xx++)
+                if (!(xx - k >= yy)) std::memset(hv.data() + (size_t)(yy * w + xx) * es, 0, es);
+        Tensor y = make(x.type, x.shape);
+        ck(cudaMemcpyAsync(y.mdata(), hv.data(), hv.size(), cudaMemcpyHostToDevice, st), "trilu H2D");
+        ck(cudaStreamSynchronize(st), "sync");
+        push(oi, 0, y);
+    } else if (op.type == "ScatterND") {
+        // src/onnxstream.cpp:7939-8074: full-rank indices only (indices [.., rank]), element-wise scatter into a copy of the input
+        if (op.in.size() != 3) fail(op, "wrong number of inputs.");
+        if (op.out.size() != 1) fail(op, "wrong number of outputs.");
+        if (!op.attrs.empty()) fail(op, "unrecognized attribute (not implemented).");
+        Tensor x = to_plain(in(oi, 0)), idx = in(oi, 1), upd = to_plain(in(oi, 2));
+        size_t rank = x.shape.size();
+        if (!rank || idx.shape.size() != rank + 1 || upd.shape.size() != rank || idx.shape[rank] != (int64_t)rank) fail(op, "invalid shape of one or more inputs.");
+        if (idx.type != DType::i64) fail(op, "wrong data type of indices.");
+        if (x.type != DType::f32 && x.type != DType::f16) fail(op, "wrong data type of input.");
+        if (upd.type != x.type) {
+            if (upd.type != DType::f32 && upd.type != DType::f16) fail(op, "wrong data type of updates.");
+            upd = convert(upd, x.type);
+        }
+        const int64_t n_upd = upd.numel();
+        if ((size_t)n_upd * rank != idx.i64->size()) fail(op, "sizes of updates and indices not compatible.");
+        auto dims = contiguous_strides(x.shape);
+        std::vector<int64_t> pos((size_t)n_upd);
+        for (int64_t i = 0; i < n_upd; i++) {
+            int64_t p_ = 0;
+            for (size_t j = 0; j < rank; j++) p_ += (*idx.i64)[(size_t)i * rank + j] * dims[j];
+            if (p_ < 0 || p_ >= x.numel()) fail(op, "invalid index in indices.");
+            pos[(size_t)i] = p_;
+        }
+        const size_t es = dtype_size(x.type);
+        Tensor y = make(x.type, x.shape);
+        ck(cudaMemcpyAsync(y.mdata(), x.data(), (size_t)x.numel() * es, cudaMemcpyDeviceToDevice, st), "scatter copy");
+        if (n_upd) {
+            DevPtr dpos = E.m_pool.alloc((size_t)n_upd * 8);
+            ck(cudaMemcpyAsync(dpos->ptr, pos.data(), (size_t)n_upd * 8, cudaMemcpyHostToDevice, st), "scatter pos H2D");
+            ck(cudaStreamSynchronize(st), "sync");   // pageable source
+            ck(osb_scatter_elems(y.mdata(), (const int64_t*)dpos->ptr, upd.data(), n_upd, (int)es, st), "osb_scatter_elems");
+        }
+        push(oi, 0, y);
+    } else if (op.type == "MaxPool") {
+        // src/onnxstream.cpp:8075-8143 + XnnPack::maxpool_nhwc 1537-1664 (padding re-symmetrised: top = (pads[0]+pads[2])/2)
+        if (op.in.size() != 1) fail(op, "wrong number of inputs.");
+        if (op.out.size() != 1) fail(op, "wrong number of outputs.");
+        std::vector<int64_t> dil, ks, pads, strides;
+        int ceil_mode = 0;
+        auto ints = [](const std::string& v) { std::vector<int64_t> r; size_t p0 = 0; while (p0 <= v.size()) { size_t c = v.find(',', p0); if (c == std::string::npos) c = v.size(); if (c > p0) r.push_back(std::stoll(v.substr(p0, c - p0))); p0 = c + 1; } return r; };
+        for (auto& a : op.attrs) {
+            if (a.first == "dilations") dil = ints(a.second);
+            else if (a.first == "ceil_mode") ceil_mode = std::stoi(a.second);
+            else if (a.first == "kernel_shape") ks = ints(a.second);
+            else if (a.first == "pads") pads = ints(a.second);
+            else if (a.first == "strides") strides = ints(a.second);
+            else fail(op, "unrecognized attribute: " + a.first + ".");
+        }
+        if (dil != std::vector<int64_t>{ 1, 1 }) fail(op, "invalid dilations attribute value (not implemented).");
+        if (ceil_mode != 0) fail(op, "invalid ceil_mode attribute value (not implemented).");
+        Tensor x = in(oi, 0);
+        if (x.type != DType::f32 && x.type != DType::f16) fail(op, "wrong data type of X.");
+        if (x.shape.size() != 4 || ks.size() != 2 || pads.size() != 4 || strides.size() != 2 || strides[0] != strides[1])
+            throw std::runtime_error("XnnPack::maxpool_nhwc: one or more arguments are invalid.");
+        if (x.shape[0] != 1) fail(op, "first dimension of input's shape must be 1 (not implemented).");
+        x = to_nhwc(x);
+        const int64_t C = x.shape[1], H = x.shape[2], W = x.shape[3];
+        const int64_t ph = pads[0] + pads[2], pw = pads[1] + pads[3];
+        if (H + ph < ks[0] || W + pw < ks[1] || strides[0] < 1) throw std::runtime_error("XnnPack::maxpool_nhwc: one or more arguments are invalid.");
+        const int64_t Ho = (H + ph - ks[0]) / strides[0] + 1, Wo = (W + pw - ks[1]) / strides[0] + 1;
+        Tensor y = make(x.type, { 1, C, Ho, Wo }, Layout::nhwc);
+        ck(osb_maxpool_nhwc(x.data(), y.mdata(), K(x.type), H, W, C, (int)ks[0], (int)ks[1], (int)strides[0], (int)(ph / 2), (int)(pw / 2), Ho, Wo, st), "osb_maxpool_nhwc");
+        push(oi, 0, y);
     } else fail(op, "operation not implemented: " + op.type);
 }
 

@@ -620,6 +620,44 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, cons
 // gather rows, fill
 // ------------------------------------------------------------------------------------------------------------
 
+// ScatterND with full-rank indices (src/onnxstream.cpp:7939-8074): out[pos[i]] = updates[i]; positions are linearised (and range
+// checked) on the host because the index tensor is int64 host data.  Duplicate positions: last writer wins is not guaranteed by
+// the reference either (it scatters from a thread pool).
+__global__ void scatter_elems_kernel(uint8_t* __restrict__ out, const int64_t* __restrict__ pos, const uint8_t* __restrict__ upd, int64_t n, int elem)
+{
+    osb_pdl_prologue();
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t p = pos[i];
+        if (elem == 2) reinterpret_cast<uint16_t*>(out)[p] = reinterpret_cast<const uint16_t*>(upd)[i];
+        else reinterpret_cast<uint32_t*>(out)[p] = reinterpret_cast<const uint32_t*>(upd)[i];
+    }
+}
+
+// MaxPool on NHWC (XnnPack::maxpool_nhwc, src/onnxstream.cpp:1537-1664): dilation 1, padded taps are ignored (-inf), one thread
+// per (output pixel, channel).
+template <typename T>
+__global__ void maxpool_nhwc_kernel(const T* __restrict__ x, T* __restrict__ y, int H, int W, int C, int kh, int kw, int stride, int pad_top, int pad_left, int Ho, int Wo)
+{
+    osb_pdl_prologue();
+    const int64_t total = (int64_t)Ho * Wo * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        int64_t pix = i / C;
+        int ox = (int)(pix % Wo), oy = (int)(pix / Wo);
+        float m = -INFINITY;
+        for (int ky = 0; ky < kh; ky++) {
+            int iy = oy * stride + ky - pad_top;
+            if (iy < 0 || iy >= H) continue;
+            for (int kx = 0; kx < kw; kx++) {
+                int ix = ox * stride + kx - pad_left;
+                if (ix < 0 || ix >= W) continue;
+                m = fmaxf(m, to_float(x[((int64_t)iy * W + ix) * C + c]));
+            }
+        }
+        y[i] = from_float<T>(m);
+    }
+}
+
 __global__ void gather_rows_kernel(const uint8_t* __restrict__ table, const int64_t* __restrict__ idx, uint8_t* __restrict__ out,
                                    int64_t n_idx, int64_t table_rows, int64_t row_bytes)
 {
@@ -992,6 +1030,26 @@ int osb_gather_rows(const void* table, const int64_t* idx, void* out, int64_t n_
     if (n_idx * row_bytes == 0) return 0;
     int threads = row_bytes >= 4096 ? 256 : 64;
     osb_launch((gather_rows_kernel), (unsigned)min<int64_t>(n_idx, 148 * 8), threads, 0, (cudaStream_t)stream, (const uint8_t*)table, idx, (uint8_t*)out, n_idx, table_rows, row_bytes);
+    return launched();
+}
+
+int osb_scatter_elems(void* out, const int64_t* pos, const void* updates, int64_t n, int elem_size, void* stream)
+{
+    if (n == 0) return 0;
+    if (elem_size != 2 && elem_size != 4) return (int)cudaErrorInvalidValue;
+    osb_launch((scatter_elems_kernel), grid_for((size_t)n, 256), 256, 0, (cudaStream_t)stream, (uint8_t*)out, pos, (const uint8_t*)updates, n, elem_size);
+    return launched();
+}
+
+int osb_maxpool_nhwc(const void* x, void* y, int dtype, int64_t H, int64_t W, int64_t C, int kh, int kw, int stride, int pad_top, int pad_left,
+                     int64_t Ho, int64_t Wo, void* stream)
+{
+    if (Ho * Wo * C == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t n = (size_t)Ho * Wo * C;
+    if (dtype == OSB_F16) osb_launch((maxpool_nhwc_kernel<__half>), grid_for(n, 256), 256, 0, st, (const __half*)x, (__half*)y, (int)H, (int)W, (int)C, kh, kw, stride, pad_top, pad_left, (int)Ho, (int)Wo);
+    else if (dtype == OSB_F32) osb_launch((maxpool_nhwc_kernel<float>), grid_for(n, 256), 256, 0, st, (const float*)x, (float*)y, (int)H, (int)W, (int)C, kh, kw, stride, pad_top, pad_left, (int)Ho, (int)Wo);
+    else return (int)cudaErrorInvalidValue;
     return launched();
 }
 

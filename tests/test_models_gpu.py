@@ -268,3 +268,64 @@ def test_w8a32_parity(engine_lib, oracle_lib, workdir, fp16):
     assert report(got["out_5F_sample"], ref)["rel_to_max"] <= (TOL["float16"] if fp16 else TOL["float32"])
     u8 = sum(os.path.getsize(os.path.join(d, f)) for f in os.listdir(d) if f.endswith(".bin"))
     assert abs(m.stats()["weight_bytes_streamed"] - u8) <= 8 * 4096      # uint8 bytes cross PCIe, not their fp32 expansion
+
+
+def test_maxpool_trilu_scatternd_argmax(engine_lib, oracle_lib, workdir):
+    """The four remaining op types of the reference's run() loop (src/onnxstream.cpp:8075 MaxPool, 7883 Trilu, 7939 ScatterND,
+    6930 ArgMax) in small graphs, engine vs the reference itself: floats within the fp32 bar, index results bit-exact."""
+    rng = np.random.default_rng(7)
+    # MaxPool after a Conv (YOLO SPPF shapes: k2 s2 p0, and k5 s1 p2 whose padding must be ignored, not zero-filled)
+    d = os.path.join(workdir, "maxpool") + "/"
+    g = emit.GraphBuilder(d, "float32", seed=11)
+    x = g.input("x", (1, 8, 12, 12))
+    c = g.conv(x, 16, 3)
+    p1 = g.node("MaxPool", [c], [(1, 16, 6, 6)], [("ceil_mode", "0"), ("dilations", "1,1"), ("kernel_shape", "2,2"), ("pads", "0,0,0,0"), ("strides", "2,2")], out_names=["poola"])
+    p2 = g.node("MaxPool", [c], [(1, 16, 12, 12)], [("ceil_mode", "0"), ("dilations", "1,1"), ("kernel_shape", "5,5"), ("pads", "2,2,2,2"), ("strides", "1,1")], out_names=["poolb"])
+    g.finish()
+    inputs = {"x": (rng.standard_normal((1, 8, 12, 12)) - 1.0).astype(np.float32)}   # mostly negative: zero padding would win the max
+    for opts in ((), FP16):
+        ref = run_model(oracle_lib, d, inputs, opts)[0]
+        got = run_model(engine_lib, d, inputs, opts)[0]
+        for n in ("poola", "poolb"):
+            assert got[n].shape == ref[n].shape
+            assert report(got[n], ref[n])["rel_to_max"] <= (TOL["float16"] if opts else TOL["float32"]), (n, opts)
+
+    # Trilu (upper, k = 1) on a float32 matrix, then a scalar Mul so that the result is an activation output
+    d = os.path.join(workdir, "trilu") + "/"
+    g = emit.GraphBuilder(d, "float32", seed=12)
+    m = g.input("m", (6, 7))
+    t = g.node("Trilu", [m, g.const(np.asarray(1, dtype=np.int64))], [(6, 7)], [("upper", "1")])
+    g.node("Mul", [t, g.scalar(2.0)], [(6, 7)], out_names=["tri"])
+    g.finish()
+    inputs = {"m": rng.standard_normal((6, 7)).astype(np.float32)}
+    ref = run_model(oracle_lib, d, inputs)[0]["tri"]
+    got = run_model(engine_lib, d, inputs)[0]["tri"]
+    assert np.array_equal(got, ref)
+    assert np.array_equal(got, np.triu(inputs["m"], 1) * 2.0)
+
+    # ScatterND with full-rank indices into a (4, 5) tensor
+    d = os.path.join(workdir, "scatter") + "/"
+    g = emit.GraphBuilder(d, "float32", seed=13)
+    data = g.input("data", (4, 5))
+    upd = g.input("upd", (2, 3))
+    idx = np.asarray([[[0, 0], [1, 4], [3, 2]], [[2, 2], [0, 3], [3, 4]]], dtype=np.int64)
+    s = g.node("ScatterND", [data, g.const(idx), upd], [(4, 5)])
+    g.node("Mul", [s, g.scalar(1.0)], [(4, 5)], out_names=["scattered"])
+    g.finish()
+    inputs = {"data": rng.standard_normal((4, 5)).astype(np.float32), "upd": rng.standard_normal((2, 3)).astype(np.float32)}
+    ref = run_model(oracle_lib, d, inputs)[0]["scattered"]
+    got = run_model(engine_lib, d, inputs)[0]["scattered"]
+    want = inputs["data"].copy()
+    want[idx[..., 0], idx[..., 1]] = inputs["upd"]
+    assert np.array_equal(ref, want) and np.array_equal(got, want)
+
+    # ArgMax over an int64 (1, D) tensor: first maximum wins
+    d = os.path.join(workdir, "argmax") + "/"
+    g = emit.GraphBuilder(d, "float32", seed=14)
+    v = g.input("v", (1, 9))
+    g.node("ArgMax", [v], [(1,)], [("axis", "-1"), ("keepdims", "0")], out_names=["arg"])
+    g.finish()
+    inputs = {"v": np.asarray([[3, -1, 7, 7, 2, 7, 0, -5, 6]], dtype=np.int64)}
+    ref = run_model(oracle_lib, d, inputs)[0]["arg"]
+    got = run_model(engine_lib, d, inputs)[0]["arg"]
+    assert np.array_equal(np.asarray(got).ravel(), [2]) and np.array_equal(np.asarray(ref).ravel(), [2])
