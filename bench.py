@@ -302,7 +302,10 @@ def main():
     roofline = {"bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05 implicit-GEMM conv / GEMM, all launches of one step)",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
                 "peak_source": peak_src, "launches": int(n_tc), "kernel_ms_per_step": tc_ms, "flops_per_step": tc_flops,
-                "algorithmic_bytes_per_step": tc_bytes, "share_of_step": tc_ms / ms_per_step if ms_per_step else None, "traffic": None}
+                "algorithmic_bytes_per_step": tc_bytes,
+                # share of the SAME eager, event-instrumented step (numerator and denominator carry the same per-launch event cost);
+                # compare with the kernel's share in profiles/r01_launches_step_final.csv
+                "share_of_step": tc_ms / float(st_e["last_gpu_ms"]) if st_e.get("last_gpu_ms") else None, "traffic": None}
     # DRAM traffic of the same kernel from the committed ncu pass (profiles/r01_tc_traffic.json, made by scripts/ncu_traffic.py):
     # per launch, like `achieved`; the algorithmic bytes per launch stand beside it
     tpath = os.path.join(ROOT, "profiles", "r01_tc_traffic.json")
