@@ -151,7 +151,12 @@ class NumpyOracle:
                 y = y + b
             return y.T.reshape(1, w.shape[0], ho, wo)
         if t == "MatMul":  # src/onnxstream.cpp:5669-5861
-            return np.matmul(x[0], x[1])
+            p, q = x[0], x[1]
+            if p.ndim == 4 and q.ndim == 4 and p.shape[1] != q.shape[1] and q.shape[1] and p.shape[1] % q.shape[1] == 0:
+                # grouped KV heads: only reachable through the ScaledDotProductAttention rewrite (src/onnxstream.cpp:3643-3695,
+                # 7767-7882), where query head h reads KV head h // (Hq / Hkv)
+                q = np.repeat(q, p.shape[1] // q.shape[1], axis=1)
+            return np.matmul(p, q)
         if t == "Gemm":  # src/onnxstream.cpp:4300-4375
             return x[0] @ x[1] + x[2]
         if t in ("Add", "Sub", "Mul", "Div"):  # src/onnxstream.cpp:5056-5175, 5394-5477, 3906-4000, 5605-5668
@@ -228,4 +233,56 @@ class NumpyOracle:
             return x[0].mean(axis=int(a["axes"]), keepdims=bool(int(a.get("keepdims", "1"))))
         if t == "Gather":  # src/onnxstream.cpp:6316-6498
             return np.take(x[0], x[1].astype(np.int64), axis=int(a.get("axis", 0)))
+        # ---- index / shape ops of the LLM graphs: int64 in, int64 out, bit-exact by construction ----
+        if t == "Shape":  # src/onnxstream.cpp:7003-7033
+            return np.asarray(x[0].shape, dtype=np.int64)
+        if t == "Cast":  # src/onnxstream.cpp:7352-7424: ONNX type ids 1 = float, 10 = float16, 6/7/9 = int32/int64/bool (all int64 here)
+            to = int(a["to"])
+            if to in (1, 10):
+                return x[0].astype(np.float64)
+            if to in (6, 7, 9):
+                return x[0].astype(np.float32).astype(np.int64) if x[0].dtype != np.int64 else x[0]
+            raise NotImplementedError("Cast to %d" % to)
+        if t == "ConstantOfShape":  # src/onnxstream.cpp:7543-7588: "value" without a decimal point -> int64 tensor
+            v = a.get("value", "0")
+            shape = tuple(int(d) for d in x[0])
+            return np.full(shape, int(v), dtype=np.int64) if "." not in v else np.full(shape, float(v), dtype=np.float64)
+        if t == "Range":  # src/onnxstream.cpp:7589-7636 (int64 only)
+            return np.arange(int(x[0].reshape(-1)[0]), int(x[1].reshape(-1)[0]), int(x[2].reshape(-1)[0]), dtype=np.int64)
+        if t in ("Less", "Greater", "Equal", "And"):  # src/onnxstream.cpp:7637-7766 (int64 operands, int64 0/1 result)
+            p, q = x[0].astype(np.int64), x[1].astype(np.int64)
+            r = {"Less": p < q, "Greater": p > q, "Equal": p == q, "And": (p != 0) & (q != 0)}[t]
+            return r.astype(np.int64)
+        if t == "Where":  # src/onnxstream.cpp:7034-7153
+            r = np.where(x[0] != 0, x[1], x[2])
+            return r.astype(np.int64) if x[1].dtype == np.int64 and x[2].dtype == np.int64 else r.astype(np.float64)
+        if t == "Expand":  # src/onnxstream.cpp:7154-7351: numpy-style broadcast of the input against the target shape
+            target = tuple(int(d) for d in x[1])
+            return np.broadcast_to(x[0], np.broadcast_shapes(x[0].shape, target)).copy()
+        if t == "Trilu":  # src/onnxstream.cpp:7883-7938: upper only, out[y][x] = x - k >= y ? in : 0
+            assert a.get("upper", "1") == "1" and x[0].ndim == 2
+            return np.triu(x[0], int(np.asarray(x[1]).reshape(-1)[0]))
+        if t == "ScatterND":  # src/onnxstream.cpp:7939-8074: full-rank indices, element-wise scatter into a copy
+            out = np.array(x[0], copy=True)
+            idx = x[1].astype(np.int64).reshape(-1, x[0].ndim)
+            out[tuple(idx[:, j] for j in range(x[0].ndim))] = x[2].reshape(-1)
+            return out
+        if t == "ArgMax":  # src/onnxstream.cpp:6930-7002: int64 (1, D), last axis, keepdims 0, first maximum
+            assert x[0].dtype == np.int64 and x[0].ndim == 2 and x[0].shape[0] == 1 and int(a.get("keepdims", "1")) == 0
+            return np.asarray([int(np.argmax(x[0][0]))], dtype=np.int64)
+        if t == "MaxPool":  # src/onnxstream.cpp:8075-8143, 1537-1664: padding re-symmetrised, padded taps ignored
+            kh, kw = (int(v) for v in a["kernel_shape"].split(","))
+            pads = [int(v) for v in a["pads"].split(",")]
+            st = int(a["strides"].split(",")[0])
+            ph, pw = pads[0] + pads[2], pads[1] + pads[3]
+            pt, pl = ph // 2, pw // 2
+            _, c, h, wd = x[0].shape
+            ho, wo = (h + ph - kh) // st + 1, (wd + pw - kw) // st + 1
+            xp = np.full((c, h + ph, wd + pw), -np.inf)
+            xp[:, pt:pt + h, pl:pl + wd] = x[0][0]
+            y = np.full((c, ho, wo), -np.inf)
+            for ky in range(kh):
+                for kx in range(kw):
+                    y = np.maximum(y, xp[:, ky:ky + st * (ho - 1) + 1:st, kx:kx + st * (wo - 1) + 1:st])
+            return y[None]
         raise NotImplementedError(t)

@@ -87,6 +87,66 @@ def test_reference_matches_torch_conv_groupnorm_silu(oracle_lib, workdir):
     assert report(ref, y)["max_abs"] <= 2e-5
 
 
+def _index_graphs(workdir):
+    """Small graphs for the op types outside the diffusion models: (dir, inputs, output name, exact?)."""
+    rng = np.random.default_rng(7)
+    out = []
+    d = os.path.join(workdir, "g_maxpool") + "/"
+    g = emit.GraphBuilder(d, "float32", seed=11)
+    x = g.input("x", (1, 8, 12, 12))
+    c = g.conv(x, 16, 3)
+    g.node("MaxPool", [c], [(1, 16, 6, 6)], [("ceil_mode", "0"), ("dilations", "1,1"), ("kernel_shape", "2,2"), ("pads", "0,0,0,0"), ("strides", "2,2")], out_names=["poola"])
+    g.node("MaxPool", [c], [(1, 16, 12, 12)], [("ceil_mode", "0"), ("dilations", "1,1"), ("kernel_shape", "5,5"), ("pads", "2,2,2,2"), ("strides", "1,1")], out_names=["poolb"])
+    g.finish()
+    xin = {"x": (rng.standard_normal((1, 8, 12, 12)) - 1.0).astype(np.float32)}
+    out += [(d, xin, "poola", False), (d, xin, "poolb", False)]
+    d = os.path.join(workdir, "g_trilu") + "/"
+    g = emit.GraphBuilder(d, "float32", seed=12)
+    m = g.input("m", (6, 7))
+    t = g.node("Trilu", [m, g.const(np.asarray(1, dtype=np.int64))], [(6, 7)], [("upper", "1")])
+    g.node("Mul", [t, g.scalar(2.0)], [(6, 7)], out_names=["tri"])
+    g.finish()
+    out.append((d, {"m": rng.standard_normal((6, 7)).astype(np.float32)}, "tri", True))
+    d = os.path.join(workdir, "g_scatter") + "/"
+    g = emit.GraphBuilder(d, "float32", seed=13)
+    data = g.input("data", (4, 5))
+    upd = g.input("upd", (2, 3))
+    idx = np.asarray([[[0, 0], [1, 4], [3, 2]], [[2, 2], [0, 3], [3, 4]]], dtype=np.int64)
+    sc = g.node("ScatterND", [data, g.const(idx), upd], [(4, 5)])
+    g.node("Mul", [sc, g.scalar(1.0)], [(4, 5)], out_names=["scattered"])
+    g.finish()
+    out.append((d, {"data": rng.standard_normal((4, 5)).astype(np.float32), "upd": rng.standard_normal((2, 3)).astype(np.float32)}, "scattered", True))
+    d = os.path.join(workdir, "g_argmax") + "/"
+    g = emit.GraphBuilder(d, "float32", seed=14)
+    v = g.input("v", (1, 9))
+    g.node("ArgMax", [v], [(1,)], [("axis", "-1"), ("keepdims", "0")], out_names=["arg"])
+    g.finish()
+    out.append((d, {"v": np.asarray([[3, -1, 7, 7, 2, 7, 0, -5, 6]], dtype=np.int64)}, "arg", True))
+    return out
+
+
+def test_restatement_matches_reference_index_ops(oracle_lib, workdir):
+    """MaxPool / Trilu / ScatterND / ArgMax (src/onnxstream.cpp:8075, 7883, 7939, 6930): numpy restatement == the reference."""
+    for d, inputs, name, exact in _index_graphs(workdir):
+        ref = run_model(oracle_lib, d, inputs, ())[0][name]
+        got = NumpyOracle(d).run(inputs)[name]
+        if exact:
+            assert np.array_equal(np.asarray(got).ravel(), np.asarray(ref).ravel()), name
+        else:
+            assert report(got, ref)["rel_to_max"] <= 5e-5, name
+
+
+def test_restatement_matches_reference_llama_decode(oracle_lib, workdir):
+    """BASELINE config[4] hot path at toy size (KV-cache decode step: Gather, rotary, RMSNorm, grouped-KV attention): numpy == reference."""
+    cfg = emit.LlamaConfig.tiny()
+    d = os.path.join(workdir, "llama_np") + "/"
+    emit.emit_llama_decode(d, cfg, "float32")
+    inputs = emit.llama_inputs(cfg)
+    ref = run_model(oracle_lib, d, inputs, ("use_scaled_dp_attn_op",))[0]["logits"]
+    got = NumpyOracle(d).run(inputs)["logits"]
+    assert report(got, ref)["rel_to_max"] <= 5e-5
+
+
 def test_golden_vectors(oracle_lib):
     """tests/golden/*.npz were produced by tests/golden/make_golden.py from oracle/_ref; the restatement and the reference
     must both still reproduce them (guards the emitter, the oracle build and the restatement against silent drift)."""
