@@ -147,6 +147,80 @@ def test_restatement_matches_reference_llama_decode(oracle_lib, workdir):
     assert report(got, ref)["rel_to_max"] <= 5e-5
 
 
+def test_torch_exporter_block_matches_torch(oracle_lib, workdir):
+    """torch.nn.Module -> model.txt + blobs (onnxstream_b200/export_torch.py, no `onnx` package), executed by the
+    reference itself, must reproduce torch: a UNet-style block with Conv, GroupNorm, SiLU, Gemm, LayerNorm, attention, GEGLU,
+    Concat, nearest upsampling and a strided Conv."""
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from onnxstream_b200.export_torch import export_module
+
+    class Block(nn.Module):
+        def __init__(s):
+            super().__init__()
+            s.c = nn.Conv2d(4, 32, 3, padding=1); s.g = nn.GroupNorm(8, 32); s.t = nn.Linear(16, 32); s.ln = nn.LayerNorm(32)
+            s.q = nn.Linear(32, 32, bias=False); s.k = nn.Linear(32, 32, bias=False); s.v = nn.Linear(32, 32, bias=False); s.o = nn.Linear(32, 32)
+            s.ff = nn.Linear(32, 256); s.ff2 = nn.Linear(128, 32); s.up = nn.Conv2d(64, 4, 3, padding=1); s.down = nn.Conv2d(4, 4, 3, stride=2, padding=1)
+
+        def forward(s, x, temb):
+            h = s.c(x)
+            h = F.silu(s.g(h)) + s.t(F.silu(temb))[:, :, None, None]
+            b, c, hh, ww = h.shape
+            t = h.flatten(2).transpose(1, 2)
+            n = s.ln(t)
+            q, k, v = (f(n).view(b, -1, 4, 8).transpose(1, 2) for f in (s.q, s.k, s.v))
+            t = t + s.o(F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, -1, 32))
+            a1, gate = s.ff(t).chunk(2, dim=-1)
+            t = t + s.ff2(a1 * F.gelu(gate))
+            u = F.interpolate(torch.cat([t.transpose(1, 2).reshape(b, c, hh, ww), h], 1), scale_factor=2.0, mode="nearest")
+            return s.down(s.up(u)) * 0.5
+
+    torch.manual_seed(0)
+    m = Block().eval()
+    x, temb = torch.randn(1, 4, 6, 6), torch.randn(1, 16)
+    ref = m(x, temb).detach().numpy()
+    for wd, opts, tol in (("float32", (), 2e-5), ("float16", ("use_fp16_arithmetic", "fuse_ops_in_attention"), 2e-2)):
+        d = os.path.join(workdir, "exp_block_" + wd) + "/"
+        info = export_module(m, (x, temb), d, wd, input_names=["sample", "t_emb"], output_names=["out_sample"])
+        assert info["inputs"] == ["sample", "t_5F_emb"] and info["outputs"] == ["out_5F_sample"]     # converter's name mangling
+        got = run_model(oracle_lib, d, dict(zip(info["inputs"], [x.numpy(), temb.numpy()])), opts)[0][info["outputs"][0]]
+        assert got.shape == ref.shape and report(got, ref)["rel_to_max"] <= tol, wd
+        # the numpy restatement agrees on the exported graph too
+        if wd == "float32":
+            npo = NumpyOracle(d).run(dict(zip(info["inputs"], [x.numpy(), temb.numpy()])))[info["outputs"][0]]
+            assert report(npo, ref)["rel_to_max"] <= 2e-5
+
+
+def test_torch_exporter_transformers_models(oracle_lib, workdir):
+    """Real library architectures with random weights: transformers' CLIPTextModel (causal-masked attention, quick-GELU) and
+    LlamaForCausalLM (RMSNorm, rotary, grouped KV heads) exported without `onnx` and run by the reference: logits == torch."""
+    import torch
+    transformers = pytest.importorskip("transformers")
+    from onnxstream_b200.export_torch import export_module
+
+    class Wrap(torch.nn.Module):
+        def __init__(s, m, f):
+            super().__init__(); s.m = m; s.f = f
+
+        def forward(s, ids):
+            return s.f(s.m, ids)
+
+    torch.manual_seed(0)
+    clip = transformers.CLIPTextModel(transformers.CLIPTextConfig(vocab_size=100, hidden_size=32, intermediate_size=64, num_hidden_layers=2,
+                                                                  num_attention_heads=4, max_position_embeddings=16)).eval()
+    llama = transformers.LlamaForCausalLM(transformers.LlamaConfig(vocab_size=128, hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                                                                   num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=32)).eval()
+    cases = [("clip", Wrap(clip, lambda m, ids: m(input_ids=ids).last_hidden_state), torch.randint(0, 100, (1, 16)), "last_hidden_state"),
+             ("llama", Wrap(llama, lambda m, ids: m(input_ids=ids, use_cache=False).logits), torch.randint(0, 128, (1, 12)), "logits")]
+    for name, w, ids, out in cases:
+        d = os.path.join(workdir, "exp_" + name) + "/"
+        info = export_module(w, (ids,), d, "float32", input_names=["input_ids"], output_names=[out])
+        ref = w(ids).detach().numpy()
+        got = run_model(oracle_lib, d, {info["inputs"][0]: ids.numpy().astype(np.int64)})[0][info["outputs"][0]]
+        assert got.shape == ref.shape and report(got, ref)["rel_to_max"] <= 2e-5, name
+
+
 def test_golden_vectors(oracle_lib):
     """tests/golden/*.npz were produced by tests/golden/make_golden.py from oracle/_ref; the restatement and the reference
     must both still reproduce them (guards the emitter, the oracle build and the restatement against silent drift)."""
