@@ -329,3 +329,36 @@ def test_maxpool_trilu_scatternd_argmax(engine_lib, oracle_lib, workdir):
     ref = run_model(oracle_lib, d, inputs)[0]["arg"]
     got = run_model(engine_lib, d, inputs)[0]["arg"]
     assert np.array_equal(np.asarray(got).ravel(), [2]) and np.array_equal(np.asarray(ref).ravel(), [2])
+
+
+@pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent: its first execution on a B200 is the driver's round-end run")
+def test_exported_transformers_models_on_engine(engine_lib, oracle_lib, workdir):
+    """torch -> export_torch -> B200 engine: transformers' CLIPTextModel and LlamaForCausalLM (GQA, rotary, RMSNorm) with random weights;
+    engine logits vs the reference's on the exported directory (the CPU suite already pins the reference against torch on the same export)."""
+    torch = pytest.importorskip("torch")
+    transformers = pytest.importorskip("transformers")
+    from onnxstream_b200.export_torch import export_module
+
+    class Wrap(torch.nn.Module):
+        def __init__(s, m, f):
+            super().__init__(); s.m = m; s.f = f
+
+        def forward(s, ids):
+            return s.f(s.m, ids)
+
+    torch.manual_seed(0)
+    clip = transformers.CLIPTextModel(transformers.CLIPTextConfig(vocab_size=100, hidden_size=32, intermediate_size=64, num_hidden_layers=2,
+                                                                  num_attention_heads=4, max_position_embeddings=16)).eval()
+    llama = transformers.LlamaForCausalLM(transformers.LlamaConfig(vocab_size=128, hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                                                                   num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=32)).eval()
+    cases = [("clip", Wrap(clip, lambda m, ids: m(input_ids=ids).last_hidden_state), torch.randint(0, 100, (1, 16)), "last_hidden_state"),
+             ("llama", Wrap(llama, lambda m, ids: m(input_ids=ids, use_cache=False).logits), torch.randint(0, 128, (1, 12)), "logits")]
+    for name, w, ids, out in cases:
+        for wd, opts in (("float32", ()), ("float16", FP16)):
+            d = os.path.join(workdir, f"exp_{name}_{wd}") + "/"
+            info = export_module(w, (ids,), d, wd, input_names=["input_ids"], output_names=[out])
+            inputs = {info["inputs"][0]: ids.numpy().astype(np.int64)}
+            ref = run_model(oracle_lib, d, inputs, opts)[0][info["outputs"][0]]
+            got = run_model(engine_lib, d, inputs, opts)[0][info["outputs"][0]]
+            assert got.shape == ref.shape
+            assert report(got, ref)["rel_to_max"] <= TOL[wd], (name, wd)
