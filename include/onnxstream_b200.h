@@ -50,6 +50,11 @@ void  model_ext_push_tensor(ModelContext* obj, const char* type, const char* nam
 long long model_ext_get_tensor_i64(ModelContext* obj, const char* name, long long* dst, long long cap, size_t* dims, size_t* ndims);
 int   model_ext_get_tensor_type(ModelContext* obj, const char* name);           /* TensorDataType value, -1 if absent */
 
+/* Host-only (works without a CUDA device): parse a model.txt text, run the engine's fusion planner and return a malloc'd report, one
+ * line per execution step "KIND n_ops first_op_type first_op_name" plus a final "#summary ..." line (free with model_free_buffer).
+ * The planner restates the reference's lookahead fusion (src/onnxstream.cpp:3576-3755) on the whole op list. */
+char* model_b200_plan_summary(const char* model_text, int fp16_arithmetic, int fuse_nodes, int fuse_attention, int use_scaled_dp_attn_op);
+
 /* stats: [0] weight ring bytes, [1] peak live streamed weight bytes, [2] largest node footprint, [3] weight bytes streamed in the
  * last run, [4] HBM-resident cached weight bytes, [5] activation pool high-water, [6] input H2D bytes, [7] output D2H bytes,
  * [8] kernel launches, [9] tcgen05 launches, [10] steps executed, [11] ops fused away, [12] last run wall ms, [13] last run GPU ms,

@@ -233,6 +233,19 @@ int model_ext_get_tensor_type(ModelContext* obj, const char* name)
     return -1;
 }
 
+char* model_b200_plan_summary(const char* model_text, int fp16_arithmetic, int fuse_nodes, int fuse_attention, int use_scaled_dp_attn_op)
+{
+    std::string r;
+    try {
+        r = osb::Engine::plan_summary(model_text ? model_text : "", fp16_arithmetic != 0, fuse_nodes != 0, fuse_attention != 0, use_scaled_dp_attn_op != 0);
+    } catch (const std::exception& e) {
+        r = std::string("=== ERROR === ") + e.what();
+    }
+    char* buf = (char*)malloc(r.size() + 1);
+    if (buf) memcpy(buf, r.c_str(), r.size() + 1);
+    return buf;
+}
+
 int model_b200_get_stats(ModelContext* obj, double* out, int n)
 {
     const EngineStats& s = obj->E().stats();

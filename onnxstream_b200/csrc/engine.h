@@ -155,10 +155,16 @@ struct HostTensor {                   // what is left in the model's tensor list
     int64_t* i64() const { return (int64_t*)buf->ptr; }
 };
 
+struct EngineNoDevice {};   // tag: construct the host-side planner only
+
 class Engine {
 public:
+    explicit Engine(EngineNoDevice);
     explicit Engine(int device = -1);
     ~Engine();
+    // Host-only planning (no CUDA device needed): parse `model_text`, run the fusion matchers, return one line per execution step
+    // ("KIND ops first_op_type first_op_name") followed by a "#summary" line.  Used by the CPU test-suite to pin the planner.
+    static std::string plan_summary(const std::string& model_text, bool fp16_arithmetic, bool fuse_nodes, bool fuse_attention, bool use_sdpa_rewrite = false);
 
     // --- the reference's public knobs (src/onnxstream.h:944-968) ---
     bool use_fp16_arithmetic = false;

@@ -2061,6 +2061,36 @@ Engine::Engine(int device)
     m_impl = std::make_unique<Impl>(*this);
 }
 
+Engine::Engine(EngineNoDevice)
+{
+    m_impl = std::make_unique<Impl>(*this);   // no stream, no pool slabs: planning only
+}
+
+std::string Engine::plan_summary(const std::string& model_text, bool fp16_arithmetic, bool fuse_nodes_, bool fuse_attention, bool use_sdpa_rewrite)
+{
+    static const char* kind_names[] = { "SINGLE", "ATTENTION", "GROUPNORM", "LAYERNORM", "GELU", "SILU", "LINEAR", "SDPA", "MHA", "CONV_ADD", "GEGLU" };
+    Engine e{ EngineNoDevice{} };
+    e.use_fp16_arithmetic = fp16_arithmetic;
+    e.fuse_nodes = fuse_nodes_;
+    e.fuse_ops_in_attention = fuse_attention;
+    e.use_scaled_dp_attn_op = use_sdpa_rewrite;
+    e.m_ops = parse_model_text(model_text, false);
+    Impl& I = *e.m_impl;
+    I.build_plan();
+    std::string out;
+    std::map<std::string, size_t> counts;
+    for (auto& s : I.steps) {
+        const char* kn = (size_t)s.kind < sizeof(kind_names) / sizeof(kind_names[0]) ? kind_names[s.kind] : "?";
+        const OpDef& op = e.m_ops[s.first];
+        out += std::string(kn) + " " + std::to_string(s.count) + " " + op.type + " " + op.name + "\n";
+        counts[kn]++;
+    }
+    out += "#summary ops=" + std::to_string(e.m_ops.size()) + " steps=" + std::to_string(I.steps.size()) + " largest_node_bytes=" + std::to_string(I.largest_node);
+    for (auto& kv : counts) out += " " + kv.first + "=" + std::to_string(kv.second);
+    out += "\n";
+    return out;
+}
+
 Engine::~Engine()
 {
     if (m_stream) cudaStreamSynchronize(m_stream);

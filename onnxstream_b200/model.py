@@ -73,6 +73,7 @@ def load_library(path: str) -> ctypes.CDLL:
         "model_b200_get_stats": ([vp, ctypes.POINTER(ctypes.c_double), ctypes.c_int], ctypes.c_int),
         "model_b200_set_comm": ([vp, vp, ctypes.c_int, ctypes.c_int], ctypes.c_int),
         "model_b200_run_resident": ([vp, ctypes.c_int], ctypes.c_double),
+        "model_b200_plan_summary": ([cp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int], vp),
         "osb_tc_profile": ([ctypes.c_int], None), "osb_tc_profile_read": ([ctypes.POINTER(ctypes.c_double)], ctypes.c_int),
         "osb_comm_unique_id": ([ctypes.c_char_p], ctypes.c_int), "osb_comm_init": ([ctypes.c_int, ctypes.c_int, ctypes.c_char_p], vp),
         "osb_comm_destroy": ([vp], None),
@@ -83,6 +84,23 @@ def load_library(path: str) -> ctypes.CDLL:
             fn.argtypes, fn.restype = args, res
     _libs[path] = lib
     return lib
+
+
+def plan_summary(model_text: str, fp16_arithmetic: bool = True, fuse_nodes: bool = True, fuse_attention: bool = True,
+                 use_scaled_dp_attn_op: bool = False, library_path: Optional[str] = None) -> str:
+    """B200 engine only, needs no GPU: the fusion plan for `model_text` -- one line per execution step
+    ("KIND n_ops first_op_type first_op_name") and a final "#summary" line (include/onnxstream_b200.h)."""
+    lib = load_library(library_path or ENGINE_LIB)
+    p = lib.model_b200_plan_summary(model_text.encode(), int(fp16_arithmetic), int(fuse_nodes), int(fuse_attention), int(use_scaled_dp_attn_op))
+    if not p:
+        raise OnnxStreamError("model_b200_plan_summary returned NULL")
+    try:
+        out = ctypes.string_at(p).decode()
+    finally:
+        lib.model_free_buffer(p)
+    if out.startswith("=== ERROR ==="):
+        raise OnnxStreamError(out)
+    return out
 
 
 class Model:

@@ -221,6 +221,36 @@ def test_torch_exporter_transformers_models(oracle_lib, workdir):
         assert got.shape == ref.shape and report(got, ref)["rel_to_max"] <= 2e-5, name
 
 
+def test_planner_fusion_on_cpu(engine_lib, workdir):
+    """The engine's planner is host code and runs without a GPU (model_b200_plan_summary): every diffusers-export pattern of a
+    UNet-shaped graph must be claimed by a fusion group, and switching the fusions off must give one step per op."""
+    from onnxstream_b200.model import plan_summary
+    g = emit.emit_unet(None, emit.UNetConfig.tiny(16), "float16", keep_in_memory=True)
+    text = g.text()
+    rep = plan_summary(text, library_path=engine_lib)
+    steps = [l.split(" ", 3) for l in rep.splitlines() if l and not l.startswith("#")]
+    summary = dict(kv.split("=") for kv in rep.splitlines()[-1].split()[1:])
+    n_ops = len([l for l in text.splitlines() if l])
+    assert int(summary["ops"]) == n_ops and sum(int(s[1]) for s in steps) == n_ops       # the groups partition the op list
+    blocks = int(summary["GEGLU"])                                                          # one GEGLU feed-forward per transformer block
+    assert blocks > 0 and int(summary["MHA"]) == 2 * blocks and int(summary["LAYERNORM"]) == 3 * blocks
+    # nothing that belongs to a pattern is left to run as a single op
+    leftovers = {s[2] for s in steps if s[0] == "SINGLE"}
+    assert not (leftovers & {"Softmax", "Erf", "InstanceNormalization", "Sigmoid", "Pow", "ReduceMean", "Sqrt", "Slice"}), leftovers
+    # every resnet output conv takes its residual in the epilogue; every GroupNorm is one group (with or without SiLU)
+    assert int(summary["CONV_ADD"]) > 0 and int(summary["GROUPNORM"]) > 0
+    # fusion off: the reference's op-by-op schedule
+    rep0 = plan_summary(text, fuse_nodes=False, fuse_attention=False, library_path=engine_lib)
+    assert int(dict(kv.split("=") for kv in rep0.splitlines()[-1].split()[1:])["steps"]) == n_ops
+    # an LLM decode graph: the ScaledDotProductAttention rewrite windows are found
+    d = os.path.join(workdir, "llama_plan") + "/"
+    emit.emit_llama_decode(d, emit.LlamaConfig.tiny(), "float32")
+    repl = plan_summary(open(d + "model.txt").read(), fp16_arithmetic=False, use_scaled_dp_attn_op=True, library_path=engine_lib)
+    assert "SDPA=%d" % emit.LlamaConfig.tiny().layers in repl.splitlines()[-1]
+    with pytest.raises(Exception):
+        plan_summary("not a model line", library_path=engine_lib)
+
+
 def test_golden_vectors(oracle_lib):
     """tests/golden/*.npz were produced by tests/golden/make_golden.py from oracle/_ref; the restatement and the reference
     must both still reproduce them (guards the emitter, the oracle build and the restatement against silent drift)."""
