@@ -16,6 +16,7 @@ struct NcclApi {
     int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
 
@@ -30,6 +31,7 @@ NcclApi& api()
     a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.handle, "ncclCommInitRank");
     a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.handle, "ncclCommDestroy");
     a.Broadcast = (decltype(a.Broadcast))dlsym(a.handle, "ncclBroadcast");
+    a.AllGather = (decltype(a.AllGather))dlsym(a.handle, "ncclAllGather");
     a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.handle, "ncclGetErrorString");
     if (!a.GetUniqueId || !a.CommInitRank || !a.Broadcast) throw std::runtime_error("onnxstream_b200: incomplete NCCL library");
     return a;
@@ -44,6 +46,14 @@ void WeightStreamer::nccl_broadcast(void* dev, size_t bytes)
     // ncclChar = 0 in ncclDataType_t; root 0 is the rank that did the H2D
     int r = api().Broadcast(dev, dev, bytes, 0, 0, (void*)m_comm, m_copy);
     if (r != 0) throw std::runtime_error(std::string("ncclBroadcast failed: ") + (api().GetErrorString ? api().GetErrorString(r) : "?"));
+}
+
+// in-place all-gather over a ring slot laid out as nranks chunks of `chunk_bytes`: rank r contributes [r * chunk, (r + 1) * chunk)
+void WeightStreamer::nccl_allgather_inplace(void* dev, size_t chunk_bytes)
+{
+    if (!api().AllGather) throw std::runtime_error("onnxstream_b200: ncclAllGather not found in the NCCL library");
+    int r = api().AllGather((const char*)dev + (size_t)m_rank * chunk_bytes, dev, chunk_bytes, 0 /* ncclChar */, (void*)m_comm, m_copy);
+    if (r != 0) throw std::runtime_error(std::string("ncclAllGather failed: ") + (api().GetErrorString ? api().GetErrorString(r) : "?"));
 }
 
 }  // namespace osb

@@ -384,8 +384,10 @@ void* ram_source_add(WeightSource* ram, const std::string& name, size_t bytes)
 // ================================================================================================================
 
 WeightStreamer::WeightStreamer(size_t capacity, bool host_mirror, ncclComm* comm, int rank, int nranks)
-    : m_cap((capacity + 255) & ~(size_t)255), m_comm(comm), m_rank(rank), m_nranks(nranks)
+    : m_cap(((capacity + 255) & ~(size_t)255) + (nranks > 1 ? (size_t)256 * nranks : 0)), m_comm(comm), m_rank(rank), m_nranks(nranks)
 {
+    // (N > 1: room for the per-rank chunk padding of the sharded upload)
+    if (const char* e = getenv("OSB_SHARDED_H2D")) m_sharded = e[0] == '1' && nranks > 1;
     check_cuda(cudaStreamCreateWithFlags(&m_copy, cudaStreamNonBlocking), "cudaStreamCreate(copy)");
     check_cuda(cudaMalloc(&m_ring, m_cap), "cudaMalloc(weight ring)");
     if (host_mirror) m_host = (char*)pinned_alloc(m_cap, "cudaHostAlloc(weight staging)");
@@ -446,6 +448,9 @@ WeightStreamer::Slot* WeightStreamer::stage(WeightSource& src, const std::vector
     size_t total = 0;
     for (auto& r : node) total += (r.bytes + 255) & ~(size_t)255;
     if (total == 0) total = 256;
+    // sharded upload: the slot is nranks equal chunks (the last ones may be padding)
+    const size_t chunk = m_sharded ? ((((total + m_nranks - 1) / m_nranks) + 255) & ~(size_t)255) : 0;
+    if (m_sharded) total = std::max(total, chunk * (size_t)m_nranks);
     size_t off = 0;
     if (!try_reserve(total, off)) {
         if (must) throw std::runtime_error("WeightStreamer: ring full although all previous nodes were released");
@@ -476,8 +481,15 @@ WeightStreamer::Slot* WeightStreamer::stage(WeightSource& src, const std::vector
         contiguous = (const char*)s.blobs[k + 1].host == (const char*)s.blobs[k].host + ((s.blobs[k].bytes + 255) & ~(size_t)255);
     if (contiguous) {
         size_t span = ((const char*)s.blobs.back().host - (const char*)s.blobs.front().host) + s.blobs.back().bytes;
-        if (do_h2d) check_cuda(cudaMemcpyAsync(s.blobs.front().dev, s.blobs.front().host, span, cudaMemcpyHostToDevice, m_copy), "cudaMemcpyAsync(node H2D)");
-        if (m_nranks > 1) nccl_broadcast(s.blobs.front().dev, span);
+        if (m_sharded) {
+            // every rank holds the same host bytes: upload slice [rank * chunk, (rank + 1) * chunk) of the node, gather the rest over NVLink
+            size_t lo = std::min(span, (size_t)m_rank * chunk), hi = std::min(span, lo + chunk);
+            if (hi > lo) check_cuda(cudaMemcpyAsync((char*)s.blobs.front().dev + lo, (const char*)s.blobs.front().host + lo, hi - lo, cudaMemcpyHostToDevice, m_copy), "cudaMemcpyAsync(node shard H2D)");
+            nccl_allgather_inplace(s.blobs.front().dev, chunk);
+        } else {
+            if (do_h2d) check_cuda(cudaMemcpyAsync(s.blobs.front().dev, s.blobs.front().host, span, cudaMemcpyHostToDevice, m_copy), "cudaMemcpyAsync(node H2D)");
+            if (m_nranks > 1) nccl_broadcast(s.blobs.front().dev, span);
+        }
         for (size_t k = 0; k < node.size(); k++) if (node[k].type != DType::i64) m_streamed += node[k].bytes;
     } else {
         for (size_t k = 0; k < node.size(); k++) {

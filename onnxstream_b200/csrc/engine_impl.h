@@ -42,6 +42,9 @@ public:
     size_t peak_live() const { return m_peak_live; }
     size_t streamed() const { return m_streamed; }
     cudaStream_t copy_stream() const { return m_copy; }
+    // N > 1 only: every rank uploads 1/N of each node over its own PCIe link and an in-place ncclAllGather completes the slot
+    // (N x the aggregate host->device bandwidth of the root-upload + ncclBroadcast default).  Opt-in until validated at N = 8.
+    void set_sharded_upload(bool on) { m_sharded = on && m_nranks > 1; }
 
 private:
     size_t m_cap = 0, m_head = 0, m_live = 0, m_peak_live = 0, m_streamed = 0;
@@ -52,10 +55,12 @@ private:
     std::vector<cudaEvent_t> m_event_pool;
     ncclComm* m_comm = nullptr;
     int m_rank = 0, m_nranks = 1;
+    bool m_sharded = false;
 
     bool try_reserve(size_t bytes, size_t& off);
     cudaEvent_t get_event();
     void nccl_broadcast(void* dev, size_t bytes);
+    void nccl_allgather_inplace(void* dev, size_t chunk_bytes);
 };
 
 }  // namespace osb
