@@ -486,11 +486,12 @@ WeightStreamer::Slot* WeightStreamer::stage(WeightSource& src, const std::vector
             size_t lo = std::min(span, (size_t)m_rank * chunk), hi = std::min(span, lo + chunk);
             if (hi > lo) check_cuda(cudaMemcpyAsync((char*)s.blobs.front().dev + lo, (const char*)s.blobs.front().host + lo, hi - lo, cudaMemcpyHostToDevice, m_copy), "cudaMemcpyAsync(node shard H2D)");
             nccl_allgather_inplace(s.blobs.front().dev, chunk);
+            m_streamed += hi - lo;     // bytes this rank moved over PCIe
         } else {
             if (do_h2d) check_cuda(cudaMemcpyAsync(s.blobs.front().dev, s.blobs.front().host, span, cudaMemcpyHostToDevice, m_copy), "cudaMemcpyAsync(node H2D)");
             if (m_nranks > 1) nccl_broadcast(s.blobs.front().dev, span);
+            for (size_t k = 0; k < node.size(); k++) if (node[k].type != DType::i64) m_streamed += node[k].bytes;
         }
-        for (size_t k = 0; k < node.size(); k++) if (node[k].type != DType::i64) m_streamed += node[k].bytes;
     } else {
         for (size_t k = 0; k < node.size(); k++) {
             const Blob& b = s.blobs[k];
