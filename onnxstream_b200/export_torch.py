@@ -36,6 +36,7 @@ class TorchExporter:
         self.env: Dict[str, object] = {}     # fx node name -> T | list[T] | python scalar | np.ndarray (host constant)
         self.input_names: List[str] = []
         self.output_names: List[str] = []
+        self.prov: Dict[str, tuple] = {}     # T.name -> how it was produced (used to canonicalise attention blocks)
 
     # ---------------------------------------------------------------------------------------------------------
     def export(self, module, example_args: Tuple, input_names: Optional[Sequence[str]] = None, output_names: Optional[Sequence[str]] = None) -> Dict:
@@ -159,6 +160,38 @@ class TorchExporter:
             arr = np.asarray(t)
         return self.g.const(arr, name=name, conv_weight=conv_weight, quantizable=quantizable)
 
+    def _canonical_heads(self, q: T, k: T, v: T):
+        """If q, k, v are each Transpose(0,2,1,3)(Reshape[1,T,H,D](MatMul(x, W))) and those nine lines are exactly the tail of the
+        emitted graph, replace them by the canonical head-split sequence and return (q [H,T,D], k^T [H,D,Tk], v [H,Tk,D])."""
+        g = self.g
+        pieces, lines = [], set()
+        for t in (q, k, v):
+            p1 = self.prov.get(t.name)
+            if not p1 or p1[0] != "transpose" or p1[2] != (0, 2, 1, 3):
+                return None
+            p2 = self.prov.get(p1[1].name)
+            if not p2 or p2[0] != "reshape" or len(p1[1].shape) != 4 or p1[1].shape[0] != 1:
+                return None
+            p3 = self.prov.get(p2[1].name)
+            if not p3 or p3[0] != "linear" or len(p2[1].shape) != 3 or p2[1].shape[0] != 1:
+                return None
+            pieces.append((p3[1], p3[2], p1[1].shape))     # (x, W, [1, T, H, D])
+            lines |= {p1[3], p2[2], p3[3]}
+        n = len(g.lines)
+        if lines != set(range(n - 9, n)):
+            return None
+        del g.lines[n - 9:]
+        outs = []
+        for idx, (x, w, (_, t, h, d)) in enumerate(pieces):
+            y = g.node("MatMul", [x, w], [(1, t, h * d)])
+            r = g.node("Reshape", [y, g.i64([1, t, h, d])], [(1, t, h, d)])
+            p = g.node("Transpose", [r], [(1, h, t, d)], [("perm", "0,2,1,3")])
+            r2 = g.node("Reshape", [p, g.i64([h, t, d])], [(h, t, d)])
+            if idx == 1:
+                r2 = g.node("Transpose", [r2], [(h, d, t)], [("perm", "0,2,1")])
+            outs.append(r2)
+        return tuple(outs)
+
     @staticmethod
     def _shape(n) -> Tuple[int, ...]:
         return tuple(int(d) for d in n.meta["val"].shape)
@@ -217,8 +250,11 @@ class TorchExporter:
                 wn = self._const(wt, name=g._uid("w") + "_transposed")
                 self.env[n.name] = g.node("Gemm", [x, wn, self._const(b)], [out_shape])
             else:
-                y = g.node("MatMul", [x, self._const(wt)], [out_shape])
-                if b is not None:
+                wT = self._const(wt)
+                y = g.node("MatMul", [x, wT], [out_shape])
+                if b is None:
+                    self.prov[y.name] = ("linear", x, wT, len(g.lines) - 1)
+                else:
                     y = g.node("Add", [self._const(b), y], [out_shape])
                 self.env[n.name] = y
         elif name == "aten.group_norm.default":
@@ -326,8 +362,15 @@ class TorchExporter:
             # the diffusers-export form of attention on [H, T, D]: MatMul(q, k^T) -> Mul(scale) -> Softmax -> MatMul(p, v)
             h, tq, d = q.shape[1:]
             tk = k.shape[2]
-            q3, k3, v3 = self._reshape(q, (h, tq, d)), self._reshape(k, (h, tk, d)), self._reshape(v, (h, tk, v.shape[3]))
-            kt = g.node("Transpose", [k3], [(h, d, tk)], [("perm", "0,2,1")])
+            canon = self._canonical_heads(q, k, v) if mask is None else None
+            if canon is not None:
+                # q/k/v = transpose(view(linear(x))) and nothing else was emitted in between: re-emit the three projections in the order
+                # of the diffusers ONNX export (projection, Reshape, Transpose, Reshape per operand; K transposed last), the 20-op
+                # window the engine turns into one grouped projection launch + one flash-attention launch
+                q3, kt, v3 = canon
+            else:
+                q3, k3, v3 = self._reshape(q, (h, tq, d)), self._reshape(k, (h, tk, d)), self._reshape(v, (h, tk, v.shape[3]))
+                kt = g.node("Transpose", [k3], [(h, d, tk)], [("perm", "0,2,1")])
             s = g.node("MatMul", [q3, kt], [(h, tq, tk)])
             s = g.node("Mul", [s, g.scalar(float(scale))], [(h, tq, tk)])
             if mask is not None:
@@ -339,7 +382,11 @@ class TorchExporter:
             self.env[n.name] = self._reshape(o, out_shape)
         elif name in ("aten.view.default", "aten.reshape.default", "aten._unsafe_view.default", "aten.flatten.using_ints", "aten.unflatten.int",
                       "aten.unsqueeze.default", "aten.squeeze.dim", "aten.squeeze.default", "aten.squeeze.dims"):
-            self.env[n.name] = self._reshape(self._act(a[0]), out_shape)
+            src = self._act(a[0])
+            y = self._reshape(src, out_shape)
+            if y is not src:
+                self.prov[y.name] = ("reshape", src, len(g.lines) - 1)
+            self.env[n.name] = y
         elif name in ("aten.permute.default", "aten.transpose.int", "aten.t.default"):
             x = self._act(a[0])
             r = len(x.shape)
@@ -351,7 +398,12 @@ class TorchExporter:
                 perm = list(range(r))
                 d0, d1 = int(a[1]) % r, int(a[2]) % r
                 perm[d0], perm[d1] = perm[d1], perm[d0]
-            self.env[n.name] = x if perm == list(range(r)) else g.node("Transpose", [x], [out_shape], [("perm", ",".join(map(str, perm)))])
+            if perm == list(range(r)):
+                self.env[n.name] = x
+            else:
+                y = g.node("Transpose", [x], [out_shape], [("perm", ",".join(map(str, perm)))])
+                self.prov[y.name] = ("transpose", x, tuple(perm), len(g.lines) - 1)
+                self.env[n.name] = y
         elif name == "aten.cat.default":
             parts = [self._act(p) for p in a[0]]
             axis = int(a[1]) if len(a) > 1 else 0

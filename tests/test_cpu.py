@@ -186,6 +186,12 @@ def test_torch_exporter_block_matches_torch(oracle_lib, workdir):
         assert info["inputs"] == ["sample", "t_5F_emb"] and info["outputs"] == ["out_5F_sample"]     # converter's name mangling
         got = run_model(oracle_lib, d, dict(zip(info["inputs"], [x.numpy(), temb.numpy()])), opts)[0][info["outputs"][0]]
         assert got.shape == ref.shape and report(got, ref)["rel_to_max"] <= tol, wd
+        if wd == "float16":
+            # the exporter writes the attention block in the diffusers-export order: the engine's planner (host code, no GPU needed)
+            # must claim it as one multi-head-attention group next to GroupNorm / LayerNorm / GEGLU
+            from onnxstream_b200.model import plan_summary
+            last = plan_summary(open(d + "model.txt").read()).splitlines()[-1]
+            assert " MHA=1" in last and " GEGLU=1" in last and " GROUPNORM=1" in last and " LAYERNORM=1" in last, last
         # the numpy restatement agrees on the exported graph too
         if wd == "float32":
             npo = NumpyOracle(d).run(dict(zip(info["inputs"], [x.numpy(), temb.numpy()])))[info["outputs"][0]]
