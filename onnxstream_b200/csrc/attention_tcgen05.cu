@@ -13,6 +13,7 @@
 // merged [T, heads*d] layout, so the exported graph's head split / merge costs nothing.  d <= 64, d % 8 == 0.
 
 #include "common.cuh"
+#include <cstdlib>
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cstdio>
@@ -38,6 +39,7 @@ struct FaParams {
     int T, Tk, d, heads;
     int q_tiles, kv_tiles;
     float scale_log2;        // scale * log2(e)
+    float tau;               // lazy-rescaling threshold in log2 units (0 = exact running maximum)
     __half* out;             // [T, ldo] merged layout, head h at column h*d
     long long ldo;
 };
@@ -298,7 +300,11 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             xw[row] = mt;
             asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
             mt = fmaxf(mt, xr[row]);
-            const float m_new = fmaxf(m_run, mt * p.scale_log2);      // scale_log2 > 0
+            // Lazy rescaling: the stale maximum is kept while the new one exceeds it by at most tau (log2 units) -- P <= 2^tau stays well
+            // inside fp16, O and l accumulate in fp32 -- so most tiles skip the O rescale and with it the wait on the previous PV MMA.
+            // tau = 0 is the exact running maximum (the default until the threshold is validated on hardware: OSB_FLASH_TAU).
+            const float m_cand = fmaxf(m_run, mt * p.scale_log2);     // scale_log2 > 0
+            const float m_new = (m_cand - m_run > p.tau) ? m_cand : m_run;
             const float alpha = ex2_approx(m_run - m_new);            // 0 on the first tile (m_run = -inf)
             const float neg_m = -m_new;
             // p = 2^(s*scale*log2e - m_new): one FFMA + one MUFU.EX2 per score, packed to fp16 as produced
@@ -447,6 +453,8 @@ extern "C" int osb_flash_attention(const void* q, int64_t ldq, const void* k, in
     p.T = (int)T; p.Tk = (int)Tk; p.d = (int)d; p.heads = (int)heads;
     p.q_tiles = (int)((T + BQ - 1) / BQ); p.kv_tiles = (int)((Tk + BKV - 1) / BKV);
     p.scale_log2 = scale * 1.4426950408889634f;
+    static const float tau_env = [] { const char* e = getenv("OSB_FLASH_TAU"); float v = e ? (float)atof(e) : 0.f; return v < 0.f ? 0.f : (v > 12.f ? 12.f : v); }();
+    p.tau = tau_env;
     p.out = (__half*)out; p.ldo = ldo;
     dim3 grid((unsigned)p.q_tiles, (unsigned)heads);
     osb_launch((flash_attention_kernel), grid, FA_THREADS, (size_t)FA_SMEM, st, mq, mk, mv, p);
