@@ -175,10 +175,10 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int kb = 0; kb < k_blocks; kb++) {
                 mbar_wait(&empty[stage], phase ^ 1);
                 if (elect_one()) {
+                    if (leader) mbar_expect_tx(&full[stage], 2 * (A_BYTES + B_BYTES));      // both CTAs' bytes land on this barrier
                     tma_load_2d_2sm(sa0 + stage * A_BYTES, &map_a, &full[stage], kb * BLOCK_K, m0);
                     tma_load_2d_2sm(sb0 + stage * B_BYTES, &map_b, &full[stage], kb * BLOCK_K, n0);
-                    if (leader) mbar_expect_tx(&full[stage], 2 * (A_BYTES + B_BYTES));      // both CTAs' bytes land on this barrier
-                    else mbar_arrive_cluster(&full[stage], 0);                              // second arrival, no bytes of its own to announce
+                    if (!leader) mbar_arrive_cluster(&full[stage], 0);                      // second arrival, no bytes of its own to announce
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
