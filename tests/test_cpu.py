@@ -223,8 +223,16 @@ def test_torch_exporter_transformers_models(oracle_lib, workdir):
         d = os.path.join(workdir, "exp_" + name) + "/"
         info = export_module(w, (ids,), d, "float32", input_names=["input_ids"], output_names=[out])
         ref = w(ids).detach().numpy()
-        got = run_model(oracle_lib, d, {info["inputs"][0]: ids.numpy().astype(np.int64)})[0][info["outputs"][0]]
+        feed = {info["inputs"][0]: ids.numpy().astype(np.int64)}
+        got = run_model(oracle_lib, d, feed)[0][info["outputs"][0]]
         assert got.shape == ref.shape and report(got, ref)["rel_to_max"] <= 2e-5, name
+        # three-way: the numpy restatement agrees with torch (and hence with the reference) on the same export
+        assert report(NumpyOracle(d).run(feed)[info["outputs"][0]], ref)["rel_to_max"] <= 2e-5, name
+        # fp16 weights + fp16 arithmetic in the reference stays within the fp16 bar of torch's fp32 forward
+        d16 = os.path.join(workdir, "exp16_" + name) + "/"
+        info16 = export_module(w, (ids,), d16, "float16", input_names=["input_ids"], output_names=[out])
+        got16 = run_model(oracle_lib, d16, feed, ("use_fp16_arithmetic", "fuse_ops_in_attention"))[0][info16["outputs"][0]]
+        assert report(got16, ref)["rel_to_max"] <= 2e-2, name
 
 
 def test_planner_fusion_on_cpu(engine_lib, workdir):
