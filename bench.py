@@ -1,21 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- SD 1.5 UNet 512x512 bs=1 denoise-step throughput on N B200s (BASELINE.json config[1] hot path).
+"""bench.py -- the BASELINE.json workloads of the B200 OnnxStream engine, one JSON line per run.
 
-One "step" = one UNet Model::run() on one 4x64x64 latent (the reference runs two per sampler step with CFG; the
-metric counts UNet runs).  fp16 weights / fp16 arithmetic / attention fusion, i.e. what sd.cpp sets
-(src/sd.cpp:1616-1683).  Synthetic SD1.5-shaped graph + seeded random weights (no checkpoints offline).
+Default workload (what the driver runs): SD 1.5 UNet 512x512 bs=1 denoise-step throughput (BASELINE config[1] hot path).
+One "step" = one UNet Model::run() on one 4x64x64 latent (the reference runs two per sampler step with CFG; the metric counts
+UNet runs).  fp16 weights / fp16 arithmetic / attention fusion, i.e. what sd.cpp sets (src/sd.cpp:1616-1683).  Synthetic
+graphs of the named architectures + seeded random weights (no checkpoints offline).
 
-  value  : steps/s with weights and inputs resident in HBM (one captured CUDA graph per step), CUDA-event timed
-  e2e    : the same metric through the reference-facing C ABI with HOST buffers: every step pushes the inputs from
-           pinned host memory, streams all 1.72 GB of weights pinned-host -> HBM ring (the CUDA WeightsProvider; N>1:
-           rank 0 uploads, NCCL broadcast) and reads the output latent back
+  value   : units/s with weights and inputs resident in HBM (one captured CUDA graph per step where the graph has no int64
+            inputs), CUDA-event timed on the compute stream
+  e2e     : the same metric through the reference-facing C ABI with HOST buffers: every step pushes the inputs from pinned host
+            memory, streams ALL weights pinned-host -> HBM ring (the CUDA WeightsProvider; N>1: every rank uploads 1/N of each
+            node over its own PCIe link and an NCCL all-gather over NVLink completes the ring slot) and reads the output back
   roofline: the dominant kernel (tcgen05 implicit-GEMM conv / GEMM) timed per launch with CUDA events in an eager pass
-  cpu_baseline: the reference's own CPU path (oracle/_ref: reference sources + XNNPACK) on the host cores
+  cpu_baseline / --impl reference: the reference's own CPU path (oracle/_ref: unmodified reference sources + XNNPACK), FULL
+            graph runs on the host cores (no prefix extrapolation for the default workload)
+  parity  : every rank checks its streamed output against its resident-weights output, and one common sample against the
+            reference's output (oracle/_ref, cached per box); the max over ranks is in the line
 
-`--impl reference` times the reference CPU implementation alone (bounded sample per step).
+Other workloads (`--workload`): sdxl_unet_w8 (SDXL 1024x1024, uint8 weights; N=2 = the CFG cond/uncond pair), sdxl_turbo_w8
+(512x512, one sample per GPU), vae_decoder_fp16, clip_text_fp32, sd15_pipeline (text encoder + 20 CFG steps + VAE decoder),
+tinyllama_decode (seq 2048).  `--all-configs FILE` runs them all and writes one line each.
 """
 import argparse
 import ctypes
+import hashlib
 import json
 import os
 import subprocess
@@ -51,9 +59,169 @@ from onnxstream_b200 import emit  # noqa: E402
 from onnxstream_b200.model import Model, ENGINE_LIB  # noqa: E402
 
 ORACLE_LIB = os.path.join(ROOT, "oracle", "_ref", "liboracle_ref.so")
-REF_THREADS = min(os.cpu_count() or 1, 32)
-os.environ.setdefault("OMP_NUM_THREADS", str(REF_THREADS))
-METRIC = "SD1.5 UNet 512x512 bs=1 denoise steps/s (one UNet Model::run per step)"
+HOST_CORES = os.cpu_count() or 1
+# XNNPACK's pthreadpool with one worker per core is far slower than a moderate pool on many-core hosts (measured r01: 128
+# workers -> 295 s per UNet run on the GPU box, vs 38 s with 8 on an 8-core host), so the reference gets min(cores, 32).
+REF_THREADS = min(HOST_CORES, 32)
+# torchrun exports OMP_NUM_THREADS=1 to every rank: ASSIGN (the oracle's shim loops are OpenMP; the engine does not use OpenMP)
+os.environ["OMP_NUM_THREADS"] = str(REF_THREADS)
+SHM = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else "/tmp"
+REF_CACHE = os.path.join(SHM, "osb200_ref_cache")
+
+FP16 = ("use_fp16_arithmetic", "fuse_ops_in_attention")
+
+
+# =====================================================================================================================
+# workloads
+# =====================================================================================================================
+class Workload:
+    name = ""
+    metric = ""
+    unit = "steps/s"
+    out_name = "out_5F_sample"
+    options = FP16
+    ref_options = ("fuse_ops_in_attention",)   # fp16 weights, fp32 XNNPACK arithmetic: the reference's --rpi mode (src/sd.cpp:1636-1638)
+    dtype = "f16"
+    tol = 3e-2            # |engine - reference| <= tol * max|reference| (fp16 arithmetic vs fp32 arithmetic on fp16 weights)
+    describe = ""
+    upcast = ()
+
+    def emit(self, d):
+        raise NotImplementedError
+
+    def inputs(self, seed):
+        raise NotImplementedError
+
+
+class SD15UNet(Workload):
+    name = "sd15_unet_fp16"
+    metric = "SD1.5 UNet 512x512 bs=1 denoise steps/s (one UNet Model::run per step)"
+
+    def __init__(self, latent=64):
+        self.cfg = emit.UNetConfig.sd15(latent)
+        self.describe = "SD1.5 UNet-shaped graph (BASELINE config[1] hot path), 4x%dx%d latent, 77x768 context, fp16 weights + fp16 arithmetic (fp32 accumulate)" % (latent, latent)
+
+    def emit(self, d):
+        return emit.emit_unet(d, self.cfg, "float16", seed=0)
+
+    def inputs(self, seed):
+        return emit.unet_inputs(self.cfg, seed=seed)
+
+
+class TinyUNet(SD15UNet):
+    name = "tiny_unet_fp16"
+    metric = "tiny UNet steps/s (plumbing check)"
+
+    def __init__(self):
+        self.cfg = emit.UNetConfig.tiny(16)
+        self.describe = "tiny SD-UNet-shaped graph, 16x16 latent"
+
+
+class SDXLUNet(Workload):
+    """SDXL base UNet, uint8 weights (the reference's W8A32 storage, onnx2txt percentile rule), sd.cpp's default arithmetic flags
+    (m_use_fp16_arithmetic: blobs are dequantised on the device into fp16 operands, fp32 accumulate).  BASELINE config[2]:
+    1024x1024, the CFG cond/uncond pair = 2 UNet runs per sampler step, one per GPU at N=2."""
+    name = "sdxl_unet_w8"
+    metric = "SDXL UNet 1024x1024 steps/s (one UNet Model::run per step; N=2 = the CFG cond/uncond pair)"
+    tol = 4e-2
+
+    def __init__(self, latent=128, name=None, metric=None):
+        self.cfg = emit.UNetConfig.sdxl(latent)
+        if name:
+            self.name = name
+        if metric:
+            self.metric = metric
+        px = latent * 8
+        self.describe = "SDXL-UNet-shaped graph, 4x%dx%d latent (%dx%d px), 77x2048 context, time_ids/text_embeds add-embedding, uint8 weights dequantised on the device, fp16 arithmetic" % (latent, latent, px, px)
+
+    def emit(self, d):
+        return emit.emit_unet(d, self.cfg, "uint8", seed=0)
+
+    def inputs(self, seed):
+        return emit.unet_inputs(self.cfg, seed=seed)
+
+
+class VAEDecoder(Workload):
+    name = "vae_decoder_fp16"
+    metric = "SD1.5 VAE decoder 64x64 -> 512x512 decodes/s"
+    unit = "decodes/s"
+    out_name = "outsample"
+    options = FP16
+    ref_options = ()
+
+    def __init__(self):
+        self.cfg = emit.VAEConfig()
+        self.describe = "SD VAE-decoder-shaped graph, 4x64x64 latent -> 3x512x512, fp16 weights + fp16 arithmetic"
+
+    def emit(self, d):
+        return emit.emit_vae_decoder(d, self.cfg, "float16")
+
+    def inputs(self, seed):
+        return {"input_2E_1": np.random.default_rng(5 + seed).standard_normal((1, 4, self.cfg.latent, self.cfg.latent)).astype(np.float32)}
+
+
+class CLIPText(Workload):
+    name = "clip_text_fp32"
+    metric = "CLIP text encoder (12 layers, 768 wide, 77 tokens) runs/s"
+    unit = "runs/s"
+    out_name = "last_5F_hidden_5F_state"
+    options = ()
+    ref_options = ()
+    dtype = "f32"
+    tol = 2e-4
+
+    def __init__(self):
+        self.cfg = emit.CLIPConfig()
+        self.describe = "CLIP-text-encoder-shaped graph, fp32 (what sd.cpp runs the text encoder in)"
+
+    def emit(self, d):
+        return emit.emit_text_encoder(d, self.cfg, "float32")
+
+    def inputs(self, seed):
+        return {"input_5F_ids": np.random.default_rng(6 + seed).integers(0, self.cfg.vocab, (1, self.cfg.tokens)).astype(np.int64)}
+
+
+class LlamaDecode(Workload):
+    """TinyLlama-1.1B-shaped single-token decode at sequence 2048 (2047 cached positions), fp16 as llm.cpp ships it (src/llm.cpp:377)."""
+    name = "tinyllama_decode"
+    metric = "TinyLlama-1.1B decode tokens/s at seq 2048 (one Model::run per token)"
+    unit = "tokens/s"
+    out_name = "logits"
+    options = ("use_fp16_arithmetic", "use_scaled_dp_attn_op")
+    ref_options = ("use_scaled_dp_attn_op",)
+    upcast = ("layernorm", "/norm/")
+
+    def __init__(self, tiny=False):
+        self.cfg = emit.LlamaConfig.tiny() if tiny else emit.LlamaConfig()
+        self.describe = "Llama-shaped decode graph: %d layers, hidden %d, %d/%d heads, vocab %d, %d cached positions, fp16 weights" % (
+            self.cfg.layers, self.cfg.hidden, self.cfg.heads, self.cfg.kv_heads, self.cfg.vocab, self.cfg.past)
+
+    def emit(self, d):
+        return emit.emit_llama_decode(d, self.cfg, "float16")
+
+    def inputs(self, seed):
+        return emit.llama_inputs(self.cfg, seed=seed)
+
+
+def make_workload(name):
+    if name == "sd15_unet_fp16":
+        return SD15UNet()
+    if name == "tiny_unet_fp16":
+        return TinyUNet()
+    if name == "sdxl_unet_w8":
+        return SDXLUNet(128)
+    if name == "sdxl_turbo_w8":
+        return SDXLUNet(64, "sdxl_turbo_w8", "SDXL Turbo UNet 512x512 1-step samples/s (one sample per GPU, shared streamed weights)")
+    if name == "vae_decoder_fp16":
+        return VAEDecoder()
+    if name == "clip_text_fp32":
+        return CLIPText()
+    if name == "tinyllama_decode":
+        return LlamaDecode()
+    raise SystemExit(f"unknown workload {name}")
+
+
+WORKLOADS = ["sd15_unet_fp16", "tiny_unet_fp16", "sdxl_unet_w8", "sdxl_turbo_w8", "vae_decoder_fp16", "clip_text_fp32", "tinyllama_decode", "sd15_pipeline"]
 
 
 def peaks():
@@ -65,25 +233,22 @@ def peaks():
 
 
 def model_dir(workload: str) -> str:
-    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else "/tmp"
-    return os.path.join(base, f"osb200_bench_{workload}") + "/"
+    return os.path.join(SHM, f"osb200_bench_{workload}") + "/"
 
 
-def ensure_model(workload: str):
-    """Emit the synthetic model directory once per box (rank 0), return (dir, cfg, flops, weight_bytes)."""
-    cfg = emit.UNetConfig.sd15(64) if workload == "sd15_unet_fp16" else emit.UNetConfig.tiny(16)
-    d = model_dir(workload)
+def ensure_model(w: Workload):
+    """Emit the synthetic model directory once per box (rank 0), return (dir, meta)."""
+    d = model_dir(w.name)
     meta = os.path.join(d, "meta.json")
     if not os.path.exists(meta):
         if RANK == 0:
-            g = emit.emit_unet(d, cfg, "float16", seed=0)
+            g = w.emit(d)
             json.dump({"flops": g.flops, "weight_bytes": g.weight_bytes, "params": g.weight_params, "ops": len(g.lines)}, open(meta + ".tmp", "w"))
             os.replace(meta + ".tmp", meta)
         else:
             while not os.path.exists(meta):
                 time.sleep(0.5)
-    m = json.load(open(meta))
-    return d, cfg, m
+    return d, json.load(open(meta))
 
 
 class ClockSampler:
@@ -116,6 +281,9 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
+# =====================================================================================================================
+# torch.distributed plumbing (NCCL; one process per GPU)
+# =====================================================================================================================
 def dist_setup():
     if WORLD == 1:
         return None
@@ -142,10 +310,24 @@ def dist_barrier(dist):
         torch.cuda.synchronize()
 
 
-def make_engine_model(d, wp, resident, graph, comm=None):
+def dist_bcast_array(dist, arr, src=0):
+    """Broadcast a float32 numpy array from rank `src` (shape known to every rank through `arr.shape` on src only)."""
+    if dist is None:
+        return arr
+    obj = [arr if RANK == src else None]
+    dist.broadcast_object_list(obj, src=src)
+    return obj[0]
+
+
+# =====================================================================================================================
+# engine / reference drivers (both through the reference's C ABI)
+# =====================================================================================================================
+def make_engine_model(d, w: Workload, wp, resident, graph, comm=None):
     m = Model(ENGINE_LIB, 0, wp)
-    m.set_option("use_fp16_arithmetic", True)
-    m.set_option("fuse_ops_in_attention", True)
+    for o in w.options:
+        m.set_option(o, True)
+    for p in w.upcast:
+        m.add_upcast_pattern(p)
     m.lib.model_set_option(m.h, b"b200_resident_weights", 1 if resident else 0)
     m.lib.model_set_option(m.h, b"b200_cuda_graph", 1 if graph else 0)
     if comm is not None:
@@ -154,17 +336,52 @@ def make_engine_model(d, wp, resident, graph, comm=None):
     return m
 
 
-def step_api(m, inputs, out_name="out_5F_sample"):
+def step_api(m, inputs, out_name):
     m.clear_tensors()
     for k, v in inputs.items():
         m.add_tensor(k, v)
     m.run()
-    return m.get_tensor(out_name)
+    return m.get_tensor(out_name) if out_name else None
+
+
+def oracle_set_threads(n):
+    lib = ctypes.CDLL(ORACLE_LIB)     # dlsym through the oracle's own dependencies reaches the libgomp it links
+    lib.omp_set_num_threads(int(n))
+
+
+def make_reference_model(d, w: Workload, model_file="model.txt"):
+    oracle_set_threads(REF_THREADS)
+    m = Model(ORACLE_LIB, REF_THREADS, "nocache")
+    for o in w.ref_options:
+        m.set_option(o, True)
+    m.read_file(d + model_file)
+    return m
+
+
+def reference_output_cached(d, w: Workload, inputs):
+    """One FULL run of the reference on `inputs`, cached per box (shared with tests/test_fullsize_gpu.py's cache layout).
+    Returns (output, seconds or None when served from the cache)."""
+    h = hashlib.sha1()
+    h.update(open(d + "model.txt", "rb").read())
+    for k in sorted(inputs):
+        h.update(k.encode()); h.update(np.ascontiguousarray(inputs[k]).tobytes())
+    h.update(repr((tuple(w.ref_options), w.out_name, "bench")).encode())
+    os.makedirs(REF_CACHE, exist_ok=True)
+    fn = os.path.join(REF_CACHE, h.hexdigest() + ".npy")
+    if os.path.exists(fn):
+        return np.load(fn), None
+    m = make_reference_model(d, w)
+    t = time.time()
+    out = step_api(m, inputs, w.out_name)
+    dt = time.time() - t
+    m.close()
+    np.save(fn + ".tmp.npy", out)
+    os.replace(fn + ".tmp.npy", fn)
+    return out, dt
 
 
 def model_lines_flops(d):
-    """Per-line FLOPs of Conv / MatMul / Gemm ops of a model.txt (for bounded CPU samples)."""
-    import re
+    """Per-line FLOPs of Conv / MatMul / Gemm ops of a model.txt (for bounded CPU samples of the large workloads)."""
     out = []
     for line in open(d + "model.txt").read().splitlines():
         if not line:
@@ -181,8 +398,8 @@ def model_lines_flops(d):
                 return [int(x) for x in s.split(",") if x]
             o = shape(outs[0])
             if typ == "Conv":
-                w = shape(ins[1])
-                fl = 2 * int(np.prod(o)) * w[1] * w[2] * w[3]
+                wsh = shape(ins[1])
+                fl = 2 * int(np.prod(o)) * wsh[1] * wsh[2] * wsh[3]
             else:
                 a = shape(ins[0])
                 fl = 2 * int(np.prod(o)) * a[-1]
@@ -190,126 +407,136 @@ def model_lines_flops(d):
     return out
 
 
-def cpu_sample(d, inputs, frac, tag):
-    """Time the reference CPU path on a prefix of the graph holding ~frac of its FLOPs; returns (seconds, actual fraction)."""
+def time_reference(d, w: Workload, inputs, steps, warmup, budget_s):
+    """FULL-graph runs of the reference CPU path: min(steps, what fits in budget_s) timed runs after min(warmup, 1) warm-up runs.
+    When a single full run does not fit the budget (SDXL 1024x1024), a FLOP-weighted prefix of the graph is timed instead and the
+    result is scaled -- stated in `sample`.  Returns (units_per_second, sample_text, seconds_per_run)."""
+    m = make_reference_model(d, w)
+    t = time.time(); step_api(m, inputs, None); t_first = time.time() - t      # warm-up run (also the calibration)
+    if t_first <= budget_s / 2.5:
+        n = int(max(1, min(steps, (budget_s - t_first) // max(t_first, 1e-3))))
+        if warmup > 1 and t_first * (n + 1) < budget_s * 0.5:
+            step_api(m, inputs, None)
+        ts = []
+        for _ in range(n):
+            t = time.time(); step_api(m, inputs, None); ts.append(time.time() - t)
+        m.close()
+        per = float(np.mean(ts))
+        return 1.0 / per, f"{n} full runs of the whole graph (all {len(open(d + 'model.txt').read().splitlines())} ops) after 1-2 warm-up runs; mean {per:.2f} s, min {min(ts):.2f} s, max {max(ts):.2f} s per run", per
+    m.close()
+    # too slow for full runs: prefix holding ~frac of the Conv/MatMul FLOPs
     lf = model_lines_flops(d)
     total = sum(f for _, f in lf)
-    acc, n = 0, 0
+    frac = max(0.02, min(0.5, budget_s / 3.0 / t_first))
+    acc, n_ops = 0, 0
     for i, (_, f) in enumerate(lf):
-        acc += f
-        n = i + 1
+        acc += f; n_ops = i + 1
         if acc >= frac * total:
             break
-    if frac >= 0.999:
-        n, acc = len(lf), total
-    fn = d + f"model_prefix_{tag}.txt"
-    open(fn, "w").write("\n".join(l for l, _ in lf[:n]) + "\n")
-    # XNNPACK's pthreadpool with one worker per core is far slower than a moderate pool on many-core hosts (measured: 128
-    # workers -> 295 s per UNet run on the GPU box, vs 38 s with 8 on an 8-core host), so the reference gets min(cores, 32).
-    m = Model(ORACLE_LIB, REF_THREADS, "nocache")
-    m.set_option("fuse_ops_in_attention", True)   # fp16 weights, fp32 arithmetic: the reference's --rpi mode (src/sd.cpp:1636-1638)
-    m.read_file(fn)
-    return m, acc / total, n
+    fn = "model_prefix_ref.txt"
+    open(d + fn, "w").write("\n".join(l for l, _ in lf[:n_ops]) + "\n")
+    m = make_reference_model(d, w, fn)
+    step_api(m, inputs, None)
+    ts = []
+    for _ in range(2):
+        t = time.time(); step_api(m, inputs, None); ts.append(time.time() - t)
+    m.close()
+    per = float(np.mean(ts)) / (acc / total)
+    return 1.0 / per, (f"one full run took {t_first:.1f} s (warm-up); timed sample = first {n_ops} of {len(lf)} graph ops = {100 * acc / total:.1f}% of the "
+                       f"Conv/MatMul FLOPs, 2 runs, scaled to the whole graph"), per
 
 
+# =====================================================================================================================
+# the reference arm (--impl reference)
+# =====================================================================================================================
 def run_reference(args):
-    d, cfg, meta = ensure_model(args.workload)
-    inputs = emit.unet_inputs(cfg)
-    cores = REF_THREADS
     if RANK != 0:
         return
+    if args.workload == "sd15_pipeline":
+        emit_line({"impl": "reference", "unavailable": "sd15_pipeline is a composite of three workloads: run their reference arms separately"})
+        return
+    w = make_workload(args.workload)
     if not os.path.exists(ORACLE_LIB):
         emit_line({"impl": "reference", "unavailable": "oracle/_ref/liboracle_ref.so missing (built from /root/reference by __graft_entry__.build())"})
         return
-    # calibrate on a small prefix, then size the per-step sample so that (K+W) steps take ~150 s
-    m, f0, _ = cpu_sample(d, inputs, 0.03, "cal")
-    t = time.time(); step_api(m, inputs, "nonexistent"); t_cal = time.time() - t
-    t = time.time(); step_api(m, inputs, "nonexistent"); t_cal = min(t_cal, time.time() - t)
-    full_est = t_cal / f0
-    budget = 150.0 / (args.steps + args.warmup)
-    frac = min(1.0, max(0.02, budget / full_est))
-    m, f, nops = cpu_sample(d, inputs, frac, "ref")
-    for _ in range(args.warmup):
-        step_api(m, inputs, "nonexistent")
-    t = time.time()
-    for _ in range(args.steps):
-        step_api(m, inputs, "nonexistent")
-    dt = (time.time() - t) / args.steps
-    value = f / dt
-    sample = f"first {nops} of {meta['ops']} graph ops = {100 * f:.1f}% of the UNet's Conv/MatMul FLOPs per step, extrapolated to one full UNet run"
+    d, meta = ensure_model(w)
+    inputs = w.inputs(0)
+    value, sample, per = time_reference(d, w, inputs, args.steps, args.warmup, budget_s=float(os.environ.get("OSB_REF_BUDGET_S", "170")))
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": w.metric, "value": value, "unit": w.unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "SD1.5 UNet-shaped graph, 4x64x64 latent, 77x768 context, fp16 weights / fp32 XNNPACK arithmetic on host cores"},
-        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "reference", "sample": sample},
-        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": w.describe + " -- reference CPU path: same blobs, fp32 XNNPACK arithmetic, ONE sample on the host cores (per-sample throughput; it does not scale with --gpus)"},
+        "cpu_baseline": {"value": value, "unit": w.unit, "cores": REF_THREADS, "host_cores": HOST_CORES, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": w.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit_line(line)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="sd15_unet_fp16", choices=["sd15_unet_fp16", "tiny_unet_fp16"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
-
-    if args.impl == "reference":
-        run_reference(args)
-        return
-
-    dist = dist_setup()
-    d, cfg, meta = ensure_model(args.workload)
+# =====================================================================================================================
+# the B200 arm
+# =====================================================================================================================
+def measure(w: Workload, args, dist, clocks=None):
+    """value / e2e / roofline / parity for one single-model workload; returns the JSON line (rank 0) or None."""
+    d, meta = ensure_model(w)
     dist_barrier(dist)
-    inputs = emit.unet_inputs(cfg, seed=RANK)   # rank r = sample r (seed + rank, src/sd.cpp:2671)
+    inputs = w.inputs(RANK)   # rank r = sample r (seed + rank, src/sd.cpp:2671)
     peak_tf, peak_bw, peak_src = peaks()
+    has_i64 = any(v.dtype == np.int64 for v in inputs.values())
 
-    # ---------------- value arm: weights + inputs resident in HBM, one CUDA graph per step ----------------
-    mv = make_engine_model(d, "ram+nocache", resident=True, graph=True)
+    # ---------------- value arm: weights + inputs resident in HBM ----------------
+    mv = make_engine_model(d, w, "ram+nocache", resident=True, graph=not has_i64)
     for _ in range(3):      # run 1 fills the HBM weight cache, run 2 warms scratch, run 3 captures the graph
-        out_v = step_api(mv, inputs)
+        out_v = step_api(mv, inputs, w.out_name)
     st_v = mv.stats()
     launches_per_step = int(st_v["kernel_launches"])
-    clocks = ClockSampler(); clocks.start()      # sampled from the warm-up through both timed regions (value and e2e)
-    mv.run_resident(args.warmup)
-    dist_barrier(dist)
-    gpu_ms = mv.run_resident(args.steps)
+    if clocks is None:
+        clocks = ClockSampler(); clocks.start()      # sampled from the warm-up through both timed regions (value and e2e)
+    if not has_i64:
+        mv.run_resident(args.warmup)
+        dist_barrier(dist)
+        gpu_ms = mv.run_resident(args.steps)
+        value_mode = "HBM-resident weights + inputs, one captured CUDA graph per step"
+    else:
+        # int64 graph inputs (token ids) keep shape arithmetic on the host: eager runs, CUDA-event time of each run's stream work
+        for _ in range(args.warmup):
+            step_api(mv, inputs, None)
+        dist_barrier(dist)
+        gpu_ms = 0.0
+        for _ in range(args.steps):
+            step_api(mv, inputs, None)
+            gpu_ms += mv.stats()["last_gpu_ms"]
+        value_mode = "HBM-resident weights, eager launches (int64 inputs are host-evaluated), CUDA-event time per run incl. the input upload"
     dist_barrier(dist)
     gpu_ms = dist_max(dist, gpu_ms)
     ms_per_step = gpu_ms / args.steps
     value = WORLD * 1000.0 / ms_per_step
 
-    # ---------------- supplementary: the same C-ABI call with host buffers but HBM-resident weights (the reference's --ram mode) ----
-    # inputs H2D from pinned memory and output D2H every step, CUDA-graph replay in between; reported beside the streaming e2e
+    # ---------------- supplementary: host inputs / outputs through the C ABI every step, weights resident ----------------
     e2e_resident = None
     e2e_r_s, e2e_r_err = float("inf"), None
     try:                      # no collectives inside the try: a rank-local failure must not strand the other ranks at a barrier
         for _ in range(2):
-            step_api(mv, inputs)
+            step_api(mv, inputs, w.out_name)
         t0r = time.perf_counter()
         for _ in range(args.steps):
-            step_api(mv, inputs)
+            step_api(mv, inputs, w.out_name)
         e2e_r_s = time.perf_counter() - t0r
     except Exception as e:    # supplementary only: never take the bench down
         e2e_r_err = str(e)
-    e2e_r_s = dist_max(dist, e2e_r_s)          # every rank takes part, whatever happened above
+    e2e_r_s = dist_max(dist, e2e_r_s)
     if e2e_r_err is None and e2e_r_s != float("inf"):
-        e2e_resident = {"value": WORLD * args.steps / e2e_r_s, "unit": "steps/s", "ms_per_step": 1000.0 * e2e_r_s / args.steps,
+        e2e_resident = {"value": WORLD * args.steps / e2e_r_s, "unit": w.unit, "ms_per_step": 1000.0 * e2e_r_s / args.steps,
                         "note": "host inputs / outputs through the C ABI every step, weights resident in HBM (b200_resident_weights, the reference's --ram mode); ranks not barrier-aligned"}
     else:
         e2e_resident = {"value": None, "note": f"failed: {e2e_r_err}"}
 
     # ---------------- roofline leg: eager pass with per-launch CUDA events on the tcgen05 kernel ----------------
     mv.lib.model_set_option(mv.h, b"b200_cuda_graph", 0)
-    step_api(mv, inputs)
+    step_api(mv, inputs, w.out_name)
     mv.lib.osb_tc_profile(1)
-    step_api(mv, inputs)
+    step_api(mv, inputs, w.out_name)
     prof = (ctypes.c_double * 4)()
-    rc = mv.lib.osb_tc_profile_read(prof)
+    mv.lib.osb_tc_profile_read(prof)
     if os.environ.get("OSB_TC_DUMP"):
         buf = ctypes.create_string_buffer(1 << 20)
         mv.lib.osb_tc_profile_dump.argtypes = [ctypes.c_char_p, ctypes.c_int]
@@ -323,17 +550,19 @@ def main():
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
                 "peak_source": peak_src, "launches": int(n_tc), "kernel_ms_per_step": tc_ms, "flops_per_step": tc_flops,
                 "algorithmic_bytes_per_step": tc_bytes,
-                # share of the SAME eager, event-instrumented step (numerator and denominator carry the same per-launch event cost);
-                # compare with the kernel's share in profiles/r01_launches_step_final.csv
+                # share of the SAME eager, event-instrumented step (numerator and denominator carry the same per-launch event cost)
                 "share_of_step": tc_ms / float(st_e["last_gpu_ms"]) if st_e.get("last_gpu_ms") else None, "traffic": None}
-    # DRAM traffic of the same kernel from the committed ncu pass (profiles/r01_tc_traffic.json, made by scripts/ncu_traffic.py):
-    # per launch, like `achieved`; the algorithmic bytes per launch stand beside it
-    tpath = os.path.join(ROOT, "profiles", "r01_tc_traffic.json")
-    if os.path.exists(tpath) and n_tc:
-        tj = json.load(open(tpath))
-        roofline["traffic"] = tj.get("dram_bytes_per_launch")
-        roofline["traffic_unit"] = "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, %d launches of one step)" % tj.get("launches", 0)
-        roofline["algorithmic_bytes_per_launch"] = tc_bytes / n_tc
+    # DRAM traffic of the same kernel from the committed ncu pass (scripts/ncu_traffic.py): per launch, like `achieved`
+    for tname in ("r02_tc_traffic.json", "r01_tc_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if w.name == "sd15_unet_fp16" and os.path.exists(tpath) and n_tc:
+            tj = json.load(open(tpath))
+            roofline["traffic"] = tj.get("dram_bytes_per_launch")
+            roofline["traffic_unit"] = "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, %d launches of one step; capture: profiles/%s%s)" % (
+                tj.get("launches", 0), tname, (", taken at commit " + tj["commit"]) if tj.get("commit") else "")
+            roofline["algorithmic_bytes_per_launch"] = tc_bytes / n_tc
+            break
+    mv.close()
     del mv
 
     # ---------------- e2e arm: host buffers through the C ABI, weights streamed every step ----------------
@@ -349,13 +578,13 @@ def main():
         comm = me.lib.osb_comm_init(WORLD, RANK, obj[0])
         assert comm, "ncclCommInitRank failed"
     me.close()
-    me = make_engine_model(d, "ram+nocache", resident=False, graph=False, comm=comm)
+    me = make_engine_model(d, w, "ram+nocache", resident=False, graph=False, comm=comm)
     for _ in range(max(2, args.warmup)):
-        out_e = step_api(me, inputs)
+        out_e = step_api(me, inputs, w.out_name)
     dist_barrier(dist)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out_e = step_api(me, inputs)
+        out_e = step_api(me, inputs, w.out_name)
     dist_barrier(dist)
     e2e_s = dist_max(dist, time.perf_counter() - t0)
     clk = clocks.stop()
@@ -363,20 +592,45 @@ def main():
     e2e_value = WORLD * args.steps / e2e_s
     h2d = int(st["weight_bytes_streamed"] + st["h2d_input_bytes"])
     d2h = int(st["d2h_output_bytes"])
-    parity = float(np.abs(out_e - out_v).max())
+
+    # ---------------- parity: EVERY rank, max over ranks in the line ----------------
+    scale_v = float(np.abs(out_v).max())
+    diff_sr = dist_max(dist, float(np.abs(out_e - out_v).max()) / max(scale_v, 1e-12))   # streamed (NCCL path at N>1) vs resident, own sample
+    parity = {"streamed_vs_resident_rel_all_ranks": diff_sr, "ranks": WORLD}
+    ref_s = None
+    if os.path.exists(ORACLE_LIB) and not args.no_cpu_baseline:
+        in0 = w.inputs(0)
+        if RANK == 0:
+            try:
+                ref0, ref_s = reference_output_cached(d, w, in0)
+            except Exception as e:    # the checker must never take the bench down
+                ref0 = None
+                parity["oracle_error"] = str(e)
+        else:
+            ref0 = None
+        ref0 = dist_bcast_array(dist, ref0)
+        if ref0 is not None:
+            got0 = out_e if RANK == 0 else step_api(me, in0, w.out_name)   # sample 0 through THIS rank's streamed engine (NCCL-fed weights)
+            err = float(np.abs(got0 - ref0).max()) / max(float(np.abs(ref0).max()), 1e-12)
+            parity["vs_reference_rel_all_ranks"] = dist_max(dist, err)
+            parity["tol"] = w.tol
+            parity["what"] = "max|engine - reference| / max|reference| on sample 0, every rank's streamed engine vs one full run of oracle/_ref (fp16 weights, fp32 XNNPACK arithmetic); max over ranks"
+            parity["ok"] = bool(parity["vs_reference_rel_all_ranks"] <= w.tol and diff_sr <= 1e-3)
+    me.close()
 
     line = {
-        "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": WORLD, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": "SD1.5 UNet-shaped graph (BASELINE config[1] hot path): %d ops, %.0f M params, %.3f TFLOP/step, 4x64x64 latent, 77x768 context, fp16 weights + fp16 arithmetic (fp32 accumulate), one sample per GPU" % (meta["ops"], meta["params"] / 1e6, meta["flops"] / 1e12),
-                   "weights": "value: HBM-resident + CUDA graph; e2e: streamed pinned-host -> HBM ring every step",
-                   "l2": "per-step working set = 1.72 GB of weights >> 126 MB L2, no flush needed", "parallelism": f"dp{WORLD} (rank r = sample r)"},
+        "metric": w.metric, "value": value, "unit": w.unit, "n_gpus": WORLD, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w.dtype, "data": "synthetic",
+        "config": {"workload": "%s: %d ops, %.0f M params, %.3f TFLOP/step; one sample per GPU" % (w.describe, meta["ops"], meta["params"] / 1e6, meta["flops"] / 1e12),
+                   "weights": "value: " + value_mode + "; e2e: streamed pinned-host -> HBM ring every step",
+                   "l2": "per-step weight stream = %.2f GB >> 126 MB L2, no flush needed" % (meta["weight_bytes"] / 1e9), "parallelism": f"dp{WORLD} (rank r = sample r)"},
         "clocks": clk,
-        "e2e": {"value": e2e_value, "unit": "steps/s", "ms_per_step": 1000.0 * e2e_s / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "e2e": {"value": e2e_value, "unit": w.unit, "ms_per_step": 1000.0 * e2e_s / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "weight_ring_bytes": int(st["weight_ring_bytes"]), "largest_node_bytes": int(st["weight_largest_node_bytes"]),
-                "peak_hbm_resident_weight_bytes": int(st["weight_ring_bytes"]), "h2d_gbs": h2d / (e2e_s / args.steps) / 1e9,
-                "max_abs_diff_vs_resident_arm": parity},
+                "peak_hbm_resident_weight_bytes": int(st["weight_peak_live_bytes"]), "h2d_gbs": h2d / (e2e_s / args.steps) / 1e9,
+                "weight_upload": ("every rank uploads 1/N of each node, ncclAllGather completes the slot" if WORLD > 1 else "cudaMemcpyAsync per node on the copy stream")},
         "e2e_resident_weights": e2e_resident,
+        "parity": parity,
         "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step, "tcgen05_launches_per_step": int(st_e["tc_launches"]),
         "roofline": roofline,
@@ -384,15 +638,84 @@ def main():
 
     if RANK == 0 and WORLD == 1 and not args.no_cpu_baseline and os.path.exists(ORACLE_LIB):
         try:
-            frac = 0.15
-            m, f, nops = cpu_sample(d, inputs, frac, "cpu")
-            t = time.time(); step_api(m, inputs, "nonexistent"); dt = time.time() - t
-            line["cpu_baseline"] = {"value": f / dt, "unit": "steps/s", "cores": REF_THREADS, "host_cores": os.cpu_count(), "kind": "reference",
-                                    "sample": f"first {nops} of {meta['ops']} graph ops ({100 * f:.1f}% of the UNet's Conv/MatMul FLOPs) through the reference's Model::run (fp16 weights, fp32 XNNPACK arithmetic), {dt:.1f} s, extrapolated to a full UNet run"}
+            # (DiskNoCache provider: every run re-reads the blobs and re-creates its operators, so the parity run above is a
+            # representative run, not a cold outlier)
+            if ref_s is not None and ref_s >= 45:
+                v, sample = 1.0 / ref_s, f"1 full run of the whole graph (the parity run), {ref_s:.1f} s"
+            else:
+                v, sample, per = time_reference(d, w, w.inputs(0), 2, 1, budget_s=100.0)
+            line["cpu_baseline"] = {"value": v, "unit": w.unit, "cores": REF_THREADS, "host_cores": HOST_CORES, "kind": "reference",
+                                    "sample": sample + " through the reference's Model::run (same blobs, fp32 XNNPACK arithmetic)"}
         except Exception as e:   # the baseline must never take the bench down
-            line["cpu_baseline"] = {"value": None, "unit": "steps/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
-    if RANK == 0:
-        emit_line(line)
+            line["cpu_baseline"] = {"value": None, "unit": w.unit, "cores": REF_THREADS, "kind": "reference", "sample": f"failed: {e}"}
+    return line if RANK == 0 else None
+
+
+def run_pipeline(args, dist):
+    """BASELINE config[1]: text encoder (cond + uncond) + 20 sampler steps x 2 UNet runs (CFG) + VAE decoder = one 512x512 image.
+    Each model is measured on its own (value / e2e as in `measure`); the image time is the sum over its calls."""
+    parts = [("clip_text_fp32", 2), ("sd15_unet_fp16", 40), ("vae_decoder_fp16", 1)]
+    clocks = ClockSampler(); clocks.start()
+    lines, t_val, t_e2e, launches, h2d, d2h = {}, 0.0, 0.0, 0, 0, 0
+    a2 = argparse.Namespace(**vars(args)); a2.no_cpu_baseline = True
+    for name, calls in parts:
+        ln = measure(make_workload(name), a2, dist, clocks=ClockSampler())
+        if RANK == 0:
+            lines[name] = ln
+            t_val += calls * ln["ms_per_step"]; t_e2e += calls * ln["e2e"]["ms_per_step"]
+            launches += calls * ln["gpu_launches_per_step"]; h2d += calls * ln["e2e"]["h2d_bytes_per_step"]; d2h += calls * ln["e2e"]["d2h_bytes_per_step"]
+    clk = clocks.stop()
+    if RANK != 0:
+        return None
+    u = lines["sd15_unet_fp16"]
+    return {
+        "metric": "SD1.5 full pipeline 512x512 images/s (2 text-encoder runs + 20 steps x 2 UNet runs + 1 VAE decode)", "value": WORLD * 1000.0 / t_val, "unit": "images/s",
+        "n_gpus": WORLD, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_val, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16", "data": "synthetic",
+        "config": {"workload": "BASELINE config[1]: CLIP-text (fp32) x2 + SD1.5 UNet fp16 x40 + VAE decoder fp16 x1, each timed over --steps runs; image time = sum of calls x per-call time (sampler host math excluded)",
+                   "parts_ms": {k: v["ms_per_step"] for k, v in lines.items()}, "parts_e2e_ms": {k: v["e2e"]["ms_per_step"] for k, v in lines.items()}},
+        "clocks": clk,
+        "e2e": {"value": WORLD * 1000.0 / t_e2e, "unit": "images/s", "ms_per_step": t_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches, "roofline": u["roofline"], "parity": {k: v.get("parity") for k, v in lines.items()},
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="sd15_unet_fp16", choices=WORKLOADS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--all-configs", default=None, help="run every BASELINE workload and append one JSON line each to this file")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    dist = dist_setup()
+    if args.all_configs:
+        for name in ["sd15_unet_fp16", "sd15_pipeline", "sdxl_unet_w8", "sdxl_turbo_w8", "vae_decoder_fp16", "tinyllama_decode"]:
+            a2 = argparse.Namespace(**vars(args)); a2.workload = name
+            if name != "sd15_unet_fp16":
+                a2.steps = min(args.steps, 10)
+            try:
+                line = run_pipeline(a2, dist) if name == "sd15_pipeline" else measure(make_workload(name), a2, dist)
+            except Exception as e:
+                line = {"workload": name, "error": str(e)} if RANK == 0 else None
+            if RANK == 0 and line is not None:
+                line["workload_key"] = name
+                with open(args.all_configs, "a") as f:
+                    f.write(json.dumps(line) + "\n")
+                if name == "sd15_unet_fp16":
+                    emit_line(line)
+    else:
+        line = run_pipeline(args, dist) if args.workload == "sd15_pipeline" else measure(make_workload(args.workload), args, dist)
+        if RANK == 0:
+            emit_line(line)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -12,17 +12,20 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(CSRC, "build")
-LIB = os.path.join(CSRC, "libonnxstream_b200.so")
+# Build variants for A/B experiments on the GPU box: OSB_BUILD_VARIANT=name OSB_NVCC_EXTRA="-DFOO" builds
+# csrc/libonnxstream_b200_<name>.so from csrc/build_<name>/ (the product library is the unnamed variant).
+VARIANT = os.environ.get("OSB_BUILD_VARIANT", "")
+OBJ = os.path.join(CSRC, "build" + ("_" + VARIANT if VARIANT else ""))
+LIB = os.path.join(CSRC, "libonnxstream_b200" + ("_" + VARIANT if VARIANT else "") + ".so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = os.environ.get("OSB_CXX", "/usr/bin/g++")
 
 CU_SOURCES = ["kernels_basic.cu", "kernels_gemm.cu", "gemm_tcgen05.cu", "attention_tcgen05.cu"]
-CPP_SOURCES = ["engine.cpp", "engine_run.cpp", "capi.cpp", "comm.cpp"]
-HEADERS = ["common.cuh", "engine.h", "engine_impl.h", "../../include/onnxstream_b200_kernels.h", "../../include/onnxstream_b200.h"]
+CPP_SOURCES = ["engine.cpp", "engine_run.cpp", "capi.cpp", "comm.cpp", "workspace.cpp"]
+HEADERS = ["common.cuh", "engine.h", "engine_impl.h", "workspace.h", "../../include/onnxstream_b200_kernels.h", "../../include/onnxstream_b200.h"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
-              "-Xcompiler", "-fPIC", "-ccbin", CXX]
+              "-Xcompiler", "-fPIC", "-ccbin", CXX] + os.environ.get("OSB_NVCC_EXTRA", "").split()
 CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-I/usr/local/cuda/include", "-Wall", "-Wno-sign-compare", "-Wno-unused-function"]
 
 
@@ -63,7 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     # keep the C++ drop-in link test (reference apps + compat_onnxstream.cpp) in step with the engine ABI
     link_script = os.path.join(os.path.dirname(HERE), "scripts", "link_reference_apps.sh")
     compat_obj = os.path.join(os.path.dirname(HERE), "build", "link_test", "compat.o")
-    if os.path.isdir("/root/reference/src") and os.path.exists(link_script) and _newer(hdrs + [os.path.join(CSRC, "compat_onnxstream.cpp"), LIB], compat_obj):
+    if not VARIANT and os.path.isdir("/root/reference/src") and os.path.exists(link_script) and _newer(hdrs + [os.path.join(CSRC, "compat_onnxstream.cpp"), LIB], compat_obj):
         r = subprocess.run(["bash", link_script], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             raise RuntimeError("link test (reference apps against the B200 engine) failed:\n" + r.stdout[-3000:])

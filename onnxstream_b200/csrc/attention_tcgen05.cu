@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
 flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                        const FaParams p)
 {
-    osb_pdl_trigger();
+    osb_pdl_trigger_entry();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sQ = smem;

@@ -41,18 +41,18 @@ NcclApi& api()
 
 namespace osb {
 
-void WeightStreamer::nccl_broadcast(void* dev, size_t bytes)
+void WeightStreamer::nccl_broadcast(void* dev, size_t bytes, cudaStream_t st)
 {
     // ncclChar = 0 in ncclDataType_t; root 0 is the rank that did the H2D
-    int r = api().Broadcast(dev, dev, bytes, 0, 0, (void*)m_comm, m_copy);
+    int r = api().Broadcast(dev, dev, bytes, 0, 0, (void*)m_comm, st);
     if (r != 0) throw std::runtime_error(std::string("ncclBroadcast failed: ") + (api().GetErrorString ? api().GetErrorString(r) : "?"));
 }
 
 // in-place all-gather over a ring slot laid out as nranks chunks of `chunk_bytes`: rank r contributes [r * chunk, (r + 1) * chunk)
-void WeightStreamer::nccl_allgather_inplace(void* dev, size_t chunk_bytes)
+void WeightStreamer::nccl_allgather_inplace(void* dev, size_t chunk_bytes, cudaStream_t st)
 {
     if (!api().AllGather) throw std::runtime_error("onnxstream_b200: ncclAllGather not found in the NCCL library");
-    int r = api().AllGather((const char*)dev + (size_t)m_rank * chunk_bytes, dev, chunk_bytes, 0 /* ncclChar */, (void*)m_comm, m_copy);
+    int r = api().AllGather((const char*)dev + (size_t)m_rank * chunk_bytes, dev, chunk_bytes, 0 /* ncclChar */, (void*)m_comm, st);
     if (r != 0) throw std::runtime_error(std::string("ncclAllGather failed: ") + (api().GetErrorString ? api().GetErrorString(r) : "?"));
 }
 

@@ -26,7 +26,16 @@ static inline int launched(int tensor_core = 0)
 // latency and prologue of kernel i+1 behind the tail of kernel i (CUDA graphs keep the programmatic edges).
 __device__ __forceinline__ void osb_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void osb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void osb_pdl_prologue() { osb_pdl_trigger(); osb_pdl_wait(); }
+// OSB_PDL_LATE (build variant): short kernels do not trigger at all (the implicit trigger at exit stands), the tcgen05 kernels
+// trigger once their last tile's main loop has been issued -- so dependents never take SM slots from CTAs that still have work.
+#ifdef OSB_PDL_LATE
+__device__ __forceinline__ void osb_pdl_trigger_entry() {}
+__device__ __forceinline__ void osb_pdl_trigger_late() { osb_pdl_trigger(); }
+#else
+__device__ __forceinline__ void osb_pdl_trigger_entry() { osb_pdl_trigger(); }
+__device__ __forceinline__ void osb_pdl_trigger_late() {}
+#endif
+__device__ __forceinline__ void osb_pdl_prologue() { osb_pdl_trigger_entry(); osb_pdl_wait(); }
 
 extern "C" int osb_pdl_enabled(void);
 

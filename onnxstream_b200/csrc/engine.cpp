@@ -3,6 +3,8 @@
 #include "engine_impl.h"
 
 #include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 #include <cctype>
 #include <cstdio>
 #include <cstring>
@@ -59,6 +61,28 @@ namespace {
 struct LocalCpuGuard {
     cpu_set_t old_set;
     bool active = false;
+    bool policy_set = false;
+    // set_mempolicy(2) without libnuma: MPOL_BIND = 2 to the GPU's node while the allocation runs, MPOL_DEFAULT = 0 afterwards
+    static long set_policy(int mode, const unsigned long* mask, unsigned long maxnode)
+    {
+#ifdef SYS_set_mempolicy
+        return syscall(SYS_set_mempolicy, mode, mask, maxnode);
+#else
+        return -1;
+#endif
+    }
+    void bind_memory_to_node_of(const std::string& bdf)
+    {
+        FILE* f = fopen(("/sys/bus/pci/devices/" + bdf + "/numa_node").c_str(), "r");
+        if (!f) return;
+        int node = -1;
+        if (fscanf(f, "%d", &node) != 1) node = -1;
+        fclose(f);
+        if (node < 0 || node >= 1024) return;
+        unsigned long mask[16] = { 0 };
+        mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+        if (set_policy(2 /* MPOL_BIND */, mask, 1024 + 1) == 0) policy_set = true;
+    }
     LocalCpuGuard()
     {
         static const bool enabled = [] { const char* e = getenv("OSB_NUMA_BIND"); return !(e && e[0] == '0'); }();
@@ -67,6 +91,7 @@ struct LocalCpuGuard {
         char bdf[32] = { 0 };
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bdf, sizeof bdf, dev) != cudaSuccess) return;
         for (char* c = bdf; *c; c++) *c = (char)tolower((unsigned char)*c);
+        bind_memory_to_node_of(bdf);     // memory policy first: it holds even when the CPU mask cannot be narrowed
         std::string path = std::string("/sys/bus/pci/devices/") + bdf + "/local_cpulist";
         FILE* f = fopen(path.c_str(), "r");
         if (!f) return;
@@ -89,7 +114,11 @@ struct LocalCpuGuard {
         if (CPU_COUNT(&want) == 0 || CPU_EQUAL(&want, &old_set)) return;
         if (sched_setaffinity(0, sizeof want, &want) == 0) active = true;
     }
-    ~LocalCpuGuard() { if (active) sched_setaffinity(0, sizeof old_set, &old_set); }
+    ~LocalCpuGuard()
+    {
+        if (policy_set) set_policy(0 /* MPOL_DEFAULT */, nullptr, 0);
+        if (active) sched_setaffinity(0, sizeof old_set, &old_set);
+    }
 };
 }  // namespace
 
@@ -98,7 +127,8 @@ void* pinned_alloc(size_t bytes, const char* what)
     LocalCpuGuard guard;
     void* p = nullptr;
     check_cuda(cudaHostAlloc(&p, std::max<size_t>(bytes, 16), cudaHostAllocDefault), what);
-    // first touch while bound: the driver pins what it allocates, but make the placement explicit for lazily backed ranges
+    // cudaHostAlloc populates and pins the pages before it returns, in this thread's context: they follow the MPOL_BIND policy and
+    // the CPU mask the guard installed (both restored on scope exit)
     return p;
 }
 
@@ -387,8 +417,10 @@ WeightStreamer::WeightStreamer(size_t capacity, bool host_mirror, ncclComm* comm
     : m_cap(((capacity + 255) & ~(size_t)255) + (nranks > 1 ? (size_t)256 * nranks : 0)), m_comm(comm), m_rank(rank), m_nranks(nranks)
 {
     // (N > 1: room for the per-rank chunk padding of the sharded upload)
-    if (const char* e = getenv("OSB_SHARDED_H2D")) m_sharded = e[0] == '1' && nranks > 1;
+    m_sharded = nranks > 1;
+    if (const char* e = getenv("OSB_SHARDED_H2D")) m_sharded = e[0] != '0' && nranks > 1;
     check_cuda(cudaStreamCreateWithFlags(&m_copy, cudaStreamNonBlocking), "cudaStreamCreate(copy)");
+    if (nranks > 1) check_cuda(cudaStreamCreateWithFlags(&m_coll, cudaStreamNonBlocking), "cudaStreamCreate(collective)");
     check_cuda(cudaMalloc(&m_ring, m_cap), "cudaMalloc(weight ring)");
     if (host_mirror) m_host = (char*)pinned_alloc(m_cap, "cudaHostAlloc(weight staging)");
 }
@@ -396,11 +428,13 @@ WeightStreamer::WeightStreamer(size_t capacity, bool host_mirror, ncclComm* comm
 WeightStreamer::~WeightStreamer()
 {
     cudaStreamSynchronize(m_copy);
-    for (auto& s : m_slots) { if (s.ready) cudaEventDestroy(s.ready); if (s.released_ev) cudaEventDestroy(s.released_ev); }
+    if (m_coll) cudaStreamSynchronize(m_coll);
+    for (auto& s : m_slots) { if (s.ready) cudaEventDestroy(s.ready); if (s.released_ev) cudaEventDestroy(s.released_ev); if (s.h2d_ev) cudaEventDestroy(s.h2d_ev); }
     for (auto e : m_event_pool) cudaEventDestroy(e);
     if (m_ring) cudaFree(m_ring);
     if (m_host) cudaFreeHost(m_host);
     cudaStreamDestroy(m_copy);
+    if (m_coll) cudaStreamDestroy(m_coll);
 }
 
 cudaEvent_t WeightStreamer::get_event()
@@ -436,6 +470,7 @@ bool WeightStreamer::try_reserve(size_t bytes, size_t& off)
         m_live -= f.bytes;
         m_event_pool.push_back(f.ready);
         m_event_pool.push_back(f.released_ev);
+        if (f.h2d_ev) m_event_pool.push_back(f.h2d_ev);
         m_slots.pop_front();
     }
     off = cand;
@@ -463,6 +498,16 @@ WeightStreamer::Slot* WeightStreamer::stage(WeightSource& src, const std::vector
     s.ready = get_event();
     s.released_ev = get_event();
     s.released = false;
+    s.h2d_ev = nullptr;
+    // N > 1: the collective of this slot runs on m_coll after this rank's upload (event), so the copy stream is free to start the
+    // next slot's upload while NVLink completes this one
+    auto after_upload = [&]() -> cudaStream_t {
+        if (!m_coll) return m_copy;
+        if (!s.h2d_ev) s.h2d_ev = get_event();
+        check_cuda(cudaEventRecord(s.h2d_ev, m_copy), "cudaEventRecord(h2d)");
+        check_cuda(cudaStreamWaitEvent(m_coll, s.h2d_ev, 0), "cudaStreamWaitEvent(collective, h2d)");
+        return m_coll;
+    };
     bool do_h2d = (m_nranks == 1) || (m_rank == 0);
     size_t cur = off;
     for (auto& r : node) {
@@ -485,11 +530,11 @@ WeightStreamer::Slot* WeightStreamer::stage(WeightSource& src, const std::vector
             // every rank holds the same host bytes: upload slice [rank * chunk, (rank + 1) * chunk) of the node, gather the rest over NVLink
             size_t lo = std::min(span, (size_t)m_rank * chunk), hi = std::min(span, lo + chunk);
             if (hi > lo) check_cuda(cudaMemcpyAsync((char*)s.blobs.front().dev + lo, (const char*)s.blobs.front().host + lo, hi - lo, cudaMemcpyHostToDevice, m_copy), "cudaMemcpyAsync(node shard H2D)");
-            nccl_allgather_inplace(s.blobs.front().dev, chunk);
+            nccl_allgather_inplace(s.blobs.front().dev, chunk, after_upload());
             m_streamed += hi - lo;     // bytes this rank moved over PCIe
         } else {
             if (do_h2d) check_cuda(cudaMemcpyAsync(s.blobs.front().dev, s.blobs.front().host, span, cudaMemcpyHostToDevice, m_copy), "cudaMemcpyAsync(node H2D)");
-            if (m_nranks > 1) nccl_broadcast(s.blobs.front().dev, span);
+            if (m_nranks > 1) nccl_broadcast(s.blobs.front().dev, span, after_upload());
             for (size_t k = 0; k < node.size(); k++) if (node[k].type != DType::i64) m_streamed += node[k].bytes;
         }
     } else {
@@ -497,11 +542,11 @@ WeightStreamer::Slot* WeightStreamer::stage(WeightSource& src, const std::vector
             const Blob& b = s.blobs[k];
             if (!b.bytes || node[k].type == DType::i64) continue;
             if (do_h2d) check_cuda(cudaMemcpyAsync(b.dev, b.host, b.bytes, cudaMemcpyHostToDevice, m_copy), "cudaMemcpyAsync(weights H2D)");
-            if (m_nranks > 1) nccl_broadcast(b.dev, b.bytes);
+            if (m_nranks > 1) nccl_broadcast(b.dev, b.bytes, after_upload());
             m_streamed += b.bytes;
         }
     }
-    check_cuda(cudaEventRecord(s.ready, m_copy), "cudaEventRecord(ready)");
+    check_cuda(cudaEventRecord(s.ready, m_coll ? m_coll : m_copy), "cudaEventRecord(ready)");
     m_live += s.bytes;
     m_peak_live = std::max(m_peak_live, m_live);
     return &s;

@@ -179,6 +179,7 @@ public:
     std::function<bool(const std::string&, const std::string&)> requires_upcast;
     bool use_scaled_dp_attn_op = false;
     std::set<std::string> outputs_convert_set;
+    std::set<std::string> force_uint8_storage_set;
     bool use_next_op_cache = false;
     bool use_nchw_convs = false;
     bool ops_printf = false;
@@ -242,6 +243,8 @@ private:
     int m_rank = 0, m_nranks = 1;
 
     void parse();
+    void invalidate_plan();
+    std::string options_signature() const;
     void run_body(bool capturing);
     bool try_replay();
     void drop_graph();

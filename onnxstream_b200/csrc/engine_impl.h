@@ -26,6 +26,7 @@ public:
         std::vector<Blob> blobs;
         cudaEvent_t ready = nullptr;     // recorded on the copy stream after the H2D (+ broadcast) of every blob
         cudaEvent_t released_ev = nullptr;  // recorded on the compute stream after the consuming kernels
+        cudaEvent_t h2d_ev = nullptr;       // N > 1: recorded on the copy stream after this rank's upload; the collective stream waits on it
         bool released = false;
     };
     struct Request { std::string name; DType type; size_t bytes; };
@@ -43,7 +44,8 @@ public:
     size_t streamed() const { return m_streamed; }
     cudaStream_t copy_stream() const { return m_copy; }
     // N > 1 only: every rank uploads 1/N of each node over its own PCIe link and an in-place ncclAllGather completes the slot
-    // (N x the aggregate host->device bandwidth of the root-upload + ncclBroadcast default).  Opt-in until validated at N = 8.
+    // (N x the aggregate host->device bandwidth of a root upload + ncclBroadcast).  Default at N > 1; OSB_SHARDED_H2D=0 selects the
+    // root-upload + broadcast variant.
     void set_sharded_upload(bool on) { m_sharded = on && m_nranks > 1; }
 
 private:
@@ -51,6 +53,7 @@ private:
     void* m_ring = nullptr;
     void* m_host = nullptr;
     cudaStream_t m_copy = nullptr;
+    cudaStream_t m_coll = nullptr;       // N > 1: NCCL collectives run here, so the upload of slot k+1 overlaps the gather of slot k
     std::deque<Slot> m_slots;
     std::vector<cudaEvent_t> m_event_pool;
     ncclComm* m_comm = nullptr;
@@ -59,8 +62,8 @@ private:
 
     bool try_reserve(size_t bytes, size_t& off);
     cudaEvent_t get_event();
-    void nccl_broadcast(void* dev, size_t bytes);
-    void nccl_allgather_inplace(void* dev, size_t chunk_bytes);
+    void nccl_broadcast(void* dev, size_t bytes, cudaStream_t st);
+    void nccl_allgather_inplace(void* dev, size_t chunk_bytes, cudaStream_t st);
 };
 
 }  // namespace osb

@@ -5,6 +5,7 @@
 // and every handler enqueues CUDA kernels on the compute stream; int64 tensors (shape arithmetic) stay on the host
 // and are evaluated with the reference's own integer semantics, bit-exactly.
 #include "engine_impl.h"
+#include "workspace.h"
 
 #include <limits>
 #include <cuda_fp16.h>
@@ -169,25 +170,43 @@ struct Engine::Impl {
     }
 
     // Make sure every weight up to and including the current step is in flight; run ahead while the ring has room.
+    // Consecutive small nodes are staged as ONE slot (one cudaMemcpyAsync, one collective): a UNet has ~700 weight-bearing nodes, most
+    // of them a few KB (biases, norm affine), and a per-node copy + event + NCCL call costs more than moving them.  A group never
+    // exceeds `group_bytes` (and therefore never the ring = the largest node), so the "HBM-resident streamed weights <= one node"
+    // bound is unchanged; the slot is released when its LAST step has been enqueued.
     void pump_weights()
     {
         if (!E.m_streamer) return;
         if (E.resident_weights && !E.m_first_run) return;  // served from the HBM cache
+        static const size_t group_bytes = [] { const char* e = getenv("OSB_WEIGHT_GROUP_KB"); return (size_t)(e ? atoi(e) : 8192) << 10; }();
         while (next_stage < steps.size()) {
-            auto& node = node_weights[next_stage];
-            if (node.empty()) { next_stage++; continue; }
+            if (node_weights[next_stage].empty()) { next_stage++; continue; }
+            // group = [next_stage, last]: grows while the sum stays under the cap (a node larger than the cap is a group of its own)
+            size_t last = next_stage, total = 0;
+            auto node_bytes = [&](size_t si) { size_t b = 0; for (auto& w : node_weights[si]) b += (w.bytes + 255) & ~(size_t)255; return b; };
+            total = node_bytes(next_stage);
+            const size_t cap = std::min(group_bytes, E.m_streamer->capacity() / 2);   // two groups in flight: upload(k+1) overlaps compute(k)
+            for (size_t j = next_stage + 1; j < steps.size(); j++) {
+                size_t b = node_bytes(j);
+                if (total + b > cap) break;
+                total += b;
+                if (b) last = j;
+            }
             bool must = next_stage <= cur_step;
             std::vector<WeightStreamer::Request> req;
-            for (auto& w : node) {
-                const TensorRef& r = E.m_ops[w.op].in[w.in];
-                bool conv_w;
-                req.push_back({ weight_file(r, conv_w), r.wtype, w.bytes });
-            }
+            for (size_t si = next_stage; si <= last; si++)
+                for (auto& w : node_weights[si]) {
+                    const TensorRef& r = E.m_ops[w.op].in[w.in];
+                    bool conv_w;
+                    req.push_back({ weight_file(r, conv_w), r.wtype, w.bytes });
+                }
             auto* slot = E.m_streamer->stage(*E.m_source, req, must);
             if (!slot) break;
-            for (size_t k = 0; k < node.size(); k++) staged[{ node[k].op, node[k].in }] = { slot, k };
-            step_slot[next_stage] = slot;
-            next_stage++;
+            size_t k = 0;
+            for (size_t si = next_stage; si <= last; si++)
+                for (auto& w : node_weights[si]) staged[{ w.op, w.in }] = { slot, k++ };
+            step_slot[last] = slot;
+            next_stage = last + 1;
         }
     }
 
@@ -2097,7 +2116,7 @@ Engine::~Engine()
     drop_graph();
     m_impl.reset();
     m_streamer.reset();
-    if (m_stream) cudaStreamDestroy(m_stream);
+    if (m_stream) { osb_workspace_release(m_stream); cudaStreamDestroy(m_stream); }
 }
 
 void Engine::set_weight_source(std::unique_ptr<WeightSource> src)
@@ -2140,8 +2159,43 @@ void Engine::parse()
     if (m_parsed) return;
     m_ops = parse_model_text(m_text, support_dynamic_shapes);
     m_parsed = true;
+    invalidate_plan();
+}
+
+// A different model text or different options: nothing derived from the old plan may survive -- the captured graph, the HBM weight
+// cache (keyed by file name + dtype only), the step list and the per-run scratch.
+void Engine::invalidate_plan()
+{
+    if (m_stream) cudaStreamSynchronize(m_stream);
+    drop_graph();
     m_first_run = true;
     m_refs_initial.clear();
+    if (m_impl) {
+        Impl& I = *m_impl;
+        I.resident.clear(); I.resident_bytes = 0;
+        I.steps.clear(); I.wplan.clear(); I.node_weights.clear();
+        I.staged.clear(); I.step_slot.clear();
+        I.store.clear(); I.order.clear(); I.silu_cache.clear();
+        I.runs_done = 0;
+    }
+    m_streamer.reset();
+}
+
+// every knob that changes the plan, the dtype of a tensor or the set of outputs
+std::string Engine::options_signature() const
+{
+    std::string s;
+    auto b = [&](bool v) { s += v ? '1' : '0'; };
+    b(use_fp16_arithmetic); b(use_uint8_qdq); b(use_uint8_arithmetic); b(fuse_ops_in_attention); b(force_fp16_storage);
+    b(support_dynamic_shapes); b(use_scaled_dp_attn_op); b(use_nchw_convs); b(resident_weights); b(fuse_nodes); b(keep_nhwc); b(flash_attention);
+    b((bool)requires_upcast);
+    s += std::to_string(gemm_impl); s += '|'; s += std::to_string(attention_fused_ops_parts); s += '|';
+    for (auto& e : extra_outputs) { s += e; s += ','; }
+    s += '|';
+    for (auto& e : outputs_convert_set) { s += e; s += ','; }
+    s += '|';
+    for (auto& e : force_uint8_storage_set) { s += e; s += ','; }
+    return s;
 }
 
 std::vector<std::pair<DType, std::string>> Engine::weights_names()
@@ -2290,8 +2344,12 @@ void Engine::run()
     auto t0 = std::chrono::high_resolution_clock::now();
     check_cuda(cudaSetDevice(m_device), "cudaSetDevice");
     parse();
-    if (use_cuda_graph && try_replay()) return;
     Impl& I = *m_impl;
+    {
+        std::string sig = options_signature();
+        if (sig != I.plan_signature) { if (!I.plan_signature.empty()) invalidate_plan(); I.plan_signature = sig; }
+    }
+    if (use_cuda_graph && try_replay()) return;
     osb_launch_count_reset();
 
     // init(): reference counts + weight schedule (src/onnxstream.cpp:3499-3548)
@@ -2394,6 +2452,7 @@ void Engine::run()
             }
         }
         if (capturing) {
+            for (auto& f : finals) if (std::get<2>(f).type == DType::i64) throw std::runtime_error("int64 graph outputs are host-evaluated: not capturable");
             capture_open = false;
             check_cuda(cudaStreamEndCapture(m_stream, &G->graph), "cudaStreamEndCapture");
             check_cuda(cudaGraphInstantiate(&G->exec, G->graph, 0), "cudaGraphInstantiate");

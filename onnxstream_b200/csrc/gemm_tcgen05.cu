@@ -16,6 +16,7 @@
 // (src/onnxstream.cpp:929-1215, 1292-1534) and the cuBLAS offload CublasOps::OpFullyConnected::run (src/onnxstream.cpp:308-352).
 
 #include "common.cuh"
+#include "workspace.h"
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cstdio>
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(NUM_THREADS, STAGES <= STAGES_SHORT ? 2 : 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_b1,
                const __grid_constant__ CUtensorMap map_b2, const TcParams p)
 {
-    osb_pdl_trigger();   // let the next kernel's CTAs be scheduled as ours drain; it waits for our completion before touching memory
+    osb_pdl_trigger_entry();   // let the next kernel's CTAs be scheduled as ours drain; it waits for our completion before touching memory
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B swizzle atoms
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -322,6 +323,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
+        osb_pdl_trigger_late();   // every MMA of this CTA is issued: the next kernel may start its prologue on SMs that drain
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;                 // TMEM lane quadrant this warp may access
@@ -496,17 +498,15 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, __half* __res
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------
-float* g_ws = nullptr;
-size_t g_ws_bytes = 0;
-int* g_counters = nullptr;       // self-resetting (arrive, done) counter pairs, one pair per output tile
-constexpr size_t WS_MAX = (size_t)96 << 20;
+constexpr size_t WS_MAX = OSB_WS_SPLITK_BYTES;   // fixed-capacity per-stream workspace (workspace.h): never re-allocated, graph-safe
 
 // pick a split factor: fill the SMs when the tile count is small, keep >= 2 k-blocks per split, stay inside the workspace
-int choose_split(int tiles, int k_blocks, size_t out_elems, cudaStream_t st)
+int choose_split(int tiles, int k_blocks, size_t out_elems, cudaStream_t st, OsbWorkspace** ws_out)
 {
     static const int forced = [] { const char* e = getenv("OSB_TC_SPLIT"); return e ? atoi(e) : 0; }();   // tuning experiments only
     // measured over every tc shape of the SD 1.5 UNet (r01 sweep): below ~32 k-blocks the second launch (the reduce) costs more
     // than the idle SMs do
+    *ws_out = nullptr;
     if ((tiles >= 100 && forced <= 0) || k_blocks < 4 || (k_blocks < 32 && forced <= 0)) return 1;
     int split = forced > 0 ? forced : 148 / tiles;
     split = std::min(split, k_blocks / 2);
@@ -515,22 +515,9 @@ int choose_split(int tiles, int k_blocks, size_t out_elems, cudaStream_t st)
     int kb_per = (k_blocks + split - 1) / split;
     split = (k_blocks + kb_per - 1) / kb_per;          // no empty splits: every CTA must run at least one k-block
     if (split <= 1) return 1;
-    size_t need = (size_t)split * out_elems * 4;
-    if (!g_counters) {
-        cudaStreamCaptureStatus cs0 = cudaStreamCaptureStatusNone;
-        cudaStreamIsCapturing(st, &cs0);
-        if (cs0 != cudaStreamCaptureStatusNone) return 1;
-        if (cudaMalloc(&g_counters, 4096 * sizeof(int)) != cudaSuccess) { g_counters = nullptr; return 1; }
-        cudaMemset(g_counters, 0, 4096 * sizeof(int));
-    }
-    if (need > g_ws_bytes) {
-        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-        cudaStreamIsCapturing(st, &cs);
-        if (cs != cudaStreamCaptureStatusNone) return 1;   // never allocate inside a capture; warm-up runs size the workspace
-        if (g_ws) { cudaStreamSynchronize(st); cudaFree(g_ws); }
-        g_ws_bytes = std::max(need, (size_t)32 << 20);
-        if (cudaMalloc(&g_ws, g_ws_bytes) != cudaSuccess) { g_ws = nullptr; g_ws_bytes = 0; return 1; }
-    }
+    OsbWorkspace* ws = osb_workspace(st, OSB_WS_SPLITK);
+    if (!ws) return 1;                                  // capturing before any eager run, or out of memory: run unsplit
+    *ws_out = ws;
     return split;
 }
 
@@ -754,10 +741,11 @@ int osb_tc_gemm_launch(const void* A, const void* B, void* C, const void* bias, 
     p.k_blocks_per_tap = (int)((K + BLOCK_K - 1) / BLOCK_K);
     p.stride = 1;
     p.C = (__half*)C; p.bias = (const __half*)bias; p.residual = (const __half*)residual; p.stride_c = sc; p.ldc = ldc;
-    p.split_k = (ldc == N && (sc == M * N || batch == 1)) ? choose_split(p.m_tiles * p.n_tiles * p.batch, p.k_blocks_per_tap, (size_t)batch * M * N, st) : 1;
-    p.ws = g_ws;
+    OsbWorkspace* wsp = nullptr;
+    p.split_k = (ldc == N && (sc == M * N || batch == 1)) ? choose_split(p.m_tiles * p.n_tiles * p.batch, p.k_blocks_per_tap, (size_t)batch * M * N, st, &wsp) : 1;
+    p.ws = wsp ? wsp->splitk : nullptr;
     // in-kernel rendezvous reduction needs every CTA resident at once and float4-aligned rows; otherwise the reduce kernel runs
-    p.counters = (p.split_k > 1 && p.N % 4 == 0 && p.ldc % 4 == 0 && (long long)p.m_tiles * p.n_tiles * p.batch * p.split_k <= num_sms() && inkernel_reduce()) ? g_counters : nullptr;
+    p.counters = (p.split_k > 1 && p.N % 4 == 0 && p.ldc % 4 == 0 && (long long)p.m_tiles * p.n_tiles * p.batch * p.split_k <= num_sms() && inkernel_reduce() && wsp) ? wsp->splitk_counters : nullptr;
     p.short_k = short_k_hint(p.taps * p.k_blocks_per_tap, p.split_k);
     return launch(ma, mb, p, st);
 }
@@ -791,7 +779,7 @@ int osb_tc_gemm_grouped_launch(const void* A, const void* const* B, void* const*
     p.stride = 1;
     p.C = (__half*)C[0]; p.C1 = (__half*)C[1]; p.C2 = (__half*)(groups > 2 ? C[2] : C[1]);
     p.bias = nullptr; p.residual = nullptr; p.stride_c = 0; p.ldc = ldc;
-    p.split_k = 1; p.ws = g_ws; p.counters = nullptr;
+    p.split_k = 1; p.ws = nullptr; p.counters = nullptr;
     p.short_k = short_k_hint(p.taps * p.k_blocks_per_tap, 1);
     return launch(ma, mb[0], p, st, &mb[1], groups > 2 ? &mb[2] : &mb[1]);
 }
@@ -832,10 +820,11 @@ int osb_tc_conv_launch(const void* x, const void* w, const void* bias, const voi
     p.stride = stride;
     p.C = (__half*)y; p.bias = (const __half*)bias; p.residual = (const __half*)residual; p.stride_c = 0; p.ldc = Cout;
     // the split-K reduce paths move float4 / half4 vectors: ragged Cout (conv_out, 3 or 4 channels) runs unsplit
-    p.split_k = (Cout % 4 == 0) ? choose_split(p.m_tiles * p.n_tiles, p.taps * p.k_blocks_per_tap, (size_t)Ho * Wo * Cout, st) : 1;
-    p.ws = g_ws;
+    OsbWorkspace* wsp = nullptr;
+    p.split_k = (Cout % 4 == 0) ? choose_split(p.m_tiles * p.n_tiles, p.taps * p.k_blocks_per_tap, (size_t)Ho * Wo * Cout, st, &wsp) : 1;
+    p.ws = wsp ? wsp->splitk : nullptr;
     // in-kernel rendezvous reduction needs every CTA resident at once and float4-aligned rows; otherwise the reduce kernel runs
-    p.counters = (p.split_k > 1 && p.N % 4 == 0 && p.ldc % 4 == 0 && (long long)p.m_tiles * p.n_tiles * p.batch * p.split_k <= num_sms() && inkernel_reduce()) ? g_counters : nullptr;
+    p.counters = (p.split_k > 1 && p.N % 4 == 0 && p.ldc % 4 == 0 && (long long)p.m_tiles * p.n_tiles * p.batch * p.split_k <= num_sms() && inkernel_reduce() && wsp) ? wsp->splitk_counters : nullptr;
     p.short_k = short_k_hint(p.taps * p.k_blocks_per_tap, p.split_k);
     return launch(ma, mb, p, st);
 }

@@ -7,6 +7,7 @@
 // multiple of the SM count, fp32 math on fp16 storage, every tensor read once and written once.
 
 #include "common.cuh"
+#include "workspace.h"
 #include <cstdio>
 #include <cstdlib>
 
@@ -915,27 +916,18 @@ int osb_reduce_mean(const void* x, void* y, int dtype, int64_t rows, int64_t col
     return launched();
 }
 
-// scratch for instance-norm partials: grown on demand, reused across calls (single compute stream)
-static double* g_inorm_partial = nullptr;
-static size_t g_inorm_partial_cap = 0;
-
 int osb_instance_norm(const void* x, void* y, int dtype, int64_t channels, int64_t n_per_c, const void* scale, const void* bias, float eps, void* stream)
 {
     if (channels * n_per_c == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     int splits = (int)max<int64_t>(1, min<int64_t>(64, (148 * 4 + channels - 1) / channels));
     while (splits > 1 && n_per_c / splits < 1024) splits--;
-    size_t need = (size_t)channels * splits * 2;
-    if (need > g_inorm_partial_cap) {
-        cudaError_t cap_status;
-        cudaStreamCaptureStatus cs;
-        cap_status = cudaStreamIsCapturing(st, &cs);
-        if (cap_status == cudaSuccess && cs != cudaStreamCaptureStatusNone) return (int)cudaErrorStreamCaptureUnsupported;
-        if (g_inorm_partial) cudaFree(g_inorm_partial);
-        g_inorm_partial_cap = need * 2 + 4096;
-        cudaError_t e = cudaMalloc(&g_inorm_partial, g_inorm_partial_cap * sizeof(double));
-        if (e != cudaSuccess) { g_inorm_partial = nullptr; g_inorm_partial_cap = 0; return (int)e; }
-    }
+    while (splits > 1 && (size_t)channels * splits * 2 > OSB_WS_INORM_DOUBLES) splits--;
+    if ((size_t)channels * splits * 2 > OSB_WS_INORM_DOUBLES) return (int)cudaErrorInvalidValue;
+    // per-stream fixed-capacity partial sums (workspace.h): never re-allocated, so a captured graph keeps a valid address
+    OsbWorkspace* ws = osb_workspace(st, OSB_WS_INORM);
+    if (!ws) return (int)cudaErrorStreamCaptureUnsupported;
+    double* g_inorm_partial = ws->inorm;
     dim3 grid((unsigned)channels, (unsigned)splits);
     if (dtype == OSB_F16) {
         osb_launch((inorm_stats_kernel<__half>), grid, 256, 0, st, (const __half*)x, g_inorm_partial, n_per_c, splits);

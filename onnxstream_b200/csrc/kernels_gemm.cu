@@ -8,6 +8,7 @@
 // from the NHWC input (M = Ho*Wo, K = kh*kw*Cin in OHWI order, N = Cout, B = the OHWI weights read as [N, K]).
 
 #include "common.cuh"
+#include "workspace.h"
 #include <cstdlib>
 
 // implemented in gemm_tcgen05.cu
@@ -471,23 +472,14 @@ int osb_gemm_ld(const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
     ConvGeom g{};
     if (dense && M <= 8 && batch == 1 && !bt && N % 8 == 0 && aligned16(B) && N >= 256 && K >= 64) {
         // weight-bandwidth path
-        // scratch: fp32 sums [M][N] followed by one arrival counter per column panel; zeroed when allocated, re-armed by the kernel
-        static float* scratch = nullptr; static size_t scratch_n = 0;
+        // scratch (per-stream, fixed capacity, workspace.h): fp32 sums [M][N] + one arrival counter per column panel; zeroed when
+        // allocated, re-armed by the kernel.  Shapes beyond the fixed capacity take the skinny kernel below.
         int vec = dtype == OSB_F16 ? 8 : 4, cols = 32 * vec;
         int gx = (int)((N + cols - 1) / cols);
-        size_t need = (size_t)M * N + (size_t)gx;
-        if (need > scratch_n) {
-            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-            cudaStreamIsCapturing(st, &cs);
-            if (cs != cudaStreamCaptureStatusNone) return (int)cudaErrorStreamCaptureUnsupported;
-            if (scratch) { cudaStreamSynchronize(st); cudaFree(scratch); }
-            scratch_n = std::max<size_t>(need, 1 << 20);
-            if (cudaMalloc(&scratch, scratch_n * 4) != cudaSuccess) { scratch = nullptr; scratch_n = 0; return (int)cudaErrorMemoryAllocation; }
-            if (cudaMemsetAsync(scratch, 0, scratch_n * 4, st) != cudaSuccess) return (int)cudaErrorUnknown;
-        }
-        // counters live at a fixed offset (end of the buffer) so that a different N never aliases un-armed sums
-        int* counters = (int*)(scratch + scratch_n) - 4096;
-        if (gx > 4096 || (size_t)M * N > scratch_n - 4096) return (int)cudaErrorInvalidValue;
+        OsbWorkspace* ws = (gx <= 4096 && (size_t)M * N <= OSB_WS_GEMV_FLOATS) ? osb_workspace(st, OSB_WS_GEMV) : nullptr;
+        if (ws) {
+        float* scratch = ws->gemv;
+        int* counters = ws->gemv_counters;
         int gy = (int)max<int64_t>(1, min<int64_t>((K + 15) / 16, (592 + gx - 1) / gx));
         int k_per = (int)((K + gy - 1) / gy);
         gy = (int)((K + k_per - 1) / k_per);
@@ -497,6 +489,7 @@ int osb_gemm_ld(const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
         else osb_launch((gemv_panel_kernel<float, 8>), grid, 128, 0, st, (const float*)A, (const float*)B, scratch, (int)M, (int)N, (int)K, k_per,
                         counters, (float*)C, (const float*)bias, (const float*)residual);
         return launched();
+        }
     }
     if (dense && M <= 8 && batch == 1) {
         int grid = bt ? (int)min<int64_t>((N + 7) / 8, 148 * 8) : (int)((N + 63) / 64);

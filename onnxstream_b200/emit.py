@@ -37,14 +37,16 @@ class T:
 def quantize_uint8(a: np.ndarray, from_left: float = 0.001, from_right: float = 0.001):
     """onnx2txt.ipynb cell 1 `quantize`: percentile range -> (uint8 array, scale, zero_point); None if not quantisable."""
     flat = a.astype(np.float32).ravel()
-    s = np.sort(flat[np.isfinite(flat)])
+    s = flat[np.isfinite(flat)]
     if len(s) == 1 and flat.size == 1:
         scale = abs(float(flat[0]))
         zero = 0 if flat[0] >= 0 else 2
         return np.array([1], dtype=np.uint8).reshape(a.shape), scale, zero
     if len(s) >= 2:
+        s = np.sort(s)
         left = float(s[int(len(s) * from_left)])
         right = float(s[int(len(s) * from_right * -1 - 1)])
+        del s
         if left > 0 and right > 0:
             left = 0.0
         elif left < 0 and right < 0:
@@ -52,8 +54,13 @@ def quantize_uint8(a: np.ndarray, from_left: float = 0.001, from_right: float = 
         if right > left:
             scale = (right - left) / 255.0
             zero = min(int(abs(left) / scale), 255)
-            q = np.clip((a.astype(np.float64) / scale) + zero, 0, 255).astype(np.uint8)
-            return q, scale, zero
+            # clip(a / scale + zero, 0, 255) in float64, truncated to uint8 -- in place: fresh multi-GB temporaries per step made the
+            # SDXL-size emission page-fault bound
+            x = a.astype(np.float64)
+            x /= scale
+            x += zero
+            np.clip(x, 0, 255, out=x)
+            return x.astype(np.uint8), scale, zero
     return None
 
 

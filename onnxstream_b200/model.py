@@ -17,7 +17,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-ENGINE_LIB = os.path.join(_PKG_DIR, "csrc", "libonnxstream_b200.so")
+ENGINE_LIB = os.environ.get("OSB_ENGINE_LIB") or os.path.join(_PKG_DIR, "csrc", "libonnxstream_b200.so")   # OSB_ENGINE_LIB: build variants (A/B runs)
 
 OPTION_NAMES = (
     "use_fp16_arithmetic", "use_uint8_qdq", "use_uint8_arithmetic", "fuse_ops_in_attention",

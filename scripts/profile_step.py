@@ -9,12 +9,13 @@ import bench  # noqa: E402
 from onnxstream_b200 import emit  # noqa: E402
 
 workload = sys.argv[1] if len(sys.argv) > 1 else "sd15_unet_fp16"
-d, cfg, meta = bench.ensure_model(workload)
-inputs = emit.unet_inputs(cfg)
-m = bench.make_engine_model(d, "ram+nocache", resident=True, graph=False)
+W = bench.make_workload(workload)
+d, meta = bench.ensure_model(W)
+inputs = W.inputs(0)
+m = bench.make_engine_model(d, W, "ram+nocache", resident=True, graph=False)
 for _ in range(2):
-    bench.step_api(m, inputs)
+    bench.step_api(m, inputs, W.out_name)
 m.lib.model_b200_profiler(1)
-bench.step_api(m, inputs)
+bench.step_api(m, inputs, W.out_name)
 m.lib.model_b200_profiler(0)
 print("profiled one step:", {k: v for k, v in m.stats().items() if k in ("kernel_launches", "tc_launches", "last_gpu_ms")})
