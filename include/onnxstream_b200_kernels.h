@@ -114,6 +114,27 @@ int osb_gemm_ld(const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
 int osb_conv2d(const void* x, const void* w, const void* bias, const void* residual, void* y,
                int64_t H, int64_t W, int64_t Cin, int64_t Cout, int kh, int kw, int stride, int pad_top, int pad_left,
                int64_t Ho, int64_t Wo, int dtype, int impl, void* stream);
+/* Conv with a second per-channel addend (`bias2`: the time-embedding row a resnet adds to conv1's output, src/onnxstream.cpp:5056-5175 Add
+ * on a [1,C,1,1] operand) and with the GroupNorm statistics of the output gathered in the epilogue: gn_stats = fp64 [2 * gn_groups]
+ * (sum, sum of squares per group of Cout / gn_groups channels), ACCUMULATED into (the caller zeroes it); *gn_done = 1 when the kernel
+ * produced them.  Both need the tensor-core path: ask osb_conv2d_fusable first. */
+int osb_conv2d_ex(const void* x, const void* w, const void* bias, const void* bias2, const void* residual, void* y, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                  int kh, int kw, int stride, int pad_top, int pad_left, int64_t Ho, int64_t Wo, int dtype, int impl, void* stream,
+                  void* gn_stats, int gn_groups, int* gn_done);
+int osb_conv2d_fusable(const void* x, const void* w, const void* y, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int kh, int kw, int stride, int dtype, int impl);
+/* GroupNorm(+SiLU) apply pass on an NHWC tensor whose statistics were gathered by the producing conv (osb_conv2d_ex): reads `stats`,
+ * writes y = silu?((x - mean) * rstd * gamma + beta), and zeroes `clear_stats` (the buffer the NEXT producer will accumulate into). */
+/* Dynamic-quantisation range of a float tensor, Model::get_percentiles (src/onnxstream.cpp:3104-3232): per reference chunk (the tensor
+ * split over `threads` pool workers, then 64 KiB buffers) the k-th smallest / largest finite value, k = (size_t)(n_chunk * from_x); min of
+ * the lows, max of the highs.  out3 = DEVICE uint32[3] initialised to {0xFFFFFFFF, 0, 0}: order-preserving keys of (low, high) and the
+ * number of chunks that produced a result; decode with osb_percentile_key_to_float. */
+int osb_percentiles(const void* x, int dtype, size_t n, int threads, float from_left, float from_right, void* out3, void* stream);
+float osb_percentile_key_to_float(unsigned key, int dtype);
+/* NHWC statistics producer for osb_group_norm_apply: stats[2 * groups] += per-group (sum, sum of squares) of y = x + addv[c]; addv and
+ * y both null = statistics of x.  cudaErrorInvalidValue for shapes the vector kernel does not cover. */
+int osb_channel_add_stats(const void* x, const void* addv, void* y, int dtype, int64_t C, int64_t HW, int groups, void* stats, void* stream);
+int osb_group_norm_apply(const void* x, void* y, int dtype, int64_t C, int64_t HW, int groups, const void* gamma, const void* beta, float eps, int fuse_silu,
+                         const void* stats, void* clear_stats, void* stream);
 
 /* Fused attention softmax(Q K^T * scale) V per head: the AttentionFusedOps branch (src/onnxstream.cpp:6696-6929).
  * q [h,Tq,d], k [h,d,Tk] when k_transposed (the diffusers export) else [h,Tk,d], v [h,Tk,d], out [h,Tq,d].
@@ -155,6 +176,9 @@ int osb_gemm_tc_eligible(int64_t M, int64_t N, int64_t K, int dtype);
 /* Per-launch timing of the tcgen05 GEMM/conv kernel (CUDA events on the launching stream; eager mode only).
  * osb_tc_profile(1) starts recording, osb_tc_profile_read fills {launches, total ms, total FLOPs, total algorithmic bytes}. */
 void osb_tc_profile(int enable);
+/* Tile decomposition of the tcgen05 GEMM / conv: 0 = one CTA per 128 x bn tile only, 1 = cost model (default), 2 = the CTA-pair
+ * kernel (tcgen05.mma.cta_group::2, 256 x bn tiles, TMA-store epilogue) wherever the shape is eligible.  Tests and A/B runs. */
+void osb_tc_set_pair_mode(int mode);
 int osb_tc_profile_read(double* out4);
 int osb_tc_profile_dump(char* buf, int cap);   /* one line per launch: M N K taps batch split conv ms gflop */
 

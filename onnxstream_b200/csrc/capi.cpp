@@ -54,6 +54,7 @@ static ModelContext* new_ctx(int threads_count, const char* wp)
     if (threads_count >= 0) {   // threads_count < 0: no backend at all (src/onnxstream.cpp:2397)
         try {
             c->engine = std::make_unique<Engine>();
+            c->engine->cpu_threads = threads_count;
             c->engine->set_weight_source(std::move(src));
         } catch (const std::exception& e) {   // no GPU: fail loudly, never fall back to a CPU path
             fprintf(stderr, "=== ERROR === %s\n", e.what());
@@ -169,6 +170,7 @@ void model_set_option(ModelContext* obj, char* name, unsigned int value)
     else if (!strcmp(name, "b200_gemm_impl")) e.gemm_impl = (int)value;
     else if (!strcmp(name, "b200_flash_attention")) e.flash_attention = v;
     else if (!strcmp(name, "b200_ring_factor_x100")) e.ring_factor = value / 100.0;
+    else if (!strcmp(name, "b200_range_data_calibrate")) e.range_data_calibrate = v;
     else set = false;
     if (!set) {
         const char* err = "model_set_option: 'name' not found.";
@@ -190,6 +192,12 @@ void model_ext_set_range(ModelContext* obj, const char* op_name, float mn, float
 char* model_ext_read_range_data(ModelContext* obj, const char* fn)
 {
     try { obj->E().read_range_data(fn); return nullptr; }
+    catch (const std::exception& e) { return dup_cstr(e.what()); }
+}
+
+char* model_ext_write_range_data(ModelContext* obj, const char* fn)
+{
+    try { obj->E().write_range_data(fn); return nullptr; }
     catch (const std::exception& e) { return dup_cstr(e.what()); }
 }
 
@@ -226,6 +234,23 @@ long long model_ext_get_tensor_i64(ModelContext* obj, const char* name, long lon
         }
     return -1;
 }
+
+// index-th tensor named `name` (batch siblings share a name, src/onnxstream.cpp:3040-3050); same return layout and ownership as
+// model_get_tensor; NULL when absent or not float32
+void* model_ext_get_tensor_at(ModelContext* obj, const char* name, unsigned int index)
+{
+    HostTensor* t = nullptr;
+    unsigned int seen = 0;
+    for (auto& h : obj->E().tensors()) if (h.name == name) { if (seen++ == index) { t = &h; break; } }
+    if (!t || t->type != DType::f32) return nullptr;
+    struct ReturnLayout { size_t dims_num; size_t* dims; size_t data_num; float* data; };
+    auto* r = (ReturnLayout*)malloc(sizeof(ReturnLayout));
+    r->dims_num = t->shape.size(); r->dims = t->shape.data(); r->data_num = t->count; r->data = t->f32();
+    return r;
+}
+
+// m_outputs_convert_set (src/onnxstream.h:961): once a name is added, only listed outputs are converted to float32 at the end of run()
+void model_ext_add_output_convert(ModelContext* obj, const char* name) { obj->E().outputs_convert_set.insert(name); }
 
 int model_ext_get_tensor_type(ModelContext* obj, const char* name)
 {

@@ -99,6 +99,7 @@ Model::Model(int threads_count)
     if (threads_count >= 0) {   // negative: no backend at all (src/onnxstream.cpp:2397)
         m_xnnpack = new XnnPack();
         m_xnnpack->engine = std::make_unique<osb::Engine>();
+        m_xnnpack->engine->cpu_threads = threads_count;
     }
 }
 
@@ -189,10 +190,12 @@ void Model::run()
     e.requires_upcast = m_requires_upcast;
     e.use_scaled_dp_attn_op = m_use_scaled_dp_attn_op;
     e.outputs_convert_set = m_outputs_convert_set;
+    e.force_uint8_storage_set = m_force_uint8_storage_set;
     e.use_nchw_convs = m_use_nchw_convs;
     e.ops_printf = m_ops_printf;
     e.ops_times_printf = m_ops_times_printf;
     e.range_data = m_range_data;
+    e.range_data_calibrate = m_range_data_calibrate;
 
     if (!m_xnnpack->source_installed) {
         auto src = std::make_unique<ProviderSource>(get_wp());
@@ -209,12 +212,7 @@ void Model::run()
         switch (t.m_type) {
         case TensorDataType::float32: { auto& v = t.get_vector<float>(); std::memcpy(e.push_input(t.m_name, osb::DType::f32, shape), v.data(), v.size() * 4); break; }
         case TensorDataType::int64: { auto& v = t.get_vector<int64_t>(); std::memcpy(e.push_input(t.m_name, osb::DType::i64, shape), v.data(), v.size() * 8); break; }
-        case TensorDataType::float16: {
-            auto& v = t.get_vector<uint16_t>();
-            float* dst = (float*)e.push_input(t.m_name, osb::DType::f32, shape);
-            for (size_t i = 0; i < v.size(); i++) { _Float16 h; std::memcpy(&h, &v[i], 2); dst[i] = (float)h; }
-            break;
-        }
+        case TensorDataType::float16: { auto& v = t.get_vector<uint16_t>(); std::memcpy(e.push_input(t.m_name, osb::DType::f16, shape), v.data(), v.size() * 2); break; }
         default: throw std::invalid_argument("Model::run: unsupported input tensor type.");
         }
     };
@@ -235,6 +233,7 @@ void Model::run()
         t.m_name = h.name;
         t.m_shape.assign(h.shape.begin(), h.shape.end());
         if (h.type == osb::DType::i64) { tensor_vector<int64_t> v(h.i64(), h.i64() + h.count); t.set_vector(std::move(v)); }
+        else if (h.type == osb::DType::f16) { tensor_vector<uint16_t> v(h.f16(), h.f16() + h.count); t.set_vector(std::move(v)); }   // outside m_outputs_convert_set
         else { tensor_vector<float> v(h.f32(), h.f32() + h.count); t.set_vector(std::move(v)); }
         push_tensor(std::move(t));
     }

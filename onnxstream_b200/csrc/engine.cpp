@@ -10,6 +10,8 @@
 #include <cstring>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -91,7 +93,8 @@ struct LocalCpuGuard {
         char bdf[32] = { 0 };
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bdf, sizeof bdf, dev) != cudaSuccess) return;
         for (char* c = bdf; *c; c++) *c = (char)tolower((unsigned char)*c);
-        bind_memory_to_node_of(bdf);     // memory policy first: it holds even when the CPU mask cannot be narrowed
+        static const bool policy = [] { const char* e = getenv("OSB_NUMA_POLICY"); return !(e && e[0] == '0'); }();
+        if (policy) bind_memory_to_node_of(bdf);     // memory policy first: it holds even when the CPU mask cannot be narrowed
         std::string path = std::string("/sys/bus/pci/devices/") + bdf + "/local_cpulist";
         FILE* f = fopen(path.c_str(), "r");
         if (!f) return;
@@ -132,11 +135,34 @@ void* pinned_alloc(size_t bytes, const char* what)
     return p;
 }
 
+// Host tensors (graph inputs / outputs) are re-created on every run with the same few sizes: cudaHostAlloc / cudaFreeHost cost
+// 0.1-1 ms each (driver ioctl + GPU mapping), so freed buffers are parked in a small size-keyed free list instead.
+namespace {
+std::mutex g_pin_mu;
+std::multimap<size_t, void*> g_pin_free;
+size_t g_pin_free_bytes = 0;
+constexpr size_t PIN_POOL_MAX = (size_t)512 << 20;
+}  // namespace
+
 PinnedBuf::PinnedBuf(size_t n) : bytes(n)
 {
+    {
+        std::lock_guard<std::mutex> lock(g_pin_mu);
+        auto it = g_pin_free.find(std::max<size_t>(n, 16));
+        if (it != g_pin_free.end()) { ptr = it->second; g_pin_free_bytes -= it->first; g_pin_free.erase(it); return; }
+    }
     ptr = pinned_alloc(n, "cudaHostAlloc(host tensor)");
 }
-PinnedBuf::~PinnedBuf() { if (ptr) cudaFreeHost(ptr); }
+PinnedBuf::~PinnedBuf()
+{
+    if (!ptr) return;
+    const size_t key = std::max<size_t>(bytes, 16);
+    {
+        std::lock_guard<std::mutex> lock(g_pin_mu);
+        if (g_pin_free_bytes + key <= PIN_POOL_MAX) { g_pin_free.emplace(key, ptr); g_pin_free_bytes += key; return; }
+    }
+    cudaFreeHost(ptr);
+}
 
 // ================================================================================================================
 // DevicePool

@@ -145,13 +145,14 @@ struct PinnedBuf {                    // page-locked host memory (cudaHostAlloc)
     ~PinnedBuf();
 };
 
-struct HostTensor {                   // what is left in the model's tensor list after run(): f32 NCHW or int64
+struct HostTensor {                   // what is left in the model's tensor list after run(): f32 NCHW, int64, or f16 (outside m_outputs_convert_set)
     std::string name;
     DType type = DType::none;
     std::vector<size_t> shape;
     std::shared_ptr<PinnedBuf> buf;
     size_t count = 0;
     float* f32() const { return (float*)buf->ptr; }
+    uint16_t* f16() const { return (uint16_t*)buf->ptr; }
     int64_t* i64() const { return (int64_t*)buf->ptr; }
 };
 
@@ -185,6 +186,8 @@ public:
     bool ops_printf = false;
     bool ops_times_printf = false;
     std::map<std::string, std::pair<float, float>> range_data;
+    bool range_data_calibrate = false;     // m_range_data_calibrate (src/onnxstream.h:964): record every op output's percentile range
+    int cpu_threads = 0;                   // the reference's pool size (Model(threads_count)): it partitions the percentile chunks
 
     // --- B200-specific knobs (set through model_set_option("b200_*")) ---
     bool resident_weights = false;   // keep converted weights in HBM after the first run (upper bound; "--ram" analogue)

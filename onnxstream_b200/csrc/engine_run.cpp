@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
+#include <thread>
 #include <tuple>
 
 namespace osb {
@@ -77,7 +78,24 @@ struct Engine::Impl {
     std::unordered_map<std::string, Tensor> resident;
     size_t resident_bytes = 0;
 
+    struct OpTime { std::string type; cudaEvent_t a, b; };
+    std::vector<OpTime> op_times;
     DevPtr gn_stats;
+    // GroupNorm statistics gathered by the producer (conv epilogue / per-channel Add) instead of a pass of their own.  `gn_ring` holds
+    // two fp64 [2 * 64] slots: a producer accumulates into the current slot (all zero by invariant), the GroupNorm's apply pass reads it
+    // and zeroes the OTHER slot, which becomes current.  The whole ring is zeroed at the start of every run.
+    DevPtr gn_ring;
+    int gn_slot = 0;
+    std::vector<long> stats_consumer;     // per step: index of the GroupNorm step that consumes this step's output (-1: none)
+    long stats_want = -1;                 // set while a producer step runs: the GroupNorm step that wants its statistics
+    int stats_groups = 0;
+    long stats_ready_for = -1;            // GroupNorm step whose statistics sit in the current slot
+    double* gn_slot_ptr(int slot) { return (double*)((char*)gn_ring->ptr + slot * 1024); }
+    static bool gn_apply_ok(const Tensor& t, int64_t C, int G)
+    {
+        const int vec = t.type == DType::f16 ? 8 : 4;
+        return (t.type == DType::f16 || t.type == DType::f32) && t.layout == Layout::nhwc && t.shape.size() == 4 && G >= 1 && G <= 64 && C % G == 0 && C % vec == 0 && C <= 4096;
+    }
     size_t cur_step = 0, cur_b = 0, cur_B = 1;
     std::unordered_map<std::string, Tensor> silu_cache;   // SiLU results of small tensors, valid for one run (see fused_silu)
     int runs_done = 0;
@@ -124,6 +142,22 @@ struct Engine::Impl {
         r.scale = x.scale; r.zero_point = x.zero_point;
         ck(osb_transpose2d(x.data(), r.mdata(), (int)dtype_size(x.type), 1, C, HW, st), "osb_transpose2d");
         return r;
+    }
+
+    Tensor quantize_dynamic(const Tensor& x);     // percentile range -> uint8 (Model::quantize, src/onnxstream.cpp:3247-3330)
+    Tensor dequantize(const Tensor& x, DType to);
+    bool percentile_range(const Tensor& x, float& lo, float& hi);
+    DevPtr pct_dev;
+    std::shared_ptr<PinnedBuf> pct_host;
+
+    // ops with a uint8 kernel under m_use_uint8_arithmetic (the reference's qu8 branches: Conv 4600-4660, MatMul 5780-5800, Add / Mul
+    // 846-927 + 1666-1746, Softmax 5971-5972) plus the type-agnostic data movers; every other op sees dequantised inputs here
+    // (the reference throws for most of them: a superset, never a different result)
+    static bool op_takes_u8(const OpDef& op)
+    {
+        static const std::set<std::string> k = { "Conv", "MatMul", "Add", "Mul", "Softmax", "Reshape", "Transpose", "Concat", "Split", "Slice", "Unsqueeze", "Squeeze",
+                                                 "Flatten", "Resize", "Gather", "Expand", "Identity" };
+        return k.count(op.type) != 0;
     }
 
     bool upcast_op(const OpDef& op) const
@@ -321,7 +355,10 @@ struct Engine::Impl {
             return t;
         }
         Tensor t = get_act(op, r.name);
+        if (t.type == DType::u8 && (!E.use_uint8_arithmetic || requires_float || !op_takes_u8(op)))
+            t = dequantize(t, (E.use_fp16_arithmetic && !requires_float && !upcast_op(op)) ? DType::f16 : DType::f32);
         if (requires_float && t.type == DType::f16) t = convert(t, DType::f32);
+        if (!E.use_fp16_arithmetic && t.type == DType::f16) t = convert(t, DType::f32);   // fp16 STORAGE (m_force_fp16_storage / fp16 inputs), fp32 arithmetic
         if (upcast_op(op) && t.type == DType::f16) t = convert(t, DType::f32);
         return t;
     }
@@ -358,9 +395,29 @@ struct Engine::Impl {
                     if (want[i] != t.shape[i] && !(E.support_dynamic_shapes && want[i] == 0)) ok = false;
             if (!ok) fail(op, "unexpected shape of output.");
         }
+        // m_range_data_calibrate (src/onnxstream.cpp:2983-3004): widen the recorded range of the producing op by this output's percentiles
+        if (E.range_data_calibrate && (t.type == DType::f16 || t.type == DType::f32)) {
+            float lo, hi;
+            if (percentile_range(t, lo, hi)) {
+                auto it = E.range_data.find(op.name);
+                if (it == E.range_data.end()) E.range_data[op.name] = { lo, hi };
+                else { it->second.first = std::min(it->second.first, lo); it->second.second = std::max(it->second.second, hi); }
+            }
+        }
+        // m_use_uint8_qdq / m_use_uint8_arithmetic: every float output is percentile-quantised to uint8 storage unless the next queued op
+        // is its only consumer (src/onnxstream.cpp:3006-3031)
+        if ((E.use_uint8_qdq || E.use_uint8_arithmetic) && (t.type == DType::f16 || t.type == DType::f32) && !next_is_sole_consumer(cur_step, o.name))
+            t = quantize_dynamic(t);
         // storage dtype rule of push_tensor (src/onnxstream.cpp:3006-3035)
         if (E.use_fp16_arithmetic && t.type == DType::f32 && !E.use_uint8_arithmetic && !E.use_uint8_qdq) {
             if (!next_is_sole_consumer(cur_step, o.name)) t = convert(t, DType::f16);
+        }
+        // m_force_fp16_storage (src/onnxstream.cpp:3764-3808): before every op the reference re-stores each fp32 tensor of m_data as fp16
+        // unless that op is its only remaining consumer -- i.e. a freshly produced fp32 tensor is rounded to fp16 storage here unless the
+        // next queued step consumes it alone.  (Names in m_force_uint8_storage_set would be percentile-quantised instead: see quantize_dynamic.)
+        if (E.force_fp16_storage && t.type == DType::f32 && !next_is_sole_consumer(cur_step, o.name)) {
+            if (E.force_uint8_storage_set.count(o.name)) t = quantize_dynamic(t);
+            else t = convert(t, DType::f16);
         }
         auto& v = store[o.name];
         if (v.empty()) order.push_back(o.name);
@@ -678,6 +735,16 @@ struct Engine::Impl {
             steps.push_back(s);
             i += s.count;
         }
+        // GroupNorm steps whose input is produced by the step right before them (conv / conv + residual / per-channel Add): that
+        // producer gathers the statistics (fuse_nodes only; the op list is unchanged, only the GroupNorm's stats pass disappears)
+        stats_consumer.assign(steps.size(), -1);
+        for (size_t j = 1; j < steps.size(); j++) {
+            if (steps[j].kind != SK_GROUPNORM) continue;
+            const Step& pstep = steps[j - 1];
+            const OpDef& last = ops[pstep.first + pstep.count - 1];
+            if (last.out.size() != 1 || last.out[0].name != ops[steps[j].first].in[0].name) continue;
+            if (pstep.kind == SK_CONV_ADD || (pstep.kind == SK_SINGLE && (last.type == "Conv" || last.type == "Add"))) stats_consumer[j - 1] = (long)j;
+        }
         largest_node = 0;
         node_weights.assign(steps.size(), {});
         for (size_t si = 0; si < steps.size(); si++) {
@@ -844,6 +911,55 @@ Tensor Engine::Impl::binary(int bop, const Tensor& a_in, const Tensor& b_in)
     return r;
 }
 
+
+// Model::quantize (src/onnxstream.cpp:3247-3330): percentile range of the tensor (get_percentiles, 0.1 % from either end, per
+// reference chunk) -> scale / zero point (range_to_scale, 3234-3245) -> XNNPACK f32->qu8 conversion.  A tensor without a usable
+// range (all values equal, non-finite ...) stays as it is, exactly like the reference (quantize returns false).
+bool Engine::Impl::percentile_range(const Tensor& x, float& lo, float& hi)
+{
+    if (x.type != DType::f16 && x.type != DType::f32) return false;
+    if (!pct_dev) { pct_dev = E.m_pool.alloc(256); pct_host = std::make_shared<PinnedBuf>(64); }
+    unsigned* h = (unsigned*)pct_host->ptr;
+    h[0] = 0xFFFFFFFFu; h[1] = 0; h[2] = 0;
+    ck(cudaMemcpyAsync(pct_dev->ptr, h, 12, cudaMemcpyHostToDevice, st), "percentiles init");
+    // the reference chunks the tensor by its pool's worker count; 0 = "all cores" there: use this host's count like it would
+    int threads = E.cpu_threads > 0 ? E.cpu_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    ck(osb_percentiles(x.data(), K(x.type), (size_t)x.numel(), threads, 0.001f, 0.001f, pct_dev->ptr, st), "osb_percentiles");
+    ck(cudaMemcpyAsync(h + 4, pct_dev->ptr, 12, cudaMemcpyDeviceToHost, st), "percentiles D2H");
+    ck(cudaStreamSynchronize(st), "percentiles sync");      // the range decides host-side parameters (scale, zero point)
+    if (h[6] == 0) return false;
+    lo = osb_percentile_key_to_float(h[4], K(x.type));
+    hi = osb_percentile_key_to_float(h[5], K(x.type));
+    return std::isfinite(lo) && std::isfinite(hi) && lo < hi;
+}
+
+static void range_to_scale(float lo, float hi, float& scale, int& zp)    // src/onnxstream.cpp:3234-3245
+{
+    if (lo > 0 && hi > 0) lo = 0;
+    else if (lo < 0 && hi < 0) hi = 0;
+    scale = (float)((hi - lo) / 255.0);
+    zp = (int)(uint8_t)(std::abs(lo) / scale);
+}
+
+Tensor Engine::Impl::quantize_dynamic(const Tensor& x)
+{
+    float lo = 0, hi = 0;
+    if (!percentile_range(x, lo, hi)) return x;
+    Tensor src = x;
+    src.scale = 0; src.zero_point = 0;
+    range_to_scale(lo, hi, src.scale, src.zero_point);
+    Tensor q = convert(src, DType::u8);
+    q.scale = src.scale; q.zero_point = src.zero_point;
+    return q;
+}
+
+Tensor Engine::Impl::dequantize(const Tensor& x, DType to)
+{
+    Tensor r = convert(x, to);       // (q - zero_point) * scale, src/onnxstream.cpp:3332-3434
+    r.scale = 0; r.zero_point = 0;
+    return r;
+}
+
 // ================================================================================================================
 // handlers
 // ================================================================================================================
@@ -936,8 +1052,15 @@ void Engine::Impl::op_conv(size_t oi, const Tensor* residual, size_t out_op)
             rr = to_nhwc(rr);
             if (rr.type != x.type) rr = convert(rr, x.type);
         }
-        ck(osb_conv2d(x.data(), w.data(), has_b ? b.data() : nullptr, residual ? rr.data() : nullptr, y.mdata(), H, W, Cin, Cout, kh, kw, stride, pad_top, pad_left, Ho, Wo,
-                      K(x.type), E.gemm_impl, st), "osb_conv2d");
+        // the GroupNorm right behind this conv wants per-group (sum, sum of squares) of the output: gathered in the epilogue
+        void* gstats = nullptr; int gdone = 0, G = 0;
+        if (stats_want >= 0 && gn_ring && cur_B == 1 && E.keep_nhwc && !is1d) {
+            G = stats_groups;
+            if (gn_apply_ok(y, Cout, G)) gstats = gn_slot_ptr(gn_slot);
+        }
+        ck(osb_conv2d_ex(x.data(), w.data(), has_b ? b.data() : nullptr, nullptr, residual ? rr.data() : nullptr, y.mdata(), H, W, Cin, Cout, kh, kw, stride, pad_top, pad_left, Ho, Wo,
+                         K(x.type), E.gemm_impl, st, gstats, G, &gdone), "osb_conv2d");
+        if (gdone) stats_ready_for = stats_want;
     }
     if (is1d) y.shape.pop_back();
     if (!E.keep_nhwc || is1d) { Tensor t = y; if (is1d) { t.shape.push_back(1); } t = to_plain(t); if (is1d) t.shape.pop_back(); y = t; }
@@ -1069,6 +1192,21 @@ void Engine::Impl::op_binary(size_t oi, int bop)
         iv = convert(tmp, c.type);
     }
     if (a.type == DType::u8 || b.type == DType::u8) fail(op, "qu8 elementwise arithmetic is not implemented in the B200 engine yet.");
+    if (stats_want >= 0 && gn_ring && cur_B == 1 && bop == OSB_BIN_ADD && a.type == b.type) {
+        // x[NHWC] + t[1,C,1,1] feeding a GroupNorm (the time-embedding add of a resnet): one pass adds and gathers the statistics
+        for (int k = 0; k < 2; k++) {
+            const Tensor& full = k ? b : a; const Tensor& vecv = k ? a : b;
+            if (full.layout != Layout::nhwc || full.shape.size() != 4 || vecv.layout != Layout::plain) continue;
+            const int64_t C = full.shape[1];
+            if (vecv.numel() != C || !(vecv.shape.size() == 4 && vecv.shape[1] == C) || !gn_apply_ok(full, C, stats_groups)) continue;
+            Tensor r = make(full.type, full.shape, Layout::nhwc);
+            if (osb_channel_add_stats(full.data(), vecv.data(), r.mdata(), K(full.type), C, full.numel() / C, stats_groups, gn_slot_ptr(gn_slot), st) == 0) {
+                stats_ready_for = stats_want;
+                push(oi, 0, r);
+                return;
+            }
+        }
+    }
     push(oi, 0, binary(bop, a, b));
 }
 
@@ -1859,6 +1997,10 @@ void Engine::Impl::fused_groupnorm(const Step& s)
     float eps = 1e-5f;
     for (auto& a : inrm.attrs) { if (a.first == "epsilon") eps = std::stof(a.second); else fail(inrm, "unrecognized attribute: " + a.first + "."); }
     Tensor x = in(i, 0);
+    // statistics the producer step left in the current ring slot; whoever does not consume them must zero the slot again
+    const bool pre = stats_ready_for == (long)cur_step;
+    stats_ready_for = -1;
+    auto drop_pre = [&] { if (pre) ck(cudaMemsetAsync(gn_slot_ptr(gn_slot), 0, 1024, st), "cudaMemsetAsync(gn slot)"); };
     (void)in(i, 1); (void)in(i + 2, 1);  // the two shape constants (validated statically by the matcher)
     Tensor gs = in(i + 1, 1), gb = in(i + 1, 2), gamma = in(i + 3, 1), beta = in(i + 4, 1);
     int64_t C = x.shape[1], HW = x.numel() / C;
@@ -1868,14 +2010,30 @@ void Engine::Impl::fused_groupnorm(const Step& s)
     if (!unit) {
         // non-trivial per-group affine: fold into per-channel gamma/beta on the host mirror is not possible for large C;
         // fall back to the unfused sequence for this group.
+        drop_pre();
         exec_unfused(s);
         return;
     }
     if (x.type != DType::f16 && x.type != DType::f32) fail(inrm, "wrong data type of input.");
     if (gamma.type != x.type) gamma = convert(gamma, x.type);
     if (beta.type != x.type) beta = convert(beta, x.type);
-    if (!gn_stats) { gn_stats = E.m_pool.alloc(2048); ck(cudaMemsetAsync(gn_stats->ptr, 0, 2048, st), "cudaMemsetAsync(gn scratch)"); }
     Tensor y = make(x.type, x.shape, x.layout);
+    static const bool split_gn = [] { const char* e = getenv("OSB_GN_SPLIT"); return !(e && e[0] == '0'); }();
+    if (split_gn && cur_B == 1 && gn_ring && gn_apply_ok(x, C, G)) {
+        // statistics: already in the current ring slot (gathered by the producing conv / Add), or one atomics pass now; then ONE
+        // streaming apply pass that also zeroes the other slot for the next producer -- no grid rendezvous, no co-residency assumption
+        bool have = pre;
+        if (!have) have = osb_channel_add_stats(x.data(), nullptr, nullptr, K(x.type), C, HW, G, gn_slot_ptr(gn_slot), st) == 0;
+        if (have) {
+            ck(osb_group_norm_apply(x.data(), y.mdata(), K(x.type), C, HW, G, gamma.data(), beta.data(), eps, s.variant == 1 ? 1 : 0,
+                                    gn_slot_ptr(gn_slot), gn_slot_ptr(gn_slot ^ 1), st), "osb_group_norm_apply");
+            gn_slot ^= 1;
+            push(s.first + s.count - 1, 0, y);
+            return;
+        }
+    }
+    drop_pre();
+    if (!gn_stats) { gn_stats = E.m_pool.alloc(2048); ck(cudaMemsetAsync(gn_stats->ptr, 0, 2048, st), "cudaMemsetAsync(gn scratch)"); }
     ck(osb_group_norm(x.data(), y.mdata(), K(x.type), x.layout == Layout::nhwc ? 1 : 0, C, HW, G, gamma.data(), beta.data(), eps, s.variant == 1 ? 1 : 0,
                       gn_stats->ptr, st), "osb_group_norm");
     push(s.first + s.count - 1, 0, y);
@@ -2031,7 +2189,20 @@ void Engine::Impl::exec_step(size_t si)
             if (b > 1) { if (cur_B > 1 && cur_B != b) fail(E.m_ops[oi], "inconsistent m_batch.size() across two or more tensors."); cur_B = b; }
         }
     pump_weights();
+    stats_want = -1;
+    if (E.fuse_nodes && si < stats_consumer.size() && stats_consumer[si] >= 0) {
+        const Step& gs = steps[(size_t)stats_consumer[si]];
+        stats_want = stats_consumer[si];
+        stats_groups = (int)E.m_ops[gs.first].out[0].shape[1];
+    }
     if (E.ops_printf) for (size_t oi = s.first; oi < s.first + s.count; oi++) printf("#%zu) %s (%s)%s\n", oi, E.m_ops[oi].type.c_str(), E.m_ops[oi].name.c_str(), s.count > 1 ? " [fused]" : "");
+    cudaEvent_t tev0 = nullptr, tev1 = nullptr;
+    if (E.ops_times_printf) {
+        // m_ops_times_printf (src/onnxstream.cpp:3812, 8199-8214): time per op TYPE; here the device time of the step's kernels
+        // (cudaEvent pair on the compute stream; the step is attributed to its first op's type, fused groups to "<type>+")
+        ck(cudaEventCreate(&tev0), "cudaEventCreate"); ck(cudaEventCreate(&tev1), "cudaEventCreate");
+        ck(cudaEventRecord(tev0, st), "cudaEventRecord");
+    }
     for (cur_b = 0; cur_b < cur_B; cur_b++) {
         switch (s.kind) {
         case SK_ATTENTION: fused_attention(s); break;
@@ -2054,6 +2225,10 @@ void Engine::Impl::exec_step(size_t si)
             for (size_t k = 0; k < E.m_ops[oi].in.size(); k++) staged.erase({ oi, k });
         auto sl = step_slot.find(si);
         if (sl != step_slot.end()) { E.m_streamer->release(sl->second, st); step_slot.erase(sl); }
+    }
+    if (tev0) {
+        ck(cudaEventRecord(tev1, st), "cudaEventRecord");
+        op_times.push_back({ E.m_ops[s.first].type + (s.count > 1 ? "+" : ""), tev0, tev1 });
     }
     wcache.clear();
     consume_inputs(s);
@@ -2213,7 +2388,7 @@ void* Engine::push_input(const std::string& name, DType type, const std::vector<
     HostTensor t;
     t.name = name; t.type = type; t.shape = shape;
     size_t n = 1; for (auto d : shape) n *= d;
-    if (type != DType::f32 && type != DType::i64) throw std::invalid_argument("Unsupported tensor data format.");
+    if (type != DType::f32 && type != DType::i64 && type != DType::f16) throw std::invalid_argument("Unsupported tensor data format.");
     t.count = n;
     t.buf = std::make_shared<PinnedBuf>(n * dtype_size(type));
     m_host_tensors.push_back(std::move(t));
@@ -2253,8 +2428,8 @@ void Engine::write_range_data(const char* filename)
 struct GraphState {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    struct In { std::string name; std::vector<size_t> shape; DevPtr dev; size_t bytes; };
-    struct Out { std::string name; std::vector<size_t> shape; DevPtr dev; size_t count; };
+    struct In { std::string name; std::vector<size_t> shape; DevPtr dev; size_t bytes; DType type; };
+    struct Out { std::string name; std::vector<size_t> shape; DevPtr dev; size_t count; DType type; };
     std::vector<In> inputs;
     std::vector<Out> outputs;
     std::vector<DevPtr> keepalive;
@@ -2282,7 +2457,7 @@ bool Engine::try_replay()
     for (auto& h : m_host_tensors) fins.push_back(&h);
     if (fins.size() != G.inputs.size()) { drop_graph(); return false; }
     for (size_t i = 0; i < fins.size(); i++)
-        if (fins[i]->type != DType::f32 || fins[i]->name != G.inputs[i].name || fins[i]->shape != G.inputs[i].shape) { drop_graph(); return false; }
+        if (fins[i]->type != G.inputs[i].type || fins[i]->name != G.inputs[i].name || fins[i]->shape != G.inputs[i].shape) { drop_graph(); return false; }
     auto t0 = std::chrono::high_resolution_clock::now();
     cudaEvent_t ev0, ev1;
     check_cuda(cudaEventCreate(&ev0), "cudaEventCreate");
@@ -2298,10 +2473,11 @@ bool Engine::try_replay()
     m_stats.d2h_output_bytes = 0;
     for (auto& o : G.outputs) {
         HostTensor h;
-        h.name = o.name; h.type = DType::f32; h.shape = o.shape; h.count = o.count;
-        h.buf = std::make_shared<PinnedBuf>(o.count * 4);
-        check_cuda(cudaMemcpyAsync(h.buf->ptr, o.dev->ptr, o.count * 4, cudaMemcpyDeviceToHost, m_stream), "output D2H");
-        m_stats.d2h_output_bytes += o.count * 4;
+        h.name = o.name; h.type = o.type; h.shape = o.shape; h.count = o.count;
+        const size_t ob = o.count * dtype_size(o.type);
+        h.buf = std::make_shared<PinnedBuf>(ob);
+        check_cuda(cudaMemcpyAsync(h.buf->ptr, o.dev->ptr, ob, cudaMemcpyDeviceToHost, m_stream), "output D2H");
+        m_stats.d2h_output_bytes += ob;
         outs.push_back(std::move(h));
     }
     check_cuda(cudaEventRecord(ev1, m_stream), "cudaEventRecord");
@@ -2403,12 +2579,15 @@ void Engine::run()
             t.i64 = std::make_shared<std::vector<int64_t>>(h.i64(), h.i64() + h.count);
             uploaded.emplace_back(t, false);
         } else {
-            t.type = DType::f32;
-            t.dev = m_pool.alloc(h.count * 4);
-            check_cuda(cudaMemcpyAsync(t.dev->ptr, h.buf->ptr, h.count * 4, cudaMemcpyHostToDevice, m_stream), "input H2D");
-            m_stats.h2d_input_bytes += h.count * 4;
-            if (G) G->inputs.push_back({ h.name, h.shape, t.dev, h.count * 4 });
-            uploaded.emplace_back(t, use_fp16_arithmetic && !use_uint8_arithmetic && !use_uint8_qdq);
+            // float32, or float16 (the C++ adapter hands fp16 tensors -- e.g. a KV cache kept out of m_outputs_convert_set -- over as they are)
+            const size_t esz = dtype_size(h.type);
+            t.type = h.type;
+            t.dev = m_pool.alloc(h.count * esz);
+            check_cuda(cudaMemcpyAsync(t.dev->ptr, h.buf->ptr, h.count * esz, cudaMemcpyHostToDevice, m_stream), "input H2D");
+            m_stats.h2d_input_bytes += h.count * esz;
+            if (G) G->inputs.push_back({ h.name, h.shape, t.dev, h.count * esz, h.type });
+            // storage rule of push_tensor for fp32 data (src/onnxstream.cpp:3006-3035), and m_force_fp16_storage (3764-3808)
+            uploaded.emplace_back(t, h.type == DType::f32 && ((use_fp16_arithmetic && !use_uint8_arithmetic && !use_uint8_qdq) || force_fp16_storage));
         }
     }
     std::vector<HostTensor> pinned_inputs = std::move(m_host_tensors);   // keep the pinned sources alive until the copies ran
@@ -2424,11 +2603,15 @@ void Engine::run()
         }
         for (auto& u : uploaded) {
             Tensor t = u.first;
-            if (u.second) { t = I.convert(t, DType::f16); t.name = u.first.name; }
+            if ((use_uint8_qdq || use_uint8_arithmetic) && (t.type == DType::f32 || t.type == DType::f16)) { t = I.quantize_dynamic(t); t.name = u.first.name; }
+            else if (u.second) { t = I.convert(t, DType::f16); t.name = u.first.name; }
             auto& v = I.store[t.name];
             if (v.empty()) I.order.push_back(t.name);
             v.push_back(std::move(t));
         }
+        if (!I.gn_ring) I.gn_ring = m_pool.alloc(2048);
+        check_cuda(cudaMemsetAsync(I.gn_ring->ptr, 0, 2048, m_stream), "cudaMemsetAsync(gn ring)");    // both statistic slots zero: the invariant every producer relies on
+        I.gn_slot = 0; I.stats_ready_for = -1; I.stats_want = -1;
         for (size_t si = 0; si < I.steps.size(); si++) I.exec_step(si);
         m_streamer->end_run(m_stream);
 
@@ -2441,6 +2624,18 @@ void Engine::run()
                 for (auto d : t0_.shape) shp.push_back((size_t)d);
                 if (t0_.type == DType::i64) { finals.emplace_back(name, shp, t0_); continue; }
                 Tensor t = I.to_plain(t0_);
+                if (t.type == DType::u8) t = I.dequantize(t, DType::f32);     // src/onnxstream.cpp:8238-8241
+                // m_outputs_convert_set (src/onnxstream.cpp:8234-8236): tensors outside a non-empty set keep their storage type
+                // (fp16 stays fp16: half the D2H bytes, and llm.cpp feeds its KV cache straight back in)
+                if (!outputs_convert_set.empty() && !outputs_convert_set.count(name) && t.type == DType::f16) {
+                    if (!t.dev || (t.dev.get() == t0_.dev.get() && capturing)) {
+                        Tensor c = I.make(DType::f16, t.shape);
+                        check_cuda(cudaMemcpyAsync(c.mdata(), t.data(), (size_t)t.numel() * 2, cudaMemcpyDeviceToDevice, m_stream), "copy");
+                        t = c;
+                    }
+                    finals.emplace_back(name, shp, t);
+                    continue;
+                }
                 if (t.type == DType::f32 && !t.dev && t.dev_raw) { Tensor c = I.make(DType::f32, t.shape); check_cuda(cudaMemcpyAsync(c.mdata(), t.dev_raw, (size_t)t.numel() * 4, cudaMemcpyDeviceToDevice, m_stream), "copy"); t = c; }
                 t = I.convert(t, DType::f32);
                 if (t.dev.get() == t0_.dev.get() && capturing) {   // graph outputs need storage the graph owns exclusively
@@ -2456,7 +2651,7 @@ void Engine::run()
             capture_open = false;
             check_cuda(cudaStreamEndCapture(m_stream, &G->graph), "cudaStreamEndCapture");
             check_cuda(cudaGraphInstantiate(&G->exec, G->graph, 0), "cudaGraphInstantiate");
-            for (auto& f : finals) if (std::get<2>(f).type != DType::i64) G->outputs.push_back({ std::get<0>(f), std::get<1>(f), std::get<2>(f).dev, (size_t)std::get<2>(f).numel() });
+            for (auto& f : finals) if (std::get<2>(f).type != DType::i64) G->outputs.push_back({ std::get<0>(f), std::get<1>(f), std::get<2>(f).dev, (size_t)std::get<2>(f).numel(), std::get<2>(f).type });
             check_cuda(cudaGraphLaunch(G->exec, m_stream), "cudaGraphLaunch");   // capture does not execute: run it once now
             G->ready = true;
             m_pool.frozen = false;
@@ -2490,14 +2685,23 @@ void Engine::run()
             h.buf = std::make_shared<PinnedBuf>(h.count * 8);
             memcpy(h.buf->ptr, t.i64->data(), h.count * 8);
         } else {
-            h.type = DType::f32;
-            h.buf = std::make_shared<PinnedBuf>(h.count * 4);
-            check_cuda(cudaMemcpyAsync(h.buf->ptr, t.data(), h.count * 4, cudaMemcpyDeviceToHost, m_stream), "output D2H");
-            m_stats.d2h_output_bytes += h.count * 4;
+            h.type = t.type;      // float32, or float16 for tensors outside m_outputs_convert_set
+            const size_t ob = h.count * dtype_size(t.type);
+            h.buf = std::make_shared<PinnedBuf>(ob);
+            check_cuda(cudaMemcpyAsync(h.buf->ptr, t.data(), ob, cudaMemcpyDeviceToHost, m_stream), "output D2H");
+            m_stats.d2h_output_bytes += ob;
         }
         m_host_tensors.push_back(std::move(h));
     }
     check_cuda(cudaStreamSynchronize(m_stream), "run sync");
+    if (!I.op_times.empty()) {
+        std::map<std::string, double> acc;
+        for (auto& o : I.op_times) { float ms = 0.f; cudaEventElapsedTime(&ms, o.a, o.b); acc[o.type] += ms; cudaEventDestroy(o.a); cudaEventDestroy(o.b); }
+        I.op_times.clear();
+        printf("\033[7m > \033[0m");
+        for (auto& e : acc) printf(" %s:%f,", e.first.c_str(), e.second);
+        printf("\n");
+    }
     I.store.clear();
     I.order.clear();
     I.silu_cache.clear();

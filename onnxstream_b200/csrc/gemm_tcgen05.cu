@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "workspace.h"
+#include "tc_ptx.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cstdio>
@@ -36,7 +37,12 @@ constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;   // 256
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
 constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;  // 16 KiB
-constexpr int smem_bytes_for(int stages) { return stages * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/; }
+#ifndef OSB_NO_EPI_EXTRAS
+constexpr int GN_SMEM_BYTES = 4 * 2048 + 2 * tcptx::GN_MAX_GROUPS * 4;
+#else
+constexpr int GN_SMEM_BYTES = 0;      // A/B build: the single-CTA kernel without the statistics / bias2 epilogue (callers must not request them)
+#endif   // GroupNorm statistics: 4 warp-private transposition buffers + the CTA accumulators
+constexpr int smem_bytes_for(int stages) { return stages * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/ + GN_SMEM_BYTES; }
 constexpr int NUM_THREADS = 192;       // 6 warps
 
 struct TcParams {
@@ -61,118 +67,15 @@ struct TcParams {
     // output
     __half* C;
     const __half* bias;
+    const __half* bias2;         // second per-column addend (the time-embedding row a resnet adds to conv1's output), or null
     const __half* residual;
+    double* gn_stats;            // != null: per-group (sum, sum of squares) of the stored output, for the GroupNorm that consumes it
+    int gn_cpg, gn_groups;       // channels per group, number of groups (N == gn_cpg * gn_groups)
     long long stride_c;          // elements between batches
     long long ldc;               // elements between output rows (== N for a dense C)
 };
 
-// ---- PTX wrappers ---------------------------------------------------------------------------------------------
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    uint32_t addr = smem_u32(bar);
-    uint32_t done = 0;
-    long long t0 = 0;
-    while (true) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-        if (done) break;
-        // watchdog: a protocol bug must surface as a launch failure, never as a hung GPU (~2 s at 2 GHz)
-        long long now = clock64();
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > 4000000000LL) { printf("tc_gemm_kernel: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
-    }
-}
-
-__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2)
-{
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                 ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-
-// The producer / MMA warps run WARP-UNIFORM control flow and issue from an elect.sync-guarded region.  (Inside an
-// `if (lane == 0)` region ptxas cannot keep the operands of UTCHMMA / UTMALDG in uniform registers and wraps every one of them
-// in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop: ~1000 issue cycles per k-block, measured with ncu source sampling.)
-__device__ __forceinline__ void tma_load_3d_s(uint32_t smem_addr, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2)
-{
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                 ::"r"(smem_addr), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-// one lane of a converged warp, chosen by the hardware (elect.sync): ptxas knows the guarded region runs on exactly one lane
-__device__ __forceinline__ bool elect_one()
-{
-    uint32_t pred = 0;
-    asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xffffffff;\n\tselp.u32 %0, 1, 0, px;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// D[tmem] (+)= A[smem] * B[smem], single CTA, fp16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// arrive on an mbarrier once all previously issued MMAs have completed (implies fence::before_thread_sync)
-__device__ __forceinline__ void umma_commit(uint64_t* bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// shared-memory matrix descriptor (see cute/arch/mma_sm100_desc.hpp SmemDescriptor): SWIZZLE_128B, version 1
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;   // LayoutType::SWIZZLE_128B
-    return d;
-}
+using namespace tcptx;
 
 // instruction descriptor for kind::f16: fp16 x fp16 -> fp32, A K-major, B K- or MN-major
 __device__ __forceinline__ uint32_t make_idesc(int b_mn_major, int bn)
@@ -207,10 +110,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t* acc_full = bars + 2 * STAGES;      // [ACC_STAGES]
     uint64_t* acc_empty = acc_full + ACC_STAGES; // [ACC_STAGES]
     uint32_t* tmem_slot = (uint32_t*)(acc_empty + ACC_STAGES);
-    volatile int* split_flag = (volatile int*)(tmem_slot + 1);
+    uint8_t* gn_buf = (uint8_t*)bars + 256;                 // [4][2048] warp-private chunk transposition buffers
+    float* gn_acc = (float*)(gn_buf + 4 * 2048);            // [2 * GN_MAX_GROUPS] per-CTA (sum, sum of squares) accumulators
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+#ifndef OSB_NO_EPI_EXTRAS
+    if (p.gn_stats && threadIdx.x < 2 * GN_MAX_GROUPS) gn_acc[threadIdx.x] = 0.f;
+#endif
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -397,13 +304,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                             for (int t = 0; t < 8; t++) f[t] += __half2float(rv.v[t]);
                         }
+#ifndef OSB_NO_EPI_EXTRAS
+                        if (p.bias2) {
+                            Vec<__half, 8> bv = load_vec<__half, 8>(p.bias2 + n);
+#pragma unroll
+                            for (int t = 0; t < 8; t++) f[t] += __half2float(bv.v[t]);
+                        }
+#endif
                         Vec<__half, 8> o;
 #pragma unroll
                         for (int t = 0; t < 8; t++) o.v[t] = __float2half_rn(f[t]);
                         store_vec<__half, 8>(crow + n, o);
+#ifndef OSB_NO_EPI_EXTRAS
+#pragma unroll
+                        for (int t = 0; t < 4; t++) v[(j >> 1) + t] = *reinterpret_cast<uint32_t*>(&o.v[2 * t]);   // keep the rounded values for the statistics
+#endif
                     }
                 }
+#ifndef OSB_NO_EPI_EXTRAS
+                if (p.gn_stats && !wrow) {
+                    // rows outside the problem (and units past N) contribute zeros
+                    uint32_t h[16];
+#pragma unroll
+                    for (int t = 0; t < 16; t++) h[t] = (row_ok && vec_ok && n0 + c + 2 * t < n_end) ? v[t] : 0u;
+                    gn_stats_chunk(smem_u32(gn_buf) + (uint32_t)q * 2048u, h, n0 + c, n_end, p.gn_cpg, gn_acc, lane);
+                }
+#endif
             }
+#ifndef OSB_NO_EPI_EXTRAS
+            if (p.gn_stats && !wrow) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                gn_stats_flush(gn_acc, p.gn_stats, p.gn_groups, (int)threadIdx.x - 64);
+            }
+#endif
             tc_fence_before();
             mbar_arrive(&acc_empty[acc]);
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
@@ -448,6 +381,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
                             }
                             if (p.bias) { a.x += __half2float(p.bias[n]); a.y += __half2float(p.bias[n + 1]); a.z += __half2float(p.bias[n + 2]); a.w += __half2float(p.bias[n + 3]); }
+                            if (p.bias2) { a.x += __half2float(p.bias2[n]); a.y += __half2float(p.bias2[n + 1]); a.z += __half2float(p.bias2[n + 2]); a.w += __half2float(p.bias2[n + 3]); }
                             if (res) { Vec<__half, 4> r4 = load_vec<__half, 4>(res + n); a.x += __half2float(r4.v[0]); a.y += __half2float(r4.v[1]); a.z += __half2float(r4.v[2]); a.w += __half2float(r4.v[3]); }
                             Vec<__half, 4> o4;
                             o4.v[0] = __float2half_rn(a.x); o4.v[1] = __float2half_rn(a.y); o4.v[2] = __float2half_rn(a.z); o4.v[3] = __float2half_rn(a.w);
@@ -472,11 +406,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
 }
 
-// split-K second pass: out[row][n] = fp16(sum_s ws[s][row][n] + bias[n] + residual[row][n]); rows = batch * M
-__global__ void splitk_reduce_kernel(const float* __restrict__ ws, __half* __restrict__ out, const __half* __restrict__ bias,
-                                     const __half* __restrict__ residual, long long rows, int N, int splits)
+// split-K second pass: out[row][n] = fp16(sum_s ws[s][row][n] + bias[n] + bias2[n] + residual[row][n]); rows = batch * M.
+// Optionally gathers the GroupNorm statistics of the result (per-block shared accumulators -> global fp64).
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, __half* __restrict__ out, const __half* __restrict__ bias, const __half* __restrict__ bias2,
+                                     const __half* __restrict__ residual, long long rows, int N, int splits, double* __restrict__ gn_stats, int gn_cpg, int gn_groups)
 {
     osb_pdl_prologue();
+    __shared__ float acc[2 * GN_MAX_GROUPS];
+    if (gn_stats) { if (threadIdx.x < 2 * GN_MAX_GROUPS) acc[threadIdx.x] = 0.f; __syncthreads(); }
     // N % 4 == 0: one float4 of every split plane per thread, fully coalesced
     const long long total4 = rows * N / 4;
     const long long plane4 = total4;
@@ -487,6 +424,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, __half* __res
         long long e = i * 4;
         int n = (int)(e % N);
         if (bias) { a.x += __half2float(bias[n]); a.y += __half2float(bias[n + 1]); a.z += __half2float(bias[n + 2]); a.w += __half2float(bias[n + 3]); }
+        if (bias2) { a.x += __half2float(bias2[n]); a.y += __half2float(bias2[n + 1]); a.z += __half2float(bias2[n + 2]); a.w += __half2float(bias2[n + 3]); }
         if (residual) {
             Vec<__half, 4> r = load_vec<__half, 4>(residual + e);
             a.x += __half2float(r.v[0]); a.y += __half2float(r.v[1]); a.z += __half2float(r.v[2]); a.w += __half2float(r.v[3]);
@@ -494,8 +432,21 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, __half* __res
         Vec<__half, 4> o;
         o.v[0] = __float2half_rn(a.x); o.v[1] = __float2half_rn(a.y); o.v[2] = __float2half_rn(a.z); o.v[3] = __float2half_rn(a.w);
         store_vec<__half, 4>(out + e, o);
+        if (gn_stats) {
+            // the 4 columns of a thread lie in one group when cpg % 4 == 0 (host guarantees it)
+            float x0 = __half2float(o.v[0]), x1 = __half2float(o.v[1]), x2 = __half2float(o.v[2]), x3 = __half2float(o.v[3]);
+            const int g = n / gn_cpg;
+            atomicAdd(&acc[2 * g], (x0 + x1) + (x2 + x3));
+            atomicAdd(&acc[2 * g + 1], fmaf(x0, x0, x1 * x1) + fmaf(x2, x2, x3 * x3));
+        }
+    }
+    if (gn_stats) {
+        __syncthreads();
+        if (threadIdx.x < 2 * gn_groups) { float v = acc[threadIdx.x]; if (v != 0.f) atomicAdd(&gn_stats[threadIdx.x], (double)v); }
     }
 }
+
+#include "gemm_pair.cuh"
 
 // ---- host side -------------------------------------------------------------------------------------------------
 constexpr size_t WS_MAX = OSB_WS_SPLITK_BYTES;   // fixed-capacity per-stream workspace (workspace.h): never re-allocated, graph-safe
@@ -593,6 +544,18 @@ bool inkernel_reduce()
     return v == 1;
 }
 
+void prof_begin(ProfRec& rec, const TcParams& p, cudaStream_t st)
+{
+    cudaEventCreate(&rec.a); cudaEventCreate(&rec.b);
+    double M = p.M, N = p.N, Kt = (double)p.K * p.taps, B = p.batch;
+    rec.flops = 2.0 * M * N * Kt * B;
+    // algorithmic bytes: A once (conv: the input image once), B once, C once (+ residual / bias reads)
+    double a_bytes = (p.bh > 0 ? M * p.K : M * Kt) * 2.0 * B;
+    rec.bytes = a_bytes + N * Kt * 2.0 * (p.bh > 0 ? 1.0 : B) + M * N * 2.0 * B * (p.residual ? 2.0 : 1.0) + (p.bias ? N * 2.0 : 0.0);
+    rec.M = p.M; rec.N = p.N; rec.K = p.K; rec.taps = p.taps; rec.batch = p.batch; rec.split = p.split_k; rec.conv = p.bh > 0;
+    cudaEventRecord(rec.a, st);
+}
+
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st, const CUtensorMap* mb1p = nullptr, const CUtensorMap* mb2p = nullptr)
 {
     const CUtensorMap& mb1 = mb1p ? *mb1p : mb;
@@ -608,23 +571,15 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cuda
     const bool short_k = p.short_k != 0;
     int grid = std::min(total, num_sms() * (short_k ? 2 : 1));
     ProfRec rec{};
-    if (g_prof) {
-        cudaEventCreate(&rec.a); cudaEventCreate(&rec.b);
-        double M = p.M, N = p.N, Kt = (double)p.K * p.taps, B = p.batch;
-        rec.flops = 2.0 * M * N * Kt * B;
-        // algorithmic bytes: A once (conv: the input image once), B once, C once (+ residual / bias reads)
-        double a_bytes = (p.bh > 0 ? M * p.K : M * Kt) * 2.0 * B;
-        rec.bytes = a_bytes + N * Kt * 2.0 * (p.bh > 0 ? 1.0 : B) + M * N * 2.0 * B * (p.residual ? 2.0 : 1.0) + (p.bias ? N * 2.0 : 0.0);
-        rec.M = p.M; rec.N = p.N; rec.K = p.K; rec.taps = p.taps; rec.batch = p.batch; rec.split = p.split_k; rec.conv = p.bh > 0;
-        cudaEventRecord(rec.a, st);
-    }
+    if (g_prof) prof_begin(rec, p, st);
     if (short_k) osb_launch((tc_gemm_kernel<STAGES_SHORT>), grid, NUM_THREADS, (size_t)smem_bytes_for(STAGES_SHORT), st, ma, mb, mb1, mb2, p);
     else osb_launch((tc_gemm_kernel<STAGES_DEEP>), grid, NUM_THREADS, (size_t)smem_bytes_for(STAGES_DEEP), st, ma, mb, mb1, mb2, p);
     if (p.split_k > 1 && !p.counters) {
         launched(1);
         long long total4 = (long long)p.batch * p.M * p.N / 4;
         int rgrid = (int)std::min<long long>((total4 + 255) / 256, 148 * 8);
-        osb_launch((splitk_reduce_kernel), rgrid, 256, 0, st, (const float*)p.ws, p.C, p.bias, p.residual, (long long)p.batch * p.M, p.N, p.split_k);
+        osb_launch((splitk_reduce_kernel), rgrid, 256, 0, st, (const float*)p.ws, p.C, p.bias, p.bias2, p.residual, (long long)p.batch * p.M, p.N, p.split_k,
+                   p.gn_stats, p.gn_cpg, p.gn_groups);
         if (g_prof) { cudaEventRecord(rec.b, st); g_prof_list.push_back(rec); }
         return launched(0);
     }
@@ -653,9 +608,87 @@ int choose_bn(int64_t m_tiles, int64_t N, int64_t batch)
     return 128;
 }
 
+
+// ---- CTA-pair kernel: host side -------------------------------------------------------------------------------------
+// Cost model (r01 finding: these kernels are bound by L2->SM bytes per CTA and k-block, and by waves): a launch costs
+// waves x bytes-per-CTA-per-k-block.  single: 128 x bn tiles over 148 SMs, (128 + bn) x 128 B; pair: 256 x bn tiles over 74 SM
+// pairs, (128 + bn / 2) x 128 B per CTA.  OSB_TC_PAIR=0 disables the pair kernel, =2 forces it wherever it is eligible.
+int g_pair_mode = -1;
+int pair_mode()
+{
+    if (g_pair_mode < 0) { const char* e = getenv("OSB_TC_PAIR"); g_pair_mode = e ? atoi(e) : 1; }
+    return g_pair_mode;
+}
+
+int choose_pair_bn(int64_t m_tiles, int64_t N, int64_t batch, bool b_kmajor, double* cost)
+{
+    static const int forced = env_int("OSB_TC_PAIR_BN");
+    const int cands_k[4] = { 64, 128, 192, 256 }, cands_mn[2] = { 128, 256 };
+    const int* cands = b_kmajor ? cands_k : cands_mn;
+    const int nc = b_kmajor ? 4 : 2;
+    const int64_t m_pairs = (m_tiles + 1) / 2;
+    const int pairs_hw = num_sms() / 2;
+    int best = 0; double best_cost = 0;
+    for (int i = 0; i < nc; i++) {
+        int bn = cands[i];
+        if (forced && bn != forced) continue;
+        if (i > 0 && bn - 64 >= N) break;                    // wider than the problem
+        int64_t tiles = m_pairs * ((N + bn - 1) / bn) * batch;
+        int64_t waves = (tiles + pairs_hw - 1) / pairs_hw;
+        double c = (double)waves * (16384.0 + 64.0 * bn);
+        if (!best || c < best_cost) { best = bn; best_cost = c; }
+    }
+    *cost = best_cost;
+    return best;
+}
+
+double single_cost(int64_t m_tiles, int64_t N, int64_t batch, int bn)
+{
+    int64_t tiles = m_tiles * ((N + bn - 1) / bn) * batch;
+    int64_t waves = (tiles + num_sms() - 1) / num_sms();
+    return (double)waves * (16384.0 + 128.0 * bn);
+}
+
+// pair kernel or single-CTA kernel?  `k_blocks` = length of the K loop, `tiles1` = tiles of the single-CTA decomposition
+bool use_pair(int64_t m_tiles, int64_t N, int64_t batch, bool b_kmajor, int k_blocks, int bn1, int* bn_pair)
+{
+    const int mode = pair_mode();
+    if (mode == 0 || m_tiles < 2 || (N % 8)) return false;
+    double cp = 0;
+    int bn = choose_pair_bn(m_tiles, N, batch, b_kmajor, &cp);
+    if (!bn) return false;
+    *bn_pair = bn;
+    if (mode == 2) return true;
+    const int64_t tiles1 = m_tiles * ((N + bn1 - 1) / bn1) * batch;
+    if (tiles1 < 100 && k_blocks >= 32) return false;      // long K over few tiles: the split-K path of the single-CTA kernel
+    if (k_blocks < 8) return false;                        // launch-latency bound: the lighter prologue wins
+    return cp < 0.9 * single_cost(m_tiles, N, batch, bn1);
+}
+
+int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const TcParams& p, cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(pairk::tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pairk::P_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int m_pairs = (p.m_tiles + 1) / 2;
+    const int total = m_pairs * p.n_tiles * p.batch;
+    const int pairs = std::min(total, num_sms() / 2);
+    ProfRec rec{};
+    if (g_prof) prof_begin(rec, p, st);
+    osb_launch((pairk::tc_pair_kernel), 2 * pairs, pairk::P_THREADS, (size_t)pairk::P_SMEM, st, ma, mb, mc, p);
+    if (g_prof) { cudaEventRecord(rec.b, st); g_prof_list.push_back(rec); }
+    return launched(1);
+}
+
 inline uint32_t next_pow2(uint32_t v) { uint32_t r = 1; while (r < v) r <<= 1; return r; }
 
 }  // namespace
+
+// 0: single-CTA kernel only, 1: cost model (default), 2: pair kernel wherever eligible (tests / A-B runs)
+extern "C" void osb_tc_set_pair_mode(int mode) { g_pair_mode = mode; }
 
 extern "C" void osb_tc_profile(int enable)
 {
@@ -728,6 +761,27 @@ int osb_tc_gemm_launch(const void* A, const void* B, void* C, const void* bias, 
     if (!make_map_rb(&ma, A, (uint64_t)K, (uint64_t)M, abatch, (uint64_t)lda * 2, (uint64_t)(sa ? sa : M * lda) * 2, BLOCK_K, BLOCK_M, &a_swap)) return (int)cudaErrorInvalidValue;
     int64_t m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
     int bn = choose_bn(m_tiles, N, batch);
+    {
+        // CTA-pair kernel (256 x bn tiles, TMA-store epilogue) where its cost model wins: dense C only
+        int bnp = 0;
+        const int k_blocks = (int)((K + BLOCK_K - 1) / BLOCK_K);
+        if (ldc == N && (batch == 1 || sc == M * N) && use_pair(m_tiles, N, batch, bt != 0, k_blocks, bn, &bnp)) {
+            CUtensorMap mc;
+            int c_swap = 0;
+            bool ok = bt ? make_map_rb(&mb, B, (uint64_t)K, (uint64_t)N, bbatch, (uint64_t)ldb * 2, (uint64_t)(sb ? sb : N * ldb) * 2, BLOCK_K, (uint32_t)(bnp / 2), &b_swap)
+                         : make_map_rb(&mb, B, (uint64_t)N, (uint64_t)K, bbatch, (uint64_t)ldb * 2, (uint64_t)(sb ? sb : K * ldb) * 2, 64, BLOCK_K, &b_swap);
+            ok = ok && make_map_rb(&mc, C, (uint64_t)N, (uint64_t)M, (uint64_t)batch, (uint64_t)ldc * 2, (uint64_t)(batch > 1 ? sc : M * ldc) * 2, 64, 32, &c_swap) && !c_swap;
+            if (ok) {
+                TcParams p{};
+                p.M = (int)M; p.N = (int)N; p.K = (int)K; p.batch = (int)batch;
+                p.bn = bnp; p.m_tiles = (int)m_tiles; p.n_tiles = (int)((N + bnp - 1) / bnp);
+                p.b_kmajor = bt ? 1 : 0; p.a_swap = a_swap; p.b_swap = b_swap;
+                p.taps = 1; p.kw = 1; p.bh = 0; p.bw = 0; p.tiles_x = 1; p.k_blocks_per_tap = k_blocks; p.stride = 1;
+                p.C = (__half*)C; p.bias = (const __half*)bias; p.residual = (const __half*)residual; p.stride_c = sc; p.ldc = ldc; p.split_k = 1;
+                return launch_pair(ma, mb, mc, p, st);
+            }
+        }
+    }
     bool okb = bt ? make_map_rb(&mb, B, (uint64_t)K, (uint64_t)N, bbatch, (uint64_t)ldb * 2, (uint64_t)(sb ? sb : N * ldb) * 2, BLOCK_K, (uint32_t)bn, &b_swap)
                   : make_map_rb(&mb, B, (uint64_t)N, (uint64_t)K, bbatch, (uint64_t)ldb * 2, (uint64_t)(sb ? sb : K * ldb) * 2, 64, BLOCK_K, &b_swap);
     if (!okb) return (int)cudaErrorInvalidValue;
@@ -794,9 +848,16 @@ bool osb_tc_conv_ok(int64_t H, int64_t W, int64_t Cin, int64_t Cout, int kh, int
     return get_encode() != nullptr;
 }
 
+// bias2: second per-channel addend or null.  gn_stats != null (and Cout % gn_groups == 0): the kernel adds the per-group (sum, sum of
+// squares) of the stored output to gn_stats[2 * groups] (fp64) and sets *gn_done = 1 -- when the chosen decomposition cannot (ragged
+// Cout, split-K with a group width that is not a multiple of 4, in-kernel reduce) *gn_done stays 0 and the caller computes them itself.
 int osb_tc_conv_launch(const void* x, const void* w, const void* bias, const void* residual, void* y, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
-                       int kh, int kw, int stride, int pad_top, int pad_left, int64_t Ho, int64_t Wo, cudaStream_t st)
+                       int kh, int kw, int stride, int pad_top, int pad_left, int64_t Ho, int64_t Wo, cudaStream_t st,
+                       const void* bias2, double* gn_stats, int gn_groups, int* gn_done)
 {
+    if (gn_done) *gn_done = 0;
+    if (gn_stats && (gn_groups < 1 || gn_groups > tcptx::GN_MAX_GROUPS || Cout % gn_groups || Cout % 8)) gn_stats = nullptr;
+    const int gn_cpg = gn_stats ? (int)(Cout / gn_groups) : 0;
     uint32_t bw = std::min<uint32_t>(128, next_pow2((uint32_t)Wo)), bh = 128 / bw;
     CUtensorMap ma, mb;
     // A: NHWC input as (C, W, H); one box = bh rows x bw pixels x 64 channels, zero-filled outside the image.  With a
@@ -807,6 +868,31 @@ int osb_tc_conv_launch(const void* x, const void* w, const void* bias, const voi
     int64_t Ktot = (int64_t)kh * kw * Cin;
     int64_t tiles_x_ = (Wo + bw - 1) / bw, m_tiles_ = tiles_x_ * ((Ho + bh - 1) / bh);
     int bn = choose_bn(m_tiles_, Cout, 1);
+    {
+        // CTA-pair kernel: each CTA of the pair takes one 128-pixel box of the same tiling; output through a (Cout, Wo, Ho) store map
+        int bnp = 0;
+        const int k_blocks = kh * kw * (int)((Cin + BLOCK_K - 1) / BLOCK_K);
+        if (Cout % 8 == 0 && use_pair(m_tiles_, Cout, 1, true, k_blocks, bn, &bnp)) {
+            CUtensorMap mc;
+            const uint32_t box_w = std::min<uint32_t>(bw, 32), box_h = 32 / box_w;
+            bool ok = make_map(&mb, w, (uint64_t)Ktot, (uint64_t)Cout, 1, (uint64_t)Ktot * 2, (uint64_t)Ktot * Cout * 2, BLOCK_K, (uint32_t)(bnp / 2), 1) &&
+                      make_map(&mc, y, (uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)Cout * 2, (uint64_t)Wo * Cout * 2, 64, box_w, box_h);
+            if (ok) {
+                TcParams p{};
+                p.bn = bnp;
+                p.M = (int)(Ho * Wo); p.N = (int)Cout; p.K = (int)Cin; p.batch = 1;
+                p.tiles_x = (int)tiles_x_; p.m_tiles = (int)m_tiles_; p.n_tiles = (int)((Cout + bnp - 1) / bnp);
+                p.b_kmajor = 1;
+                p.taps = kh * kw; p.kw = kw; p.pad_top = pad_top; p.pad_left = pad_left; p.Wo = (int)Wo; p.Ho = (int)Ho; p.bw = (int)bw; p.bh = (int)bh;
+                p.k_blocks_per_tap = (int)((Cin + BLOCK_K - 1) / BLOCK_K);
+                p.stride = stride;
+                p.C = (__half*)y; p.bias = (const __half*)bias; p.residual = (const __half*)residual; p.stride_c = 0; p.ldc = Cout; p.split_k = 1;
+                p.bias2 = (const __half*)bias2; p.gn_stats = gn_stats; p.gn_cpg = gn_cpg; p.gn_groups = gn_groups;
+                if (gn_stats && gn_done) *gn_done = 1;
+                return launch_pair(ma, mb, mc, p, st);
+            }
+        }
+    }
     if (!make_map(&mb, w, (uint64_t)Ktot, (uint64_t)Cout, 1, (uint64_t)Ktot * 2, (uint64_t)Ktot * Cout * 2, BLOCK_K, (uint32_t)bn, 1)) return (int)cudaErrorInvalidValue;
     TcParams p{};
     p.bn = bn;
@@ -826,5 +912,9 @@ int osb_tc_conv_launch(const void* x, const void* w, const void* bias, const voi
     // in-kernel rendezvous reduction needs every CTA resident at once and float4-aligned rows; otherwise the reduce kernel runs
     p.counters = (p.split_k > 1 && p.N % 4 == 0 && p.ldc % 4 == 0 && (long long)p.m_tiles * p.n_tiles * p.batch * p.split_k <= num_sms() && inkernel_reduce() && wsp) ? wsp->splitk_counters : nullptr;
     p.short_k = short_k_hint(p.taps * p.k_blocks_per_tap, p.split_k);
+    p.bias2 = (const __half*)bias2;
+    // statistics: the tile epilogue (unsplit) or the reduce kernel (split-K; needs 4 consecutive columns inside one group)
+    const bool stats_ok = gn_stats && (p.split_k == 1 || (!p.counters && gn_cpg % 4 == 0));
+    if (stats_ok) { p.gn_stats = gn_stats; p.gn_cpg = gn_cpg; p.gn_groups = gn_groups; if (gn_done) *gn_done = 1; }
     return launch(ma, mb, p, st);
 }

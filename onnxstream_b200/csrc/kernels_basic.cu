@@ -7,6 +7,7 @@
 // multiple of the SM count, fp32 math on fp16 storage, every tensor read once and written once.
 
 #include "common.cuh"
+#include <cstring>
 #include "workspace.h"
 #include <cstdio>
 #include <cstdlib>
@@ -38,8 +39,10 @@ __global__ void quant_kernel(const S* __restrict__ src, uint8_t* __restrict__ ds
 {
     osb_pdl_prologue();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        float q = rintf(to_float(src[i]) / scale) + (float)zp;
-        dst[i] = (uint8_t)fminf(fmaxf(q, 0.f), 255.f);
+        // XNNPACK f32-qu8-vcvt (xnn_run_convert_nc_f32_qu8): x * (1 / scale), clamp to [0 - zp, 255 - zp], round to nearest even, + zp
+        float q = to_float(src[i]) * (1.0f / scale);
+        q = fminf(fmaxf(q, (float)(0 - zp)), (float)(255 - zp));
+        dst[i] = (uint8_t)((int)rintf(q) + zp);
     }
 }
 
@@ -446,8 +449,11 @@ __global__ void gn_stats_nhwc_kernel(const T* __restrict__ x, double* __restrict
 // CTA's pixel strip; 256/(C/8) pixels are in flight per iteration.  Per-channel partials are folded into the 2*G group
 // bins with shared-memory atomics, then one double atomic per bin and CTA.
 template <typename T, int VEC>
-__global__ void gn_stats_nhwc_vec_kernel(const T* __restrict__ x, double* __restrict__ stats, int C, int64_t HW, int groups, int64_t pix_per_cta)
+__global__ void gn_stats_nhwc_vec_kernel(const T* __restrict__ x, double* __restrict__ stats, int C, int64_t HW, int groups, int64_t pix_per_cta,
+                                         const T* __restrict__ addv = nullptr, T* __restrict__ y = nullptr)
 {
+    // addv / y != null: y = x + addv[c] (the per-channel time-embedding add of a resnet) is written on the way and the statistics
+    // are those of y -- the producer side of a GroupNorm whose apply pass is gn_apply_pre_kernel
     osb_pdl_prologue();
     extern __shared__ float sm[];  // 2 * groups
     for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) sm[i] = 0.f;
@@ -457,11 +463,21 @@ __global__ void gn_stats_nhwc_vec_kernel(const T* __restrict__ x, double* __rest
     const int cv = threadIdx.x % tpp, pr = threadIdx.x / tpp;
     int64_t p0 = (int64_t)blockIdx.x * pix_per_cta, p1 = min(p0 + pix_per_cta, HW);
     if (pr < rows) {
-        float s[VEC], q[VEC];
+        float s[VEC], q[VEC], a[VEC];
 #pragma unroll
-        for (int k = 0; k < VEC; k++) { s[k] = 0.f; q[k] = 0.f; }
+        for (int k = 0; k < VEC; k++) { s[k] = 0.f; q[k] = 0.f; a[k] = 0.f; }
+        if (addv) {
+            Vec<T, VEC> av = load_vec<T, VEC>(addv + cv * VEC);
+#pragma unroll
+            for (int k = 0; k < VEC; k++) a[k] = to_float(av.v[k]);
+        }
         for (int64_t p = p0 + pr; p < p1; p += rows) {
             Vec<T, VEC> v = load_vec<T, VEC>(x + p * C + cv * VEC);
+            if (y) {
+#pragma unroll
+                for (int k = 0; k < VEC; k++) v.v[k] = from_float<T>(to_float(v.v[k]) + a[k]);
+                store_vec<T, VEC>(y + p * C + cv * VEC, v);
+            }
 #pragma unroll
             for (int k = 0; k < VEC; k++) { float f = to_float(v.v[k]); s[k] += f; q[k] += f * f; }
         }
@@ -615,6 +631,125 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, cons
         }
         store_vec<T, VEC>(y + e, v);
     }
+}
+
+
+// GroupNorm(+SiLU) apply pass for statistics gathered by the producing conv's epilogue (osb_conv2d_ex): one streaming pass, no grid
+// rendezvous.  Each CTA folds (mean, rstd, gamma, beta) into a per-channel (scale, shift) table in shared memory, then y = x * scale[c] +
+// shift[c] over its strip of NHWC pixels with 16-byte vectors.  CTA 0 zeroes `clear_stats` -- the buffer the NEXT statistics producer
+// in stream order accumulates into (its previous reader finished before this kernel started).
+template <typename T, int VEC>
+__global__ void gn_apply_pre_kernel(const T* __restrict__ x, T* __restrict__ y, const double* __restrict__ stats, double* __restrict__ clear_stats,
+                                    int C, int64_t HW, int groups, const T* __restrict__ gamma, const T* __restrict__ beta, float eps, int silu)
+{
+    osb_pdl_prologue();
+    extern __shared__ float tab[];          // [2 * C]: scale, shift
+    float* scale = tab; float* shift = tab + C;
+    const int cpg = C / groups;
+    const double inv_n = 1.0 / ((double)cpg * (double)HW);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const double mean = stats[2 * g] * inv_n;
+        const double var = stats[2 * g + 1] * inv_n - mean * mean;
+        const float rstd = rsqrtf(fmaxf((float)var, 0.f) + eps);
+        const float ga = gamma ? to_float(gamma[c]) : 1.f, be = beta ? to_float(beta[c]) : 0.f;
+        scale[c] = rstd * ga;
+        shift[c] = be - (float)mean * rstd * ga;
+    }
+    if (blockIdx.x == 0 && clear_stats) for (int t = threadIdx.x; t < 2 * groups; t += blockDim.x) clear_stats[t] = 0.0;
+    __syncthreads();
+    const int vpp = C / VEC;                                  // vectors per pixel
+    const int64_t nvec = HW * vpp;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % vpp) * VEC;
+        Vec<T, VEC> v = load_vec<T, VEC>(x + i * VEC);
+#pragma unroll
+        for (int k = 0; k < VEC; k++) {
+            float o = fmaf(to_float(v.v[k]), scale[c0 + k], shift[c0 + k]);
+            if (silu) o = o / (1.f + __expf(-o));
+            v.v[k] = from_float<T>(o);
+        }
+        store_vec<T, VEC>(y + i * VEC, v);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// dynamic-quantisation range: Model::get_percentiles (src/onnxstream.cpp:3104-3232) + FloatAsUInt::get_percentiles (2302-2386)
+// ------------------------------------------------------------------------------------------------------------
+// The reference splits the tensor across its `threads` pool workers (get_start_and_end, 3091-3102), each worker walks its span in
+// 64 KiB chunks, sorts a chunk's bit patterns and takes the k-th smallest / k-th largest FINITE value with k = (size_t)(n * 0.001f);
+// the tensor's range is the min of the chunk lows and the max of the chunk highs.  Here: one CTA per chunk, the chunk's values as
+// order-preserving integer keys in shared memory, two radix selects (8 bits per round) instead of a sort, atomicMin / atomicMax on
+// the keys.  out[0] = min low key (init 0xFFFFFFFF), out[1] = max high key (init 0), out[2] = number of chunks that had a result.
+constexpr unsigned PCT_SENTINEL = 0xFFFFFFFFu;
+
+__device__ unsigned pct_select(const unsigned* keys, int n, unsigned rank, int bits, unsigned* hist, unsigned* bcast)
+{
+    unsigned prefix = 0, mask = 0;
+    for (int shift = bits - 8; shift >= 0; shift -= 8) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            unsigned k = keys[i];
+            if (k != PCT_SENTINEL && (k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned cum = 0, d = 0;
+            for (; d < 256; d++) { if (cum + hist[d] > rank) break; cum += hist[d]; }
+            bcast[0] = d; bcast[1] = rank - cum;
+        }
+        __syncthreads();
+        prefix |= bcast[0] << shift; mask |= 255u << shift; rank = bcast[1];
+        __syncthreads();
+    }
+    return prefix;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024, 1)
+percentile_chunks_kernel(const T* __restrict__ x, size_t size, size_t threads, size_t chunk, float from_left, float from_right, unsigned* __restrict__ out)
+{
+    extern __shared__ unsigned pk[];            // [chunk] keys
+    __shared__ unsigned hist[256], bcast[2], n_finite;
+    // span of reference worker blockIdx.y (get_start_and_end), chunk blockIdx.x inside it
+    size_t per = size / threads; if (!per) per = 1;
+    const size_t i = blockIdx.y;
+    const size_t start = i * per, end = i >= threads - 1 ? size : (i + 1) * per;
+    if (start >= end || start >= size) return;
+    const size_t c0 = start + (size_t)blockIdx.x * chunk;
+    if (c0 >= end) return;
+    const int n = (int)min(chunk, end - c0);
+    constexpr bool half = sizeof(T) == 2;
+    if (threadIdx.x == 0) n_finite = 0;
+    __syncthreads();
+    unsigned local = 0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        unsigned key;
+        if (half) {
+            unsigned h = reinterpret_cast<const unsigned short*>(x)[c0 + j];
+            bool fin = (h & 0x7C00u) != 0x7C00u;
+            key = fin ? ((h & 0x8000u) ? (~h & 0xFFFFu) : (h | 0x8000u)) : PCT_SENTINEL;
+            local += fin;
+        } else {
+            unsigned u = reinterpret_cast<const unsigned*>(x)[c0 + j];
+            bool fin = (u & 0x7F800000u) != 0x7F800000u;
+            key = fin ? ((u & 0x80000000u) ? ~u : (u | 0x80000000u)) : PCT_SENTINEL;
+            if (key == PCT_SENTINEL) key = 0xFFFFFFFEu;      // (cannot happen for a finite value; keeps the sentinel exclusive)
+            local += fin;
+        }
+        pk[j] = key;
+    }
+    atomicAdd(&n_finite, local);
+    __syncthreads();
+    const unsigned m = n_finite;
+    const size_t kl = (size_t)((float)n * from_left), kr = (size_t)((float)n * from_right);
+    if (kl >= m || kr >= m) return;              // FloatAsUInt::get_percentiles returns nullopt: this chunk contributes nothing
+    const int bits = half ? 16 : 32;
+    const unsigned lo = pct_select(pk, n, (unsigned)kl, bits, hist, bcast);
+    const unsigned hi = pct_select(pk, n, m - 1 - (unsigned)kr, bits, hist, bcast);
+    if (threadIdx.x == 0) { atomicMin(&out[0], lo); atomicMax(&out[1], hi); atomicAdd(&out[2], 1u); }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -982,8 +1117,8 @@ int osb_group_norm(const void* x, void* y, int dtype, int nhwc, int64_t C, int64
             int64_t c2 = min<int64_t>(HW, 148 * 2);
             int64_t ppc2 = (HW + c2 - 1) / c2;
             c2 = (HW + ppc2 - 1) / ppc2;
-            if (dtype == OSB_F16) osb_launch((gn_stats_nhwc_vec_kernel<__half, 8>), (unsigned)c2, 256, smem, st, (const __half*)x, stats, (int)C, HW, groups, ppc2);
-            else if (dtype == OSB_F32) osb_launch((gn_stats_nhwc_vec_kernel<float, 4>), (unsigned)c2, 256, smem, st, (const float*)x, stats, (int)C, HW, groups, ppc2);
+            if (dtype == OSB_F16) osb_launch((gn_stats_nhwc_vec_kernel<__half, 8>), (unsigned)c2, 256, smem, st, (const __half*)x, stats, (int)C, HW, groups, ppc2, (const __half*)nullptr, (__half*)nullptr);
+            else if (dtype == OSB_F32) osb_launch((gn_stats_nhwc_vec_kernel<float, 4>), (unsigned)c2, 256, smem, st, (const float*)x, stats, (int)C, HW, groups, ppc2, (const float*)nullptr, (float*)nullptr);
             else return (int)cudaErrorInvalidValue;
             goto stats_done;
         }
@@ -1015,6 +1150,77 @@ stats_done:
             osb_launch((gn_apply_kernel<float, 1>), grid_for(n, 256), 256, 0, st, (const float*)x, (float*)y, stats, nhwc, C, HW, groups, (const float*)gamma, (const float*)beta, eps, fuse_silu);
     }
     return launched();
+}
+
+int osb_group_norm_apply(const void* x, void* y, int dtype, int64_t C, int64_t HW, int groups, const void* gamma, const void* beta, float eps, int fuse_silu,
+                         const void* stats, void* clear_stats, void* stream)
+{
+    if (C * HW == 0) return 0;
+    const int vec = dtype == OSB_F16 ? 8 : 4;
+    if (groups < 1 || C % groups || C % vec || C > 4096 || !aligned16(x) || !aligned16(y)) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = sizeof(float) * 2 * (size_t)C;
+    const int64_t nvec = HW * (C / vec);
+    // every CTA pays the table set-up (C channels): keep >= 8 vectors per thread, at most 2 CTAs per SM
+    const int grid = (int)max<int64_t>(1, min<int64_t>((nvec + 256 * 8 - 1) / (256 * 8), 148 * 2));
+    if (dtype == OSB_F16) osb_launch((gn_apply_pre_kernel<__half, 8>), grid, 256, smem, st, (const __half*)x, (__half*)y, (const double*)stats, (double*)clear_stats, (int)C, HW, groups, (const __half*)gamma, (const __half*)beta, eps, fuse_silu);
+    else if (dtype == OSB_F32) osb_launch((gn_apply_pre_kernel<float, 4>), grid, 256, smem, st, (const float*)x, (float*)y, (const double*)stats, (double*)clear_stats, (int)C, HW, groups, (const float*)gamma, (const float*)beta, eps, fuse_silu);
+    else return (int)cudaErrorInvalidValue;
+    return launched();
+}
+
+// NHWC statistics producer for osb_group_norm_apply: stats[2 * groups] += per-group (sum, sum of squares) of y = x + addv[c] (addv / y may
+// both be null: statistics of x).  Returns cudaErrorInvalidValue for shapes the vector kernel does not cover (callers then take osb_group_norm).
+int osb_channel_add_stats(const void* x, const void* addv, void* y, int dtype, int64_t C, int64_t HW, int groups, void* stats, void* stream)
+{
+    if (C * HW == 0) return 0;
+    const int vec = dtype == OSB_F16 ? 8 : 4;
+    if ((dtype != OSB_F16 && dtype != OSB_F32) || groups < 1 || C % groups || C % vec || C / vec > 256 || !aligned16(x) || (y && !aligned16(y)) || (addv && !aligned16(addv)) || ((addv == nullptr) != (y == nullptr)))
+        return (int)cudaErrorInvalidValue;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t c2 = min<int64_t>(HW, 148 * 2);
+    int64_t ppc2 = (HW + c2 - 1) / c2;
+    c2 = (HW + ppc2 - 1) / ppc2;
+    size_t smem = sizeof(float) * 2 * groups;
+    if (dtype == OSB_F16) osb_launch((gn_stats_nhwc_vec_kernel<__half, 8>), (unsigned)c2, 256, smem, st, (const __half*)x, (double*)stats, (int)C, HW, groups, ppc2, (const __half*)addv, (__half*)y);
+    else osb_launch((gn_stats_nhwc_vec_kernel<float, 4>), (unsigned)c2, 256, smem, st, (const float*)x, (double*)stats, (int)C, HW, groups, ppc2, (const float*)addv, (float*)y);
+    return launched();
+}
+
+// Range of a float tensor for dynamic quantisation (Model::get_percentiles): out3 is a DEVICE array of 3 uint32 (see the kernel); the
+// caller initialises it to { 0xFFFFFFFF, 0, 0 } and decodes the order-preserving keys with osb_percentile_key_to_float.
+int osb_percentiles(const void* x, int dtype, size_t n, int threads, float from_left, float from_right, void* out3, void* stream)
+{
+    if (n == 0) return 0;
+    if (dtype != OSB_F16 && dtype != OSB_F32) return (int)cudaErrorInvalidValue;
+    if (threads < 1) threads = 1;
+    const size_t chunk = dtype == OSB_F16 ? 32768 : 16384;       // m_perthread_buffer_size (64 KiB) / sizeof(element)
+    size_t per = n / (size_t)threads; if (!per) per = 1;
+    const size_t longest = std::max(per, n - per * ((size_t)threads - 1 < n / per ? (size_t)threads - 1 : n / per));
+    dim3 grid((unsigned)((longest + chunk - 1) / chunk), (unsigned)threads);
+    const size_t smem = chunk * sizeof(unsigned);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(percentile_chunks_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32768 * 4));
+        cudaFuncSetAttribute(percentile_chunks_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(16384 * 4));
+        attr = true;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == OSB_F16) percentile_chunks_kernel<__half><<<grid, 1024, smem, st>>>((const __half*)x, n, (size_t)threads, chunk, from_left, from_right, (unsigned*)out3);
+    else percentile_chunks_kernel<float><<<grid, 1024, smem, st>>>((const float*)x, n, (size_t)threads, chunk, from_left, from_right, (unsigned*)out3);
+    return launched();
+}
+
+float osb_percentile_key_to_float(unsigned key, int dtype)
+{
+    if (dtype == OSB_F16) {
+        unsigned short h = (key & 0x8000u) ? (unsigned short)(key & 0x7FFFu) : (unsigned short)(~key & 0xFFFFu);
+        __half hv; memcpy(&hv, &h, 2);
+        return __half2float(hv);
+    }
+    unsigned u = (key & 0x80000000u) ? (key & 0x7FFFFFFFu) : ~key;
+    float f; memcpy(&f, &u, 4);
+    return f;
 }
 
 int osb_gather_rows(const void* table, const int64_t* idx, void* out, int64_t n_idx, int64_t table_rows, int64_t row_bytes, void* stream)

@@ -17,7 +17,7 @@ int osb_tc_gemm_launch(const void* A, const void* B, void* C, const void* bias, 
                        int b_transposed, cudaStream_t st, int64_t lda, int64_t ldb, int64_t ldc);
 int osb_tc_conv_launch(const void* x, const void* w, const void* bias, const void* residual, void* y,
                        int64_t H, int64_t W, int64_t Cin, int64_t Cout, int kh, int kw, int stride, int pad_top, int pad_left,
-                       int64_t Ho, int64_t Wo, cudaStream_t st);
+                       int64_t Ho, int64_t Wo, cudaStream_t st, const void* bias2, double* gn_stats, int gn_groups, int* gn_done);
 int osb_tc_gemm_grouped_launch(const void* A, const void* const* B, void* const* C, int groups, int64_t M, int64_t N, int64_t K, int bt, cudaStream_t st,
                                int64_t lda, int64_t ldb, int64_t ldc);
 bool osb_tc_gemm_ok(int64_t M, int64_t N, int64_t K, int b_transposed, const void* A, const void* B, const void* C, int64_t sa, int64_t sb, int64_t sc,
@@ -504,12 +504,27 @@ int osb_gemm_ld(const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
 int osb_conv2d(const void* x, const void* w, const void* bias, const void* residual, void* y, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
                int kh, int kw, int stride, int pad_top, int pad_left, int64_t Ho, int64_t Wo, int dtype, int impl, void* stream)
 {
+    return osb_conv2d_ex(x, w, bias, nullptr, residual, y, H, W, Cin, Cout, kh, kw, stride, pad_top, pad_left, Ho, Wo, dtype, impl, stream, nullptr, 0, nullptr);
+}
+
+// 1 when osb_conv2d_ex will take the tensor-core path for this problem, i.e. when `bias2` and `gn_stats` are honoured
+int osb_conv2d_fusable(const void* x, const void* w, const void* y, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int kh, int kw, int stride, int dtype, int impl)
+{
+    return dtype == OSB_F16 && impl != 1 && Cout % 8 == 0 && osb_tc_conv_ok(H, W, Cin, Cout, kh, kw, stride, x, w, y) ? 1 : 0;
+}
+
+int osb_conv2d_ex(const void* x, const void* w, const void* bias, const void* bias2, const void* residual, void* y, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                  int kh, int kw, int stride, int pad_top, int pad_left, int64_t Ho, int64_t Wo, int dtype, int impl, void* stream,
+                  void* gn_stats, int gn_groups, int* gn_done)
+{
+    if (gn_done) *gn_done = 0;
     if (Ho * Wo * Cout == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype != OSB_F16 && dtype != OSB_F32) return (int)cudaErrorInvalidValue;
     bool tc_ok = dtype == OSB_F16 && osb_tc_conv_ok(H, W, Cin, Cout, kh, kw, stride, x, w, y);
     if (impl == 2 && !tc_ok) return (int)cudaErrorInvalidValue;
-    if (tc_ok && impl != 1) return osb_tc_conv_launch(x, w, bias, residual, y, H, W, Cin, Cout, kh, kw, stride, pad_top, pad_left, Ho, Wo, st);
+    if (tc_ok && impl != 1) return osb_tc_conv_launch(x, w, bias, residual, y, H, W, Cin, Cout, kh, kw, stride, pad_top, pad_left, Ho, Wo, st, bias2, (double*)gn_stats, gn_groups, gn_done);
+    if (bias2) return (int)cudaErrorInvalidValue;     // callers ask osb_conv2d_fusable first
     ConvGeom g{ (int)H, (int)W, (int)Cin, kh, kw, stride, pad_top, pad_left, (int)Ho, (int)Wo };
     int64_t M = Ho * Wo, N = Cout, K = (int64_t)kh * kw * Cin;
     if (dtype == OSB_F16) return launch_igemm<__half>((const __half*)x, (const __half*)w, (__half*)y, bias, (const __half*)residual, 1, M, N, K, 0, 0, 0, 1, true, g, st);

@@ -70,6 +70,7 @@ def load_library(path: str) -> ctypes.CDLL:
                                       ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)], ctypes.c_longlong),
         "model_ext_get_tensor_type": ([vp, cp], ctypes.c_int),
         "model_ext_push_tensor": ([vp, cp, cp, ui, ctypes.POINTER(ui), vp], None),
+        "model_ext_get_tensor_at": ([vp, cp, ui], vp), "model_ext_add_output_convert": ([vp, cp], None),
         "model_b200_get_stats": ([vp, ctypes.POINTER(ctypes.c_double), ctypes.c_int], ctypes.c_int),
         "model_b200_set_comm": ([vp, vp, ctypes.c_int, ctypes.c_int], ctypes.c_int),
         "model_b200_run_resident": ([vp, ctypes.c_int], ctypes.c_double),
@@ -187,8 +188,9 @@ class Model:
         ptr = self.lib.model_add_tensor(self.h, t.encode(), name.encode(), array.ndim, dims)
         ctypes.memmove(ptr, array.ctypes.data, array.nbytes)
 
-    def get_tensor(self, name: str) -> Optional[np.ndarray]:
-        ptr = self.lib.model_get_tensor(self.h, name.encode())
+    def get_tensor(self, name: str, index: int = 0) -> Optional[np.ndarray]:
+        """index > 0 (B200 engine only): the index-th batch sibling pushed / produced under `name`."""
+        ptr = self.lib.model_get_tensor(self.h, name.encode()) if index == 0 else self.lib.model_ext_get_tensor_at(self.h, name.encode(), index)
         if not ptr:
             return None
         view = ctypes.cast(ptr, ctypes.POINTER(_TensorView)).contents

@@ -43,3 +43,10 @@ gemm(4096, 2560, 320)
 gemm(4096, 320, 1280)
 gemm(4096, 4096, 4096)
 gemm(8192, 8192, 8192)
+gemm(8192, 8192, 8192, 0)
+conv(128, 128, 320, 320, 3)      # SDXL 1024x1024 first level
+conv(128, 128, 640, 320, 3)
+conv(256, 256, 256, 256, 3)      # VAE decoder
+conv(512, 512, 128, 128, 3)
+conv(64, 64, 320, 320, 3)
+conv(32, 32, 640, 640, 3)

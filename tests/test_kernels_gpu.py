@@ -22,6 +22,8 @@ def K(engine_lib):
     lib.osb_conv2d.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, ci, ci, ci, i64, i64, ci, ci, vp]
     lib.osb_tc_launch_count.restype = ctypes.c_uint64
     lib.osb_launch_count_reset.restype = None
+    lib.osb_tc_set_pair_mode.argtypes = [ci]
+    lib.osb_tc_set_pair_mode.restype = None
     return lib
 
 
@@ -59,6 +61,59 @@ GEMM_CASES = [
     (1, 64, 32, 64, 0, False, True),
     (1, 1024, 16, 16, 0, True, False),
 ]
+
+
+PAIR_GEMM_CASES = [
+    # the CTA-pair kernel (cta_group::2, 256 x bn tiles, TMA-store epilogue) forced on: both B majors, ragged M / N / K, odd number
+    # of 128-row tiles (the pair's second half is empty), batch, bias / residual, every tile width
+    (1, 256, 256, 128, 1, False, False),
+    (1, 256, 256, 128, 0, False, False),
+    (1, 300, 136, 72, 1, True, True),
+    (1, 300, 136, 72, 0, True, True),
+    (1, 384, 64, 64, 1, True, False),
+    (1, 640, 192, 200, 1, False, True),
+    (1, 4096, 320, 320, 0, True, True),
+    (1, 4096, 320, 1280, 1, True, True),
+    (1, 1024, 2560, 640, 0, True, False),
+    (1, 2048, 640, 5760, 1, True, False),
+    (3, 520, 264, 136, 1, False, True),
+    (2, 512, 512, 256, 0, True, False),
+    (1, 8192, 1024, 512, 1, False, False),    # several tiles per pair: accumulator double buffering, staging reuse across tiles
+]
+
+
+@pytest.mark.parametrize("case", PAIR_GEMM_CASES)
+def test_gemm_f16_pair_kernel(K, case):
+    K.osb_tc_set_pair_mode(2)
+    try:
+        test_gemm_f16(K, case, 2)
+    finally:
+        K.osb_tc_set_pair_mode(1)
+
+
+PAIR_CONV_CASES = [
+    (64, 64, 320, 320, 3, 1, 1, True, True),
+    (32, 32, 96, 72, 3, 1, 1, False, False),      # ragged channels
+    (24, 40, 32, 40, 3, 1, 1, True, False),       # non power-of-two width: boxes clipped by the store
+    (256, 256, 32, 16, 3, 1, 1, True, False),     # wide image: bw = 128, one row segment per CTA
+    (16, 16, 64, 64, 3, 2, 1, True, False),       # strided
+    (64, 64, 320, 320, 3, 2, 1, True, False),
+    (16, 16, 64, 128, 1, 1, 0, True, True),
+    (32, 32, 640, 640, 3, 1, 1, True, True),
+    (64, 64, 640, 640, 3, 1, 1, True, False),     # the 1.08-wave layer of the single-CTA kernel
+    (128, 128, 128, 256, 3, 1, 1, True, True),    # VAE-decoder-like: many tiles per pair
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CONV_CASES)
+def test_conv_f16_pair_kernel(K, case):
+    K.osb_tc_set_pair_mode(2)
+    try:
+        K.osb_launch_count_reset()
+        test_conv_f16(K, case, 0)
+        assert K.osb_tc_launch_count() >= 1
+    finally:
+        K.osb_tc_set_pair_mode(1)
 
 
 @pytest.mark.parametrize("case", GEMM_CASES)
@@ -142,6 +197,93 @@ def test_conv_f16(K, case, impl):
     if has_res:
         ref = ref + res.double(); absref = absref + res.double().abs()
     _check(y, ref, absref, f"conv {case} impl {impl}")
+
+
+GN_CONV_CASES = [
+    # H, W, Cin, Cout, k, stride, groups, residual, bias2, pair_mode
+    (64, 64, 320, 320, 3, 1, 32, True, False, 1),     # cpg = 10: groups straddle 32-column chunks and 128-column tiles
+    (64, 64, 320, 320, 3, 1, 32, False, True, 2),     # same through the CTA-pair kernel, with the time-embedding addend
+    (32, 32, 320, 640, 3, 1, 32, False, True, 1),
+    (32, 32, 640, 640, 1, 1, 32, True, False, 2),
+    (16, 16, 1280, 1280, 3, 1, 32, True, False, 1),   # split-K: statistics in the reduce kernel (cpg = 40)
+    (8, 8, 1280, 1280, 3, 1, 32, False, True, 1),
+    (16, 16, 64, 64, 3, 1, 8, True, True, 1),         # tiny-model shapes (cpg = 8), ragged tile
+    (24, 40, 32, 40, 3, 1, 5, False, False, 1),       # cpg = 8, non power-of-two width
+    (128, 128, 128, 128, 3, 1, 32, True, False, 2),   # cpg = 4 (VAE decoder), several tiles per pair
+]
+
+
+@pytest.mark.parametrize("case", GN_CONV_CASES)
+def test_conv_epilogue_gn_stats_and_bias2(K, case):
+    """osb_conv2d_ex: conv + bias + bias2 (per-channel addend) + residual, with the GroupNorm statistics of the STORED fp16 output
+    gathered in the epilogue (tile epilogue, CTA-pair epilogue or split-K reduce kernel) -- then osb_group_norm_apply on them
+    against a float64 GroupNorm of the same tensor."""
+    import torch
+    import torch.nn.functional as Fn
+    vp, i64, ci, cf = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
+    K.osb_conv2d_ex.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, ci, ci, ci, i64, i64, ci, ci, vp, vp, ci, ctypes.POINTER(ci)]
+    K.osb_group_norm_apply.argtypes = [vp, vp, ci, i64, i64, ci, vp, vp, cf, ci, vp, vp, vp]
+    H, W, Cin, Cout, k, s, G, has_res, has_b2, pair_mode = case
+    pad = k // 2
+    g = torch.Generator(device="cuda").manual_seed(H * 3 + Cout)
+    x = torch.randn(H, W, Cin, device="cuda", generator=g).half()
+    w = (torch.randn(Cout, k, k, Cin, device="cuda", generator=g) / (k * k * Cin) ** 0.5).half()
+    bias = torch.randn(Cout, device="cuda", generator=g).half()
+    bias2 = torch.randn(Cout, device="cuda", generator=g).half() if has_b2 else None
+    Ho, Wo = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1
+    res = torch.randn(Ho, Wo, Cout, device="cuda", generator=g).half() if has_res else None
+    y = torch.full((Ho, Wo, Cout), float("nan"), device="cuda", dtype=torch.half)
+    stats = torch.zeros(2 * G, device="cuda", dtype=torch.float64)
+    done = ci(0)
+    K.osb_tc_set_pair_mode(pair_mode)
+    try:
+        rc = K.osb_conv2d_ex(x.data_ptr(), w.data_ptr(), bias.data_ptr(), bias2.data_ptr() if has_b2 else None, res.data_ptr() if has_res else None, y.data_ptr(),
+                             H, W, Cin, Cout, k, k, s, pad, pad, Ho, Wo, F16, 0, _stream(), stats.data_ptr(), G, ctypes.byref(done))
+    finally:
+        K.osb_tc_set_pair_mode(1)
+    assert rc == 0
+    torch.cuda.synchronize()
+    xn = x.double().permute(2, 0, 1)[None]; wn = w.double().permute(0, 3, 1, 2)
+    ref = Fn.conv2d(xn, wn, None, stride=s, padding=pad)[0].permute(1, 2, 0) + bias.double()
+    absref = Fn.conv2d(xn.abs(), wn.abs(), None, stride=s, padding=pad)[0].permute(1, 2, 0) + bias.double().abs()
+    if has_b2:
+        ref = ref + bias2.double(); absref = absref + bias2.double().abs()
+    if has_res:
+        ref = ref + res.double(); absref = absref + res.double().abs()
+    _check(y, ref, absref, f"conv_ex {case}")
+    assert done.value == 1, "the kernel did not report the statistics"
+    yd = y.double().reshape(Ho * Wo, G, Cout // G)
+    want = torch.stack([yd.sum(dim=(0, 2)), (yd * yd).sum(dim=(0, 2))], dim=1).reshape(-1)
+    err = (stats - want).abs() / (torch.stack([yd.abs().sum(dim=(0, 2)), (yd * yd).sum(dim=(0, 2))], dim=1).reshape(-1) + 1e-9)
+    assert float(err.max()) <= 2e-5, f"statistics off by {float(err.max()):.3g} (relative to sum|y| / sum y^2)"
+    # apply pass: GroupNorm + SiLU from those statistics; the `clear` buffer is zeroed on the way
+    gamma = (1 + 0.1 * torch.randn(Cout, device="cuda", generator=g)).half(); beta = (0.1 * torch.randn(Cout, device="cuda", generator=g)).half()
+    out = torch.empty_like(y); clear = torch.ones(2 * G, device="cuda", dtype=torch.float64)
+    assert K.osb_group_norm_apply(y.data_ptr(), out.data_ptr(), F16, Cout, Ho * Wo, G, gamma.data_ptr(), beta.data_ptr(), 1e-5, 1, stats.data_ptr(), clear.data_ptr(), _stream()) == 0
+    torch.cuda.synchronize()
+    mean = yd.mean(dim=(0, 2), keepdim=True); var = yd.var(dim=(0, 2), unbiased=False, keepdim=True)
+    gn = ((yd - mean) / torch.sqrt(var + 1e-5)).reshape(Ho, Wo, Cout) * gamma.double() + beta.double()
+    gn = gn * torch.sigmoid(gn)
+    assert float((out.double() - gn).abs().max()) <= 2e-3 * max(1.0, float(gn.abs().max()))
+    assert float(clear.abs().max()) == 0.0
+
+
+def test_channel_add_stats(K):
+    import torch
+    vp, i64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    K.osb_channel_add_stats.argtypes = [vp, vp, vp, ci, i64, i64, ci, vp, vp]
+    for (HW, C, G) in [(4096, 320, 32), (256, 1280, 32), (64, 64, 8)]:
+        g = torch.Generator(device="cuda").manual_seed(C)
+        x = torch.randn(HW, C, device="cuda", generator=g).half(); t = torch.randn(C, device="cuda", generator=g).half()
+        y = torch.empty_like(x); stats = torch.zeros(2 * G, device="cuda", dtype=torch.float64)
+        assert K.osb_channel_add_stats(x.data_ptr(), t.data_ptr(), y.data_ptr(), F16, C, HW, G, stats.data_ptr(), _stream()) == 0
+        torch.cuda.synchronize()
+        want_y = (x.float() + t.float()).half()
+        assert torch.equal(y, want_y)
+        yd = y.double().reshape(HW, G, C // G)
+        want = torch.stack([yd.sum(dim=(0, 2)), (yd * yd).sum(dim=(0, 2))], dim=1).reshape(-1)
+        scale = torch.stack([yd.abs().sum(dim=(0, 2)), (yd * yd).sum(dim=(0, 2))], dim=1).reshape(-1)
+        assert float(((stats - want).abs() / scale).max()) <= 2e-5
 
 
 def test_qu8_gemm_and_conv_bit_exact(K):
