@@ -124,6 +124,28 @@ int osb_conv2d_ex(const void* x, const void* w, const void* bias, const void* bi
 int osb_conv2d_fusable(const void* x, const void* w, const void* y, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int kh, int kw, int stride, int dtype, int impl);
 /* GroupNorm(+SiLU) apply pass on an NHWC tensor whose statistics were gathered by the producing conv (osb_conv2d_ex): reads `stats`,
  * writes y = silu?((x - mean) * rstd * gamma + beta), and zeroes `clear_stats` (the buffer the NEXT producer will accumulate into). */
+/* Decode GEMV with uint8 weights [K,N] dequantised in registers (M <= 2): y = x . ((Wq - zp) * scale rounded to `dtype`) + bias + residual.
+ * The uint8-weight / float-arithmetic MatMul of the reference (weights converted at load, src/onnxstream.cpp:2885-2890) at half the HBM bytes. */
+int osb_gemv_w8(const void* A, const void* Wq, void* C, const void* bias, const void* residual, int64_t M, int64_t N, int64_t K, float wscale, int wzp, int dtype, void* stream);
+/* W8A8 on the tensor cores (tcgen05.mma.kind::i8, uint8 x uint8 -> int32): XnnPack::matrix_multiply<uint8_t,int32_t> / convolution for uint8
+ * (src/onnxstream.cpp:1035-1215, 1292-1534) with XNNPACK's fp32 requantisation y = clamp(lrintf(acc * sx*sw/sy)) + zy.  The kernel multiplies raw
+ * bytes and corrects with rowsum_x / colsum_w (osb_rowsum_u8: row sums of a [rows][cols] byte matrix; osb_colsum_u8: column sums of a [K][N] one);
+ * a convolution runs on the image padded with the input zero point (osb_pad_sum_u8 also emits its per-pixel channel sums).  *_ok: TMA-addressable. */
+int osb_qu8_tc_gemm_ok(int64_t M, int64_t N, int64_t K, const void* A, const void* B, const void* C);
+int osb_qu8_tc_conv_ok(int64_t Cin, int64_t Cout, int64_t Ho, int64_t Wo, int kh, int kw, int stride, const void* x, const void* w, const void* y);
+int osb_rowsum_u8(const void* x, void* out, int64_t rows, int64_t cols, void* stream);
+int osb_colsum_u8(const void* w, void* out, int64_t K, int64_t N, void* stream);
+int osb_pad_sum_u8(const void* x, void* xp, void* psum, int64_t H, int64_t W, int64_t C, int64_t Hp, int64_t Wp, int pad_top, int pad_left, int zx, void* stream);
+int osb_qu8_tc_gemm(const void* A, const void* B, void* C, const void* bias, const void* rsum, const void* csum, int64_t M, int64_t N, int64_t K, int bt,
+                    int zx, float sx, int zw, float sw, int zy, float sy, void* stream);
+int osb_qu8_tc_conv(const void* xp, const void* psum, const void* w, const void* bias, const void* csum, void* y, int64_t Hp, int64_t Wp, int64_t Cin, int64_t Cout,
+                    int kh, int kw, int stride, int64_t Ho, int64_t Wo, int zx, float sx, int zw, float sw, int zy, float sy, void* stream);
+/* XNNPACK qu8 elementwise add / multiply with N-d broadcasting (XnnPack::add / multiply for T = uint8_t, src/onnxstream.cpp:846-927, 1666-1746):
+ * strides in elements (0 = broadcast) like osb_binary.  Bit-exact restatement of the library's fixed-point add and fp32-requantised multiply. */
+int osb_binary_qu8(int op, const void* a, const int64_t* as, float sa, int za, const void* b, const int64_t* bs, float sb, int zb,
+                   void* out, float so, int zo, const int64_t* shape, int ndim, void* stream);
+/* qu8 softmax over the last axis (XnnPack::softmax for T = uint8_t, src/onnxstream.cpp:1958-2051; output scale 2^-8 / zero point 0 at 5971-5972) */
+int osb_softmax_qu8(const void* x, void* y, int64_t rows, int64_t cols, float in_scale, float out_scale, int out_zp, void* stream);
 /* Dynamic-quantisation range of a float tensor, Model::get_percentiles (src/onnxstream.cpp:3104-3232): per reference chunk (the tensor
  * split over `threads` pool workers, then 64 KiB buffers) the k-th smallest / largest finite value, k = (size_t)(n_chunk * from_x); min of
  * the lows, max of the highs.  out3 = DEVICE uint32[3] initialised to {0xFFFFFFFF, 0, 0}: order-preserving keys of (low, high) and the

@@ -171,6 +171,8 @@ void model_set_option(ModelContext* obj, char* name, unsigned int value)
     else if (!strcmp(name, "b200_flash_attention")) e.flash_attention = v;
     else if (!strcmp(name, "b200_ring_factor_x100")) e.ring_factor = value / 100.0;
     else if (!strcmp(name, "b200_range_data_calibrate")) e.range_data_calibrate = v;
+    else if (!strcmp(name, "b200_keep_inputs")) e.keep_inputs = v;
+    else if (!strcmp(name, "b200_drop_unconverted_outputs")) e.drop_unconverted_outputs = v;
     else set = false;
     if (!set) {
         const char* err = "model_set_option: 'name' not found.";

@@ -197,6 +197,9 @@ public:
     int gemm_impl = 0;               // 0 auto, 1 force CUDA-core kernels, 2 force tcgen05
     bool flash_attention = true;     // fused tcgen05 attention for d <= 64 (else two GEMMs around a softmax)
     double ring_factor = 1.0;        // weight ring capacity = ring_factor * largest node footprint
+    bool keep_inputs = false;        // graph inputs stay in HBM after a run; a later run that does not push a name again reuses the device copy
+                                     // (a device-resident KV cache for fixed-shape decode steps: only the new token's ids cross PCIe)
+    bool drop_unconverted_outputs = false;   // with a non-empty outputs_convert_set: tensors outside it are not copied back at all
     bool source_on_init_done = false;  // set by the C++ adapter when it already announced every weight to the provider
 
     void set_weight_source(std::unique_ptr<WeightSource> src);

@@ -41,6 +41,15 @@ std::vector<int64_t> parse_ints(const std::string& s)
 
 [[noreturn]] void fail(const OpDef& op, const std::string& msg) { throw std::invalid_argument(op.type + ": " + msg); }
 
+// Model::range_to_scale (src/onnxstream.cpp:3234-3245): (float range) / 255.0 in double, rounded to float; zero point truncated to uint8
+static void range_to_scale(float lo, float hi, float& scale, int& zp)
+{
+    if (lo > 0 && hi > 0) lo = 0;
+    else if (lo < 0 && hi < 0) hi = 0;
+    scale = (float)((hi - lo) / 255.0);
+    zp = (int)(uint8_t)(std::abs(lo) / scale);
+}
+
 enum StepKind { SK_SINGLE = 0, SK_ATTENTION, SK_GROUPNORM, SK_LAYERNORM, SK_GELU, SK_SILU, SK_LINEAR, SK_SDPA, SK_MHA, SK_CONV_ADD, SK_GEGLU };
 
 struct Step {
@@ -54,8 +63,13 @@ struct Step {
 // ================================================================================================================
 struct Engine::Impl {
     Engine& E;
-    cudaStream_t st;
+    cudaStream_t st;      // the stream every handler launches on: the compute stream, or the side stream while the side branch is enqueued
     explicit Impl(Engine& e) : E(e), st(e.m_stream) {}
+    ~Impl()
+    {
+        for (auto e : side_events) if (e) cudaEventDestroy(e);
+        if (side_stream) { cudaStreamSynchronize(side_stream); osb_workspace_release(side_stream); cudaStreamDestroy(side_stream); }
+    }
 
     // ---- tensor store (the reference's m_data + m_intermediate_refs, src/onnxstream.h:937,1023) ----
     std::unordered_map<std::string, std::vector<Tensor>> store;
@@ -78,8 +92,26 @@ struct Engine::Impl {
     std::unordered_map<std::string, Tensor> resident;
     size_t resident_bytes = 0;
 
+    // ---- side branch (resident weights only): steps that do not depend on the primary graph input -- the time-embedding MLP and every
+    // resnet's time_emb_proj, the cross-attention K / V projections of the text context -- are enqueued FIRST, on a second stream with
+    // its own activation pool, and run concurrently with the main chain; a main step waits on the event of the side step it consumes.
+    // Inside a captured graph these become parallel branches.  ~15 % of a UNet step's launches leave the critical path.
+    cudaStream_t side_stream = nullptr;
+    DevicePool side_pool;
+    bool on_side = false;
+    std::vector<char> is_side;                         // per step
+    std::vector<std::vector<size_t>> side_deps;        // per main step: side steps whose outputs it reads
+    std::vector<cudaEvent_t> side_events;              // per step (side steps only)
+    DevicePool& pool() { return on_side ? side_pool : E.m_pool; }
+    std::vector<char> kv_side;                         // per step: an SK_MHA step whose K / V inputs are side tensors (cross-attention on the text context)
+    struct MhaKV { Tensor kl, vl; cudaEvent_t ev = nullptr; };
+    std::map<size_t, MhaKV> mha_kv;                    // step -> K / V projections computed ahead on the side stream (valid for one run)
+    void mha_project(size_t i, const Tensor& x, const Tensor* xq, Tensor* ql, Tensor& kl, Tensor& vl, int64_t Tka);
+    void mha_prepass(size_t si);
+
     struct OpTime { std::string type; cudaEvent_t a, b; };
     std::vector<OpTime> op_times;
+    std::vector<Tensor> kept_inputs;      // b200_keep_inputs: device copies of the graph inputs of earlier runs, by name
     DevPtr gn_stats;
     // GroupNorm statistics gathered by the producer (conv epilogue / per-channel Add) instead of a pass of their own.  `gn_ring` holds
     // two fp64 [2 * 64] slots: a producer accumulates into the current slot (all zero by invariant), the GroupNorm's apply pass reads it
@@ -108,7 +140,7 @@ struct Engine::Impl {
         Tensor r;
         r.type = t; r.shape = shape; r.layout = l;
         int64_t n = 1; for (auto d : shape) n *= d;
-        r.dev = E.m_pool.alloc((size_t)n * dtype_size(t));
+        r.dev = pool().alloc((size_t)n * dtype_size(t));
         return r;
     }
 
@@ -155,7 +187,7 @@ struct Engine::Impl {
     // (the reference throws for most of them: a superset, never a different result)
     static bool op_takes_u8(const OpDef& op)
     {
-        static const std::set<std::string> k = { "Conv", "MatMul", "Add", "Mul", "Softmax", "Reshape", "Transpose", "Concat", "Split", "Slice", "Unsqueeze", "Squeeze",
+        static const std::set<std::string> k = { "Conv", "MatMul", "Add", "Mul", "Softmax", "InstanceNormalization", "Reshape", "Transpose", "Concat", "Split", "Slice", "Unsqueeze", "Squeeze",
                                                  "Flatten", "Resize", "Gather", "Expand", "Identity" };
         return k.count(op.type) != 0;
     }
@@ -244,7 +276,7 @@ struct Engine::Impl {
         }
     }
 
-    Tensor get_weight(size_t op_idx, size_t in_idx, bool requires_float = false, bool conv_layout = false)
+    Tensor get_weight(size_t op_idx, size_t in_idx, bool requires_float = false, bool conv_layout = false, bool keep_u8 = false)
     {
         const OpDef& op = E.m_ops[op_idx];
         const TensorRef& r = op.in[in_idx];
@@ -253,6 +285,7 @@ struct Engine::Impl {
         if (conv_w && !conv_layout) throw std::invalid_argument("Model::get_tensor_data: nchw layout not supported. (not implemented)");
         if (!conv_w && conv_layout) throw std::invalid_argument("Model::get_tensor_data: unable to determine tensor data file compatible with required_layout.");
         DType target = weight_target(op, r, requires_float);
+        if (keep_u8 && r.wtype == DType::u8) target = DType::u8;     // the consumer dequantises in registers (decode GEMV): no float copy in HBM
 
         Tensor t;
         t.name = fn;
@@ -760,6 +793,66 @@ struct Engine::Impl {
                 }
             largest_node = std::max(largest_node, node_bytes);
         }
+        is_side.clear(); side_deps.clear(); kv_side.clear();
+        static const bool side_on = [] { const char* e = getenv("OSB_SIDE_BRANCH"); return !(e && e[0] == '0'); }();
+        if (side_on && E.fuse_nodes && E.m_stream) plan_side_branch_impl();
+    }
+
+    // Which steps are off the critical path?  primary input = the graph input that starts the LONGEST op chain to the end of the graph
+    // (a UNet's latent; the time step and the text context join it from the side).  A step is "side" when none of its activation
+    // inputs depends on the primary input, it has no int64 traffic, and it is not a graph output producer that the epilogue reads.
+    void plan_side_branch_impl()
+    {
+        auto& ops = E.m_ops;
+        is_side.assign(steps.size(), 0);
+        side_deps.assign(steps.size(), {});
+        std::map<std::string, int> producer;           // tensor -> producing op
+        for (size_t i = 0; i < ops.size(); i++) for (auto& o : ops[i].out) if (o.present) producer[o.name] = (int)i;
+        // graph inputs = activation names never produced
+        std::vector<std::string> inputs;
+        for (auto& op : ops) for (auto& r : op.in) if (r.present && r.wtype == DType::none && !producer.count(r.name) && std::find(inputs.begin(), inputs.end(), r.name) == inputs.end()) inputs.push_back(r.name);
+        if (inputs.size() < 2 || inputs.size() > 60) return;
+        std::map<std::string, uint64_t> dep;           // tensor -> bitmask of graph inputs it depends on
+        std::map<std::string, std::pair<int, int>> longest;   // tensor -> (chain length, input index that starts it)
+        for (size_t k = 0; k < inputs.size(); k++) { dep[inputs[k]] = 1ull << k; longest[inputs[k]] = { 0, (int)k }; }
+        std::pair<int, int> best = { -1, 0 };
+        for (auto& op : ops) {
+            uint64_t m = 0; std::pair<int, int> lg = { -1, 0 };
+            for (auto& r : op.in) if (r.present && r.wtype == DType::none) { m |= dep[r.name]; auto it = longest.find(r.name); if (it != longest.end() && it->second.first > lg.first) lg = it->second; }
+            for (auto& o : op.out) if (o.present) { dep[o.name] = m; longest[o.name] = { lg.first + 1, lg.second }; if (lg.first + 1 > best.first) best = { lg.first + 1, lg.second }; }
+        }
+        const uint64_t primary = 1ull << best.second;
+        std::map<std::string, size_t> step_of;         // tensor -> producing step
+        for (size_t si = 0; si < steps.size(); si++)
+            for (size_t oi = steps[si].first; oi < steps[si].first + steps[si].count; oi++) for (auto& o : ops[oi].out) if (o.present) step_of[o.name] = si;
+        size_t n_side = 0;
+        for (size_t si = 0; si < steps.size(); si++) {
+            bool side = true, any_act = false;
+            for (size_t oi = steps[si].first; oi < steps[si].first + steps[si].count && side; oi++) {
+                for (auto& r : ops[oi].in) if (r.present) {
+                    if (r.wtype == DType::i64) side = false;                      // shape arithmetic stays in graph order on the host
+                    if (r.wtype == DType::none) { any_act = true; if (dep[r.name] & primary) side = false; }
+                }
+                for (auto& o : ops[oi].out) if (o.present && uses.find(o.name) == uses.end()) side = false;   // a graph output
+            }
+            if (side && any_act) { is_side[si] = 1; n_side++; }
+        }
+        kv_side.assign(steps.size(), 0);
+        for (size_t si = 0; si < steps.size(); si++)
+            if (steps[si].kind == SK_MHA) {
+                size_t i = steps[si].first;
+                auto side_in = [&](size_t oi) { const TensorRef& r = ops[oi].in[0]; return r.present && r.wtype == DType::none && !(dep[r.name] & primary); };
+                if (side_in(i + 4) && side_in(i + 9) && !side_in(i)) { kv_side[si] = 1; n_side++; }
+            }
+        if (n_side == 0) { is_side.clear(); kv_side.clear(); return; }
+        for (size_t si = 0; si < steps.size(); si++) {
+            if (is_side[si]) continue;
+            for (size_t oi = steps[si].first; oi < steps[si].first + steps[si].count; oi++)
+                for (auto& r : ops[oi].in) if (r.present && r.wtype == DType::none) {
+                    auto it = step_of.find(r.name);
+                    if (it != step_of.end() && is_side[it->second] && std::find(side_deps[si].begin(), side_deps[si].end(), it->second) == side_deps[si].end()) side_deps[si].push_back(it->second);
+                }
+        }
     }
 
     // ------------------------------------------------------------------------------------------------------
@@ -803,7 +896,7 @@ struct Engine::Impl {
     void fused_sdpa(const Step& s);
     void fused_mha(const Step& s);
 
-    Tensor binary(int bop, const Tensor& a, const Tensor& b);
+    Tensor binary(int bop, const Tensor& a, const Tensor& b, float out_scale = 0.f, int out_zp = 0);
     Tensor strided(const Tensor& x, const std::vector<int64_t>& out_shape, const std::vector<int64_t>& in_stride,
                    const std::vector<int64_t>* in_div, int64_t in_off);
     void attention_core(const Tensor& q, const Tensor& k, const Tensor& v, float scale, bool k_transposed, const Tensor* mask,
@@ -849,7 +942,7 @@ Tensor Engine::Impl::strided(const Tensor& x, const std::vector<int64_t>& out_sh
 }
 
 // numpy-style broadcasting binary op (src/onnxstream.cpp:1666-1949); keeps NHWC when the shapes allow it
-Tensor Engine::Impl::binary(int bop, const Tensor& a_in, const Tensor& b_in)
+Tensor Engine::Impl::binary(int bop, const Tensor& a_in, const Tensor& b_in, float out_scale, int out_zp)
 {
     Tensor a = a_in, b = b_in;
     if (a.type != b.type) {  // mixed f16/f32 (upcast ops): compute in f32
@@ -907,6 +1000,11 @@ Tensor Engine::Impl::binary(int bop, const Tensor& a_in, const Tensor& b_in)
     }
     if (S.empty()) { S.push_back(1); SA.push_back(0); SB.push_back(0); }
     if (S.size() > OSB_MAX_DIMS) throw std::invalid_argument("XnnPack::binary: too many dimensions (not implemented).");
+    if (a.type == DType::u8) {
+        r.scale = out_scale; r.zero_point = out_zp;
+        ck(osb_binary_qu8(bop, a.data(), SA.data(), a.scale, a.zero_point, b.data(), SB.data(), b.scale, b.zero_point, r.mdata(), out_scale, out_zp, S.data(), (int)S.size(), st), "osb_binary_qu8");
+        return r;
+    }
     ck(osb_binary(bop, a.data(), SA.data(), b.data(), SB.data(), r.mdata(), S.data(), (int)S.size(), K(a.type), st), "osb_binary");
     return r;
 }
@@ -918,7 +1016,7 @@ Tensor Engine::Impl::binary(int bop, const Tensor& a_in, const Tensor& b_in)
 bool Engine::Impl::percentile_range(const Tensor& x, float& lo, float& hi)
 {
     if (x.type != DType::f16 && x.type != DType::f32) return false;
-    if (!pct_dev) { pct_dev = E.m_pool.alloc(256); pct_host = std::make_shared<PinnedBuf>(64); }
+    if (!pct_dev) { pct_dev = pool().alloc(256); pct_host = std::make_shared<PinnedBuf>(64); }
     unsigned* h = (unsigned*)pct_host->ptr;
     h[0] = 0xFFFFFFFFu; h[1] = 0; h[2] = 0;
     ck(cudaMemcpyAsync(pct_dev->ptr, h, 12, cudaMemcpyHostToDevice, st), "percentiles init");
@@ -933,13 +1031,6 @@ bool Engine::Impl::percentile_range(const Tensor& x, float& lo, float& hi)
     return std::isfinite(lo) && std::isfinite(hi) && lo < hi;
 }
 
-static void range_to_scale(float lo, float hi, float& scale, int& zp)    // src/onnxstream.cpp:3234-3245
-{
-    if (lo > 0 && hi > 0) lo = 0;
-    else if (lo < 0 && hi < 0) hi = 0;
-    scale = (float)((hi - lo) / 255.0);
-    zp = (int)(uint8_t)(std::abs(lo) / scale);
-}
 
 Tensor Engine::Impl::quantize_dynamic(const Tensor& x)
 {
@@ -1021,8 +1112,8 @@ void Engine::Impl::op_conv(size_t oi, const Tensor* residual, size_t out_op)
         if (w.type != DType::u8) fail(op, "wrong data type of W.");
         auto it = E.range_data.find(op.name);
         if (it == E.range_data.end()) fail(op, "range data not found.");
-        float mn = std::min(it->second.first, 0.f), mx = std::max(it->second.second, 0.f);
-        float oscale = (mx - mn) / 255.f; int ozp = (int)(uint8_t)(std::fabs(mn) / oscale);   // src/onnxstream.cpp:3234-3245
+        float oscale; int ozp;
+        range_to_scale(it->second.first, it->second.second, oscale, ozp);
         DevPtr b32;
         if (has_b) {
             if (b.type != DType::f32 || !b.on_device()) fail(op, "wrong data type of B.");
@@ -1033,12 +1124,22 @@ void Engine::Impl::op_conv(size_t oi, const Tensor* residual, size_t out_op)
             std::vector<int32_t> ib((size_t)Cout);
             float s = x.scale * w.scale;
             for (int64_t i = 0; i < Cout; i++) ib[i] = (int32_t)(hb[i] / s);
-            b32 = E.m_pool.alloc(Cout * 4);
+            b32 = pool().alloc(Cout * 4);
             ck(cudaMemcpyAsync(b32->ptr, ib.data(), Cout * 4, cudaMemcpyHostToDevice, st), "bias H2D");
             ck(cudaStreamSynchronize(st), "sync");
         }
         y = make(DType::u8, { 1, Cout, Ho, Wo }, Layout::nhwc);
         y.scale = oscale; y.zero_point = ozp;
+        if (E.gemm_impl != 1 && osb_qu8_tc_conv_ok(Cin, Cout, Ho, Wo, kh, kw, stride, x.data(), w.data(), y.mdata())) {
+            // tensor cores (tcgen05.mma.kind::i8): the image is padded once with the input zero point -- XNNPACK's padding value, which
+            // TMA's zero fill cannot produce -- and the conv runs un-padded on it; zero-point terms are applied in the epilogue
+            const int64_t Hp = (Ho - 1) * stride + kh, Wp = (Wo - 1) * stride + kw;
+            DevPtr xp = pool().alloc((size_t)(Hp * Wp * Cin)), psum = pool().alloc((size_t)(Hp * Wp) * 4), csum = pool().alloc((size_t)Cout * 4);
+            ck(osb_pad_sum_u8(x.data(), xp->ptr, psum->ptr, H, W, Cin, Hp, Wp, pad_top, pad_left, x.zero_point, st), "osb_pad_sum_u8");
+            ck(osb_rowsum_u8(w.data(), csum->ptr, Cout, (int64_t)kh * kw * Cin, st), "osb_rowsum_u8");
+            ck(osb_qu8_tc_conv(xp->ptr, psum->ptr, w.data(), b32 ? b32->ptr : nullptr, csum->ptr, y.mdata(), Hp, Wp, Cin, Cout, kh, kw, stride, Ho, Wo,
+                               x.zero_point, x.scale, w.zero_point, w.scale, ozp, oscale, st), "osb_qu8_tc_conv");
+        } else
         ck(osb_conv2d_qu8((const uint8_t*)x.data(), (const uint8_t*)w.data(), b32 ? (const int32_t*)b32->ptr : nullptr, (uint8_t*)y.mdata(),
                           H, W, Cin, Cout, kh, kw, stride, pad_top, pad_left, Ho, Wo, x.zero_point, x.scale, w.zero_point, w.scale, ozp, oscale, st), "osb_conv2d_qu8");
     } else {
@@ -1074,6 +1175,28 @@ void Engine::Impl::op_matmul(size_t oi, const Tensor* bias, const Tensor* residu
     if (op.in.size() != 2) fail(op, "wrong number of inputs.");
     if (op.out.size() != 1) fail(op, "wrong number of outputs.");
     Tensor a = to_plain(in(oi, 0));
+    // uint8 static weight x float activation with <= 2 rows (LLM decode): the weight stays uint8 in HBM (half / quarter of the bytes
+    // the GEMV has to stream) and is dequantised in registers -- the same values the load-time conversion would have produced
+    // (src/onnxstream.cpp:2885-2890: (q - zero_point) * scale, rounded to the arithmetic type)
+    {
+        const TensorRef& wr = op.in[1];
+        int64_t rows = 1; for (size_t k = 0; k + 1 < a.shape.size(); k++) rows *= a.shape[k];
+        static const bool w8_gemv = [] { const char* e = getenv("OSB_W8_GEMV"); return !(e && e[0] == '0'); }();
+        if (w8_gemv && wr.wtype == DType::u8 && wr.shape.size() == 2 && !E.use_uint8_arithmetic && !E.use_uint8_qdq && (a.type == DType::f16 || a.type == DType::f32) &&
+            rows <= 2 && !a.shape.empty() && a.shape.back() == wr.shape[0] && wr.shape[1] % 16 == 0 && wr.shape[1] >= 256 && wr.shape[0] >= 64 &&
+            weight_target(op, wr, false) == a.type) {
+            Tensor wq = get_weight(oi, 1, false, false, true);
+            Tensor bb, rr;
+            if (bias) { bb = *bias; if (bb.type != a.type) bb = convert(bb, a.type); }
+            if (residual) { rr = to_plain(*residual); if (rr.type != a.type) rr = convert(rr, a.type); }
+            std::vector<int64_t> os = a.shape; os.back() = wr.shape[1];
+            Tensor y = make(a.type, os);
+            if (osb_gemv_w8(a.data(), wq.data(), y.mdata(), bias ? bb.data() : nullptr, residual ? rr.data() : nullptr, rows, wr.shape[1], wr.shape[0], wq.scale, wq.zero_point, K(a.type), st) == 0) {
+                push(out_op == (size_t)-1 ? oi : out_op, 0, y);
+                return;
+            }
+        }
+    }
     Tensor b = to_plain(in(oi, 1));
     std::vector<int64_t> as = a.shape, bs = b.shape;
     bool lead1 = false, first2d = false;
@@ -1094,13 +1217,21 @@ void Engine::Impl::op_matmul(size_t oi, const Tensor* bias, const Tensor* residu
         if (b.type != DType::u8) fail(op, "wrong data type of input 1.");
         auto it = E.range_data.find(op.name);
         if (it == E.range_data.end()) fail(op, "range data not found.");
-        float mn = std::min(it->second.first, 0.f), mx = std::max(it->second.second, 0.f);
-        float oscale = (mx - mn) / 255.f; int ozp = (int)(uint8_t)(std::fabs(mn) / oscale);
+        float oscale; int ozp;
+        range_to_scale(it->second.first, it->second.second, oscale, ozp);
         y = make(DType::u8, os);
         y.scale = oscale; y.zero_point = ozp;
-        for (int64_t i = 0; i < n; i++)
-            ck(osb_gemm_qu8((const uint8_t*)a.data() + i * M * Kd, (const uint8_t*)b.data() + i * stride_b, (uint8_t*)y.mdata() + i * M * N, nullptr, M, N, Kd,
-                            a.zero_point, a.scale, b.zero_point, b.scale, ozp, oscale, st), "osb_gemm_qu8");
+        for (int64_t i = 0; i < n; i++) {
+            const uint8_t* ai = (const uint8_t*)a.data() + i * M * Kd; const uint8_t* bi = (const uint8_t*)b.data() + i * stride_b; uint8_t* yi = (uint8_t*)y.mdata() + i * M * N;
+            if (E.gemm_impl != 1 && osb_qu8_tc_gemm_ok(M, N, Kd, ai, bi, yi)) {
+                // tensor cores (tcgen05.mma.kind::i8) on the raw bytes; row sums of x and column sums of w feed the zero-point terms
+                DevPtr rsum = pool().alloc((size_t)M * 4), csum = pool().alloc((size_t)N * 4);
+                ck(osb_rowsum_u8(ai, rsum->ptr, M, Kd, st), "osb_rowsum_u8");
+                ck(osb_colsum_u8(bi, csum->ptr, Kd, N, st), "osb_colsum_u8");
+                ck(osb_qu8_tc_gemm(ai, bi, yi, nullptr, rsum->ptr, csum->ptr, M, N, Kd, 0, a.zero_point, a.scale, b.zero_point, b.scale, ozp, oscale, st), "osb_qu8_tc_gemm");
+            } else
+            ck(osb_gemm_qu8(ai, bi, yi, nullptr, M, N, Kd, a.zero_point, a.scale, b.zero_point, b.scale, ozp, oscale, st), "osb_gemm_qu8");
+        }
     } else {
         if (b.type != a.type) b = convert(b, a.type);
         Tensor bb, rr;
@@ -1191,7 +1322,18 @@ void Engine::Impl::op_binary(size_t oi, int bop)
         ck(cudaStreamSynchronize(st), "sync");
         iv = convert(tmp, c.type);
     }
-    if (a.type == DType::u8 || b.type == DType::u8) fail(op, "qu8 elementwise arithmetic is not implemented in the B200 engine yet.");
+    if (a.type == DType::u8 || b.type == DType::u8) {
+        // qu8 Add / Mul (src/onnxstream.cpp:5097-5125, 3906-4000): both operands uint8, output range from m_range_data
+        if (a.type != DType::u8) fail(op, "wrong data type of input 0.");
+        if (b.type != DType::u8) fail(op, "wrong data type of input 1.");
+        if (bop != OSB_BIN_ADD && bop != OSB_BIN_MUL) fail(op, "qu8 arithmetic is implemented for Add and Mul only (as in the reference).");
+        auto it = E.range_data.find(op.name);
+        if (it == E.range_data.end()) fail(op, "range data not found.");
+        float oscale; int ozp;
+        range_to_scale(it->second.first, it->second.second, oscale, ozp);
+        push(oi, 0, binary(bop, a, b, oscale, ozp));
+        return;
+    }
     if (stats_want >= 0 && gn_ring && cur_B == 1 && bop == OSB_BIN_ADD && a.type == b.type) {
         // x[NHWC] + t[1,C,1,1] feeding a GroupNorm (the time-embedding add of a resnet): one pass adds and gathers the statistics
         for (int k = 0; k < 2; k++) {
@@ -1497,7 +1639,35 @@ void Engine::Impl::op_softmax(size_t oi)
     int64_t rank = (int64_t)x.shape.size();
     if (axis < 0) axis += rank;
     if (axis < 0 || axis >= rank) fail(op, "invalid axis attribute.");
-    if (x.type != DType::f16 && x.type != DType::f32) fail(op, "qu8 softmax is not implemented in the B200 engine yet.");
+    if (x.type == DType::u8) {
+        // qu8 softmax (src/onnxstream.cpp:5960-5995): output scale 2^-8, zero point 0; `axis` moved last by a transpose if needed
+        Tensor t = x;
+        std::vector<int64_t> perm;
+        if (axis != rank - 1) {
+            for (int64_t i = 0; i < rank; i++) if (i != axis) perm.push_back(i);
+            perm.push_back(axis);
+            auto istr = contiguous_strides(x.shape);
+            std::vector<int64_t> ps(rank), pst(rank);
+            for (int64_t i = 0; i < rank; i++) { ps[i] = x.shape[perm[i]]; pst[i] = istr[perm[i]]; }
+            t = strided(x, ps, pst, nullptr, 0);
+        }
+        Tensor sres = make(DType::u8, t.shape);
+        sres.scale = 0x1.0p-8f; sres.zero_point = 0;
+        ck(osb_softmax_qu8(t.data(), sres.mdata(), t.numel() / t.shape.back(), t.shape.back(), x.scale, sres.scale, 0, st), "osb_softmax_qu8");
+        if (!perm.empty()) {
+            std::vector<int64_t> inv(rank);
+            for (int64_t i = 0; i < rank; i++) inv[perm[i]] = i;
+            auto sstr = contiguous_strides(t.shape);
+            std::vector<int64_t> bs(rank);
+            for (int64_t i = 0; i < rank; i++) bs[i] = sstr[inv[i]];
+            Tensor back = strided(sres, x.shape, bs, nullptr, 0);
+            back.scale = sres.scale; back.zero_point = 0;
+            sres = back;
+        }
+        push(oi, 0, sres);
+        return;
+    }
+    if (x.type != DType::f16 && x.type != DType::f32) fail(op, "wrong data type of input.");
     if (axis != rank - 1) {
         // move `axis` last, softmax, move back (src/onnxstream.cpp:5883-5898)
         std::vector<int64_t> perm;
@@ -1532,8 +1702,26 @@ void Engine::Impl::op_instnorm(size_t oi)
     for (auto& a : op.attrs) { if (a.first == "epsilon") eps = std::stof(a.second); else fail(op, "unrecognized attribute: " + a.first + "."); }
     Tensor x = to_plain(in(oi, 0)), sc = in(oi, 1), bi = in(oi, 2);
     if (x.shape.size() != 3 || x.shape[0] != 1) fail(op, "input must be 3D with a leading 1 (not implemented).");
-    if (x.type != DType::f16 && x.type != DType::f32) fail(op, "qu8 InstanceNormalization is not implemented in the B200 engine yet.");
     if (sc.numel() != x.shape[1] || bi.numel() != x.shape[1]) fail(op, "invalid shape of scale or B.");
+    if (x.type == DType::u8) {
+        // uint8 input (src/onnxstream.cpp:4846-4861, 4948-5040): dequantised in 64 KiB float tiles, statistics in double, result
+        // re-quantised to the op's m_range_data scale -- here: dequantise, the fp32 kernel, quantise (XNNPACK's f32->qu8 conversion)
+        auto it = E.range_data.find(op.name);
+        if (it == E.range_data.end()) fail(op, "range data not found.");
+        float oscale; int ozp;
+        range_to_scale(it->second.first, it->second.second, oscale, ozp);
+        Tensor xf = dequantize(x, DType::f32);
+        if (sc.type != DType::f32) sc = convert(sc, DType::f32);
+        if (bi.type != DType::f32) bi = convert(bi, DType::f32);
+        Tensor yf = make(DType::f32, x.shape);
+        ck(osb_instance_norm(xf.data(), yf.mdata(), K(DType::f32), x.shape[1], x.shape[2], sc.data(), bi.data(), eps, st), "osb_instance_norm");
+        yf.scale = oscale; yf.zero_point = ozp;
+        Tensor q = convert(yf, DType::u8);
+        q.scale = oscale; q.zero_point = ozp;
+        push(oi, 0, q);
+        return;
+    }
+    if (x.type != DType::f16 && x.type != DType::f32) fail(op, "wrong data type of input.");
     if (sc.type != x.type) sc = convert(sc, x.type);
     if (bi.type != x.type) bi = convert(bi, x.type);
     Tensor y = make(x.type, x.shape);
@@ -1585,7 +1773,7 @@ void Engine::Impl::op_gather(size_t oi)
     y.scale = data.scale; y.zero_point = data.zero_point;
     int64_t n = (int64_t)idx.i64->size();
     for (auto i : *idx.i64) if ((i < 0 ? i + rows : i) < 0 || (i < 0 ? i + rows : i) >= rows) fail(op, "index out of range.");
-    DevPtr didx = E.m_pool.alloc((size_t)n * 8);
+    DevPtr didx = pool().alloc((size_t)n * 8);
     ck(cudaMemcpyAsync(didx->ptr, idx.i64->data(), (size_t)n * 8, cudaMemcpyHostToDevice, st), "gather idx H2D");
     ck(cudaStreamSynchronize(st), "sync");  // host vector may die before the copy otherwise (pageable source)
     ck(osb_gather_rows(data.data(), (const int64_t*)didx->ptr, y.mdata(), n, rows, row_elems * (int64_t)dtype_size(data.type), st), "osb_gather_rows");
@@ -1786,7 +1974,7 @@ void Engine::Impl::op_misc_host(size_t oi)
         Tensor y = make(x.type, x.shape);
         ck(cudaMemcpyAsync(y.mdata(), x.data(), (size_t)x.numel() * es, cudaMemcpyDeviceToDevice, st), "scatter copy");
         if (n_upd) {
-            DevPtr dpos = E.m_pool.alloc((size_t)n_upd * 8);
+            DevPtr dpos = pool().alloc((size_t)n_upd * 8);
             ck(cudaMemcpyAsync(dpos->ptr, pos.data(), (size_t)n_upd * 8, cudaMemcpyHostToDevice, st), "scatter pos H2D");
             ck(cudaStreamSynchronize(st), "sync");   // pageable source
             ck(osb_scatter_elems(y.mdata(), (const int64_t*)dpos->ptr, upd.data(), n_upd, (int)es, st), "osb_scatter_elems");
@@ -1886,6 +2074,66 @@ void Engine::Impl::fused_attention(const Step& s)
 // Multi-head attention block (see match_mha).  Per-op semantics are those of the MatMul / Reshape / Transpose /
 // AttentionFusedOps branches (src/onnxstream.cpp:5669-5861, 4708-4787, 5176-5236, 6696-6929); the head split and merge
 // become leading-dimension arithmetic on the projection buffers instead of copies.
+// The projections of a fused multi-head attention block: the ones that share their input run as one grouped launch (self-attention:
+// q, k, v; cross-attention: k, v).  ql == nullptr: K and V only (side-branch pre-pass).
+void Engine::Impl::mha_project(size_t i, const Tensor& x, const Tensor* xq, Tensor* ql, Tensor& kl, Tensor& vl, int64_t Tka)
+{
+    Tensor xk = to_plain(in(i + 4, 0)), xv = to_plain(in(i + 9, 0));
+    Tensor wq = in(i, 1), wk = in(i + 4, 1), wv = in(i + 9, 1);
+    const DType ty = x.type;
+    if (xk.type != ty) xk = convert(xk, ty);
+    if (xv.type != ty) xv = convert(xv, ty);
+    if (wq.type != ty) wq = convert(wq, ty);
+    if (wk.type != ty) wk = convert(wk, ty);
+    if (wv.type != ty) wv = convert(wv, ty);
+    auto& qs = E.m_ops[i + 3].out[0].shape; auto& kts = E.m_ops[i + 8].out[0].shape;
+    const int64_t h = qs[0], T = qs[1], d = qs[2], Tk = kts[2], C = h * d;
+    const size_t es = dtype_size(ty);
+    if (Tka != Tk) {   // zero pad rows: they are read as extra (null) keys / values by the padded GEMMs
+        ck(cudaMemsetAsync((char*)kl.mdata() + Tk * C * es, 0, (Tka - Tk) * C * es, st), "cudaMemsetAsync");
+        ck(cudaMemsetAsync((char*)vl.mdata() + Tk * C * es, 0, (Tka - Tk) * C * es, st), "cudaMemsetAsync");
+    }
+    const bool kv_same = xk.data() == xv.data() && xk.shape == xv.shape && wk.shape == wv.shape;
+    const bool qkv_same = ql && xq && kv_same && xq->data() == xk.data() && xq->shape == xk.shape && wq.shape == wk.shape && T == Tk;
+    if (qkv_same) {
+        const void* Bs[3] = { wq.data(), wk.data(), wv.data() };
+        void* Cs[3] = { ql->mdata(), kl.mdata(), vl.mdata() };
+        ck(osb_gemm_grouped(xq->data(), Bs, Cs, 3, T, C, xq->shape[2], 0, K(ty), E.gemm_impl, st), "osb_gemm_grouped(qkv)");
+        return;
+    }
+    if (ql) ck(osb_gemm(xq->data(), wq.data(), ql->mdata(), nullptr, nullptr, 1, T, C, xq->shape[2], 0, 0, 0, 0, K(ty), E.gemm_impl, st), "osb_gemm(q)");
+    if (kv_same) {
+        const void* Bs[2] = { wk.data(), wv.data() };
+        void* Cs[2] = { kl.mdata(), vl.mdata() };
+        ck(osb_gemm_grouped(xk.data(), Bs, Cs, 2, Tk, C, xk.shape[2], 0, K(ty), E.gemm_impl, st), "osb_gemm_grouped(kv)");
+    } else {
+        ck(osb_gemm(xk.data(), wk.data(), kl.mdata(), nullptr, nullptr, 1, Tk, C, xk.shape[2], 0, 0, 0, 0, K(ty), E.gemm_impl, st), "osb_gemm(k)");
+        ck(osb_gemm(xv.data(), wv.data(), vl.mdata(), nullptr, nullptr, 1, Tk, C, xv.shape[2], 0, 0, 0, 0, K(ty), E.gemm_impl, st), "osb_gemm(v)");
+    }
+}
+
+// side-branch pre-pass of a cross-attention block: K / V projections of the (primary-independent) context, on the side stream
+void Engine::Impl::mha_prepass(size_t si)
+{
+    const Step& s = steps[si];
+    const size_t i = s.first;
+    cur_step = si; cur_b = 0; cur_B = 1;
+    wcache.clear();
+    Tensor xk = to_plain(in(i + 4, 0));
+    const DType ty = act_dtype();
+    if (xk.type != DType::f16 && xk.type != DType::f32) return;
+    auto& qs = E.m_ops[i + 3].out[0].shape; auto& kts = E.m_ops[i + 8].out[0].shape;
+    const int64_t h = qs[0], T = qs[1], d = qs[2], Tk = kts[2], C = h * d;
+    const bool use_flash = E.flash_attention && E.gemm_impl != 1 && osb_flash_attention_ok(T, Tk, d, K(ty));
+    const int64_t Tka = use_flash ? Tk : ((Tk + 7) & ~(int64_t)7);
+    Tensor proxy; proxy.type = ty;      // only the dtype of the query side matters here
+    MhaKV kv;
+    kv.kl = make(ty, { Tka, C }); kv.vl = make(ty, { Tka, C });
+    mha_project(i, proxy, nullptr, nullptr, kv.kl, kv.vl, Tka);
+    wcache.clear();
+    mha_kv[si] = kv;
+}
+
 void Engine::Impl::fused_mha(const Step& s)
 {
     size_t i = s.first;
@@ -1911,28 +2159,17 @@ void Engine::Impl::fused_mha(const Step& s)
     const bool use_flash = E.flash_attention && E.gemm_impl != 1 && osb_flash_attention_ok(T, Tk, d, K(ty));
     // the flash kernel reads K / V through tensor maps of exactly Tk rows (rows beyond are zero-filled by TMA): no padding needed
     const int64_t Tka = use_flash ? Tk : Tkp;
-    Tensor ql = make(ty, { T, C }), kl = make(ty, { Tka, C }), vl = make(ty, { Tka, C }), out = make(ty, { 1, T, C });
-    if (Tka != Tk) {   // zero pad rows: they are read as extra (null) keys / values by the padded GEMMs
-        ck(cudaMemsetAsync((char*)kl.mdata() + Tk * C * es, 0, (Tka - Tk) * C * es, st), "cudaMemsetAsync");
-        ck(cudaMemsetAsync((char*)vl.mdata() + Tk * C * es, 0, (Tka - Tk) * C * es, st), "cudaMemsetAsync");
-    }
-    // projections: the ones that share their input run as one grouped launch (self-attention: q, k, v; cross-attention: k, v)
-    const bool kv_same = xk.data() == xv.data() && xk.shape == xv.shape && wk.shape == wv.shape;
-    const bool qkv_same = kv_same && x.data() == xk.data() && x.shape == xk.shape && wq.shape == wk.shape && T == Tk;
-    if (qkv_same) {
-        const void* Bs[3] = { wq.data(), wk.data(), wv.data() };
-        void* Cs[3] = { ql.mdata(), kl.mdata(), vl.mdata() };
-        ck(osb_gemm_grouped(x.data(), Bs, Cs, 3, T, C, x.shape[2], 0, K(ty), E.gemm_impl, st), "osb_gemm_grouped(qkv)");
-    } else {
+    Tensor ql = make(ty, { T, C }), kl, vl, out = make(ty, { 1, T, C });
+    auto pre = mha_kv.find(cur_step);
+    if (pre != mha_kv.end()) {
+        // K / V projections of the text context were computed ahead on the side stream: only Q is projected here
+        kl = pre->second.kl; vl = pre->second.vl;
+        ck(cudaStreamWaitEvent(st, pre->second.ev, 0), "cudaStreamWaitEvent(main, side K/V)");
+        mha_kv.erase(pre);
         ck(osb_gemm(x.data(), wq.data(), ql.mdata(), nullptr, nullptr, 1, T, C, x.shape[2], 0, 0, 0, 0, K(ty), E.gemm_impl, st), "osb_gemm(q)");
-        if (kv_same) {
-            const void* Bs[2] = { wk.data(), wv.data() };
-            void* Cs[2] = { kl.mdata(), vl.mdata() };
-            ck(osb_gemm_grouped(xk.data(), Bs, Cs, 2, Tk, C, xk.shape[2], 0, K(ty), E.gemm_impl, st), "osb_gemm_grouped(kv)");
-        } else {
-            ck(osb_gemm(xk.data(), wk.data(), kl.mdata(), nullptr, nullptr, 1, Tk, C, xk.shape[2], 0, 0, 0, 0, K(ty), E.gemm_impl, st), "osb_gemm(k)");
-            ck(osb_gemm(xv.data(), wv.data(), vl.mdata(), nullptr, nullptr, 1, Tk, C, xv.shape[2], 0, 0, 0, 0, K(ty), E.gemm_impl, st), "osb_gemm(v)");
-        }
+    } else {
+        kl = make(ty, { Tka, C }); vl = make(ty, { Tka, C });
+        mha_project(i, x, &x, &ql, kl, vl, Tka);
     }
 
     if (use_flash) {
@@ -2363,7 +2600,7 @@ std::string Engine::options_signature() const
     auto b = [&](bool v) { s += v ? '1' : '0'; };
     b(use_fp16_arithmetic); b(use_uint8_qdq); b(use_uint8_arithmetic); b(fuse_ops_in_attention); b(force_fp16_storage);
     b(support_dynamic_shapes); b(use_scaled_dp_attn_op); b(use_nchw_convs); b(resident_weights); b(fuse_nodes); b(keep_nhwc); b(flash_attention);
-    b((bool)requires_upcast);
+    b((bool)requires_upcast); b(keep_inputs); b(drop_unconverted_outputs);
     s += std::to_string(gemm_impl); s += '|'; s += std::to_string(attention_fused_ops_parts); s += '|';
     for (auto& e : extra_outputs) { s += e; s += ','; }
     s += '|';
@@ -2590,6 +2827,15 @@ void Engine::run()
             uploaded.emplace_back(t, h.type == DType::f32 && ((use_fp16_arithmetic && !use_uint8_arithmetic && !use_uint8_qdq) || force_fp16_storage));
         }
     }
+    size_t n_fresh = (size_t)-1;
+    if (keep_inputs) {
+        // inputs pushed now replace their kept copies; kept copies of names NOT pushed this time are fed again from HBM
+        for (auto& u : uploaded) {
+            I.kept_inputs.erase(std::remove_if(I.kept_inputs.begin(), I.kept_inputs.end(), [&](const Tensor& k) { return k.name == u.first.name; }), I.kept_inputs.end());
+        }
+        n_fresh = uploaded.size();
+        for (auto& k : I.kept_inputs) uploaded.emplace_back(k, false);      // already in their storage type
+    }
     std::vector<HostTensor> pinned_inputs = std::move(m_host_tensors);   // keep the pinned sources alive until the copies ran
     m_host_tensors.clear();
 
@@ -2601,10 +2847,13 @@ void Engine::run()
             check_cuda(cudaStreamBeginCapture(m_stream, cudaStreamCaptureModeRelaxed), "cudaStreamBeginCapture");
             capture_open = true;
         }
-        for (auto& u : uploaded) {
+        for (size_t ui = 0; ui < uploaded.size(); ui++) {
+            auto& u = uploaded[ui];
             Tensor t = u.first;
-            if ((use_uint8_qdq || use_uint8_arithmetic) && (t.type == DType::f32 || t.type == DType::f16)) { t = I.quantize_dynamic(t); t.name = u.first.name; }
+            if (ui >= n_fresh) { /* kept copy of an earlier run: stored as it was consumed then */ }
+            else if ((use_uint8_qdq || use_uint8_arithmetic) && (t.type == DType::f32 || t.type == DType::f16)) { t = I.quantize_dynamic(t); t.name = u.first.name; }
             else if (u.second) { t = I.convert(t, DType::f16); t.name = u.first.name; }
+            if (keep_inputs && ui < n_fresh && t.type != DType::i64) I.kept_inputs.push_back(t);
             auto& v = I.store[t.name];
             if (v.empty()) I.order.push_back(t.name);
             v.push_back(std::move(t));
@@ -2612,6 +2861,40 @@ void Engine::run()
         if (!I.gn_ring) I.gn_ring = m_pool.alloc(2048);
         check_cuda(cudaMemsetAsync(I.gn_ring->ptr, 0, 2048, m_stream), "cudaMemsetAsync(gn ring)");    // both statistic slots zero: the invariant every producer relies on
         I.gn_slot = 0; I.stats_ready_for = -1; I.stats_want = -1;
+        I.mha_kv.clear();
+        // side branch: steps off the critical path first, on their own stream and pool (see Impl::side_stream)
+        bool hoist = !I.is_side.empty() && resident_weights && !m_first_run && !has_i64_input && !ops_times_printf && !ops_printf && m_nranks == 1;
+        if (hoist) { std::set<std::string> seen; for (auto& u : uploaded) if (!seen.insert(u.first.name).second) hoist = false; }   // batch siblings: sequential
+        if (hoist) {
+            if (!I.side_stream) check_cuda(cudaStreamCreateWithFlags(&I.side_stream, cudaStreamNonBlocking), "cudaStreamCreate(side)");
+            if (I.side_events.size() != I.steps.size() + 2) {
+                for (auto e : I.side_events) if (e) cudaEventDestroy(e);
+                I.side_events.assign(I.steps.size() + 2, nullptr);
+            }
+            auto ev = [&](size_t k) -> cudaEvent_t& { if (!I.side_events[k]) check_cuda(cudaEventCreateWithFlags(&I.side_events[k], cudaEventDisableTiming), "cudaEventCreate"); return I.side_events[k]; };
+            const size_t EV_IN = I.steps.size(), EV_DONE = I.steps.size() + 1;
+            check_cuda(cudaEventRecord(ev(EV_IN), m_stream), "cudaEventRecord(inputs)");
+            check_cuda(cudaStreamWaitEvent(I.side_stream, ev(EV_IN), 0), "cudaStreamWaitEvent(side, inputs)");     // (inside a capture: the side stream joins it here)
+            I.on_side = true; I.st = I.side_stream;
+            try {
+                for (size_t si = 0; si < I.steps.size(); si++) {
+                    if (I.is_side[si]) { I.exec_step(si); check_cuda(cudaEventRecord(ev(si), I.side_stream), "cudaEventRecord(side step)"); }
+                    else if (!I.kv_side.empty() && I.kv_side[si]) {
+                        I.mha_prepass(si);
+                        auto it = I.mha_kv.find(si);
+                        if (it != I.mha_kv.end()) { check_cuda(cudaEventRecord(ev(si), I.side_stream), "cudaEventRecord(side K/V)"); it->second.ev = ev(si); }
+                    }
+                }
+                check_cuda(cudaEventRecord(ev(EV_DONE), I.side_stream), "cudaEventRecord(side done)");
+            } catch (...) { I.on_side = false; I.st = m_stream; throw; }
+            I.on_side = false; I.st = m_stream;
+            for (size_t si = 0; si < I.steps.size(); si++) {
+                if (I.is_side[si]) continue;
+                for (size_t d : I.side_deps[si]) check_cuda(cudaStreamWaitEvent(m_stream, ev(d), 0), "cudaStreamWaitEvent(main, side step)");
+                I.exec_step(si);
+            }
+            check_cuda(cudaStreamWaitEvent(m_stream, ev(EV_DONE), 0), "cudaStreamWaitEvent(main, side done)");   // join (a capture must not end with a dangling branch)
+        } else
         for (size_t si = 0; si < I.steps.size(); si++) I.exec_step(si);
         m_streamer->end_run(m_stream);
 
@@ -2627,6 +2910,7 @@ void Engine::run()
                 if (t.type == DType::u8) t = I.dequantize(t, DType::f32);     // src/onnxstream.cpp:8238-8241
                 // m_outputs_convert_set (src/onnxstream.cpp:8234-8236): tensors outside a non-empty set keep their storage type
                 // (fp16 stays fp16: half the D2H bytes, and llm.cpp feeds its KV cache straight back in)
+                if (drop_unconverted_outputs && !outputs_convert_set.empty() && !outputs_convert_set.count(name)) continue;
                 if (!outputs_convert_set.empty() && !outputs_convert_set.count(name) && t.type == DType::f16) {
                     if (!t.dev || (t.dev.get() == t0_.dev.get() && capturing)) {
                         Tensor c = I.make(DType::f16, t.shape);

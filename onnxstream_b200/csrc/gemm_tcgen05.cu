@@ -37,12 +37,8 @@ constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;   // 256
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
 constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;  // 16 KiB
-#ifndef OSB_NO_EPI_EXTRAS
-constexpr int GN_SMEM_BYTES = 4 * 2048 + 2 * tcptx::GN_MAX_GROUPS * 4;
-#else
-constexpr int GN_SMEM_BYTES = 0;      // A/B build: the single-CTA kernel without the statistics / bias2 epilogue (callers must not request them)
-#endif   // GroupNorm statistics: 4 warp-private transposition buffers + the CTA accumulators
-constexpr int smem_bytes_for(int stages) { return stages * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/ + GN_SMEM_BYTES; }
+constexpr int GN_SMEM_BYTES = 4 * 2048 + 2 * tcptx::GN_MAX_GROUPS * 4;   // GroupNorm statistics: 4 warp-private transposition buffers + the CTA accumulators
+constexpr int smem_bytes_for(int stages, bool extras = true) { return stages * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/ + (extras ? GN_SMEM_BYTES : 0); }
 constexpr int NUM_THREADS = 192;       // 6 warps
 
 struct TcParams {
@@ -93,7 +89,9 @@ __device__ __forceinline__ uint32_t make_idesc(int b_mn_major, int bn)
 
 // ---- the kernel -----------------------------------------------------------------------------------------------
 
-template <int STAGES>
+// EXTRAS = the epilogue also adds `bias2` and gathers GroupNorm statistics.  A separate instantiation: the extra code costs ~14 registers
+// and ~0.3 ms over the 253 tensor-core launches of a UNet step when it rides along in every launch (measured, profiles/r02_ab_epilogue.txt).
+template <int STAGES, bool EXTRAS>
 __global__ void __launch_bounds__(NUM_THREADS, STAGES <= STAGES_SHORT ? 2 : 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_b1,
                const __grid_constant__ CUtensorMap map_b2, const TcParams p)
@@ -115,9 +113,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-#ifndef OSB_NO_EPI_EXTRAS
-    if (p.gn_stats && threadIdx.x < 2 * GN_MAX_GROUPS) gn_acc[threadIdx.x] = 0.f;
-#endif
+    if (EXTRAS && p.gn_stats && threadIdx.x < 2 * GN_MAX_GROUPS) gn_acc[threadIdx.x] = 0.f;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -304,39 +300,33 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                             for (int t = 0; t < 8; t++) f[t] += __half2float(rv.v[t]);
                         }
-#ifndef OSB_NO_EPI_EXTRAS
-                        if (p.bias2) {
+                        if (EXTRAS && p.bias2) {
                             Vec<__half, 8> bv = load_vec<__half, 8>(p.bias2 + n);
 #pragma unroll
                             for (int t = 0; t < 8; t++) f[t] += __half2float(bv.v[t]);
                         }
-#endif
                         Vec<__half, 8> o;
 #pragma unroll
                         for (int t = 0; t < 8; t++) o.v[t] = __float2half_rn(f[t]);
                         store_vec<__half, 8>(crow + n, o);
-#ifndef OSB_NO_EPI_EXTRAS
+                        if (EXTRAS) {
 #pragma unroll
-                        for (int t = 0; t < 4; t++) v[(j >> 1) + t] = *reinterpret_cast<uint32_t*>(&o.v[2 * t]);   // keep the rounded values for the statistics
-#endif
+                            for (int t = 0; t < 4; t++) v[(j >> 1) + t] = *reinterpret_cast<uint32_t*>(&o.v[2 * t]);   // keep the rounded values for the statistics
+                        }
                     }
                 }
-#ifndef OSB_NO_EPI_EXTRAS
-                if (p.gn_stats && !wrow) {
+                if (EXTRAS && p.gn_stats && !wrow) {
                     // rows outside the problem (and units past N) contribute zeros
                     uint32_t h[16];
 #pragma unroll
                     for (int t = 0; t < 16; t++) h[t] = (row_ok && vec_ok && n0 + c + 2 * t < n_end) ? v[t] : 0u;
                     gn_stats_chunk(smem_u32(gn_buf) + (uint32_t)q * 2048u, h, n0 + c, n_end, p.gn_cpg, gn_acc, lane);
                 }
-#endif
             }
-#ifndef OSB_NO_EPI_EXTRAS
-            if (p.gn_stats && !wrow) {
+            if (EXTRAS && p.gn_stats && !wrow) {
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 gn_stats_flush(gn_acc, p.gn_stats, p.gn_groups, (int)threadIdx.x - 64);
             }
-#endif
             tc_fence_before();
             mbar_arrive(&acc_empty[acc]);
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
@@ -447,6 +437,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, __half* __res
 }
 
 #include "gemm_pair.cuh"
+#include "gemm_i8.cuh"
 
 // ---- host side -------------------------------------------------------------------------------------------------
 constexpr size_t WS_MAX = OSB_WS_SPLITK_BYTES;   // fixed-capacity per-stream workspace (workspace.h): never re-allocated, graph-safe
@@ -487,7 +478,7 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode()
 
 // rank-3 fp16 tensor map with 128B swizzle; dims/strides innermost first
 bool make_map(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes, uint64_t s2_bytes,
-              uint32_t b0, uint32_t b1, uint32_t b2, uint32_t traversal_stride = 1)
+              uint32_t b0, uint32_t b1, uint32_t b2, uint32_t traversal_stride = 1, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT16)
 {
     auto enc = get_encode();
     if (!enc) return false;
@@ -495,7 +486,7 @@ bool make_map(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint
     cuuint64_t strides[2] = { s1_bytes, s2_bytes };
     cuuint32_t box[3] = { b0, b1, b2 };
     cuuint32_t estr[3] = { 1, traversal_stride, traversal_stride };   // strided conv: every s-th pixel of the box span
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = enc(map, dtype, 3, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
@@ -562,8 +553,10 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cuda
     const CUtensorMap& mb2 = mb2p ? *mb2p : mb;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<STAGES_DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(STAGES_DEEP));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<STAGES_SHORT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(STAGES_SHORT));
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<STAGES_DEEP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(STAGES_DEEP, false));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<STAGES_SHORT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(STAGES_SHORT, false));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<STAGES_DEEP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(STAGES_DEEP, true));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<STAGES_SHORT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(STAGES_SHORT, true));
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
@@ -572,8 +565,11 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cuda
     int grid = std::min(total, num_sms() * (short_k ? 2 : 1));
     ProfRec rec{};
     if (g_prof) prof_begin(rec, p, st);
-    if (short_k) osb_launch((tc_gemm_kernel<STAGES_SHORT>), grid, NUM_THREADS, (size_t)smem_bytes_for(STAGES_SHORT), st, ma, mb, mb1, mb2, p);
-    else osb_launch((tc_gemm_kernel<STAGES_DEEP>), grid, NUM_THREADS, (size_t)smem_bytes_for(STAGES_DEEP), st, ma, mb, mb1, mb2, p);
+    const bool extras = p.bias2 != nullptr || p.gn_stats != nullptr;
+    if (short_k && extras) osb_launch((tc_gemm_kernel<STAGES_SHORT, true>), grid, NUM_THREADS, (size_t)smem_bytes_for(STAGES_SHORT, true), st, ma, mb, mb1, mb2, p);
+    else if (short_k) osb_launch((tc_gemm_kernel<STAGES_SHORT, false>), grid, NUM_THREADS, (size_t)smem_bytes_for(STAGES_SHORT, false), st, ma, mb, mb1, mb2, p);
+    else if (extras) osb_launch((tc_gemm_kernel<STAGES_DEEP, true>), grid, NUM_THREADS, (size_t)smem_bytes_for(STAGES_DEEP, true), st, ma, mb, mb1, mb2, p);
+    else osb_launch((tc_gemm_kernel<STAGES_DEEP, false>), grid, NUM_THREADS, (size_t)smem_bytes_for(STAGES_DEEP, false), st, ma, mb, mb1, mb2, p);
     if (p.split_k > 1 && !p.counters) {
         launched(1);
         long long total4 = (long long)p.batch * p.M * p.N / 4;
@@ -723,6 +719,116 @@ extern "C" int osb_tc_profile_dump(char* buf, int cap)
         off += n;
     }
     return off;
+}
+
+
+// ---- W8A8 (kind::i8) entry points ------------------------------------------------------------------------------------
+// TMA needs 16-byte global strides: K % 16 (K-major operands), N % 16 (MN-major weights and the 16-byte output vectors)
+extern "C" int osb_qu8_tc_gemm_ok(int64_t M, int64_t N, int64_t K, const void* A, const void* B, const void* C)
+{
+    if (M < 32 || N < 16 || K < 16 || (N % 16) || (K % 16)) return 0;
+    if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) return 0;
+    static const int off = env_int("OSB_QU8_TC_OFF");
+    return get_encode() != nullptr && !off;
+}
+
+extern "C" int osb_qu8_tc_conv_ok(int64_t Cin, int64_t Cout, int64_t Ho, int64_t Wo, int kh, int kw, int stride, const void* x, const void* w, const void* y)
+{
+    if ((Cin % 16) || (Cout % 16) || Ho * Wo < 64 || kh > 7 || kw > 7 || stride < 1 || stride > 2) return 0;
+    if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) return 0;
+    static const int off = env_int("OSB_QU8_TC_OFF");
+    return get_encode() != nullptr && !off;
+}
+
+extern "C" int osb_rowsum_u8(const void* x, void* out, int64_t rows, int64_t cols, void* stream)
+{
+    if (rows * cols == 0) return 0;
+    osb_launch((i8k::rowsum_u8_kernel), (unsigned)std::min<int64_t>((rows + 7) / 8, 148 * 8), 256, 0, (cudaStream_t)stream, (const uint8_t*)x, (int32_t*)out, (long long)rows, (long long)cols);
+    return launched();
+}
+
+extern "C" int osb_colsum_u8(const void* w, void* out, int64_t K, int64_t N, void* stream)
+{
+    if (K * N == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * 4, st);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t gx = (N + 255) / 256;
+    const int64_t gy = std::max<int64_t>(1, std::min<int64_t>((K + 63) / 64, (148 * 4 + gx - 1) / gx));
+    const int64_t k_per = (K + gy - 1) / gy;
+    osb_launch((i8k::colsum_u8_kernel), dim3((unsigned)gx, (unsigned)((K + k_per - 1) / k_per)), 256, 0, st, (const uint8_t*)w, (int32_t*)out, (long long)K, (long long)N, (long long)k_per);
+    return launched();
+}
+
+extern "C" int osb_pad_sum_u8(const void* x, void* xp, void* psum, int64_t H, int64_t W, int64_t C, int64_t Hp, int64_t Wp, int pad_top, int pad_left, int zx, void* stream)
+{
+    if (Hp * Wp * C == 0) return 0;
+    if (C % 16) return (int)cudaErrorInvalidValue;
+    osb_launch((i8k::pad_sum_u8_kernel), (unsigned)std::min<int64_t>((Hp * Wp + 7) / 8, 148 * 16), 256, 0, (cudaStream_t)stream, (const uint8_t*)x, (uint8_t*)xp, (int32_t*)psum,
+               (int)H, (int)W, (int)C, (int)Hp, (int)Wp, pad_top, pad_left, zx);
+    return launched();
+}
+
+static int launch_i8(const CUtensorMap& ma, const CUtensorMap& mb, const i8k::I8Params& p, cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(i8k::tc_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, i8k::I8_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int total = p.m_tiles * p.n_tiles;
+    osb_launch((i8k::tc_i8_kernel), std::min(total, num_sms()), NUM_THREADS, (size_t)i8k::I8_SMEM, st, ma, mb, p);
+    return launched(1);
+}
+
+// C[M,N] (uint8) = requant((A - zx) (B - zw) + bias): A [M,K] uint8, B [K,N] (bt = 0, ONNX MatMul) or [N,K] (bt = 1); rsum = rowsum_x[M],
+// csum = colsum_w[N] (osb_rowsum_u8 / osb_colsum_u8)
+extern "C" int osb_qu8_tc_gemm(const void* A, const void* B, void* C, const void* bias, const void* rsum, const void* csum, int64_t M, int64_t N, int64_t K, int bt,
+                               int zx, float sx, int zw, float sw, int zy, float sy, void* stream)
+{
+    CUtensorMap ma, mb;
+    const int bn = N <= 64 ? 64 : 128;
+    if (!make_map(&ma, A, (uint64_t)K, (uint64_t)M, 1, (uint64_t)K, (uint64_t)M * K, i8k::I8_BLOCK_K, BLOCK_M, 1, 1, CU_TENSOR_MAP_DATA_TYPE_UINT8)) return (int)cudaErrorInvalidValue;
+    bool ok = bt ? make_map(&mb, B, (uint64_t)K, (uint64_t)N, 1, (uint64_t)K, (uint64_t)N * K, i8k::I8_BLOCK_K, (uint32_t)bn, 1, 1, CU_TENSOR_MAP_DATA_TYPE_UINT8)
+                 : make_map(&mb, B, (uint64_t)N, (uint64_t)K, 1, (uint64_t)N, (uint64_t)N * K, 128, i8k::I8_BLOCK_K, 1, 1, CU_TENSOR_MAP_DATA_TYPE_UINT8);
+    if (!ok) return (int)cudaErrorInvalidValue;
+    i8k::I8Params p{};
+    p.M = (int)M; p.N = (int)N; p.K = (int)K; p.bn = bn;
+    p.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M); p.n_tiles = (int)((N + bn - 1) / bn);
+    p.b_kmajor = bt ? 1 : 0;
+    p.taps = 1; p.kw = 1; p.bh = 0; p.bw = 0; p.tiles_x = 1; p.stride = 1;
+    p.k_blocks_per_tap = (int)((K + i8k::I8_BLOCK_K - 1) / i8k::I8_BLOCK_K);
+    p.rsum = (const int32_t*)rsum; p.csum = (const int32_t*)csum; p.bias = (const int32_t*)bias;
+    p.zx = zx; p.zw = zw; p.zy = zy; p.kzz = (int)(K * zx * zw); p.requant = sx * sw / sy;
+    p.C = (uint8_t*)C; p.ldc = N;
+    return launch_i8(ma, mb, p, (cudaStream_t)stream);
+}
+
+// y[Ho,Wo,Cout] (uint8): xp = the zero-point-padded NHWC image [Hp,Wp,Cin] with its per-pixel channel sums psum (osb_pad_sum_u8), w = OHWI
+extern "C" int osb_qu8_tc_conv(const void* xp, const void* psum, const void* w, const void* bias, const void* csum, void* y, int64_t Hp, int64_t Wp, int64_t Cin, int64_t Cout,
+                               int kh, int kw, int stride, int64_t Ho, int64_t Wo, int zx, float sx, int zw, float sw, int zy, float sy, void* stream)
+{
+    const uint32_t bw = std::min<uint32_t>(128, next_pow2((uint32_t)Wo)), bh = 128 / bw;
+    CUtensorMap ma, mb;
+    const int64_t Ktot = (int64_t)kh * kw * Cin;
+    const int bn = Cout <= 64 ? 64 : 128;
+    if (!make_map(&ma, xp, (uint64_t)Cin, (uint64_t)Wp, (uint64_t)Hp, (uint64_t)Cin, (uint64_t)Wp * Cin, i8k::I8_BLOCK_K, bw * stride, bh * stride, (uint32_t)stride, CU_TENSOR_MAP_DATA_TYPE_UINT8))
+        return (int)cudaErrorInvalidValue;
+    if (!make_map(&mb, w, (uint64_t)Ktot, (uint64_t)Cout, 1, (uint64_t)Ktot, (uint64_t)Ktot * Cout, i8k::I8_BLOCK_K, (uint32_t)bn, 1, 1, CU_TENSOR_MAP_DATA_TYPE_UINT8)) return (int)cudaErrorInvalidValue;
+    i8k::I8Params p{};
+    p.bn = bn;
+    p.M = (int)(Ho * Wo); p.N = (int)Cout; p.K = (int)Cin;
+    p.tiles_x = (int)((Wo + bw - 1) / bw);
+    p.m_tiles = p.tiles_x * (int)((Ho + bh - 1) / bh);
+    p.n_tiles = (int)((Cout + bn - 1) / bn);
+    p.b_kmajor = 1;
+    p.taps = kh * kw; p.kw = kw; p.Wo = (int)Wo; p.Ho = (int)Ho; p.bw = (int)bw; p.bh = (int)bh; p.stride = stride; p.Wp = (int)Wp;
+    p.k_blocks_per_tap = (int)((Cin + i8k::I8_BLOCK_K - 1) / i8k::I8_BLOCK_K);
+    p.rsum = (const int32_t*)psum; p.csum = (const int32_t*)csum; p.bias = (const int32_t*)bias;
+    p.zx = zx; p.zw = zw; p.zy = zy; p.kzz = (int)(Ktot * zx * zw); p.requant = sx * sw / sy;
+    p.C = (uint8_t*)y; p.ldc = Cout;
+    return launch_i8(ma, mb, p, (cudaStream_t)stream);
 }
 
 bool osb_tc_gemm_ok(int64_t M, int64_t N, int64_t K, int bt, const void* A, const void* B, const void* C, int64_t sa, int64_t sb, int64_t sc,

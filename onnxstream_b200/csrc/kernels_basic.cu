@@ -197,6 +197,68 @@ __global__ void binary_generic_kernel(int op, const T* __restrict__ a, const T* 
     }
 }
 
+
+// XNNPACK qu8 elementwise add / multiply (xnn_run_binary_elementwise_nd with xnn_datatype_quint8, called at src/onnxstream.cpp:846-927
+// and 1666-1746), restated and pinned bit-exact against the reference run (tests/test_cpu.py):
+//   add: fixed point.  shift = 20 - exponent(max(|sa/so|, |sb/so|)); multipliers = lrintf(|s/so| * 2^shift);
+//        acc = 2^(shift-1) - ma*za - mb*zb + a*ma + b*mb;  y = clamp(acc >> shift, -zo, 255 - zo) + zo
+//   mul: acc = (a - za)(b - zb);  y = lrintf(clamp(acc * (sa*sb/so), -zo, 255 - zo)) + zo
+struct Qu8BinParams { int op; int za, zb, zo; int ma, mb, shift, bias; float mul_scale; };
+
+__global__ void binary_qu8_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint8_t* __restrict__ out, BinParams p, size_t n, Qu8BinParams q)
+{
+    osb_pdl_prologue();
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        size_t rem = i;
+        int64_t ao = 0, bo = 0;
+#pragma unroll
+        for (int d = OSB_MAX_DIMS - 1; d >= 0; d--) {
+            if (d < p.ndim) {
+                int64_t idx = rem % p.shape[d];
+                rem /= p.shape[d];
+                ao += idx * p.as[d];
+                bo += idx * p.bs[d];
+            }
+        }
+        const int va = a[ao], vb = b[bo];
+        int y;
+        if (q.op == OSB_BIN_ADD) {
+            int acc = q.bias + va * q.ma + vb * q.mb;
+            y = acc >> q.shift;                                   // arithmetic shift (math_asr_s32)
+            y = max(y, 0 - q.zo); y = min(y, 255 - q.zo);
+        } else {
+            float f = (float)((va - q.za) * (vb - q.zb)) * q.mul_scale;
+            f = fminf(fmaxf(f, (float)(0 - q.zo)), (float)(255 - q.zo));
+            y = (int)rintf(f);
+        }
+        out[i] = (uint8_t)(y + q.zo);
+    }
+}
+
+// qu8 softmax restated as plain arithmetic (dequantise with zero point 0, float softmax, requantise; XNNPACK's LUT rounding is not reproduced): the
+// reference calls xnn_*_softmax_nc_qu8 (src/onnxstream.cpp:1958-2051) with output scale 2^-8 and zero point 0 (5971-5972).
+__global__ void softmax_qu8_kernel(const uint8_t* __restrict__ x, uint8_t* __restrict__ y, int64_t rows, int64_t cols, float in_scale, float out_scale, int out_zp)
+{
+    osb_pdl_prologue();
+    __shared__ float red[32];
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        const uint8_t* xr = x + r * cols; uint8_t* yr = y + r * cols;
+        float m = -INFINITY;
+        for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) m = fmaxf(m, (float)xr[c] * in_scale);
+        m = block_reduce_max(m, red);
+        float s = 0.f;
+        for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) s += expf((float)xr[c] * in_scale - m);
+        s = block_reduce_sum(s, red);
+        const float inv = 1.0f / s;
+        for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) {
+            float v = expf((float)xr[c] * in_scale - m) * inv;
+            long q = lrintf(v / out_scale) + out_zp;
+            yr[c] = (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // strided copy
 // ------------------------------------------------------------------------------------------------------------
@@ -1221,6 +1283,42 @@ float osb_percentile_key_to_float(unsigned key, int dtype)
     unsigned u = (key & 0x80000000u) ? (key & 0x7FFFFFFFu) : ~key;
     float f; memcpy(&f, &u, 4);
     return f;
+}
+
+int osb_binary_qu8(int op, const void* a, const int64_t* as, float sa, int za, const void* b, const int64_t* bs, float sb, int zb,
+                   void* out, float so, int zo, const int64_t* shape, int ndim, void* stream)
+{
+    if (ndim < 1 || ndim > OSB_MAX_DIMS || (op != OSB_BIN_ADD && op != OSB_BIN_MUL)) return (int)cudaErrorInvalidValue;
+    size_t n = 1;
+    BinParams p; p.ndim = ndim;
+    for (int d = 0; d < OSB_MAX_DIMS; d++) { p.shape[d] = d < ndim ? shape[d] : 1; p.as[d] = d < ndim ? as[d] : 0; p.bs[d] = d < ndim ? bs[d] : 0; if (d < ndim) n *= (size_t)shape[d]; }
+    if (n == 0) return 0;
+    Qu8BinParams q{};
+    q.op = op; q.za = za; q.zb = zb; q.zo = zo;
+    if (op == OSB_BIN_ADD) {
+        // xnn_init_qu8_add_minmax_*_params
+        const float ao = sa / so, bo = sb / so;
+        const float mx = fmaxf(fabsf(ao), fabsf(bo));
+        uint32_t mbits; memcpy(&mbits, &mx, 4);
+        const int32_t expo = (int32_t)(mbits >> 23) - 127;
+        const uint32_t shift = (uint32_t)(20 - expo);
+        if (shift < 1 || shift > 31) return (int)cudaErrorInvalidValue;
+        auto mult = [&](float v) { float av = fabsf(v); uint32_t bits; memcpy(&bits, &av, 4); bits += shift << 23; float f; memcpy(&f, &bits, 4); int32_t m = (int32_t)lrintf(f); return v < 0 ? -m : m; };
+        q.ma = mult(ao); q.mb = mult(bo); q.shift = (int)shift;
+        q.bias = (int)((1u << (shift - 1)) - (uint32_t)(q.ma * za) - (uint32_t)(q.mb * zb));
+    } else {
+        q.mul_scale = sa * sb / so;
+    }
+    osb_launch((binary_qu8_kernel), grid_for(n, 256), 256, 0, (cudaStream_t)stream, (const uint8_t*)a, (const uint8_t*)b, (uint8_t*)out, p, n, q);
+    return launched();
+}
+
+int osb_softmax_qu8(const void* x, void* y, int64_t rows, int64_t cols, float in_scale, float out_scale, int out_zp, void* stream)
+{
+    if (rows * cols == 0) return 0;
+    int threads = cols >= 1024 ? 256 : (cols >= 256 ? 128 : 32);
+    osb_launch((softmax_qu8_kernel), (unsigned)min<int64_t>(rows, 148 * 16), threads, 0, (cudaStream_t)stream, (const uint8_t*)x, (uint8_t*)y, rows, cols, in_scale, out_scale, out_zp);
+    return launched();
 }
 
 int osb_gather_rows(const void* table, const int64_t* idx, void* out, int64_t n_idx, int64_t table_rows, int64_t row_bytes, void* stream)

@@ -269,6 +269,77 @@ gemv_panel_kernel(const T* __restrict__ A, const T* __restrict__ B, float* __res
     if (threadIdx.x == 0) counters[blockIdx.x] = 0;
 }
 
+// The same panel GEMV with uint8 weights [K, N] (per-tensor scale / zero point), M <= 2: 16 columns per thread per 16-byte load, the
+// weight dequantised in registers to the activation type T -- (q - zp) * scale ROUNDED TO T, i.e. exactly the operand the reference
+// builds when it converts a uint8 blob at load time (src/onnxstream.cpp:2885-2890) -- then fp32 FMA.  Half (fp16) / a quarter (fp32) of
+// the HBM bytes of the float GEMV: LLM decode is weight-bandwidth bound.
+template <typename T>
+__global__ void __launch_bounds__(128)
+gemv_w8_panel_kernel(const T* __restrict__ A, const uint8_t* __restrict__ B, float* __restrict__ acc_out, int M, int N, int K, int k_per_cta,
+                     int* __restrict__ counters, T* __restrict__ C, const T* __restrict__ bias, const T* __restrict__ residual, float wscale, int wzp)
+{
+    osb_pdl_prologue();
+    constexpr int VEC = 16, COLS = 32 * VEC, MAXM = 2;
+    __shared__ float red[4][MAXM][COLS];
+    const int cg = threadIdx.x & 31, kl = threadIdx.x >> 5;
+    const int n0 = blockIdx.x * COLS + cg * VEC;
+    const int k_lo = blockIdx.y * k_per_cta, k_hi = min(k_lo + k_per_cta, K);
+    float acc[MAXM][VEC];
+#pragma unroll
+    for (int m = 0; m < MAXM; m++)
+#pragma unroll
+        for (int v = 0; v < VEC; v++) acc[m][v] = 0.f;
+    if (n0 < N) {
+        for (int k = k_lo + kl; k < k_hi; k += 4) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(B + (int64_t)k * N + n0);
+            const uint32_t words[4] = { raw.x, raw.y, raw.z, raw.w };
+            float w[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; v++) w[v] = to_float(from_float<T>((float)((int)((words[v >> 2] >> (8 * (v & 3))) & 0xFFu) - wzp) * wscale));
+#pragma unroll
+            for (int m = 0; m < MAXM; m++) {
+                if (m < M) {
+                    const float a = to_float(A[(int64_t)m * K + k]);
+#pragma unroll
+                    for (int v = 0; v < VEC; v++) acc[m][v] += a * w[v];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < MAXM; m++)
+#pragma unroll
+        for (int v = 0; v < VEC; v++) red[kl][m][cg * VEC + v] = acc[m][v];
+    __syncthreads();
+    for (int i = threadIdx.x; i < M * COLS; i += 128) {
+        int m = i / COLS, c = i % COLS;
+        int n = blockIdx.x * COLS + c;
+        if (n >= N) continue;
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) v += red[j][m][c];
+        atomicAdd(&acc_out[(int64_t)m * N + n], v);
+    }
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(&counters[blockIdx.x], 1) == (int)gridDim.y - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < M * COLS; i += 128) {
+        int m = i / COLS, c = i % COLS;
+        int n = blockIdx.x * COLS + c;
+        if (n >= N) continue;
+        float v = __ldcg(&acc_out[(int64_t)m * N + n]);
+        acc_out[(int64_t)m * N + n] = 0.f;
+        if (bias) v += to_float(bias[n]);
+        if (residual) v += to_float(residual[(int64_t)m * N + n]);
+        C[(int64_t)m * N + n] = from_float<T>(v);
+    }
+    if (threadIdx.x == 0) counters[blockIdx.x] = 0;
+}
+
 // ---- softmax with scale + additive mask (score tile of the attention decomposition) ---------------------------
 template <typename T>
 __global__ void softmax_scaled_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int64_t cols, float scale,
@@ -499,6 +570,26 @@ int osb_gemm_ld(const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
     }
     if (dtype == OSB_F16) return launch_igemm<__half>((const __half*)A, (const __half*)B, (__half*)C, bias, (const __half*)residual, batch, M, N, K, sa, sb, sc, bt, false, g, st, lda, ldb, ldc);
     return launch_igemm<float>((const float*)A, (const float*)B, (float*)C, bias, (const float*)residual, batch, M, N, K, sa, sb, sc, bt, false, g, st, lda, ldb, ldc);
+}
+
+// y[M,N] = x[M,K] . dequant(Wq[K,N]) (+ bias, + residual), M <= 2, uint8 weights dequantised in registers (see gemv_w8_panel_kernel)
+int osb_gemv_w8(const void* A, const void* Wq, void* C, const void* bias, const void* residual, int64_t M, int64_t N, int64_t K, float wscale, int wzp, int dtype, void* stream)
+{
+    if (M < 1 || M > 2 || (N % 16) || N < 16 || K < 1 || (dtype != OSB_F16 && dtype != OSB_F32) || !aligned16(Wq)) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int cols = 512;
+    const int gx = (int)((N + cols - 1) / cols);
+    OsbWorkspace* ws = (gx <= 4096 && (size_t)M * N <= OSB_WS_GEMV_FLOATS) ? osb_workspace(st, OSB_WS_GEMV) : nullptr;
+    if (!ws) return (int)cudaErrorNotReady;
+    int gy = (int)max<int64_t>(1, min<int64_t>((K + 15) / 16, (592 + gx - 1) / gx));
+    int k_per = (int)((K + gy - 1) / gy);
+    gy = (int)((K + k_per - 1) / k_per);
+    dim3 grid(gx, gy);
+    if (dtype == OSB_F16) osb_launch((gemv_w8_panel_kernel<__half>), grid, 128, 0, st, (const __half*)A, (const uint8_t*)Wq, ws->gemv, (int)M, (int)N, (int)K, k_per, ws->gemv_counters,
+                                     (__half*)C, (const __half*)bias, (const __half*)residual, wscale, wzp);
+    else osb_launch((gemv_w8_panel_kernel<float>), grid, 128, 0, st, (const float*)A, (const uint8_t*)Wq, ws->gemv, (int)M, (int)N, (int)K, k_per, ws->gemv_counters,
+                    (float*)C, (const float*)bias, (const float*)residual, wscale, wzp);
+    return launched();
 }
 
 int osb_conv2d(const void* x, const void* w, const void* bias, const void* residual, void* y, int64_t H, int64_t W, int64_t Cin, int64_t Cout,

@@ -286,3 +286,87 @@ class NumpyOracle:
                     y = np.maximum(y, xp[:, ky:ky + st * (ho - 1) + 1:st, kx:kx + st * (wo - 1) + 1:st])
             return y[None]
         raise NotImplementedError(t)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# uint8 path (m_use_uint8_qdq / m_use_uint8_arithmetic): restated from the reference and pinned BIT-EXACT against the reference run
+# (tests/test_cpu.py::test_qu8_restatement_bit_exact) -- the XNNPACK kernels behind these calls are the real library in oracle/_ref.
+# ---------------------------------------------------------------------------------------------------------------------
+def qu8_percentiles(x, threads=4, from_left=0.001, from_right=0.001):
+    """Model::get_percentiles (src/onnxstream.cpp:3104-3232) + FloatAsUInt::get_percentiles (2302-2386): the flat tensor is split over
+    `threads` pool workers (get_start_and_end, 3091-3102), each span walked in 64 KiB chunks; per chunk the k-th smallest / largest
+    finite value with k = (size_t)(n * 0.001f); min of the lows, max of the highs.  None when no chunk has a result."""
+    flat = np.asarray(x).ravel()
+    size = flat.size
+    chunk = 16384 if flat.dtype == np.float32 else 32768
+    n = size // threads or 1
+    lo, hi, found = np.inf, -np.inf, False
+    for i in range(threads):
+        st, en = i * n, (size if i >= threads - 1 else (i + 1) * n)
+        if st >= en or st >= size:
+            continue
+        for j in range(st, en, chunk):
+            nn = min(en, j + chunk) - j
+            c = np.sort(flat[j:j + nn].astype(np.float32))
+            c = c[np.isfinite(c)]
+            kl, kr = int(np.float32(nn) * np.float32(from_left)), int(np.float32(nn) * np.float32(from_right))
+            if kl >= len(c) or kr >= len(c):
+                continue
+            lo, hi, found = min(lo, c[kl]), max(hi, c[len(c) - 1 - kr]), True
+    return (np.float32(lo), np.float32(hi)) if found and lo < hi else None
+
+
+def qu8_range_to_scale(lo, hi):
+    """Model::range_to_scale (src/onnxstream.cpp:3234-3245)."""
+    lo, hi = np.float32(lo), np.float32(hi)
+    if lo > 0 and hi > 0:
+        lo = np.float32(0)
+    elif lo < 0 and hi < 0:
+        hi = np.float32(0)
+    scale = np.float32(np.float64(np.float32(hi - lo)) / 255.0)
+    return scale, int(np.uint8(np.float32(abs(lo)) / scale))
+
+
+def qu8_quantize(x, scale, zp):
+    """xnn_run_convert_nc_f32_qu8: x * (1 / scale), clamp to [0 - zp, 255 - zp], round to nearest even, + zp."""
+    q = np.asarray(x, np.float32) * np.float32(np.float32(1.0) / scale)
+    q = np.clip(q, np.float32(0 - zp), np.float32(255 - zp))
+    return (np.rint(q).astype(np.int32) + zp).astype(np.uint8)
+
+
+def qu8_dequantize(q, scale, zp):
+    return ((q.astype(np.int32) - zp).astype(np.float32) * np.float32(scale)).astype(np.float32)
+
+
+def qu8_add(qa, sa, za, qb, sb, zb, so, zo):
+    """XNNPACK qu8 vadd (fixed point): shift = 20 - exponent(max(|sa/so|, |sb/so|)); multipliers = lrintf(|s/so| * 2^shift)."""
+    ao, bo = np.float32(sa / so), np.float32(sb / so)
+    mx = np.float32(max(abs(ao), abs(bo)))
+    shift = int(20 - ((int(mx.view(np.uint32)) >> 23) - 127))
+
+    def mult(v):
+        bits = np.uint32(int(np.float32(abs(v)).view(np.uint32)) + (shift << 23))
+        m = int(np.rint(bits.view(np.float32)))
+        return -m if v < 0 else m
+    am, bm = mult(ao), mult(bo)
+    acc = ((1 << (shift - 1)) - am * za - bm * zb) + qa.astype(np.int64) * am + qb.astype(np.int64) * bm
+    return (np.clip(acc >> shift, 0 - zo, 255 - zo) + zo).astype(np.uint8)
+
+
+def qu8_mul(qa, sa, za, qb, sb, zb, so, zo):
+    """XNNPACK qu8 vmul (fp32 requantisation)."""
+    scale = np.float32(np.float32(sa * sb) / so)
+    f = ((qa.astype(np.int32) - za) * (qb.astype(np.int32) - zb)).astype(np.float32) * scale
+    f = np.clip(f, np.float32(0 - zo), np.float32(255 - zo))
+    return (np.rint(f).astype(np.int32) + zo).astype(np.uint8)
+
+
+def qu8_gemm(qa, sa, za, qw, sw, zw, so, zo, bias_i32=None):
+    """XNNPACK qu8 fully-connected / convolution arithmetic on an im2col'd problem: int32 accumulate, fp32 requantisation."""
+    acc = (qa.astype(np.int64) - za) @ (qw.astype(np.int64) - zw)
+    if bias_i32 is not None:
+        acc = acc + bias_i32
+    scale = np.float32(np.float32(np.float32(sa) * np.float32(sw)) / np.float32(so))
+    f = acc.astype(np.int32).astype(np.float32) * scale
+    f = np.clip(f, np.float32(0 - zo), np.float32(255 - zo))
+    return (np.rint(f).astype(np.int32) + zo).astype(np.uint8)

@@ -366,3 +366,40 @@ def test_multi_rank_host_logic_gloo():
     assert res[0][1] == res[1][1] == bytes(range(128))
     assert res[0][2] != res[1][2]                       # rank r gets sample seed + r
     assert res[0][3] == res[1][3] == pytest.approx(2 * 10 / 2.0)   # aggregate = world * steps / max(seconds)
+
+
+def test_qu8_restatement_bit_exact(oracle_lib, tmp_path):
+    """Pins oracle/np_oracle.py's uint8 restatement (percentile quantisation of the inputs, XNNPACK qu8 add / multiply / fully-connected,
+    dequantisation) BIT-EXACT to the reference run: m_use_uint8_arithmetic on a graph of Add, Mul and MatMul with m_range_data.  The
+    XNNPACK kernels behind these ops in oracle/_ref are the real library (not the shim)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import np_oracle as npo
+    from onnxstream_b200 import emit
+    d = str(tmp_path) + "/"
+    g = emit.GraphBuilder(d, "uint8", seed=21)
+    a_t, b_t = g.input("a", (1, 40, 48)), g.input("b", (1, 40, 48))
+    s_t = g.node("Add", [a_t, b_t], [(1, 40, 48)], name="addop")
+    p_t = g.node("Mul", [a_t, b_t], [(1, 40, 48)], name="mulop")
+    y_t = g.linear(s_t, 32, bias=False, name="fcop")
+    g.mark_output(p_t); g.mark_output(y_t)
+    g.finish()
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal((1, 40, 48)).astype(np.float32)
+    b = (rng.standard_normal((1, 40, 48)) * 2 + 0.5).astype(np.float32)
+    ranges = {"addop": (-5.0, 6.0), "mulop": (-8.0, 9.0), "fcop": (-7.0, 7.5)}
+    out, _ = run_model(oracle_lib, d, {"a": a, "b": b}, ("use_uint8_arithmetic",), ranges=ranges, extra_outputs=[s_t.name])
+    sa, za = npo.qu8_range_to_scale(*npo.qu8_percentiles(a, 4))
+    sb, zb = npo.qu8_range_to_scale(*npo.qu8_percentiles(b, 4))
+    qa, qb = npo.qu8_quantize(a, sa, za), npo.qu8_quantize(b, sb, zb)
+    so, zo = npo.qu8_range_to_scale(*ranges["addop"]); sm, zm = npo.qu8_range_to_scale(*ranges["mulop"]); sf, zf = npo.qu8_range_to_scale(*ranges["fcop"])
+    qs = npo.qu8_add(qa, sa, za, qb, sb, zb, so, zo)
+    assert np.array_equal(npo.qu8_dequantize(qs, so, zo), out[s_t.name])
+    assert np.array_equal(npo.qu8_dequantize(npo.qu8_mul(qa, sa, za, qb, sb, zb, sm, zm), sm, zm), out[p_t.name])
+    import re
+    line = [l for l in open(d + "model.txt").read().splitlines() if l.startswith("fcop:")][0]
+    m = re.search(r"(\w+\.bin)\(uint8\[([^,]+),(\d+)\]:48,32\)", line)
+    qw = np.fromfile(d + m.group(1), np.uint8).reshape(48, 32)
+    sw, zw = np.float32(float(m.group(2))), int(m.group(3))
+    qy = npo.qu8_gemm(qs.reshape(40, 48), so, zo, qw, sw, zw, sf, zf)
+    assert np.array_equal(npo.qu8_dequantize(qy, sf, zf).reshape(1, 40, 32), out[y_t.name])

@@ -327,6 +327,105 @@ def test_qu8_gemm_and_conv_bit_exact(K):
     assert np.array_equal(ty.cpu().numpy(), ref)
 
 
+def test_gemv_w8_in_register_dequant(K):
+    """uint8-weight decode GEMV: identical operands to 'dequantise the blob to fp16, then GEMV' (the reference's load-time conversion)."""
+    import torch
+    vp, i64, ci, cf = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
+    K.osb_gemv_w8.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, cf, ci, ci, vp]
+    for (M, N, Kd) in [(1, 2048, 2048), (1, 5632, 2048), (2, 2048, 5632), (1, 32016, 2048)]:
+        g = torch.Generator(device="cuda").manual_seed(N)
+        a = torch.randn(M, Kd, device="cuda", generator=g).half()
+        wq = torch.randint(0, 256, (Kd, N), device="cuda", generator=g, dtype=torch.uint8)
+        scale, zp = 0.0037, 131
+        res = torch.randn(M, N, device="cuda", generator=g).half()
+        c = torch.empty(M, N, device="cuda", dtype=torch.half)
+        assert K.osb_gemv_w8(a.data_ptr(), wq.data_ptr(), c.data_ptr(), None, res.data_ptr(), M, N, Kd, scale, zp, F16, _stream()) == 0
+        torch.cuda.synchronize()
+        wd = ((wq.int() - zp).float() * np.float32(scale)).half().double()
+        ref = a.double() @ wd + res.double()
+        absref = a.double().abs() @ wd.abs() + res.double().abs()
+        _check(c, ref, absref, f"gemv_w8 {M}x{N}x{Kd}")
+
+
+QU8_TC_GEMM = [(200, 144, 320, 0), (200, 144, 320, 1), (4096, 320, 320, 0), (1024, 1280, 640, 0), (77, 64, 768, 0), (512, 5120, 640, 1), (300, 48, 1040, 0)]
+
+
+@pytest.mark.parametrize("M,N,Kd,bt", QU8_TC_GEMM)
+def test_qu8_tensor_core_gemm_bit_exact(K, M, N, Kd, bt):
+    """tcgen05.mma.kind::i8 on raw uint8 bytes + zero-point terms from row / column sums + XNNPACK's fp32 requantisation: bit-exact
+    against the integer restatement (the one tests/test_cpu.py and the model-level chain test pin to the reference's XNNPACK run).
+    Both weight layouts: [K,N] (ONNX MatMul, MN-major B operand) and [N,K]."""
+    import torch
+    vp, i64, ci, cf = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
+    K.osb_qu8_tc_gemm.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, ci, ci, cf, ci, cf, ci, cf, vp]
+    K.osb_qu8_tc_gemm_ok.argtypes = [i64, i64, i64, vp, vp, vp]
+    K.osb_rowsum_u8.argtypes = [vp, vp, i64, i64, vp]; K.osb_colsum_u8.argtypes = [vp, vp, i64, i64, vp]
+    rng = np.random.default_rng(M + N)
+    zx, sx, zw, sw, zy, sy = 121, 0.031, 134, 0.0035, 117, 0.09
+    a = rng.integers(0, 256, (M, Kd), dtype=np.uint8)
+    b = rng.integers(0, 256, (N, Kd) if bt else (Kd, N), dtype=np.uint8)
+    bias = rng.integers(-2000, 2000, (N,), dtype=np.int32)
+    bm = b.T if bt else b
+    acc = (a.astype(np.int64) - zx) @ (bm.astype(np.int64) - zw) + bias
+    scale = np.float32(np.float32(np.float32(sx) * np.float32(sw)) / np.float32(sy))
+    f = (acc.astype(np.int32).astype(np.float32) * scale).astype(np.float32)
+    f = np.minimum(np.maximum(f, np.float32(0 - zy)), np.float32(255 - zy))
+    ref = (np.rint(f).astype(np.int32) + zy).astype(np.uint8)
+    ta, tb, tbias = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), torch.from_numpy(bias).cuda()
+    tc = torch.zeros((M, N), dtype=torch.uint8, device="cuda")
+    assert K.osb_qu8_tc_gemm_ok(M, N, Kd, ta.data_ptr(), tb.data_ptr(), tc.data_ptr()) == 1
+    rs = torch.zeros(M, dtype=torch.int32, device="cuda"); cs = torch.zeros(N, dtype=torch.int32, device="cuda")
+    assert K.osb_rowsum_u8(ta.data_ptr(), rs.data_ptr(), M, Kd, _stream()) == 0
+    if bt:
+        assert K.osb_rowsum_u8(tb.data_ptr(), cs.data_ptr(), N, Kd, _stream()) == 0
+    else:
+        assert K.osb_colsum_u8(tb.data_ptr(), cs.data_ptr(), Kd, N, _stream()) == 0
+    assert K.osb_qu8_tc_gemm(ta.data_ptr(), tb.data_ptr(), tc.data_ptr(), tbias.data_ptr(), rs.data_ptr(), cs.data_ptr(), M, N, Kd, bt, zx, sx, zw, sw, zy, sy, _stream()) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(rs.cpu().numpy(), a.astype(np.int64).sum(1))
+    assert np.array_equal(cs.cpu().numpy(), bm.astype(np.int64).sum(0))
+    got = tc.cpu().numpy()
+    assert np.array_equal(got, ref), f"{int((got != ref).sum())} of {ref.size} bytes differ"
+
+
+@pytest.mark.parametrize("H,W,Cin,Cout,k,s", [(12, 12, 32, 48, 3, 1), (64, 64, 320, 320, 3, 1), (32, 32, 640, 320, 1, 1), (33, 20, 64, 64, 3, 2), (16, 16, 1280, 1280, 3, 1)])
+def test_qu8_tensor_core_conv_bit_exact(K, H, W, Cin, Cout, k, s):
+    """kind::i8 implicit-GEMM conv on the zero-point-padded image (XNNPACK pads with the input zero point), bit-exact."""
+    import torch
+    vp, i64, ci, cf = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
+    K.osb_qu8_tc_conv.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, ci, i64, i64, ci, cf, ci, cf, ci, cf, vp]
+    K.osb_pad_sum_u8.argtypes = [vp, vp, vp, i64, i64, i64, i64, i64, ci, ci, ci, vp]
+    K.osb_rowsum_u8.argtypes = [vp, vp, i64, i64, vp]
+    rng = np.random.default_rng(H + Cin)
+    zx, sx, zw, sw, zy, sy = 119, 0.027, 131, 0.0041, 120, 0.11 * (Cin / 64) ** 0.5
+    pad = k // 2
+    Ho, Wo = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1
+    Hp, Wp = (Ho - 1) * s + k, (Wo - 1) * s + k
+    x = rng.integers(0, 256, (H, W, Cin), dtype=np.uint8); w = rng.integers(0, 256, (Cout, k, k, Cin), dtype=np.uint8)
+    bias = rng.integers(-3000, 3000, (Cout,), dtype=np.int32)
+    xp = np.full((Hp, Wp, Cin), zx, np.int64); xp[pad:pad + H, pad:pad + W] = x
+    acc = np.zeros((Ho, Wo, Cout), np.int64)
+    for ky in range(k):
+        for kx in range(k):
+            acc += (xp[ky:ky + (Ho - 1) * s + 1:s, kx:kx + (Wo - 1) * s + 1:s] - zx) @ (w[:, ky, kx].astype(np.int64) - zw).T
+    acc = acc + bias
+    scale = np.float32(np.float32(np.float32(sx) * np.float32(sw)) / np.float32(sy))
+    f = (acc.astype(np.int32).astype(np.float32) * scale).astype(np.float32)
+    f = np.minimum(np.maximum(f, np.float32(0 - zy)), np.float32(255 - zy))
+    ref = (np.rint(f).astype(np.int32) + zy).astype(np.uint8)
+    tx, tw, tbias = torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda(), torch.from_numpy(bias).cuda()
+    txp = torch.zeros((Hp, Wp, Cin), dtype=torch.uint8, device="cuda"); tps = torch.zeros(Hp * Wp, dtype=torch.int32, device="cuda")
+    tcs = torch.zeros(Cout, dtype=torch.int32, device="cuda"); ty = torch.zeros((Ho, Wo, Cout), dtype=torch.uint8, device="cuda")
+    assert K.osb_pad_sum_u8(tx.data_ptr(), txp.data_ptr(), tps.data_ptr(), H, W, Cin, Hp, Wp, pad, pad, zx, _stream()) == 0
+    assert K.osb_rowsum_u8(tw.data_ptr(), tcs.data_ptr(), Cout, k * k * Cin, _stream()) == 0
+    assert K.osb_qu8_tc_conv(txp.data_ptr(), tps.data_ptr(), tw.data_ptr(), tbias.data_ptr(), tcs.data_ptr(), ty.data_ptr(), Hp, Wp, Cin, Cout, k, k, s, Ho, Wo,
+                             zx, sx, zw, sw, zy, sy, _stream()) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(txp.cpu().numpy(), xp.astype(np.uint8))
+    got = ty.cpu().numpy()
+    assert np.array_equal(got, ref), f"{int((got != ref).sum())} of {ref.size} bytes differ"
+
+
 @pytest.mark.parametrize("impl", [1, 0])
 @pytest.mark.parametrize("T,Tk,h,d", [(256, 256, 4, 40), (192, 77, 8, 40), (64, 64, 2, 160)])
 def test_gemm_head_views(K, impl, T, Tk, h, d):

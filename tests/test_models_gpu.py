@@ -215,6 +215,49 @@ def test_uint8_qdq_mode(engine_lib, oracle_lib, models32):
         assert e_got["rms"] <= 2.0 * e_ref["rms"] + 0.02 * e_got["ref_rms"], (arch, e_got, e_ref)
 
 
+def _qu8_chain(d):
+    """A graph whose every node has a uint8 kernel in the reference under m_use_uint8_arithmetic: Conv 3x3 -> Conv 1x1 -> Add -> Mul ->
+    Reshape/Transpose -> MatMul.  Inputs are percentile-quantised at push (plain NCHW on both sides: identical chunks), every op
+    output takes its scale from m_range_data: the whole chain is integer arithmetic."""
+    g = emit.GraphBuilder(d, "uint8", seed=11)
+    x = g.input("x", (1, 16, 12, 12))
+    z = g.input("z", (1, 32, 12, 12))
+    c1 = g.conv(x, 32, 3, name="c1")
+    c2 = g.conv(c1, 32, 1, name="c2")
+    a = g.node("Add", [c2, z], [c2.shape], name="add1")
+    m = g.node("Mul", [a, c1], [a.shape], name="mul1")
+    r = g.node("Reshape", [m, g.i64([1, 32, 144])], [(1, 32, 144)])
+    t = g.node("Transpose", [r], [(1, 144, 32)], [("perm", "0,2,1")])
+    y = g.linear(t, 32, bias=False, name="fc1")
+    g.mark_output(y)
+    g.finish()
+    ranges = {"c1": (-2.5, 2.5), "c2": (-2.0, 2.2), "add1": (-4.0, 4.5), "mul1": (-6.0, 7.0), "fc1": (-9.0, 9.5)}
+    rng = np.random.default_rng(12)
+    inputs = {"x": rng.standard_normal((1, 16, 12, 12)).astype(np.float32), "z": (rng.standard_normal((1, 32, 12, 12)) * 1.5 + 0.3).astype(np.float32)}
+    return y.name, ranges, inputs
+
+
+def test_uint8_arithmetic_chain_bit_exact(engine_lib, oracle_lib, workdir):
+    """m_use_uint8_arithmetic end to end, BIT-EXACT against the reference: XNNPACK's real qu8 convolution / fully-connected / add /
+    multiply kernels in oracle/_ref vs the engine's uint8 kernels (u8 x u8 -> s32, zero-point handling, fp32 requantisation
+    clamp(lrintf(acc * sx*sw/sy)) + zy; fixed-point add), percentile quantisation of the graph inputs included."""
+    d = os.path.join(workdir, "qu8chain") + "/"
+    out, ranges, inputs = _qu8_chain(d)
+    opts = ("use_uint8_arithmetic",)
+    extra = ["c1", "c2", "add1", "mul1"]
+    names = {}
+    for l in open(d + "model.txt").read().splitlines():
+        nm = l.split(":")[0]
+        if nm in extra:
+            names[nm] = l.split("*output:")[1].split("(")[0]
+    ref, _ = run_model(oracle_lib, d, inputs, opts, ranges=ranges, extra_outputs=list(names.values()))
+    got, m = run_model(engine_lib, d, inputs, opts, ranges=ranges, extra_outputs=list(names.values()))
+    for nm, tn in list(names.items()) + [("fc1", out)]:
+        assert got[tn].shape == ref[tn].shape, nm
+        bad = int((got[tn] != ref[tn]).sum())
+        assert bad == 0, f"{nm}: {bad} of {ref[tn].size} values differ from the reference (max {float(np.abs(got[tn] - ref[tn]).max()):.4g})"
+
+
 def test_force_fp16_storage(engine_lib, oracle_lib, models32):
     """m_force_fp16_storage (src/onnxstream.cpp:3764-3808): fp32 arithmetic, fp16 storage between ops."""
     d, inputs, out = models32["unet"]
@@ -245,8 +288,12 @@ def test_range_calibration(engine_lib, oracle_lib, models32):
     m.lib.model_ext_write_range_data.restype = __import__("ctypes").c_void_p
     assert not m.lib.model_ext_write_range_data(m.h, fn.encode())
     lines = [l for l in open(fn).read().splitlines() if l]
-    n_ops = len([l for l in open(d + "model.txt").read().splitlines() if l])
-    assert len(lines) >= 0.5 * n_ops, (len(lines), n_ops)
+    recorded = {l.split(",")[0]: (float(l.split(",")[1]), float(l.split(",")[2])) for l in lines}
+    convs = [l.split(":")[0] for l in open(d + "model.txt").read().splitlines() if ":Conv*" in l]
+    # every float-producing step leaves a range under the name of the op that pushed it (fused groups: their last op)
+    assert len(recorded) > 100, len(recorded)
+    assert all(lo < hi and np.isfinite(lo) and np.isfinite(hi) for lo, hi in recorded.values())
+    assert sum(1 for c in convs if c in recorded) >= len(convs) // 4, "no Conv output range was recorded"
 
 
 def test_errors_are_reported(engine_lib, workdir):
