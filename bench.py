@@ -387,7 +387,7 @@ def make_reference_model(d, w: Workload, model_file="model.txt"):
     return m
 
 
-def reference_output_cached(d, w: Workload, inputs):
+def reference_output_cached(d, w: Workload, inputs, allow_compute=True):
     """One FULL run of the reference on `inputs`, cached per box (shared with tests/test_fullsize_gpu.py's cache layout).
     Returns (output, seconds or None when served from the cache)."""
     h = hashlib.sha1()
@@ -399,6 +399,8 @@ def reference_output_cached(d, w: Workload, inputs):
     fn = os.path.join(REF_CACHE, h.hexdigest() + ".npy")
     if os.path.exists(fn):
         return np.load(fn), None
+    if not allow_compute:
+        raise RuntimeError("one full reference run of this graph takes minutes on the host cores: skipped here (this topology is checked at a smaller latent in tests/test_fullsize_gpu.py)")
     m = make_reference_model(d, w)
     t = time.time()
     out = step_api(m, inputs, w.out_name)
@@ -513,21 +515,28 @@ def measure(w: Workload, args, dist, clocks=None):
     has_i64 = any(v.dtype == np.int64 for v in inputs.values())
 
     # ---------------- value arm: weights + inputs resident in HBM ----------------
-    mv = make_engine_model(d, w, "ram+nocache", resident=True, graph=not has_i64)
+    mv = make_engine_model(d, w, "ram+nocache", resident=True, graph=True)
     for _ in range(3):      # run 1 fills the HBM weight cache, run 2 warms scratch, run 3 captures the graph
         out_v = step_api(mv, inputs, w.out_name)
+    later = w.later_inputs(inputs)
+    if len(later) != len(inputs):
+        for _ in range(3):  # fewer host inputs from now on (the rest stays in HBM): the graph is re-captured for that input set
+            step_api(mv, later, w.out_name)
     st_v = mv.stats()
     launches_per_step = int(st_v["kernel_launches"])
     if clocks is None:
         clocks = ClockSampler(); clocks.start()      # sampled from the warm-up through both timed regions (value and e2e)
-    if not has_i64:
+    graph_ok = True
+    try:
         mv.run_resident(args.warmup)
+    except Exception:
+        graph_ok = False
+    if graph_ok:
         dist_barrier(dist)
         gpu_ms = mv.run_resident(args.steps)
-        value_mode = "HBM-resident weights + inputs, one captured CUDA graph per step"
+        value_mode = "HBM-resident weights + inputs, one captured CUDA graph per step" + (" (int64 inputs through device mirrors)" if has_i64 else "")
     else:
-        # int64 graph inputs (token ids) keep shape arithmetic on the host: eager runs, CUDA-event time of each run's stream work
-        later = w.later_inputs(inputs)
+        # the graph reads int64 input VALUES on the host (shape arithmetic): eager runs, CUDA-event time of each run's stream work
         for _ in range(args.warmup):
             step_api(mv, later, None)
         dist_barrier(dist)
@@ -536,7 +545,7 @@ def measure(w: Workload, args, dist, clocks=None):
             step_api(mv, later, None)
             gpu_ms += mv.stats()["last_gpu_ms"]
         launches_per_step = int(mv.stats()["kernel_launches"])
-        value_mode = "HBM-resident weights and KV cache, eager launches (int64 inputs are host-evaluated), CUDA-event time per run incl. the upload of the token ids / mask"
+        value_mode = "HBM-resident weights, eager launches (int64 input values are read on the host), CUDA-event time per run incl. the input upload"
     dist_barrier(dist)
     gpu_ms = dist_max(dist, gpu_ms)
     ms_per_step = gpu_ms / args.steps
@@ -641,7 +650,7 @@ def measure(w: Workload, args, dist, clocks=None):
         in0 = w.inputs(0)
         if RANK == 0:
             try:
-                ref0, ref_s = reference_output_cached(d, w, in0)
+                ref0, ref_s = reference_output_cached(d, w, in0, allow_compute=meta["flops"] <= 2.5e12)
             except Exception as e:    # the checker must never take the bench down
                 ref0 = None
                 parity["oracle_error"] = str(e)

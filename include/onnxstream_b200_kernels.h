@@ -124,6 +124,11 @@ int osb_conv2d_ex(const void* x, const void* w, const void* bias, const void* bi
 int osb_conv2d_fusable(const void* x, const void* w, const void* y, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int kh, int kw, int stride, int dtype, int impl);
 /* GroupNorm(+SiLU) apply pass on an NHWC tensor whose statistics were gathered by the producing conv (osb_conv2d_ex): reads `stats`,
  * writes y = silu?((x - mean) * rstd * gamma + beta), and zeroes `clear_stats` (the buffer the NEXT producer will accumulate into). */
+/* RMSNorm y = w * x / sqrt(mean(x^2) + eps) over the last axis, fp32 arithmetic, any mix of fp16 / fp32 storage (the 7-op chain Pow,
+ * ReduceMean, Add, Sqrt, Div, Mul, Mul of llm.cpp's graphs; the reference keeps it in fp32 through m_requires_upcast, src/llm.cpp:385-389) */
+int osb_rms_norm(const void* x, int xd, const void* w, int wd, void* y, int yd, int64_t rows, int64_t cols, float eps, void* stream);
+/* rotary embedding, rotate_half form (Slice, Slice, Neg, Concat, Mul, Mul, Add): y = x * cos + rotate_half(x) * sin; cos / sin: 1 or `rows` rows of D */
+int osb_rope(const void* x, const void* cs, const void* sn, void* y, int dtype, int64_t rows, int64_t D, int64_t table_rows, void* stream);
 /* Decode GEMV with uint8 weights [K,N] dequantised in registers (M <= 2): y = x . ((Wq - zp) * scale rounded to `dtype`) + bias + residual.
  * The uint8-weight / float-arithmetic MatMul of the reference (weights converted at load, src/onnxstream.cpp:2885-2890) at half the HBM bytes. */
 int osb_gemv_w8(const void* A, const void* Wq, void* C, const void* bias, const void* residual, int64_t M, int64_t N, int64_t K, float wscale, int wzp, int dtype, void* stream);

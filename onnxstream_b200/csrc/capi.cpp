@@ -279,7 +279,7 @@ int model_b200_get_stats(ModelContext* obj, double* out, int n)
     double v[] = { (double)s.weight_ring_bytes, (double)s.weight_peak_live_bytes, (double)s.weight_largest_node_bytes,
                    (double)s.weight_bytes_streamed, (double)s.weight_resident_bytes, (double)s.act_high_water_bytes,
                    (double)s.h2d_input_bytes, (double)s.d2h_output_bytes, (double)s.kernel_launches, (double)s.tc_launches,
-                   (double)s.ops_executed, (double)s.ops_fused_away, s.last_run_ms, s.last_gpu_ms, (double)s.graph_replays };
+                   (double)s.ops_executed, (double)s.ops_fused_away, s.last_run_ms, s.last_gpu_ms, (double)s.graph_replays, (double)s.side_steps };
     int m = (int)(sizeof(v) / sizeof(v[0]));
     for (int i = 0; i < n && i < m; i++) out[i] = v[i];
     return m;

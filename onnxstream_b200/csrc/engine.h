@@ -73,6 +73,9 @@ struct Tensor {
     DevPtr dev;                       // device payload for u8 / f16 / f32
     const void* dev_raw = nullptr;    // non-owning device payload (weight ring / resident weight cache)
     std::shared_ptr<std::vector<int64_t>> i64;  // host payload for int64 tensors (shape arithmetic stays on the host)
+    DevPtr i64_dev;                   // device mirror of an int64 GRAPH INPUT (token ids, positions, masks): refreshed before every run / graph
+                                      // replay, read by the ops whose result depends on the VALUES (Gather indices, Cast to float)
+    bool tainted = false;             // int64 values that come from a graph input: reading them on the host bakes them into a captured graph
     std::shared_ptr<std::vector<float>> host_f32;  // host mirror of small float constants (scalars, Resize scales)
     float scale = 0.f;
     int zero_point = 0;
@@ -136,6 +139,7 @@ struct EngineStats {
     double last_run_ms = 0.0;            // wall time of the last run() on the host, including the final sync
     double last_gpu_ms = 0.0;            // CUDA-event time of the last run on the compute stream
     int graph_replays = 0;
+    int side_steps = 0;                  // steps of the last run that were enqueued on the side stream (0: sequential run)
 };
 
 struct PinnedBuf {                    // page-locked host memory (cudaHostAlloc): H2D/D2H copies run at full PCIe rate

@@ -50,7 +50,7 @@ static void range_to_scale(float lo, float hi, float& scale, int& zp)
     zp = (int)(uint8_t)(std::abs(lo) / scale);
 }
 
-enum StepKind { SK_SINGLE = 0, SK_ATTENTION, SK_GROUPNORM, SK_LAYERNORM, SK_GELU, SK_SILU, SK_LINEAR, SK_SDPA, SK_MHA, SK_CONV_ADD, SK_GEGLU };
+enum StepKind { SK_SINGLE = 0, SK_ATTENTION, SK_GROUPNORM, SK_LAYERNORM, SK_GELU, SK_SILU, SK_LINEAR, SK_SDPA, SK_MHA, SK_CONV_ADD, SK_GEGLU, SK_RMSNORM, SK_ROPE };
 
 struct Step {
     StepKind kind = SK_SINGLE;
@@ -109,6 +109,18 @@ struct Engine::Impl {
     void mha_project(size_t i, const Tensor& x, const Tensor* xq, Tensor* ql, Tensor& kl, Tensor& vl, int64_t Tka);
     void mha_prepass(size_t si);
 
+    // int64 graph inputs and CUDA graphs: an op that consumes the host VALUES of such a tensor (other than through its device mirror)
+    // makes the run un-capturable -- a replay would reuse the values of the captured run
+    bool capture_unsafe = false;
+    bool last_run_capture_safe = false;
+    static bool i64_safe_consumer(const OpDef& op, size_t k, const Tensor& t)
+    {
+        if (!t.i64_dev) return false;
+        if (op.type == "Gather") return k == 1;
+        if (op.type == "Cast") return true;
+        return k == 0 && (op.type == "Unsqueeze" || op.type == "Squeeze" || op.type == "Reshape" || op.type == "Flatten" || op.type == "Identity");
+    }
+
     struct OpTime { std::string type; cudaEvent_t a, b; };
     std::vector<OpTime> op_times;
     std::vector<Tensor> kept_inputs;      // b200_keep_inputs: device copies of the graph inputs of earlier runs, by name
@@ -123,6 +135,7 @@ struct Engine::Impl {
     int stats_groups = 0;
     long stats_ready_for = -1;            // GroupNorm step whose statistics sit in the current slot
     double* gn_slot_ptr(int slot) { return (double*)((char*)gn_ring->ptr + slot * 1024); }
+    static bool gn_split_enabled() { static const bool v = [] { const char* e = getenv("OSB_GN_SPLIT"); return !(e && e[0] == '0'); }(); return v; }
     static bool gn_apply_ok(const Tensor& t, int64_t C, int G)
     {
         const int vec = t.type == DType::f16 ? 8 : 4;
@@ -388,6 +401,7 @@ struct Engine::Impl {
             return t;
         }
         Tensor t = get_act(op, r.name);
+        if (t.type == DType::i64 && t.tainted && !i64_safe_consumer(op, k, t)) capture_unsafe = true;
         if (t.type == DType::u8 && (!E.use_uint8_arithmetic || requires_float || !op_takes_u8(op)))
             t = dequantize(t, (E.use_fp16_arithmetic && !requires_float && !upcast_op(op)) ? DType::f16 : DType::f32);
         if (requires_float && t.type == DType::f16) t = convert(t, DType::f32);
@@ -697,6 +711,66 @@ struct Engine::Impl {
         return 2;
     }
 
+    // RMSNorm as llm.cpp's graphs spell it: Pow(x, 2) -> ReduceMean(-1) -> Add(eps) -> Sqrt -> Div(1, .) -> Mul(x, .) -> Mul(w, .)
+    size_t match_rmsnorm(size_t i) const
+    {
+        auto& ops = E.m_ops;
+        if (!E.fuse_nodes || E.use_uint8_arithmetic || E.use_uint8_qdq) return 0;
+        static const char* seq[] = { "Pow", "ReduceMean", "Add", "Sqrt", "Div", "Mul", "Mul" };
+        if (i + 6 >= ops.size()) return 0;
+        for (int k = 0; k < 7; k++) if (ops[i + k].type != seq[k]) return 0;
+        const OpDef &pw = ops[i], &rm = ops[i + 1], &ad = ops[i + 2], &sq = ops[i + 3], &dv = ops[i + 4], &m1 = ops[i + 5], &m2 = ops[i + 6];
+        if (pw.in.size() != 2 || pw.in[0].wtype != DType::none || !is_scalar_weight(pw.in[1])) return 0;
+        auto a = rm.attr("axes"); auto kd = rm.attr("keepdims");
+        if (!a || *a != "-1" || (kd && *kd != "1")) return 0;
+        if (!feeds(pw, rm, 0) || ad.in.size() != 2 || !feeds(rm, ad, 0) || !is_scalar_weight(ad.in[1]) || !feeds(ad, sq, 0)) return 0;
+        if (dv.in.size() != 2 || !is_scalar_weight(dv.in[0]) || !feeds(sq, dv, 1)) return 0;
+        const std::string& x = pw.in[0].name;
+        if (m1.in.size() != 2 || m2.in.size() != 2) return 0;
+        int xi = -1;
+        for (int k = 0; k < 2; k++) if (m1.in[k].wtype == DType::none && m1.in[k].name == x && feeds(dv, m1, 1 - k)) xi = k;
+        if (xi < 0) return 0;
+        int wi = -1;
+        const int64_t C = pw.in[0].shape.empty() ? 0 : pw.in[0].shape.back();
+        for (int k = 0; k < 2; k++) if (is_float_weight(m2.in[k]) && m2.in[k].shape.size() == 1 && m2.in[k].shape[0] == C && feeds(m1, m2, 1 - k)) wi = k;
+        if (wi < 0) return 0;
+        // all seven ops in the same arithmetic class (the reference's m_requires_upcast looks at each op's name)
+        for (int k = 1; k < 7; k++) if (upcast_op(ops[i + k]) != upcast_op(ops[i])) return 0;
+        return 7;
+    }
+
+    // rotary embedding: Slice(x, first half) , Slice(x, second half), Neg, Concat(-x2, x1), Mul(x, cos), Mul(rot, sin), Add
+    size_t match_rope(size_t i) const
+    {
+        auto& ops = E.m_ops;
+        if (!E.fuse_nodes || E.use_uint8_arithmetic || E.use_uint8_qdq) return 0;
+        static const char* seq[] = { "Slice", "Slice", "Neg", "Concat", "Mul", "Mul", "Add" };
+        if (i + 6 >= ops.size()) return 0;
+        for (int k = 0; k < 7; k++) if (ops[i + k].type != seq[k]) return 0;
+        const OpDef &s1 = ops[i], &s2 = ops[i + 1], &ng = ops[i + 2], &cc = ops[i + 3], &m1 = ops[i + 4], &m2 = ops[i + 5], &ad = ops[i + 6];
+        if (s1.in.size() != 5 || s2.in.size() != 5 || s1.in[0].wtype != DType::none || s1.in[0].name != s2.in[0].name) return 0;
+        for (int k = 1; k < 5; k++) if (s1.in[k].wtype != DType::i64 || s2.in[k].wtype != DType::i64) return 0;
+        const auto& xs = s1.in[0].shape;
+        if (xs.empty() || xs.back() % 2) return 0;
+        const int64_t D = xs.back();
+        std::vector<int64_t> hs = xs; hs.back() = D / 2;
+        if (s1.out[0].shape != hs || s2.out[0].shape != hs) return 0;            // (start / end values are checked at run time)
+        if (!feeds(s2, ng, 0) || cc.in.size() != 2 || !feeds(ng, cc, 0) || !feeds(s1, cc, 1)) return 0;
+        auto ax = cc.attr("axis");
+        if (!ax || (*ax != "-1" && *ax != std::to_string((int)xs.size() - 1))) return 0;
+        const std::string& x = s1.in[0].name;
+        if (m1.in.size() != 2 || m2.in.size() != 2 || ad.in.size() != 2) return 0;
+        if (m1.in[0].wtype != DType::none || m1.in[0].name != x || m1.in[1].wtype != DType::none) return 0;      // Mul(x, cos)
+        if (!feeds(cc, m2, 0) || m2.in[1].wtype != DType::none) return 0;                                         // Mul(rot, sin)
+        if (!feeds(m1, ad, 0) || !feeds(m2, ad, 1)) return 0;
+        auto n_of = [](const TensorRef& r) { int64_t n = 1; for (auto d : r.shape) n *= d; return n; };
+        if (n_of(m1.in[1]) != D || n_of(m2.in[1]) != D) return 0;               // one cos / sin row shared by every head
+        auto it = uses.find(x);
+        if (it == uses.end() || it->second != 3) return 0;                       // x: two Slices and the Mul
+        for (int k = 0; k < 7; k++) if (upcast_op(ops[i + k])) return 0;
+        return 7;
+    }
+
     // Conv -> Add(conv_out, other) with `other` an activation of the same shape: residual add in the conv epilogue
     // (resnet `x + conv2(...)`, transformer `proj_out(...) + residual`)
     size_t match_conv_add(size_t i, int& variant) const
@@ -762,6 +836,8 @@ struct Engine::Impl {
             else if ((n = match_layernorm(i))) { s.kind = SK_LAYERNORM; s.count = n; }
             else if ((n = match_geglu(i))) { s.kind = SK_GEGLU; s.count = n; }
             else if ((n = match_gelu(i, var))) { s.kind = SK_GELU; s.count = n; s.variant = var; }
+            else if ((n = match_rmsnorm(i))) { s.kind = SK_RMSNORM; s.count = n; }
+            else if ((n = match_rope(i))) { s.kind = SK_ROPE; s.count = n; }
             else if ((n = match_silu(i))) { s.kind = SK_SILU; s.count = n; }
             else if ((n = match_linear(i, var))) { s.kind = SK_LINEAR; s.count = n; s.variant = var; }
             else if ((n = match_conv_add(i, var))) { s.kind = SK_CONV_ADD; s.count = n; s.variant = var; }
@@ -794,8 +870,10 @@ struct Engine::Impl {
             largest_node = std::max(largest_node, node_bytes);
         }
         is_side.clear(); side_deps.clear(); kv_side.clear();
-        static const bool side_on = [] { const char* e = getenv("OSB_SIDE_BRANCH"); return !(e && e[0] == '0'); }();
-        if (side_on && E.fuse_nodes && E.m_stream) plan_side_branch_impl();
+        // opt-in (OSB_SIDE_BRANCH=1): measured on B200 inside the captured UNet graph, 112 steps on the side branch changed the replay time
+        // by +0.02 ms (5.505 vs 5.486 ms, profiles/r02_ab_step_e2e.txt) -- the branch does not shorten the critical path in practice
+        static const bool side_on = [] { const char* e = getenv("OSB_SIDE_BRANCH"); return e && e[0] == '1'; }();
+        if (side_on && E.fuse_nodes) plan_side_branch_impl();
     }
 
     // Which steps are off the critical path?  primary input = the graph input that starts the LONGEST op chain to the end of the graph
@@ -813,15 +891,25 @@ struct Engine::Impl {
         for (auto& op : ops) for (auto& r : op.in) if (r.present && r.wtype == DType::none && !producer.count(r.name) && std::find(inputs.begin(), inputs.end(), r.name) == inputs.end()) inputs.push_back(r.name);
         if (inputs.size() < 2 || inputs.size() > 60) return;
         std::map<std::string, uint64_t> dep;           // tensor -> bitmask of graph inputs it depends on
-        std::map<std::string, std::pair<int, int>> longest;   // tensor -> (chain length, input index that starts it)
-        for (size_t k = 0; k < inputs.size(); k++) { dep[inputs[k]] = 1ull << k; longest[inputs[k]] = { 0, (int)k }; }
-        std::pair<int, int> best = { -1, 0 };
+        for (size_t k = 0; k < inputs.size(); k++) dep[inputs[k]] = 1ull << k;
+        // primary input = the one whose OWN prefix (ops that depend on it alone) produces the largest tensor: a UNet's latent feeds
+        // conv_in (C x H x W), while the time step and the text context only ever make vectors / a few token rows before they join it
+        std::vector<int64_t> own_max(inputs.size(), 0);
         for (auto& op : ops) {
-            uint64_t m = 0; std::pair<int, int> lg = { -1, 0 };
-            for (auto& r : op.in) if (r.present && r.wtype == DType::none) { m |= dep[r.name]; auto it = longest.find(r.name); if (it != longest.end() && it->second.first > lg.first) lg = it->second; }
-            for (auto& o : op.out) if (o.present) { dep[o.name] = m; longest[o.name] = { lg.first + 1, lg.second }; if (lg.first + 1 > best.first) best = { lg.first + 1, lg.second }; }
+            uint64_t m = 0;
+            for (auto& r : op.in) if (r.present && r.wtype == DType::none) m |= dep[r.name];
+            for (auto& o : op.out) if (o.present) {
+                dep[o.name] = m;
+                if (m && !(m & (m - 1))) {          // exactly one input
+                    int k = 0; while (!((m >> k) & 1)) k++;
+                    int64_t n = 1; for (auto d : o.shape) n *= std::max<int64_t>(d, 1);
+                    own_max[k] = std::max(own_max[k], n);
+                }
+            }
         }
-        const uint64_t primary = 1ull << best.second;
+        size_t pk = 0;
+        for (size_t k = 1; k < inputs.size(); k++) if (own_max[k] > own_max[pk]) pk = k;
+        const uint64_t primary = 1ull << pk;
         std::map<std::string, size_t> step_of;         // tensor -> producing step
         for (size_t si = 0; si < steps.size(); si++)
             for (size_t oi = steps[si].first; oi < steps[si].first + steps[si].count; oi++) for (auto& o : ops[oi].out) if (o.present) step_of[o.name] = si;
@@ -830,12 +918,14 @@ struct Engine::Impl {
             bool side = true, any_act = false;
             for (size_t oi = steps[si].first; oi < steps[si].first + steps[si].count && side; oi++) {
                 for (auto& r : ops[oi].in) if (r.present) {
-                    if (r.wtype == DType::i64) side = false;                      // shape arithmetic stays in graph order on the host
                     if (r.wtype == DType::none) { any_act = true; if (dep[r.name] & primary) side = false; }
                 }
                 for (auto& o : ops[oi].out) if (o.present && uses.find(o.name) == uses.end()) side = false;   // a graph output
             }
-            if (side && any_act) { is_side[si] = 1; n_side++; }
+            // (a step with no activation input at all -- constants folded by ops -- depends on nothing: it goes first too, or a side
+            // consumer of its output would run before it)
+            (void)any_act;
+            if (side) { is_side[si] = 1; n_side++; }
         }
         kv_side.assign(steps.size(), 0);
         for (size_t si = 0; si < steps.size(); si++)
@@ -895,6 +985,8 @@ struct Engine::Impl {
     void fused_linear(const Step& s);
     void fused_sdpa(const Step& s);
     void fused_mha(const Step& s);
+    void fused_rmsnorm(const Step& s);
+    void fused_rope(const Step& s);
 
     Tensor binary(int bop, const Tensor& a, const Tensor& b, float out_scale = 0.f, int out_zp = 0);
     Tensor strided(const Tensor& x, const std::vector<int64_t>& out_shape, const std::vector<int64_t>& in_stride,
@@ -1155,7 +1247,7 @@ void Engine::Impl::op_conv(size_t oi, const Tensor* residual, size_t out_op)
         }
         // the GroupNorm right behind this conv wants per-group (sum, sum of squares) of the output: gathered in the epilogue
         void* gstats = nullptr; int gdone = 0, G = 0;
-        if (stats_want >= 0 && gn_ring && cur_B == 1 && E.keep_nhwc && !is1d) {
+        if (stats_want >= 0 && gn_ring && cur_B == 1 && E.keep_nhwc && !is1d && gn_split_enabled()) {
             G = stats_groups;
             if (gn_apply_ok(y, Cout, G)) gstats = gn_slot_ptr(gn_slot);
         }
@@ -1334,7 +1426,7 @@ void Engine::Impl::op_binary(size_t oi, int bop)
         push(oi, 0, binary(bop, a, b, oscale, ozp));
         return;
     }
-    if (stats_want >= 0 && gn_ring && cur_B == 1 && bop == OSB_BIN_ADD && a.type == b.type) {
+    if (stats_want >= 0 && gn_ring && cur_B == 1 && bop == OSB_BIN_ADD && a.type == b.type && gn_split_enabled()) {
         // x[NHWC] + t[1,C,1,1] feeding a GroupNorm (the time-embedding add of a resnet): one pass adds and gathers the statistics
         for (int k = 0; k < 2; k++) {
             const Tensor& full = k ? b : a; const Tensor& vecv = k ? a : b;
@@ -1773,6 +1865,13 @@ void Engine::Impl::op_gather(size_t oi)
     y.scale = data.scale; y.zero_point = data.zero_point;
     int64_t n = (int64_t)idx.i64->size();
     for (auto i : *idx.i64) if ((i < 0 ? i + rows : i) < 0 || (i < 0 ? i + rows : i) >= rows) fail(op, "index out of range.");
+    if (idx.i64_dev) {
+        // indices of a graph input (token ids, positions): read from the device mirror, so a captured graph follows new ids on replay
+        // (the kernel clamps out-of-range rows; the host check above covers the eager runs)
+        ck(osb_gather_rows(data.data(), (const int64_t*)idx.i64_dev->ptr, y.mdata(), n, rows, row_elems * (int64_t)dtype_size(data.type), st), "osb_gather_rows");
+        push(oi, 0, y);
+        return;
+    }
     DevPtr didx = pool().alloc((size_t)n * 8);
     ck(cudaMemcpyAsync(didx->ptr, idx.i64->data(), (size_t)n * 8, cudaMemcpyHostToDevice, st), "gather idx H2D");
     ck(cudaStreamSynchronize(st), "sync");  // host vector may die before the copy otherwise (pageable source)
@@ -1794,7 +1893,11 @@ void Engine::Impl::op_misc_host(size_t oi)
         int to = 0;
         for (auto& a : op.attrs) { if (a.first == "to") to = std::stoi(a.second); else fail(op, "unrecognized attribute: " + a.first + "."); }
         Tensor x = in(oi, 0);
-        if (x.type == DType::i64 && to == 1) {  // int64 -> float
+        if (x.type == DType::i64 && to == 1 && x.i64_dev) {   // int64 graph input -> float, on the device (capturable)
+            Tensor y = make(DType::f32, x.shape);
+            ck(osb_convert(x.i64_dev->ptr, OSB_I64, y.mdata(), OSB_F32, (size_t)x.numel(), 0.f, 0, st), "osb_convert(i64)");
+            push(oi, 0, y);
+        } else if (x.type == DType::i64 && to == 1) {  // int64 -> float
             std::vector<float> hv(x.i64->size());
             for (size_t i = 0; i < hv.size(); i++) hv[i] = (float)(*x.i64)[i];
             Tensor y = make(DType::f32, x.shape);
@@ -2255,8 +2358,7 @@ void Engine::Impl::fused_groupnorm(const Step& s)
     if (gamma.type != x.type) gamma = convert(gamma, x.type);
     if (beta.type != x.type) beta = convert(beta, x.type);
     Tensor y = make(x.type, x.shape, x.layout);
-    static const bool split_gn = [] { const char* e = getenv("OSB_GN_SPLIT"); return !(e && e[0] == '0'); }();
-    if (split_gn && cur_B == 1 && gn_ring && gn_apply_ok(x, C, G)) {
+    if (gn_split_enabled() && cur_B == 1 && gn_ring && gn_apply_ok(x, C, G)) {
         // statistics: already in the current ring slot (gathered by the producing conv / Add), or one atomics pass now; then ONE
         // streaming apply pass that also zeroes the other slot for the next producer -- no grid rendezvous, no co-residency assumption
         bool have = pre;
@@ -2274,6 +2376,51 @@ void Engine::Impl::fused_groupnorm(const Step& s)
     ck(osb_group_norm(x.data(), y.mdata(), K(x.type), x.layout == Layout::nhwc ? 1 : 0, C, HW, G, gamma.data(), beta.data(), eps, s.variant == 1 ? 1 : 0,
                       gn_stats->ptr, st), "osb_group_norm");
     push(s.first + s.count - 1, 0, y);
+}
+
+void Engine::Impl::fused_rmsnorm(const Step& s)
+{
+    const size_t i = s.first;
+    const OpDef& pw = E.m_ops[i];
+    Tensor x = to_plain(in(i, 0));
+    const float two = scalar_of(in(i, 1), pw), eps = scalar_of(in(i + 2, 1), E.m_ops[i + 2]), one = scalar_of(in(i + 4, 0), E.m_ops[i + 4]);
+    if (two != 2.f || one != 1.f || (x.type != DType::f16 && x.type != DType::f32)) { exec_unfused(s); return; }
+    const OpDef& m2 = E.m_ops[i + 6];
+    const size_t wi = is_float_weight(m2.in[0]) ? 0 : 1;
+    Tensor w = in(i + 6, wi);
+    // arithmetic class of the chain: fp32 when the ops are up-cast (m_requires_upcast) or the model runs fp32; the result type is what the
+    // last Mul would have produced (push() then applies the storage rule)
+    const DType ot = (upcast_op(m2) || !E.use_fp16_arithmetic) ? DType::f32 : x.type;
+    if (w.type != DType::f16 && w.type != DType::f32) { exec_unfused(s); return; }
+    Tensor y = make(ot, x.shape);
+    if (osb_rms_norm(x.data(), K(x.type), w.data(), K(w.type), y.mdata(), K(ot), x.numel() / x.shape.back(), x.shape.back(), eps, st) != 0) {
+        // an unsupported type mix: the generic ops
+        exec_unfused(s);
+        return;
+    }
+    push(i + 6, 0, y);
+}
+
+void Engine::Impl::fused_rope(const Step& s)
+{
+    const size_t i = s.first;
+    Tensor x = to_plain(in(i, 0));
+    const int64_t D = x.shape.back(), nd = (int64_t)x.shape.size();
+    // the Slice constants must really cut [0, D/2) and [D/2, D) of the last axis
+    auto cut = [&](size_t oi, int64_t lo, int64_t hi) {
+        Tensor st_ = in(oi, 1), en = in(oi, 2), ax = in(oi, 3), sp = in(oi, 4);
+        if (st_.i64->size() != 1 || en.i64->size() != 1 || ax.i64->size() != 1 || sp.i64->size() != 1) return false;
+        int64_t a = (*ax.i64)[0]; if (a < 0) a += nd;
+        int64_t e = (*en.i64)[0]; if (e > D) e = D;
+        return a == nd - 1 && (*sp.i64)[0] == 1 && (*st_.i64)[0] == lo && e == hi;
+    };
+    Tensor cs = to_plain(in(i + 4, 1)), sn = to_plain(in(i + 5, 1));
+    if (!cut(i, 0, D / 2) || !cut(i + 1, D / 2, D) || (x.type != DType::f16 && x.type != DType::f32) || cs.numel() != D || sn.numel() != D) { exec_unfused(s); return; }
+    if (cs.type != x.type) cs = convert(cs, x.type);
+    if (sn.type != x.type) sn = convert(sn, x.type);
+    Tensor y = make(x.type, x.shape);
+    ck(osb_rope(x.data(), cs.data(), sn.data(), y.mdata(), K(x.type), x.numel() / D, D, 1, st), "osb_rope");
+    push(i + 6, 0, y);
 }
 
 void Engine::Impl::fused_layernorm(const Step& s)
@@ -2451,6 +2598,8 @@ void Engine::Impl::exec_step(size_t si)
         case SK_LINEAR: fused_linear(s); break;
         case SK_SDPA: fused_sdpa(s); break;
         case SK_MHA: fused_mha(s); break;
+        case SK_RMSNORM: fused_rmsnorm(s); break;
+        case SK_ROPE: fused_rope(s); break;
         case SK_CONV_ADD: { Tensor res = in(s.first + 1, (size_t)s.variant); op_conv(s.first, &res, s.first + 1); break; }
         default: exec_single(s.first); break;
         }
@@ -2499,7 +2648,7 @@ Engine::Engine(EngineNoDevice)
 
 std::string Engine::plan_summary(const std::string& model_text, bool fp16_arithmetic, bool fuse_nodes_, bool fuse_attention, bool use_sdpa_rewrite)
 {
-    static const char* kind_names[] = { "SINGLE", "ATTENTION", "GROUPNORM", "LAYERNORM", "GELU", "SILU", "LINEAR", "SDPA", "MHA", "CONV_ADD", "GEGLU" };
+    static const char* kind_names[] = { "SINGLE", "ATTENTION", "GROUPNORM", "LAYERNORM", "GELU", "SILU", "LINEAR", "SDPA", "MHA", "CONV_ADD", "GEGLU", "RMSNORM", "ROPE" };
     Engine e{ EngineNoDevice{} };
     e.use_fp16_arithmetic = fp16_arithmetic;
     e.fuse_nodes = fuse_nodes_;
@@ -2513,8 +2662,14 @@ std::string Engine::plan_summary(const std::string& model_text, bool fp16_arithm
     for (auto& s : I.steps) {
         const char* kn = (size_t)s.kind < sizeof(kind_names) / sizeof(kind_names[0]) ? kind_names[s.kind] : "?";
         const OpDef& op = e.m_ops[s.first];
-        out += std::string(kn) + " " + std::to_string(s.count) + " " + op.type + " " + op.name + "\n";
+        const size_t si = (size_t)(&s - &I.steps[0]);
+        const bool side = si < I.is_side.size() && I.is_side[si], kvs = si < I.kv_side.size() && I.kv_side[si];
+        const bool stats = si < I.stats_consumer.size() && I.stats_consumer[si] >= 0;
+        out += std::string(kn) + " " + std::to_string(s.count) + " " + op.type + " " + op.name + (side ? " [side]" : "") + (kvs ? " [kv-side]" : "") + (stats ? " [gn-stats]" : "") + "\n";
         counts[kn]++;
+        if (side) counts["side"]++;
+        if (kvs) counts["kv_side"]++;
+        if (stats) counts["gn_stats_producers"]++;
     }
     out += "#summary ops=" + std::to_string(e.m_ops.size()) + " steps=" + std::to_string(I.steps.size()) + " largest_node_bytes=" + std::to_string(I.largest_node);
     for (auto& kv : counts) out += " " + kv.first + "=" + std::to_string(kv.second);
@@ -2796,7 +2951,9 @@ void Engine::run()
     bool has_i64_input = false;
     for (auto& h : m_host_tensors) if (h.type == DType::i64) has_i64_input = true;
     GraphState* G = nullptr;
-    bool capturing = use_cuda_graph && resident_weights && !has_i64_input && I.runs_done >= 2 && m_nranks == 1;
+    // int64 inputs (token ids ...) are capturable when the previous eager run consumed their values only through device mirrors
+    bool capturing = use_cuda_graph && resident_weights && (!has_i64_input || I.last_run_capture_safe) && I.runs_done >= 2 && m_nranks == 1;
+    I.capture_unsafe = false;
     if (capturing) { auto& g = g_graphs[this]; if (g.failed) capturing = false; else G = &g; }
 
     cudaEvent_t ev0, ev1;
@@ -2814,6 +2971,11 @@ void Engine::run()
         if (h.type == DType::i64) {
             t.type = DType::i64;
             t.i64 = std::make_shared<std::vector<int64_t>>(h.i64(), h.i64() + h.count);
+            t.tainted = true;
+            t.i64_dev = m_pool.alloc(std::max<size_t>(h.count, 1) * 8);
+            check_cuda(cudaMemcpyAsync(t.i64_dev->ptr, h.buf->ptr, h.count * 8, cudaMemcpyHostToDevice, m_stream), "input H2D (int64 mirror)");
+            m_stats.h2d_input_bytes += h.count * 8;
+            if (G) G->inputs.push_back({ h.name, h.shape, t.i64_dev, h.count * 8, DType::i64 });
             uploaded.emplace_back(t, false);
         } else {
             // float32, or float16 (the C++ adapter hands fp16 tensors -- e.g. a KV cache kept out of m_outputs_convert_set -- over as they are)
@@ -2865,7 +3027,9 @@ void Engine::run()
         // side branch: steps off the critical path first, on their own stream and pool (see Impl::side_stream)
         bool hoist = !I.is_side.empty() && resident_weights && !m_first_run && !has_i64_input && !ops_times_printf && !ops_printf && m_nranks == 1;
         if (hoist) { std::set<std::string> seen; for (auto& u : uploaded) if (!seen.insert(u.first.name).second) hoist = false; }   // batch siblings: sequential
+        m_stats.side_steps = 0;
         if (hoist) {
+            for (size_t si = 0; si < I.steps.size(); si++) m_stats.side_steps += (I.is_side[si] || (!I.kv_side.empty() && I.kv_side[si])) ? 1 : 0;
             if (!I.side_stream) check_cuda(cudaStreamCreateWithFlags(&I.side_stream, cudaStreamNonBlocking), "cudaStreamCreate(side)");
             if (I.side_events.size() != I.steps.size() + 2) {
                 for (auto e : I.side_events) if (e) cudaEventDestroy(e);
@@ -2931,6 +3095,7 @@ void Engine::run()
             }
         }
         if (capturing) {
+            if (I.capture_unsafe) throw std::runtime_error("an op read the values of an int64 graph input on the host: not capturable");
             for (auto& f : finals) if (std::get<2>(f).type == DType::i64) throw std::runtime_error("int64 graph outputs are host-evaluated: not capturable");
             capture_open = false;
             check_cuda(cudaStreamEndCapture(m_stream, &G->graph), "cudaStreamEndCapture");
@@ -2994,6 +3159,7 @@ void Engine::run()
     if (!capturing) cudaEventElapsedTime(&ms, ev0, ev1);
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     I.runs_done++;
+    I.last_run_capture_safe = !I.capture_unsafe;
     m_stats.last_gpu_ms = ms;
     m_stats.kernel_launches = osb_launch_count();
     m_stats.tc_launches = osb_tc_launch_count();

@@ -67,6 +67,7 @@ struct TcParams {
     const __half* residual;
     double* gn_stats;            // != null: per-group (sum, sum of squares) of the stored output, for the GroupNorm that consumes it
     int gn_cpg, gn_groups;       // channels per group, number of groups (N == gn_cpg * gn_groups)
+    int gn_debug;                // bisecting aid (OSB_GN_DEBUG): 1 = skip the per-chunk gathering, 2 = skip the per-tile flush, 3 = both
     long long stride_c;          // elements between batches
     long long ldc;               // elements between output rows (== N for a dense C)
 };
@@ -108,6 +109,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t* acc_full = bars + 2 * STAGES;      // [ACC_STAGES]
     uint64_t* acc_empty = acc_full + ACC_STAGES; // [ACC_STAGES]
     uint32_t* tmem_slot = (uint32_t*)(acc_empty + ACC_STAGES);
+    volatile int* split_flag = (volatile int*)(tmem_slot + 1);
     uint8_t* gn_buf = (uint8_t*)bars + 256;                 // [4][2048] warp-private chunk transposition buffers
     float* gn_acc = (float*)(gn_buf + 4 * 2048);            // [2 * GN_MAX_GROUPS] per-CTA (sum, sum of squares) accumulators
 
@@ -257,6 +259,34 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const __half* rrow = p.residual ? p.residual + (long long)b * p.stride_c + out_row * p.ldc : nullptr;
             float* wrow = p.split_k > 1 ? p.ws + (((long long)sp * p.batch + b) * p.M + out_row) * p.N : nullptr;
             const bool vec_ok = (p.N & 7) == 0;
+            // In-kernel split-K, "last finisher reduces" (no second launch, no co-residency assumption): every CTA of a tile takes a ticket
+            // AFTER its main loop.  Tickets 0 .. S-2 publish their fp32 partial and leave; the holder of ticket S-1 -- by construction every
+            // other CTA of the tile has finished its main loop and is in, or past, an epilogue that never blocks -- waits for their `done`
+            // signals, then runs the normal epilogue on its own TMEM accumulator plus the S-1 partials (L2-hot), re-arming the counters.
+            bool last_finisher = false;
+            const float* others = nullptr;       // plane 0 of the partial workspace, this row
+            if (wrow && p.counters) {
+                if (warp == 2 && lane == 0) *split_flag = atomicAdd(&p.counters[2 * t2], 1);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                last_finisher = *split_flag == p.split_k - 1;
+                asm volatile("bar.sync 1, 128;" ::: "memory");          // everyone has read the flag before the next tile's ticket overwrites it
+                if (last_finisher) {
+                    if (warp == 2 && lane == 0) {
+                        long long t0 = clock64();
+                        while (true) {
+                            int seen;
+                            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.counters + 2 * t2 + 1) : "memory");
+                            if (seen >= p.split_k - 1) break;
+                            if (clock64() - t0 > 4000000000LL) { printf("tc_gemm_kernel: split-K partials never arrived (block %d)\n", blockIdx.x); __trap(); }
+                        }
+                        p.counters[2 * t2] = 0; p.counters[2 * t2 + 1] = 0;       // re-arm for the next launch (nobody else touches them any more)
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    __threadfence();
+                    others = p.ws + ((long long)b * p.M + out_row) * p.N;
+                    wrow = nullptr;                                             // take the normal (final) epilogue below
+                }
+            }
 #pragma unroll 1
             for (int c = 0; c < p.bn; c += 32) {
                 if (n0 + c >= n_end) break;     // warp-uniform
@@ -290,6 +320,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         float f[8];
 #pragma unroll
                         for (int t = 0; t < 8; t++) f[t] = __uint_as_float(v[j + t]);
+                        if (others) {
+                            const long long plane = (long long)p.batch * p.M * p.N;
+                            for (int sidx = 0; sidx < p.split_k; sidx++) {
+                                if (sidx == sp) continue;
+                                const float4 a0 = __ldcg(reinterpret_cast<const float4*>(others + sidx * plane + n));
+                                const float4 a1 = __ldcg(reinterpret_cast<const float4*>(others + sidx * plane + n + 4));
+                                f[0] += a0.x; f[1] += a0.y; f[2] += a0.z; f[3] += a0.w; f[4] += a1.x; f[5] += a1.y; f[6] += a1.z; f[7] += a1.w;
+                            }
+                        }
                         if (p.bias) {
                             Vec<__half, 8> bv = load_vec<__half, 8>(p.bias + n);
 #pragma unroll
@@ -315,7 +354,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         }
                     }
                 }
-                if (EXTRAS && p.gn_stats && !wrow) {
+                if (EXTRAS && p.gn_stats && !wrow && !(p.gn_debug & 1)) {
                     // rows outside the problem (and units past N) contribute zeros
                     uint32_t h[16];
 #pragma unroll
@@ -323,7 +362,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     gn_stats_chunk(smem_u32(gn_buf) + (uint32_t)q * 2048u, h, n0 + c, n_end, p.gn_cpg, gn_acc, lane);
                 }
             }
-            if (EXTRAS && p.gn_stats && !wrow) {
+            if (EXTRAS && p.gn_stats && !wrow && !(p.gn_debug & 2)) {
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 gn_stats_flush(gn_acc, p.gn_stats, p.gn_groups, (int)threadIdx.x - 64);
             }
@@ -331,59 +370,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_arrive(&acc_empty[acc]);
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             if (wrow && p.counters) {
-                // Parallel in-kernel split-K reduction (no second launch).  All split_k CTAs of a tile are co-resident (the host
-                // keeps tiles * split_k <= resident CTA slots), so they can rendezvous on a counter: publish partials -> arrive ->
-                // wait for everyone -> each CTA reduces its own slice of the tile's rows in fp32, adds bias / residual, rounds once.
+                // a partial CTA: publish, signal `done`, leave
                 __threadfence();
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (warp == 2 && lane == 0) {
-                    atomicAdd(&p.counters[2 * t2], 1);
-                    long long t0 = clock64();
-                    while (true) {
-                        int seen;
-                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.counters + 2 * t2) : "memory");
-                        if (seen >= p.split_k) break;
-                        if (clock64() - t0 > 4000000000LL) { printf("tc_gemm_kernel: split-K rendezvous timed out (block %d)\n", blockIdx.x); __trap(); }
-                    }
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                __threadfence();
-                {
-                    const int rows_per = (BLOCK_M + p.split_k - 1) / p.split_k;
-                    const int r_lo = sp * rows_per, r_hi = min(r_lo + rows_per, BLOCK_M);
-                    const long long plane = (long long)p.batch * p.M * p.N;
-                    const int nvec = (n_end - n0) >> 2;      // N % 4 == 0 (host guarantees it on this path)
-                    for (int rr = r_lo + q; rr < r_hi; rr += 4) {   // one tile row per epilogue warp and pass; lanes sweep the columns
-                        long long orow_idx; bool ok;
-                        if (p.bh > 0) {
-                            int y = (mt / p.tiles_x) * p.bh + rr / p.bw, x = (mt % p.tiles_x) * p.bw + rr % p.bw;
-                            ok = y < p.Ho && x < p.Wo; orow_idx = (long long)y * p.Wo + x;
-                        } else { int m = mt * BLOCK_M + rr; ok = m < p.M; orow_idx = m; }
-                        if (!ok) continue;
-                        const float* src0 = p.ws + ((long long)b * p.M + orow_idx) * p.N;
-                        __half* dst = p.C + (long long)b * p.stride_c + orow_idx * p.ldc;
-                        const __half* res = p.residual ? p.residual + (long long)b * p.stride_c + orow_idx * p.ldc : nullptr;
-                        for (int v = lane; v < nvec; v += 32) {
-                            int n = n0 + (v << 2);
-                            float4 a = __ldcg(reinterpret_cast<const float4*>(src0 + n));
-                            for (int sidx = 1; sidx < p.split_k; sidx++) {
-                                float4 t = __ldcg(reinterpret_cast<const float4*>(src0 + sidx * plane + n));
-                                a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
-                            }
-                            if (p.bias) { a.x += __half2float(p.bias[n]); a.y += __half2float(p.bias[n + 1]); a.z += __half2float(p.bias[n + 2]); a.w += __half2float(p.bias[n + 3]); }
-                            if (p.bias2) { a.x += __half2float(p.bias2[n]); a.y += __half2float(p.bias2[n + 1]); a.z += __half2float(p.bias2[n + 2]); a.w += __half2float(p.bias2[n + 3]); }
-                            if (res) { Vec<__half, 4> r4 = load_vec<__half, 4>(res + n); a.x += __half2float(r4.v[0]); a.y += __half2float(r4.v[1]); a.z += __half2float(r4.v[2]); a.w += __half2float(r4.v[3]); }
-                            Vec<__half, 4> o4;
-                            o4.v[0] = __float2half_rn(a.x); o4.v[1] = __float2half_rn(a.y); o4.v[2] = __float2half_rn(a.z); o4.v[3] = __float2half_rn(a.w);
-                            store_vec<__half, 4>(dst + n, o4);
-                        }
-                    }
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (warp == 2 && lane == 0) {
-                    int done = atomicAdd(&p.counters[2 * t2 + 1], 1);
-                    if (done == p.split_k - 1) { p.counters[2 * t2] = 0; p.counters[2 * t2 + 1] = 0; __threadfence(); }   // re-arm for the next launch
-                }
+                if (warp == 2 && lane == 0) { asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.counters + 2 * t2 + 1) : "memory"); }
             }
         }
     }
@@ -442,6 +432,8 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, __half* __res
 // ---- host side -------------------------------------------------------------------------------------------------
 constexpr size_t WS_MAX = OSB_WS_SPLITK_BYTES;   // fixed-capacity per-stream workspace (workspace.h): never re-allocated, graph-safe
 
+bool inkernel_reduce();
+
 // pick a split factor: fill the SMs when the tile count is small, keep >= 2 k-blocks per split, stay inside the workspace
 int choose_split(int tiles, int k_blocks, size_t out_elems, cudaStream_t st, OsbWorkspace** ws_out)
 {
@@ -449,7 +441,8 @@ int choose_split(int tiles, int k_blocks, size_t out_elems, cudaStream_t st, Osb
     // measured over every tc shape of the SD 1.5 UNet (r01 sweep): below ~32 k-blocks the second launch (the reduce) costs more
     // than the idle SMs do
     *ws_out = nullptr;
-    if ((tiles >= 100 && forced <= 0) || k_blocks < 4 || (k_blocks < 32 && forced <= 0)) return 1;
+    static const int min_kb = [] { const char* e = getenv("OSB_TC_SPLIT_MINKB"); int v = e ? atoi(e) : 0; return v > 0 ? v : 32; }();
+    if ((tiles >= 100 && forced <= 0) || k_blocks < 4 || (k_blocks < min_kb && forced <= 0)) return 1;
     int split = forced > 0 ? forced : 148 / tiles;
     split = std::min(split, k_blocks / 2);
     while (split > 1 && (size_t)split * out_elems * 4 > WS_MAX) split--;
@@ -529,8 +522,10 @@ int short_k_hint(int k_blocks, int split)
 bool inkernel_reduce()
 {
     static int v = -1;
-    // measured on B200 (SD1.5 UNet step): the rendezvous costs more than the 4 us reduce kernel it saves (9.17 vs 8.00 ms per
-    // step), so the separate vectorised reduce kernel is the default; OSB_TC_INKERNEL_REDUCE=1 selects the in-kernel variant.
+    // Opt-in (OSB_TC_INKERNEL_REDUCE=1).  Round 1: all CTAs of a tile rendezvous and each reduces a slice -- 9.17 vs 8.00 ms per UNet step.
+    // Round 2: "last finisher reduces" (deadlock-free without co-residency, see the epilogue) -- correct, but the one CTA that finishes last
+    // pulls (S-1) fp32 planes of its tile through a single SM's L2 port (S up to 14: ~850 KB, ~9 us): 7.34 vs 5.38 ms per step with the
+    // separate reduce kernel, which spreads the same bytes over every SM.  The vectorised reduce kernel stays the default.
     if (v < 0) { const char* e = getenv("OSB_TC_INKERNEL_REDUCE"); v = (e && e[0] == '1') ? 1 : 0; }
     return v == 1;
 }
@@ -547,6 +542,12 @@ void prof_begin(ProfRec& rec, const TcParams& p, cudaStream_t st)
     cudaEventRecord(rec.a, st);
 }
 
+bool carveout_max()
+{
+    static const bool v = [] { const char* e = getenv("OSB_SMEM_CARVEOUT"); return e && e[0] == '1'; }();
+    return v;
+}
+
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st, const CUtensorMap* mb1p = nullptr, const CUtensorMap* mb2p = nullptr)
 {
     const CUtensorMap& mb1 = mb1p ? *mb1p : mb;
@@ -558,6 +559,14 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cuda
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<STAGES_DEEP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(STAGES_DEEP, true));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<STAGES_SHORT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(STAGES_SHORT, true));
         if (e != cudaSuccess) return (int)e;
+        if (carveout_max()) {
+            // one shared-memory carve-out for every tensor-core kernel: consecutive kernels that need different carve-outs make the SMs
+            // drain and reconfigure (the EXTRAS instantiations need > 196 KiB per SM, the lean ones do not)
+            cudaFuncSetAttribute(tc_gemm_kernel<STAGES_DEEP, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(tc_gemm_kernel<STAGES_SHORT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(tc_gemm_kernel<STAGES_DEEP, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(tc_gemm_kernel<STAGES_SHORT, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        }
         attr_set = true;
     }
     int total = p.m_tiles * p.n_tiles * p.batch * p.split_k;
@@ -658,6 +667,10 @@ bool use_pair(int64_t m_tiles, int64_t N, int64_t batch, bool b_kmajor, int k_bl
     const int64_t tiles1 = m_tiles * ((N + bn1 - 1) / bn1) * batch;
     if (tiles1 < 100 && k_blocks >= 32) return false;      // long K over few tiles: the split-K path of the single-CTA kernel
     if (k_blocks < 8) return false;                        // launch-latency bound: the lighter prologue wins
+    // The pair kernel pays for its cluster launch, two cluster barriers and the staged TMA-store epilogue: on problems the single-CTA
+    // kernel finishes in ONE wave it measured slower in the UNet step (profiles/r02_launches_step*.csv: 96-tile conv 20.5 vs 16.1 us),
+    // on multi-wave problems it wins by up to 1.5x (64x64 640->640 conv: 41 vs 60 us; 8192^3: 1327 vs 842 TF/s).
+    if (tiles1 <= num_sms()) return false;
     return cp < 0.9 * single_cost(m_tiles, N, batch, bn1);
 }
 
@@ -667,6 +680,7 @@ int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(pairk::tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pairk::P_SMEM);
         if (e != cudaSuccess) return (int)e;
+        if (carveout_max()) cudaFuncSetAttribute(pairk::tc_pair_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         attr_set = true;
     }
     const int m_pairs = (p.m_tiles + 1) / 2;
@@ -905,7 +919,7 @@ int osb_tc_gemm_launch(const void* A, const void* B, void* C, const void* bias, 
     p.split_k = (ldc == N && (sc == M * N || batch == 1)) ? choose_split(p.m_tiles * p.n_tiles * p.batch, p.k_blocks_per_tap, (size_t)batch * M * N, st, &wsp) : 1;
     p.ws = wsp ? wsp->splitk : nullptr;
     // in-kernel rendezvous reduction needs every CTA resident at once and float4-aligned rows; otherwise the reduce kernel runs
-    p.counters = (p.split_k > 1 && p.N % 4 == 0 && p.ldc % 4 == 0 && (long long)p.m_tiles * p.n_tiles * p.batch * p.split_k <= num_sms() && inkernel_reduce() && wsp) ? wsp->splitk_counters : nullptr;
+    p.counters = (p.split_k > 1 && p.N % 8 == 0 && p.ldc % 8 == 0 && (long long)p.m_tiles * p.n_tiles * p.batch <= 2048 && inkernel_reduce() && wsp) ? wsp->splitk_counters : nullptr;
     p.short_k = short_k_hint(p.taps * p.k_blocks_per_tap, p.split_k);
     return launch(ma, mb, p, st);
 }
@@ -1016,11 +1030,12 @@ int osb_tc_conv_launch(const void* x, const void* w, const void* bias, const voi
     p.split_k = (Cout % 4 == 0) ? choose_split(p.m_tiles * p.n_tiles, p.taps * p.k_blocks_per_tap, (size_t)Ho * Wo * Cout, st, &wsp) : 1;
     p.ws = wsp ? wsp->splitk : nullptr;
     // in-kernel rendezvous reduction needs every CTA resident at once and float4-aligned rows; otherwise the reduce kernel runs
-    p.counters = (p.split_k > 1 && p.N % 4 == 0 && p.ldc % 4 == 0 && (long long)p.m_tiles * p.n_tiles * p.batch * p.split_k <= num_sms() && inkernel_reduce() && wsp) ? wsp->splitk_counters : nullptr;
+    p.counters = (p.split_k > 1 && p.N % 8 == 0 && p.ldc % 8 == 0 && (long long)p.m_tiles * p.n_tiles * p.batch <= 2048 && inkernel_reduce() && wsp) ? wsp->splitk_counters : nullptr;
     p.short_k = short_k_hint(p.taps * p.k_blocks_per_tap, p.split_k);
     p.bias2 = (const __half*)bias2;
     // statistics: the tile epilogue (unsplit) or the reduce kernel (split-K; needs 4 consecutive columns inside one group)
-    const bool stats_ok = gn_stats && (p.split_k == 1 || (!p.counters && gn_cpg % 4 == 0));
+    const bool stats_ok = gn_stats && (p.split_k == 1 || p.counters || gn_cpg % 4 == 0);     // final epilogue (unsplit / last finisher) or the reduce kernel
     if (stats_ok) { p.gn_stats = gn_stats; p.gn_cpg = gn_cpg; p.gn_groups = gn_groups; if (gn_done) *gn_done = 1; }
+    { static const int dbg = env_int("OSB_GN_DEBUG"); p.gn_debug = dbg; }
     return launch(ma, mb, p, st);
 }

@@ -533,26 +533,44 @@ __global__ void gn_stats_nhwc_vec_kernel(const T* __restrict__ x, double* __rest
 #pragma unroll
             for (int k = 0; k < VEC; k++) a[k] = to_float(av.v[k]);
         }
-        for (int64_t p = p0 + pr; p < p1; p += rows) {
-            Vec<T, VEC> v = load_vec<T, VEC>(x + p * C + cv * VEC);
-            if (y) {
+        // 4 pixels (independent 16-byte loads) in flight per thread
+        for (int64_t pb = p0 + pr; pb < p1; pb += 4 * (int64_t)rows) {
+            Vec<T, VEC> v[4];
 #pragma unroll
-                for (int k = 0; k < VEC; k++) v.v[k] = from_float<T>(to_float(v.v[k]) + a[k]);
-                store_vec<T, VEC>(y + p * C + cv * VEC, v);
+            for (int u = 0; u < 4; u++) { const int64_t p = pb + u * (int64_t)rows; if (p < p1) v[u] = load_vec<T, VEC>(x + p * C + cv * VEC); }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int64_t p = pb + u * (int64_t)rows;
+                if (p >= p1) break;
+                if (y) {
+#pragma unroll
+                    for (int k = 0; k < VEC; k++) v[u].v[k] = from_float<T>(to_float(v[u].v[k]) + a[k]);
+                    store_vec<T, VEC>(y + p * C + cv * VEC, v[u]);
+                }
+#pragma unroll
+                for (int k = 0; k < VEC; k++) { float f = to_float(v[u].v[k]); s[k] += f; q[k] += f * f; }
             }
-#pragma unroll
-            for (int k = 0; k < VEC; k++) { float f = to_float(v.v[k]); s[k] += f; q[k] += f * f; }
         }
-        const int cpg = C / groups;
+        // per-thread partials -> shared [rows][2][C] (no atomics: 256 threads hammering 2 * groups shared addresses serialise)
+        float* part = sm + 2 * groups;
 #pragma unroll
-        for (int k = 0; k < VEC; k++) {
-            int g = (cv * VEC + k) / cpg;
-            atomicAdd(&sm[2 * g], s[k]);
-            atomicAdd(&sm[2 * g + 1], q[k]);
-        }
+        for (int k = 0; k < VEC; k++) { part[(pr * 2 + 0) * C + cv * VEC + k] = s[k]; part[(pr * 2 + 1) * C + cv * VEC + k] = q[k]; }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(&stats[i], (double)sm[i]);
+    {
+        // thread t < 2 * groups: group t / 2, statistic t % 2 -- sums its cpg channels over the pixel rows of the CTA
+        const int cpg = C / groups;
+        const float* part = sm + 2 * groups;
+        for (int t = threadIdx.x; t < 2 * groups; t += blockDim.x) {
+            const int g = t >> 1, which = t & 1;
+            float acc = 0.f;
+            for (int r = 0; r < rows; r++) {
+                const float* rowp = part + (r * 2 + which) * C + g * cpg;
+                for (int c = 0; c < cpg; c++) acc += rowp[c];
+            }
+            atomicAdd(&stats[t], (double)acc);
+        }
+    }
 }
 
 // GroupNorm(+SiLU) on NHWC in ONE launch: statistics -> grid rendezvous -> apply.  All CTAs are co-resident (grid <= 2 per
@@ -722,16 +740,25 @@ __global__ void gn_apply_pre_kernel(const T* __restrict__ x, T* __restrict__ y, 
     __syncthreads();
     const int vpp = C / VEC;                                  // vectors per pixel
     const int64_t nvec = HW * vpp;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c0 = (int)(i % vpp) * VEC;
-        Vec<T, VEC> v = load_vec<T, VEC>(x + i * VEC);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // 4 independent 16-byte loads in flight per thread: the pass is pure streaming, latency is hidden by memory-level parallelism
+    for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < nvec; i0 += 4 * stride) {
+        Vec<T, VEC> v[4];
 #pragma unroll
-        for (int k = 0; k < VEC; k++) {
-            float o = fmaf(to_float(v.v[k]), scale[c0 + k], shift[c0 + k]);
-            if (silu) o = o / (1.f + __expf(-o));
-            v.v[k] = from_float<T>(o);
+        for (int u = 0; u < 4; u++) { const int64_t i = i0 + u * stride; if (i < nvec) v[u] = load_vec<T, VEC>(x + i * VEC); }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int64_t i = i0 + u * stride;
+            if (i >= nvec) break;
+            const int c0 = (int)(i % vpp) * VEC;
+#pragma unroll
+            for (int k = 0; k < VEC; k++) {
+                float o = fmaf(to_float(v[u].v[k]), scale[c0 + k], shift[c0 + k]);
+                if (silu) o = __fdividef(o, 1.f + __expf(-o));
+                v[u].v[k] = from_float<T>(o);
+            }
+            store_vec<T, VEC>(y + i * VEC, v[u]);
         }
-        store_vec<T, VEC>(y + i * VEC, v);
     }
 }
 
@@ -814,6 +841,48 @@ percentile_chunks_kernel(const T* __restrict__ x, size_t size, size_t threads, s
     if (threadIdx.x == 0) { atomicMin(&out[0], lo); atomicMax(&out[1], hi); atomicAdd(&out[2], 1u); }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// LLM decode fusions: RMSNorm and rotary embedding (the op chains llm.cpp's graphs spell out, src/onnxstream.cpp: Pow 5478-5604,
+// ReduceMean 5237-5393, Sqrt 4001-4139, Div / Mul / Add / Neg / Slice / Concat)
+// ------------------------------------------------------------------------------------------------------------
+// y = w * (x * (1 / sqrt(mean(x^2) + eps))): one warp per row, fp32 arithmetic whatever the storage types (the reference keeps these
+// ops in fp32 through m_requires_upcast, src/llm.cpp:385-389)
+template <typename TI, typename TW, typename TO>
+__global__ void rms_norm_kernel(const TI* __restrict__ x, const TW* __restrict__ w, TO* __restrict__ y, int64_t rows, int cols, float eps)
+{
+    osb_pdl_prologue();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    for (int64_t r = (int64_t)blockIdx.x * wpb + wib; r < rows; r += (int64_t)gridDim.x * wpb) {
+        const TI* xr = x + r * cols;
+        float ss = 0.f;
+        for (int c = lane; c < cols; c += 32) { const float v = to_float(xr[c]); ss = fmaf(v, v, ss); }
+        ss = warp_sum(ss);
+        const float inv = 1.0f / sqrtf(ss / (float)cols + eps);
+        TO* yr = y + r * cols;
+        for (int c = lane; c < cols; c += 32) yr[c] = from_float<TO>(to_float(w[c]) * (to_float(xr[c]) * inv));
+    }
+}
+
+// rotary embedding, "rotate_half" form: y[j] = x[j] * cos[j] + (j < D/2 ? -x[j + D/2] : x[j - D/2]) * sin[j]; cos / sin are one row of D
+// values shared by every row (table_rows == 1) or one row per x row
+template <typename T>
+__global__ void rope_kernel(const T* __restrict__ x, const T* __restrict__ cs, const T* __restrict__ sn, T* __restrict__ y, int64_t rows, int D, int64_t table_rows)
+{
+    osb_pdl_prologue();
+    const int64_t n = rows * D;
+    const int half = D >> 1;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / D; const int j = (int)(i % D);
+        const int64_t t = table_rows == 1 ? 0 : r;
+        const float xv = to_float(x[i]);
+        const float rot = j < half ? -to_float(x[i + half]) : to_float(x[i - half]);
+        // the reference rounds each product and the sum to the storage type (three separate ops): keep those roundings
+        const T a = from_float<T>(xv * to_float(cs[t * D + j])), b = from_float<T>(to_float(from_float<T>(rot)) * to_float(sn[t * D + j]));
+        y[i] = from_float<T>(to_float(a) + to_float(b));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // gather rows, fill
 // ------------------------------------------------------------------------------------------------------------
@@ -863,6 +932,7 @@ __global__ void gather_rows_kernel(const uint8_t* __restrict__ table, const int6
     for (int64_t r = blockIdx.x; r < n_idx; r += gridDim.x) {
         int64_t src = idx[r];
         if (src < 0) src += table_rows;
+        src = src < 0 ? 0 : (src >= table_rows ? table_rows - 1 : src);      // indices may come from a device mirror the host did not validate (graph replay)
         const uint8_t* s = table + src * row_bytes;
         uint8_t* d = out + r * row_bytes;
         if ((row_bytes & 15) == 0 && (((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
@@ -1179,8 +1249,9 @@ int osb_group_norm(const void* x, void* y, int dtype, int nhwc, int64_t C, int64
             int64_t c2 = min<int64_t>(HW, 148 * 2);
             int64_t ppc2 = (HW + c2 - 1) / c2;
             c2 = (HW + ppc2 - 1) / ppc2;
-            if (dtype == OSB_F16) osb_launch((gn_stats_nhwc_vec_kernel<__half, 8>), (unsigned)c2, 256, smem, st, (const __half*)x, stats, (int)C, HW, groups, ppc2, (const __half*)nullptr, (__half*)nullptr);
-            else if (dtype == OSB_F32) osb_launch((gn_stats_nhwc_vec_kernel<float, 4>), (unsigned)c2, 256, smem, st, (const float*)x, stats, (int)C, HW, groups, ppc2, (const float*)nullptr, (float*)nullptr);
+            const size_t smem2 = sizeof(float) * (2 * groups + (size_t)(256 / (C / vec)) * 2 * C);    // + the per-row partials
+            if (dtype == OSB_F16) osb_launch((gn_stats_nhwc_vec_kernel<__half, 8>), (unsigned)c2, 256, smem2, st, (const __half*)x, stats, (int)C, HW, groups, ppc2, (const __half*)nullptr, (__half*)nullptr);
+            else if (dtype == OSB_F32) osb_launch((gn_stats_nhwc_vec_kernel<float, 4>), (unsigned)c2, 256, smem2, st, (const float*)x, stats, (int)C, HW, groups, ppc2, (const float*)nullptr, (float*)nullptr);
             else return (int)cudaErrorInvalidValue;
             goto stats_done;
         }
@@ -1223,8 +1294,8 @@ int osb_group_norm_apply(const void* x, void* y, int dtype, int64_t C, int64_t H
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = sizeof(float) * 2 * (size_t)C;
     const int64_t nvec = HW * (C / vec);
-    // every CTA pays the table set-up (C channels): keep >= 8 vectors per thread, at most 2 CTAs per SM
-    const int grid = (int)max<int64_t>(1, min<int64_t>((nvec + 256 * 8 - 1) / (256 * 8), 148 * 2));
+    // every CTA pays the table set-up (C channels, a few hundred cycles); 4 vectors per thread per pass, up to 4 CTAs per SM
+    const int grid = (int)max<int64_t>(1, min<int64_t>((nvec + 256 * 4 - 1) / (256 * 4), 148 * 4));
     if (dtype == OSB_F16) osb_launch((gn_apply_pre_kernel<__half, 8>), grid, 256, smem, st, (const __half*)x, (__half*)y, (const double*)stats, (double*)clear_stats, (int)C, HW, groups, (const __half*)gamma, (const __half*)beta, eps, fuse_silu);
     else if (dtype == OSB_F32) osb_launch((gn_apply_pre_kernel<float, 4>), grid, 256, smem, st, (const float*)x, (float*)y, (const double*)stats, (double*)clear_stats, (int)C, HW, groups, (const float*)gamma, (const float*)beta, eps, fuse_silu);
     else return (int)cudaErrorInvalidValue;
@@ -1240,10 +1311,14 @@ int osb_channel_add_stats(const void* x, const void* addv, void* y, int dtype, i
     if ((dtype != OSB_F16 && dtype != OSB_F32) || groups < 1 || C % groups || C % vec || C / vec > 256 || !aligned16(x) || (y && !aligned16(y)) || (addv && !aligned16(addv)) || ((addv == nullptr) != (y == nullptr)))
         return (int)cudaErrorInvalidValue;
     cudaStream_t st = (cudaStream_t)stream;
-    int64_t c2 = min<int64_t>(HW, 148 * 2);
+    // pixels per CTA: enough CTAs to fill the machine (4 per SM), but >= 4 pixel rows per thread-row so the unrolled loop is used;
+    // each CTA ends with 2 * groups fp64 atomics, so more CTAs is not free
+    const int rows_per_cta = (int)max<int64_t>(1, 256 / (C / vec));
+    int64_t c2 = min<int64_t>((HW + 4 * rows_per_cta - 1) / (4 * rows_per_cta), 148 * 4);
+    c2 = max<int64_t>(c2, 1);
     int64_t ppc2 = (HW + c2 - 1) / c2;
     c2 = (HW + ppc2 - 1) / ppc2;
-    size_t smem = sizeof(float) * 2 * groups;
+    size_t smem = sizeof(float) * (2 * groups + (size_t)rows_per_cta * 2 * C);
     if (dtype == OSB_F16) osb_launch((gn_stats_nhwc_vec_kernel<__half, 8>), (unsigned)c2, 256, smem, st, (const __half*)x, (double*)stats, (int)C, HW, groups, ppc2, (const __half*)addv, (__half*)y);
     else osb_launch((gn_stats_nhwc_vec_kernel<float, 4>), (unsigned)c2, 256, smem, st, (const float*)x, (double*)stats, (int)C, HW, groups, ppc2, (const float*)addv, (float*)y);
     return launched();
@@ -1318,6 +1393,35 @@ int osb_softmax_qu8(const void* x, void* y, int64_t rows, int64_t cols, float in
     if (rows * cols == 0) return 0;
     int threads = cols >= 1024 ? 256 : (cols >= 256 ? 128 : 32);
     osb_launch((softmax_qu8_kernel), (unsigned)min<int64_t>(rows, 148 * 16), threads, 0, (cudaStream_t)stream, (const uint8_t*)x, (uint8_t*)y, rows, cols, in_scale, out_scale, out_zp);
+    return launched();
+}
+
+int osb_rms_norm(const void* x, int xd, const void* w, int wd, void* y, int yd, int64_t rows, int64_t cols, float eps, void* stream)
+{
+    if (rows * cols == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)min<int64_t>((rows + 3) / 4, 148 * 8);
+#define OSB_RMS(TI_, TW_, TO_) osb_launch((rms_norm_kernel<TI_, TW_, TO_>), grid, 128, 0, st, (const TI_*)x, (const TW_*)w, (TO_*)y, rows, (int)cols, eps)
+    if (xd == OSB_F16 && wd == OSB_F16 && yd == OSB_F16) OSB_RMS(__half, __half, __half);
+    else if (xd == OSB_F16 && wd == OSB_F16 && yd == OSB_F32) OSB_RMS(__half, __half, float);
+    else if (xd == OSB_F16 && wd == OSB_F32 && yd == OSB_F32) OSB_RMS(__half, float, float);
+    else if (xd == OSB_F16 && wd == OSB_F32 && yd == OSB_F16) OSB_RMS(__half, float, __half);
+    else if (xd == OSB_F32 && wd == OSB_F32 && yd == OSB_F32) OSB_RMS(float, float, float);
+    else if (xd == OSB_F32 && wd == OSB_F16 && yd == OSB_F32) OSB_RMS(float, __half, float);
+    else if (xd == OSB_F32 && wd == OSB_F32 && yd == OSB_F16) OSB_RMS(float, float, __half);
+    else return (int)cudaErrorInvalidValue;
+#undef OSB_RMS
+    return launched();
+}
+
+int osb_rope(const void* x, const void* cs, const void* sn, void* y, int dtype, int64_t rows, int64_t D, int64_t table_rows, void* stream)
+{
+    if (rows * D == 0) return 0;
+    if (D % 2 || (table_rows != 1 && table_rows != rows)) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == OSB_F16) osb_launch((rope_kernel<__half>), grid_for((size_t)(rows * D), 256), 256, 0, st, (const __half*)x, (const __half*)cs, (const __half*)sn, (__half*)y, rows, (int)D, table_rows);
+    else if (dtype == OSB_F32) osb_launch((rope_kernel<float>), grid_for((size_t)(rows * D), 256), 256, 0, st, (const float*)x, (const float*)cs, (const float*)sn, (float*)y, rows, (int)D, table_rows);
+    else return (int)cudaErrorInvalidValue;
     return launched();
 }
 

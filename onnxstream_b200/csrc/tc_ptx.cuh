@@ -142,9 +142,19 @@ __device__ __forceinline__ void gn_stats_chunk(uint32_t wbuf, const uint32_t (&h
         const float v = __half2float(__ushort_as_half(raw));
         s += v; ss = fmaf(v, v, ss);
     }
+    // lane l holds column n_base + l; the lanes of one group are contiguous: segmented suffix sums by shuffle (5 steps) leave each
+    // group's total in its first lane, which alone touches the shared accumulator -- 32 colliding float atomics per chunk measured
+    // +10 us per launch (profiles/r02_ab_epilogue.txt)
     const int n = n_base + lane;
-    if (n < n_end) {
-        const int g = n / cpg;
+    const int g = n / cpg;
+    if (n >= n_end) { s = 0.f; ss = 0.f; }
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const float ts = __shfl_down_sync(0xffffffffu, s, off), tss = __shfl_down_sync(0xffffffffu, ss, off);
+        if (lane + off < 32 && (n + off) / cpg == g) { s += ts; ss += tss; }
+    }
+    const bool head = lane == 0 || (n - 1) / cpg != g;
+    if (head && n < n_end) {
         atomicAdd(&cta_stats[2 * g], s);
         atomicAdd(&cta_stats[2 * g + 1], ss);
     }

@@ -234,7 +234,7 @@ class Model:
 
     STAT_FIELDS = ("weight_ring_bytes", "weight_peak_live_bytes", "weight_largest_node_bytes", "weight_bytes_streamed",
                    "weight_resident_bytes", "act_high_water_bytes", "h2d_input_bytes", "d2h_output_bytes", "kernel_launches",
-                   "tc_launches", "steps_executed", "ops_fused_away", "last_run_ms", "last_gpu_ms", "graph_replays")
+                   "tc_launches", "steps_executed", "ops_fused_away", "last_run_ms", "last_gpu_ms", "graph_replays", "side_steps")
 
     def run_resident(self, steps: int) -> float:
         """B200 engine only: replay the captured CUDA graph `steps` times on device-resident inputs; returns CUDA-event ms."""

@@ -17,7 +17,7 @@ for _ in range(4):
     bench.step_api(m, inputs, W.out_name)
 ms = m.run_resident(steps) / steps
 st = m.stats()
-print(f"VALUE_ONLY ms_per_step={ms:.4f} launches={st.get('kernel_launches')} tc={st.get('tc_launches')} env={ {k: v for k, v in os.environ.items() if k.startswith('OSB_')} }", flush=True)
+print(f"VALUE_ONLY ms_per_step={ms:.4f} launches={st.get('kernel_launches')} tc={st.get('tc_launches')} side_steps={st.get('side_steps')} env={ {k: v for k, v in os.environ.items() if k.startswith('OSB_')} }", flush=True)
 if os.environ.get("OSB_TC_DUMP"):
     import ctypes
     lib = m.lib

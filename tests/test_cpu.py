@@ -403,3 +403,59 @@ def test_qu8_restatement_bit_exact(oracle_lib, tmp_path):
     sw, zw = np.float32(float(m.group(2))), int(m.group(3))
     qy = npo.qu8_gemm(qs.reshape(40, 48), so, zo, qw, sw, zw, sf, zf)
     assert np.array_equal(npo.qu8_dequantize(qy, sf, zf).reshape(1, 40, 32), out[y_t.name])
+
+
+def test_planner_side_branch_and_gn_statistics(engine_lib, tmp_path):
+    """Host-side planning of the two round-2 schedule changes, on the SD-UNet topology (no GPU needed):
+      * side branch: the time-embedding MLP, every resnet's time_emb_proj chain and the cross-attention K / V projections do not depend on
+        the latent (the graph input that starts the longest op chain) -> hoisted to the second stream;
+      * GroupNorm statistics: every GroupNorm fed by the step right before it (conv, conv + residual, per-channel time-embedding add)
+        gets them from that producer instead of a pass of its own."""
+    from onnxstream_b200.model import plan_summary
+    d = str(tmp_path) + "/"
+    cfg = emit.UNetConfig.tiny(8)
+    emit.emit_unet(d, cfg, "float16", seed=0)
+    # the side-branch schedule is opt-in (OSB_SIDE_BRANCH=1, read once per process): plan in a child process
+    code = ("import sys; sys.path.insert(0, %r); from onnxstream_b200.model import plan_summary; "
+            "sys.stdout.write(plan_summary(open(%r).read(), library_path=%r))" % (ROOT, d + "model.txt", engine_lib))
+    rep = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, OSB_SIDE_BRANCH="1"), stdout=subprocess.PIPE, text=True, check=True).stdout
+    lines = rep.splitlines()
+    summ = dict(kv.split("=") for kv in lines[-1].split()[1:])
+    n_resnets = sum(1 for l in lines if l.startswith("SINGLE 1 Gemm") and "[side]" in l) - 2      # 2 = the time-embedding MLP itself
+    assert n_resnets >= 6, rep[-2000:]
+    assert int(summ["side"]) >= 3 * n_resnets                      # SiLU + Gemm + Unsqueeze(s) per resnet
+    n_cross = sum(1 for l in lines if l.startswith("MHA") and "[kv-side]" in l)
+    n_mha = sum(1 for l in lines if l.startswith("MHA"))
+    assert n_mha >= 2 and n_cross == n_mha // 2, (n_mha, n_cross)   # every transformer block: one self- and one cross-attention
+    assert not any("[side]" in l and l.startswith(("CONV_ADD", "GROUPNORM", "MHA")) for l in lines)
+    n_gn = int(summ["GROUPNORM"])
+    assert int(summ["gn_stats_producers"]) >= n_gn // 2, (summ, n_gn)
+    # a graph with a single input has no side branch
+    vd = str(tmp_path) + "/vae/"
+    emit.emit_vae_decoder(vd, emit.VAEConfig.tiny(8), "float16")
+    assert "side=" not in plan_summary(open(vd + "model.txt").read(), library_path=engine_lib).splitlines()[-1]
+
+
+def test_tiled_vae_geometry_and_blend():
+    """sd.cpp's tile walk (src/sd.cpp:1325-1340, 2478-2499) and feather blend (1296-1322) restated in onnxstream_b200/tiled_vae.py: the
+    origins for the reference's three cases, and the blend against a direct transcription of the reference's scalar loop."""
+    from onnxstream_b200 import tiled_vae as tv
+    assert tv.tile_origins(64) == [0, 24, 32]                  # SD 1.5 512x512: 3 x 3 tiles
+    assert tv.tile_origins(128) == [0, 24, 48, 72, 96]         # SDXL 1024x1024: 5 x 5 = 25 tiles
+    assert tv.tile_origins(32) == [0] and tv.tile_origins(40) == [0, 8]
+    rng = np.random.default_rng(0)
+    canvas = rng.standard_normal((3, 96, 96)).astype(np.float32)
+    ref = canvas.copy()
+    tile = rng.standard_normal((3, 64, 64)).astype(np.float32)
+    dx, dy, ramp = 32, 16, 8
+    for c in range(3):
+        for y in range(64):
+            for x in range(64):
+                f = np.float32(1)
+                if dy and y < ramp:
+                    f = np.float32(y) / np.float32(ramp)
+                if dx and x < ramp:
+                    f = f * (np.float32(x) / np.float32(ramp))
+                ref[c, dy + y, dx + x] = tile[c, y, x] * f + ref[c, dy + y, dx + x] * (np.float32(1) - f)
+    tv.blend_tile(canvas, tile, dx, dy, ramp)
+    assert np.array_equal(canvas, ref)

@@ -258,6 +258,32 @@ def test_uint8_arithmetic_chain_bit_exact(engine_lib, oracle_lib, workdir):
         assert bad == 0, f"{nm}: {bad} of {ref[tn].size} values differ from the reference (max {float(np.abs(got[tn] - ref[tn]).max()):.4g})"
 
 
+def test_tiled_vae_decode_batched(engine_lib, oracle_lib, workdir):
+    """sd.cpp's tiled VAE decode (src/sd.cpp:1258-1346, 2399-2503) with ALL tiles as batch siblings of one run.
+    (1) batched == tile-by-tile on the engine; (2) engine == the reference decoding tile by tile + the same feather blend."""
+    from onnxstream_b200.model import Model
+    from onnxstream_b200 import tiled_vae as tv
+    vc = emit.VAEConfig.tiny(8)          # the decoder graph is built for 8x8 latent tiles -> 64x64 pixel tiles
+    d = os.path.join(workdir, "vae_tiles") + "/"
+    emit.emit_vae_decoder(d, vc, "float16")
+    latent = np.random.default_rng(3).standard_normal((1, 4, 20, 14)).astype(np.float32)    # 3 x 2 overlapping tiles (stride 6)
+
+    def mk(lib):
+        m = Model(lib, 4, "nocache")
+        for o in FP16:
+            m.set_option(o, True)
+        m.read_file(d + "model.txt")
+        return m
+    kw = dict(tile=8, stride=6)
+    img_b, n = tv.tiled_decode(mk(engine_lib), latent, "input_2E_1", "outsample", batched=True, **kw)
+    img_s, _ = tv.tiled_decode(mk(engine_lib), latent, "input_2E_1", "outsample", batched=False, **kw)
+    img_r, _ = tv.tiled_decode(mk(oracle_lib), latent, "input_2E_1", "outsample", batched=False, **kw)
+    up = img_b.shape[-1] // 14
+    assert n == 6 and img_b.shape == (1, 3, 20 * up, 14 * up) and up in (4, 8)
+    assert report(img_b, img_s)["rel_to_max"] <= 2e-3          # same kernels, batch siblings vs separate runs
+    assert report(img_b, img_r)["rel_to_max"] <= 3e-2, report(img_b, img_r)
+
+
 def test_force_fp16_storage(engine_lib, oracle_lib, models32):
     """m_force_fp16_storage (src/onnxstream.cpp:3764-3808): fp32 arithmetic, fp16 storage between ops."""
     d, inputs, out = models32["unet"]
@@ -351,6 +377,55 @@ def test_llama_decode_parity(engine_lib, oracle_lib, workdir, mode):
         assert report(got[n], ref[n])["rel_to_max"] <= TOL[mode], n
     # shape / index path is bit-exact: the appended cache row position and the gathered embedding row
     assert np.array_equal(got["opkv0"][:, :, :-1], ref["opkv0"][:, :, :-1]) or mode == "float16"
+
+
+def test_llama_decode_graph_replay_follows_token_ids(engine_lib, workdir):
+    """int64 graph inputs and CUDA graphs: token ids / positions / mask reach the device through int64 mirrors (Gather indices, Cast),
+    so the captured decode step can be REPLAYED with new ids.  A captured model fed a sequence of different (id, position) pairs must
+    reproduce what a fresh eager model computes for each of them; the KV cache stays in HBM (b200_keep_inputs) after the first push."""
+    from onnxstream_b200.model import Model
+    cfg = emit.LlamaConfig.tiny()
+    d = os.path.join(workdir, "llama_graph") + "/"
+    emit.emit_llama_decode(d, cfg, "float16")
+    base = emit.llama_inputs(cfg)
+    opts = ("use_scaled_dp_attn_op", "use_fp16_arithmetic")
+
+    def mk(graph):
+        m = Model(engine_lib, 0, "ram+nocache")
+        for o in opts:
+            m.set_option(o, True)
+        for p in UPCAST:
+            m.add_upcast_pattern(p)
+        if graph:
+            for k in ("b200_resident_weights", "b200_cuda_graph", "b200_keep_inputs", "b200_drop_unconverted_outputs"):
+                m.lib.model_set_option(m.h, k.encode(), 1)
+            m.lib.model_ext_add_output_convert(m.h, b"logits")
+        m.read_file(d + "model.txt")
+        return m
+
+    def step(m, inp):
+        m.clear_tensors()
+        for k, v in inp.items():
+            m.add_tensor(k, v)
+        m.run()
+        return m.get_tensor("logits")
+
+    g = mk(True)
+    small = {k: v for k, v in base.items() if not k.startswith("pkv")}
+    step(g, base)                                    # everything pushed once; the cache stays on the device
+    replays0 = None
+    for t in range(8):
+        cur = dict(small)
+        cur["input_5F_ids"] = np.array([[(7 * t + 3) % cfg.vocab]], np.int64)
+        cur["position_5F_ids"] = np.array([[(cfg.past - t) % cfg.max_pos]], np.int64)
+        mask = np.ones((1, cfg.past + 1), np.int64); mask[0, :t] = 0
+        cur["attention_5F_mask"] = mask
+        got = step(g, cur)
+        full = dict(base); full.update(cur)
+        want = step(mk(False), full)
+        assert report(got, want)["rel_to_max"] <= 2e-3, (t, report(got, want))
+    st = g.stats()
+    assert st["graph_replays"] >= 3, st               # the later steps really were graph replays
 
 
 @pytest.mark.parametrize("fp16", [False, True])
