@@ -658,7 +658,9 @@ def measure(w: Workload, args, dist, clocks=None):
             ref0 = None
         ref0 = dist_bcast_array(dist, ref0)
         if ref0 is not None:
-            got0 = out_e if RANK == 0 else step_api(me, in0, w.out_name)   # sample 0 through THIS rank's streamed engine (NCCL-fed weights)
+            # sample 0 through THIS rank's streamed engine (NCCL-fed weights).  EVERY rank steps, rank 0 included: the weight stream's
+            # all-gather is a collective, a rank that skipped the step would leave the others waiting in it
+            got0 = step_api(me, in0, w.out_name)
             err = float(np.abs(got0 - ref0).max()) / max(float(np.abs(ref0).max()), 1e-12)
             parity["vs_reference_rel_all_ranks"] = dist_max(dist, err)
             parity["tol"] = w.tol

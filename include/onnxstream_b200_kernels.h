@@ -34,13 +34,16 @@ int osb_unary(int op, const void* x, void* y, int dtype, size_t n, float alpha, 
 /* N-d broadcasting binary ops: XnnPack::add/subtract/multiply/divide (src/onnxstream.cpp:846-927, 1666-1949).
  * Shapes are right-aligned and padded to `ndim` by the caller; stride 0 marks a broadcast dimension.
  * OSB_BIN_MUL_GELU computes a * gelu_erf(b) (GEGLU gate), OSB_BIN_MUL_SIGMOID a * sigmoid(b). */
-enum { OSB_BIN_ADD = 0, OSB_BIN_SUB, OSB_BIN_MUL, OSB_BIN_DIV, OSB_BIN_MUL_GELU, OSB_BIN_MUL_SIGMOID };
+enum { OSB_BIN_ADD = 0, OSB_BIN_SUB, OSB_BIN_MUL, OSB_BIN_DIV, OSB_BIN_MUL_GELU, OSB_BIN_MUL_SIGMOID, OSB_BIN_SILU_MUL /* silu(a) * b: gated MLP */ };
 int osb_binary(int op, const void* a, const int64_t* a_strides, const void* b, const int64_t* b_strides,
                void* out, const int64_t* out_shape, int ndim, int dtype, void* stream);
 
 /* Generic strided gather-copy: out[i0..] = in[in_offset + sum_k (i_k / in_div[k]) * in_stride[k]], written at
  * out_offset + sum_k i_k * out_stride[k].  Covers XnnPack::transpose (src/onnxstream.cpp:1748-1809), Concat
  * (4140-4299), Split (5999-6119), Slice (6499-6695), Expand (7154-7351) and nearest Resize (6120-6315, in_div = scale). */
+/* Concat of two tensors along one axis in one launch (src/onnxstream.cpp Concat branch, two inputs): outer slices of a_bytes / b_bytes each.
+   cudaErrorNotSupported (801) unless both slice sizes and all three pointers are multiples of 16 bytes. */
+int osb_concat2(const void* a, const void* b, void* out, int64_t outer, int64_t a_bytes, int64_t b_bytes, void* stream);
 int osb_strided_copy(const void* in, void* out, int elem_size, int ndim, const int64_t* shape,
                      const int64_t* in_stride, const int64_t* in_div, int64_t in_offset,
                      const int64_t* out_stride, int64_t out_offset, void* stream);
@@ -132,6 +135,11 @@ int osb_rope(const void* x, const void* cs, const void* sn, void* y, int dtype, 
 /* Decode GEMV with uint8 weights [K,N] dequantised in registers (M <= 2): y = x . ((Wq - zp) * scale rounded to `dtype`) + bias + residual.
  * The uint8-weight / float-arithmetic MatMul of the reference (weights converted at load, src/onnxstream.cpp:2885-2890) at half the HBM bytes. */
 int osb_gemv_w8(const void* A, const void* Wq, void* C, const void* bias, const void* residual, int64_t M, int64_t N, int64_t K, float wscale, int wzp, int dtype, void* stream);
+/* 2 or 3 GEMVs that share their input rows (q / k / v projections, gate / up of a gated MLP: consecutive MatMul nodes of llm.cpp's graphs,
+   src/onnxstream.cpp:5669-5861) as one launch; wdtype OSB_U8 = uint8 weights dequantised in registers.  cudaErrorNotSupported (801) when the
+   shapes are outside the grouped kernels: launch them one by one. */
+int osb_gemv_grouped(const void* A, const void* const* B, void* const* C, const int64_t* N, const float* wscale, const int* wzp, int groups,
+                     int64_t M, int64_t K, int wdtype, int dtype, void* stream);
 /* W8A8 on the tensor cores (tcgen05.mma.kind::i8, uint8 x uint8 -> int32): XnnPack::matrix_multiply<uint8_t,int32_t> / convolution for uint8
  * (src/onnxstream.cpp:1035-1215, 1292-1534) with XNNPACK's fp32 requantisation y = clamp(lrintf(acc * sx*sw/sy)) + zy.  The kernel multiplies raw
  * bytes and corrects with rowsum_x / colsum_w (osb_rowsum_u8: row sums of a [rows][cols] byte matrix; osb_colsum_u8: column sums of a [K][N] one);

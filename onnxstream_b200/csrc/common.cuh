@@ -52,6 +52,22 @@ static inline void osb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);   // errors surface through launched() / cudaGetLastError
 }
 
+// Cooperative launch: the driver gang-schedules the grid (every CTA resident at once, or the launch fails with
+// cudaErrorCooperativeLaunchTooLarge) -- what a kernel with a grid-wide rendezvous needs when other work (NCCL kernels, a second
+// stream) may hold SMs.
+template <typename... KArgs, typename... Args>
+static inline void osb_launch_coop(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 static inline int grid_for(size_t work_items, int threads)
 {
     size_t blocks = (work_items + threads - 1) / threads;

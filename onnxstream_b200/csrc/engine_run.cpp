@@ -50,7 +50,7 @@ static void range_to_scale(float lo, float hi, float& scale, int& zp)
     zp = (int)(uint8_t)(std::abs(lo) / scale);
 }
 
-enum StepKind { SK_SINGLE = 0, SK_ATTENTION, SK_GROUPNORM, SK_LAYERNORM, SK_GELU, SK_SILU, SK_LINEAR, SK_SDPA, SK_MHA, SK_CONV_ADD, SK_GEGLU, SK_RMSNORM, SK_ROPE };
+enum StepKind { SK_SINGLE = 0, SK_ATTENTION, SK_GROUPNORM, SK_LAYERNORM, SK_GELU, SK_SILU, SK_LINEAR, SK_SDPA, SK_MHA, SK_CONV_ADD, SK_GEGLU, SK_RMSNORM, SK_ROPE, SK_GEMV_GROUP, SK_SWIGLU };
 
 struct Step {
     StepKind kind = SK_SINGLE;
@@ -711,6 +711,54 @@ struct Engine::Impl {
         return 2;
     }
 
+    // decode-shaped MatMul: activation with <= 8 rows times a static 2-D weight
+    bool is_gemv_matmul(const OpDef& mm) const
+    {
+        if (mm.type != "MatMul" || mm.in.size() != 2 || mm.out.size() != 1 || mm.in[0].wtype != DType::none || !is_float_weight(mm.in[1]) || mm.in[1].shape.size() != 2) return false;
+        const auto& as = mm.in[0].shape;
+        if (as.empty() || as.back() != mm.in[1].shape[0]) return false;
+        int64_t rows = 1; for (size_t k = 0; k + 1 < as.size(); k++) rows *= as[k];
+        return rows >= 1 && rows <= 8 && !upcast_op(mm);
+    }
+    // 2 or 3 consecutive decode MatMuls of the same activation (q / k / v projections): one grouped GEMV launch
+    size_t match_gemv_group(size_t i) const
+    {
+        auto& ops = E.m_ops;
+        if (!E.fuse_nodes || E.use_uint8_arithmetic || E.use_uint8_qdq) return 0;
+        size_t n = 0;
+        while (n < 3 && i + n < ops.size()) {
+            const OpDef& mm = ops[i + n];
+            if (!is_gemv_matmul(mm)) break;
+            if (n && (mm.in[0].name != ops[i].in[0].name || mm.in[1].shape[0] != ops[i].in[1].shape[0] || (mm.in[1].wtype == DType::u8) != (ops[i].in[1].wtype == DType::u8))) break;
+            n++;
+        }
+        // leave the last MatMul to the Linear matcher when an Add takes its result (bias / residual epilogue)
+        if (n >= 2 && i + n < ops.size() && ops[i + n].type == "Add")
+            for (auto& r : ops[i + n].in) if (r.present && r.wtype == DType::none && r.name == ops[i + n - 1].out[0].name) { n--; break; }
+        return n >= 2 ? n : 0;
+    }
+    // gated MLP of llm.cpp's graphs: MatMul(x, Wg) -> Sigmoid -> Mul (SiLU) -> MatMul(x, Wu) -> Mul: one grouped GEMV + one elementwise pass
+    size_t match_swiglu(size_t i) const
+    {
+        auto& ops = E.m_ops;
+        if (!E.fuse_nodes || E.use_uint8_arithmetic || E.use_uint8_qdq) return 0;
+        if (i + 4 >= ops.size()) return 0;
+        const OpDef &g = ops[i], &sg = ops[i + 1], &m1 = ops[i + 2], &u = ops[i + 3], &m2 = ops[i + 4];
+        if (!is_gemv_matmul(g) || !is_gemv_matmul(u) || sg.type != "Sigmoid" || m1.type != "Mul" || m2.type != "Mul") return 0;
+        if (g.in[0].name != u.in[0].name || g.in[1].shape != u.in[1].shape || (g.in[1].wtype == DType::u8) != (u.in[1].wtype == DType::u8)) return 0;
+        if (upcast_op(sg) || upcast_op(m1) || upcast_op(m2) || m1.in.size() != 2 || m2.in.size() != 2) return 0;
+        const std::string& gn = g.out[0].name;
+        auto it = uses.find(gn);
+        if (it == uses.end() || it->second != 2) return 0;                       // the gate feeds Sigmoid and the SiLU Mul only
+        if (sg.in.size() != 1 || sg.in[0].name != gn || sg.in[0].wtype != DType::none) return 0;
+        bool silu = false;
+        for (int k = 0; k < 2; k++) if (m1.in[k].wtype == DType::none && m1.in[k].name == gn && feeds(sg, m1, 1 - k)) silu = true;
+        if (!silu) return 0;
+        bool gate = false;
+        for (int k = 0; k < 2; k++) if (feeds(m1, m2, k) && feeds(u, m2, 1 - k)) gate = true;
+        return gate ? 5 : 0;
+    }
+
     // RMSNorm as llm.cpp's graphs spell it: Pow(x, 2) -> ReduceMean(-1) -> Add(eps) -> Sqrt -> Div(1, .) -> Mul(x, .) -> Mul(w, .)
     size_t match_rmsnorm(size_t i) const
     {
@@ -800,7 +848,17 @@ struct Engine::Impl {
         if (ad.in.size() != 2) return 0;
         int bias_idx = -1;
         for (int k = 0; k < 2; k++) if (is_float_weight(ad.in[k]) && ad.in[k].shape.size() == 1 && ad.in[k].shape[0] == N) bias_idx = k;
-        if (bias_idx < 0 || !feeds(mm, ad, 1 - bias_idx)) return 0;
+        if (bias_idx < 0) {
+            // MatMul -> Add(activation of the same shape): the residual add of a bias-free projection (LLM blocks) in the GEMM / GEMV epilogue
+            if (upcast_op(mm) || upcast_op(ad)) return 0;
+            for (int k = 0; k < 2; k++)
+                if (feeds(mm, ad, k) && ad.in[1 - k].present && ad.in[1 - k].wtype == DType::none && ad.in[1 - k].shape == mm.out[0].shape && ad.in[1 - k].name != mm.out[0].name) {
+                    variant = 16 | (k == 0 ? 4 : 0);
+                    return 2;
+                }
+            return 0;
+        }
+        if (!feeds(mm, ad, 1 - bias_idx)) return 0;
         variant = bias_idx;  // which Add input is the bias
         if (upcast_op(mm) != upcast_op(ad)) return 0;
         // optional residual
@@ -838,6 +896,8 @@ struct Engine::Impl {
             else if ((n = match_gelu(i, var))) { s.kind = SK_GELU; s.count = n; s.variant = var; }
             else if ((n = match_rmsnorm(i))) { s.kind = SK_RMSNORM; s.count = n; }
             else if ((n = match_rope(i))) { s.kind = SK_ROPE; s.count = n; }
+            else if ((n = match_swiglu(i))) { s.kind = SK_SWIGLU; s.count = n; }
+            else if ((n = match_gemv_group(i))) { s.kind = SK_GEMV_GROUP; s.count = n; }
             else if ((n = match_silu(i))) { s.kind = SK_SILU; s.count = n; }
             else if ((n = match_linear(i, var))) { s.kind = SK_LINEAR; s.count = n; s.variant = var; }
             else if ((n = match_conv_add(i, var))) { s.kind = SK_CONV_ADD; s.count = n; s.variant = var; }
@@ -986,6 +1046,9 @@ struct Engine::Impl {
     void fused_sdpa(const Step& s);
     void fused_mha(const Step& s);
     void fused_rmsnorm(const Step& s);
+    void fused_gemv_group(const Step& s);
+    void fused_swiglu(const Step& s);
+    bool gemv_group(const Tensor& a, const size_t* op_idx, int n, Tensor* outs);
     void fused_rope(const Step& s);
 
     Tensor binary(int bop, const Tensor& a, const Tensor& b, float out_scale = 0.f, int out_zp = 0);
@@ -1330,6 +1393,24 @@ void Engine::Impl::op_matmul(size_t oi, const Tensor* bias, const Tensor* residu
         if (bias) { bb = *bias; if (bb.type != a.type) bb = convert(bb, a.type); }
         if (residual) { rr = to_plain(*residual); if (rr.type != a.type) rr = convert(rr, a.type); }
         y = make(a.type, os);
+        const int64_t vec = 16 / (int64_t)dtype_size(a.type);
+        if (E.resident_weights && op.in[1].wtype != DType::none && op.in[1].shape.size() == 2 && n == 1 && M <= 8 && N >= 256 && N % vec != 0 && Kd >= 64) {
+            // decode GEMV against a resident weight whose rows are not 16-byte granular (a 32003-entry vocabulary): a row-padded copy,
+            // made once and kept with the resident weights, lets the vector GEMV stream it (the scalar kernel ran at a fifth of the rate)
+            const int64_t Np = (N + vec - 1) / vec * vec;
+            const std::string pkey = op.in[1].name + "|pad" + std::to_string((int)a.type);
+            auto it = resident.find(pkey);
+            if (it == resident.end()) {
+                Tensor bp = make(a.type, { Kd, Np });
+                ck(cudaMemsetAsync(bp.mdata(), 0, (size_t)(Kd * Np) * dtype_size(a.type), st), "cudaMemsetAsync(padded weight)");
+                ck(cudaMemcpy2DAsync(bp.mdata(), (size_t)Np * dtype_size(a.type), b.data(), (size_t)N * dtype_size(a.type), (size_t)N * dtype_size(a.type), (size_t)Kd,
+                                     cudaMemcpyDeviceToDevice, st), "cudaMemcpy2DAsync(padded weight)");
+                resident_bytes += (size_t)(Kd * Np) * dtype_size(a.type);
+                it = resident.emplace(pkey, bp).first;
+            }
+            ck(osb_gemm_ld(a.data(), Kd, it->second.data(), Np, y.mdata(), N, bias ? bb.data() : nullptr, residual ? rr.data() : nullptr, 1, M, N, Kd,
+                           0, 0, 0, 0, K(a.type), E.gemm_impl, st), "osb_gemm_ld(padded weight)");
+        } else
         ck(osb_gemm(a.data(), b.data(), y.mdata(), bias ? bb.data() : nullptr, residual ? rr.data() : nullptr, n, M, N, Kd,
                     M * Kd, stride_b, M * N, 0, K(a.type), E.gemm_impl, st), "osb_gemm");
     }
@@ -1543,6 +1624,22 @@ void Engine::Impl::op_transpose(size_t oi)
         }
     }
     x = to_plain(x);
+    {
+        // a permutation that only moves unit axes around (LLM decode: (1, 1, heads, d) <-> (1, heads, 1, d)) leaves the bytes where they are
+        bool valid = true, view = true; int64_t last = -1;
+        for (size_t k = 0; k < perm.size() && valid; k++) {
+            if (perm[k] < 0 || perm[k] >= (int64_t)perm.size()) { valid = false; break; }
+            if (x.shape[perm[k]] == 1) continue;
+            if (perm[k] < last) view = false;
+            last = perm[k];
+        }
+        if (valid && view) {
+            Tensor y = x;
+            y.shape.resize(perm.size());
+            for (size_t k = 0; k < perm.size(); k++) y.shape[k] = x.shape[perm[k]];
+            push(oi, 0, y); return;
+        }
+    }
     auto istr = contiguous_strides(x.shape);
     std::vector<int64_t> os(perm.size()), is(perm.size());
     for (size_t i = 0; i < perm.size(); i++) { if (perm[i] < 0 || perm[i] >= (int64_t)perm.size()) fail(op, "invalid perm attribute."); os[i] = x.shape[perm[i]]; is[i] = istr[perm[i]]; }
@@ -1602,6 +1699,15 @@ void Engine::Impl::op_concat(size_t oi)
     int64_t outer = 1, inner = 1, total_axis = os[axis];
     if (nhwc_path) { outer = os[2] * os[3]; inner = 1; }
     else { for (int64_t d = 0; d < axis; d++) outer *= os[d]; for (size_t d = axis + 1; d < rank; d++) inner *= os[d]; }
+    if (xs.size() == 2 && !nhwc_path) {
+        // two sources (KV-cache append): one launch when everything is 16-byte granular
+        const int64_t es = (int64_t)dtype_size(ty);
+        if (osb_concat2(xs[0].data(), xs[1].data(), y.mdata(), outer, xs[0].shape[axis] * inner * es, xs[1].shape[axis] * inner * es, st) == 0) {
+            push(oi, 0, y);
+            return;
+        }
+        (void)cudaGetLastError();
+    }
     int64_t off = 0;
     for (auto& t : xs) {
         int64_t len = t.shape[axis] * inner;
@@ -2382,7 +2488,11 @@ void Engine::Impl::fused_rmsnorm(const Step& s)
 {
     const size_t i = s.first;
     const OpDef& pw = E.m_ops[i];
-    Tensor x = to_plain(in(i, 0));
+    // the kernel reads fp16 or fp32 and computes in fp32 either way: no up-cast copy of the input (in() would make one for an
+    // m_requires_upcast op); quantised storage goes through in() as usual
+    Tensor x = get_act(pw, pw.in[0].name);
+    if (x.type != DType::f16 && x.type != DType::f32) x = in(i, 0);
+    x = to_plain(x);
     const float two = scalar_of(in(i, 1), pw), eps = scalar_of(in(i + 2, 1), E.m_ops[i + 2]), one = scalar_of(in(i + 4, 0), E.m_ops[i + 4]);
     if (two != 2.f || one != 1.f || (x.type != DType::f16 && x.type != DType::f32)) { exec_unfused(s); return; }
     const OpDef& m2 = E.m_ops[i + 6];
@@ -2390,7 +2500,11 @@ void Engine::Impl::fused_rmsnorm(const Step& s)
     Tensor w = in(i + 6, wi);
     // arithmetic class of the chain: fp32 when the ops are up-cast (m_requires_upcast) or the model runs fp32; the result type is what the
     // last Mul would have produced (push() then applies the storage rule)
-    const DType ot = (upcast_op(m2) || !E.use_fp16_arithmetic) ? DType::f32 : x.type;
+    DType ot = (upcast_op(m2) || !E.use_fp16_arithmetic) ? DType::f32 : x.type;
+    // push() would round an fp32 result to fp16 storage right away unless the next step is its only consumer: write those bits directly
+    // (one rounding of the same fp32 value either way)
+    if (ot == DType::f32 && E.use_fp16_arithmetic && !E.use_uint8_arithmetic && !E.use_uint8_qdq && !E.range_data_calibrate &&
+        !next_is_sole_consumer(cur_step, m2.out[0].name)) ot = DType::f16;
     if (w.type != DType::f16 && w.type != DType::f32) { exec_unfused(s); return; }
     Tensor y = make(ot, x.shape);
     if (osb_rms_norm(x.data(), K(x.type), w.data(), K(w.type), y.mdata(), K(ot), x.numel() / x.shape.back(), x.shape.back(), eps, st) != 0) {
@@ -2421,6 +2535,64 @@ void Engine::Impl::fused_rope(const Step& s)
     Tensor y = make(x.type, x.shape);
     ck(osb_rope(x.data(), cs.data(), sn.data(), y.mdata(), K(x.type), x.numel() / D, D, 1, st), "osb_rope");
     push(i + 6, 0, y);
+}
+
+// n (2 or 3) MatMul nodes x[rows <= 8, K] . W_g[K, N_g] sharing x: one grouped GEMV launch.  false = not expressible (the caller runs the
+// nodes one by one); nothing has been pushed in that case.
+bool Engine::Impl::gemv_group(const Tensor& a, const size_t* op_idx, int n, Tensor* outs)
+{
+    if (a.type != DType::f16 && a.type != DType::f32) return false;
+    int64_t rows = 1; for (size_t k = 0; k + 1 < a.shape.size(); k++) rows *= a.shape[k];
+    const int64_t Kd = a.shape.back();
+    static const bool w8_gemv = [] { const char* e = getenv("OSB_W8_GEMV"); return !(e && e[0] == '0'); }();
+    static const bool grouped = [] { const char* e = getenv("OSB_GEMV_GROUPED"); return !(e && e[0] == '0'); }();
+    if (!grouped) return false;
+    bool u8 = true, flt = true;
+    for (int g = 0; g < n; g++) {
+        const OpDef& op = E.m_ops[op_idx[g]];
+        const TensorRef& wr = op.in[1];
+        if (wr.shape[0] != Kd) return false;
+        const bool w_u8 = w8_gemv && wr.wtype == DType::u8 && rows <= 2 && wr.shape[1] % 16 == 0 && wr.shape[1] >= 256 && Kd >= 64 && weight_target(op, wr, false) == a.type;
+        u8 = u8 && w_u8;
+        flt = flt && (wr.wtype != DType::u8 || !w8_gemv) && wr.shape[1] % 8 == 0 && wr.shape[1] >= 256;
+    }
+    if (!u8 && !flt) return false;
+    const void* B[3]; void* C[3]; int64_t N[3]; float ws[3]; int wz[3];
+    Tensor wt[3];
+    for (int g = 0; g < n; g++) {
+        const OpDef& op = E.m_ops[op_idx[g]];
+        wt[g] = u8 ? get_weight(op_idx[g], 1, false, false, true) : in(op_idx[g], 1);
+        if (!u8 && wt[g].type != a.type) wt[g] = convert(wt[g], a.type);
+        std::vector<int64_t> os = a.shape; os.back() = op.in[1].shape[1];
+        outs[g] = make(a.type, os);
+        B[g] = wt[g].data(); C[g] = outs[g].mdata(); N[g] = op.in[1].shape[1]; ws[g] = wt[g].scale; wz[g] = wt[g].zero_point;
+    }
+    const int rc = osb_gemv_grouped(a.data(), B, C, N, ws, wz, n, rows, Kd, u8 ? OSB_U8 : K(a.type), K(a.type), st);
+    if (rc == (int)cudaErrorNotSupported) return false;
+    ck(rc, "osb_gemv_grouped");
+    return true;
+}
+
+void Engine::Impl::fused_gemv_group(const Step& s)
+{
+    Tensor a = to_plain(in(s.first, 0));
+    size_t idx[3]; Tensor outs[3];
+    for (size_t g = 0; g < s.count; g++) idx[g] = s.first + g;
+    if (!gemv_group(a, idx, (int)s.count, outs)) { exec_unfused(s); return; }
+    for (size_t g = 0; g < s.count; g++) push(idx[g], 0, outs[g]);
+}
+
+void Engine::Impl::fused_swiglu(const Step& s)
+{
+    const size_t i = s.first;
+    Tensor a = to_plain(in(i, 0));
+    size_t idx[2] = { i, i + 3 }; Tensor outs[2];
+    if (!gemv_group(a, idx, 2, outs)) { exec_unfused(s); return; }
+    // silu(gate) * up in fp32, one rounding (the fused-step convention of this engine: GELU, GEGLU, SiLU behave the same way)
+    Tensor y = make(a.type, outs[0].shape);
+    const int64_t n = y.numel(), one = 1;
+    ck(osb_binary(OSB_BIN_SILU_MUL, outs[0].data(), &one, outs[1].data(), &one, y.mdata(), &n, 1, K(a.type), st), "osb_binary(silu_mul)");
+    push(i + 4, 0, y);
 }
 
 void Engine::Impl::fused_layernorm(const Step& s)
@@ -2511,6 +2683,11 @@ void Engine::Impl::fused_silu(const Step& s)
 void Engine::Impl::fused_linear(const Step& s)
 {
     size_t i = s.first;
+    if (s.variant & 16) {
+        Tensor res = in(i + 1, (s.variant & 4) ? 1 : 0);
+        op_matmul(i, nullptr, &res, i + 1);
+        return;
+    }
     int bias_idx = s.variant & 3;
     Tensor bias = in(i + 1, (size_t)bias_idx);
     if (s.count == 3) {
@@ -2599,6 +2776,8 @@ void Engine::Impl::exec_step(size_t si)
         case SK_SDPA: fused_sdpa(s); break;
         case SK_MHA: fused_mha(s); break;
         case SK_RMSNORM: fused_rmsnorm(s); break;
+        case SK_GEMV_GROUP: fused_gemv_group(s); break;
+        case SK_SWIGLU: fused_swiglu(s); break;
         case SK_ROPE: fused_rope(s); break;
         case SK_CONV_ADD: { Tensor res = in(s.first + 1, (size_t)s.variant); op_conv(s.first, &res, s.first + 1); break; }
         default: exec_single(s.first); break;
@@ -2648,7 +2827,7 @@ Engine::Engine(EngineNoDevice)
 
 std::string Engine::plan_summary(const std::string& model_text, bool fp16_arithmetic, bool fuse_nodes_, bool fuse_attention, bool use_sdpa_rewrite)
 {
-    static const char* kind_names[] = { "SINGLE", "ATTENTION", "GROUPNORM", "LAYERNORM", "GELU", "SILU", "LINEAR", "SDPA", "MHA", "CONV_ADD", "GEGLU", "RMSNORM", "ROPE" };
+    static const char* kind_names[] = { "SINGLE", "ATTENTION", "GROUPNORM", "LAYERNORM", "GELU", "SILU", "LINEAR", "SDPA", "MHA", "CONV_ADD", "GEGLU", "RMSNORM", "ROPE", "GEMV_GROUP", "SWIGLU" };
     Engine e{ EngineNoDevice{} };
     e.use_fp16_arithmetic = fp16_arithmetic;
     e.fuse_nodes = fuse_nodes_;

@@ -106,6 +106,7 @@ __device__ __forceinline__ float apply_binary(int op, float a, float b)
     case OSB_BIN_DIV: return a / b;
     case OSB_BIN_MUL_GELU: return a * (0.5f * b * (1.f + erff(b * 0.70710678118654752f)));
     case OSB_BIN_MUL_SIGMOID: return a / (1.f + expf(-b));
+    case OSB_BIN_SILU_MUL: return (a / (1.f + expf(-a))) * b;
     default: return a;
     }
 }
@@ -864,6 +865,29 @@ __global__ void rms_norm_kernel(const TI* __restrict__ x, const TW* __restrict__
     }
 }
 
+// few rows (a decode step has one): a whole CTA per row -- 256 threads, 4 independent loads each per pass, block reduction -- instead of one
+// warp walking the row with one load in flight (22 us for 2048 columns, ncu r02_launches_llama.csv)
+template <typename TI, typename TW, typename TO>
+__global__ void __launch_bounds__(256) rms_norm_block_kernel(const TI* __restrict__ x, const TW* __restrict__ w, TO* __restrict__ y, int cols, float eps)
+{
+    osb_pdl_prologue();
+    __shared__ float red[8];
+    const TI* xr = x + (int64_t)blockIdx.x * cols;
+    TO* yr = y + (int64_t)blockIdx.x * cols;
+    float ss = 0.f;
+#pragma unroll 4
+    for (int c = threadIdx.x; c < cols; c += 256) { const float v = to_float(xr[c]); ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) tot += red[k];
+    const float inv = 1.0f / sqrtf(tot / (float)cols + eps);
+#pragma unroll 4
+    for (int c = threadIdx.x; c < cols; c += 256) yr[c] = from_float<TO>(to_float(w[c]) * (to_float(xr[c]) * inv));
+}
+
 // rotary embedding, "rotate_half" form: y[j] = x[j] * cos[j] + (j < D/2 ? -x[j + D/2] : x[j - D/2]) * sin[j]; cos / sin are one row of D
 // values shared by every row (table_rows == 1) or one row per x row
 template <typename T>
@@ -878,8 +902,9 @@ __global__ void rope_kernel(const T* __restrict__ x, const T* __restrict__ cs, c
         const float xv = to_float(x[i]);
         const float rot = j < half ? -to_float(x[i + half]) : to_float(x[i - half]);
         // the reference rounds each product and the sum to the storage type (three separate ops): keep those roundings
-        const T a = from_float<T>(xv * to_float(cs[t * D + j])), b = from_float<T>(to_float(from_float<T>(rot)) * to_float(sn[t * D + j]));
-        y[i] = from_float<T>(to_float(a) + to_float(b));
+        // (__fmul_rn / __fadd_rn: no fused multiply-add across the three ops in fp32 either)
+        const T a = from_float<T>(__fmul_rn(xv, to_float(cs[t * D + j]))), b = from_float<T>(__fmul_rn(to_float(from_float<T>(rot)), to_float(sn[t * D + j])));
+        y[i] = from_float<T>(__fadd_rn(to_float(a), to_float(b)));
     }
 }
 
@@ -1078,6 +1103,27 @@ int osb_binary(int op, const void* a, const int64_t* as, const void* b, const in
     return (int)cudaErrorInvalidValue;
 }
 
+// Concat of two sources along one axis as ONE launch: out[o][0:la) = a[o][:], out[o][la:la+lb) = b[o][:], lengths in 16-byte units
+// (KV-cache append of a decode step: la = cached rows, lb = one row)
+__global__ void concat2_vec_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out, int64_t outer, int64_t la, int64_t lb)
+{
+    osb_pdl_prologue();
+    const int64_t lo = la + lb, n = outer * lo;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t o = i / lo, j = i - o * lo;
+        out[i] = j < la ? a[o * la + j] : b[o * lb + (j - la)];
+    }
+}
+
+int osb_concat2(const void* a, const void* b, void* out, int64_t outer, int64_t a_bytes, int64_t b_bytes, void* stream)
+{
+    if (outer * (a_bytes + b_bytes) == 0) return 0;
+    if ((a_bytes | b_bytes) & 15 || !aligned16(a) || !aligned16(b) || !aligned16(out)) return (int)cudaErrorNotSupported;
+    osb_launch((concat2_vec_kernel), grid_for((size_t)(outer * (a_bytes + b_bytes) / 16), 256), 256, 0, (cudaStream_t)stream,
+               (const uint4*)a, (const uint4*)b, (uint4*)out, outer, a_bytes / 16, b_bytes / 16);
+    return launched();
+}
+
 int osb_strided_copy(const void* in, void* out, int elem_size, int ndim, const int64_t* shape, const int64_t* in_stride, const int64_t* in_div,
                      int64_t in_offset, const int64_t* out_stride, int64_t out_offset, void* stream)
 {
@@ -1226,14 +1272,25 @@ int osb_group_norm(const void* x, void* y, int dtype, int nhwc, int64_t C, int64
             // one CTA per SM by default (every CTA must be co-resident for the rendezvous; fewer CTAs = fewer same-address atomics)
             static const int cta_cap = [] { const char* e = getenv("OSB_GN_CTAS"); int v = e ? atoi(e) : 0; return v > 0 ? v : 148; }();
             int threads = C / vec <= 256 ? 256 : 512;
-            // co-residency bound: 512-thread CTAs are only guaranteed one slot per SM, 256-thread CTAs two
-            int64_t c2 = std::min<int64_t>(HW, std::min(cta_cap, threads == 512 ? 148 : 296));
-            int64_t ppc2 = (HW + c2 - 1) / c2;
-            c2 = (HW + ppc2 - 1) / ppc2;
             size_t smem = sizeof(float) * 2 * groups;
-            if (dtype == OSB_F16) osb_launch((gn_fused_nhwc_kernel<__half, 8>), (unsigned)c2, threads, smem, st, (const __half*)x, (__half*)y, fstats, counters, (int)C, HW, groups, ppc2, (const __half*)gamma, (const __half*)beta, eps, fuse_silu);
-            else osb_launch((gn_fused_nhwc_kernel<float, 4>), (unsigned)c2, threads, smem, st, (const float*)x, (float*)y, fstats, counters, (int)C, HW, groups, ppc2, (const float*)gamma, (const float*)beta, eps, fuse_silu);
-            return launched();
+            // co-residency bound from the device itself (SM count x resident CTAs of THIS kernel at this block size), and a cooperative
+            // launch so the driver gang-schedules the grid: with SMs held by other work the launch waits (or fails) instead of spinning
+            int dev = 0, sms = 0, occ = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (dtype == OSB_F16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_fused_nhwc_kernel<__half, 8>, threads, smem);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_fused_nhwc_kernel<float, 4>, threads, smem);
+            const int64_t resident = (int64_t)sms * std::min(occ, 2);
+            if (resident >= 1) {
+                int64_t c2 = std::min<int64_t>(HW, std::min<int64_t>(cta_cap, resident));
+                int64_t ppc2 = (HW + c2 - 1) / c2;
+                c2 = (HW + ppc2 - 1) / ppc2;
+                if (dtype == OSB_F16) osb_launch_coop((gn_fused_nhwc_kernel<__half, 8>), (unsigned)c2, threads, smem, st, (const __half*)x, (__half*)y, fstats, counters, (int)C, HW, groups, ppc2, (const __half*)gamma, (const __half*)beta, eps, fuse_silu);
+                else osb_launch_coop((gn_fused_nhwc_kernel<float, 4>), (unsigned)c2, threads, smem, st, (const float*)x, (float*)y, fstats, counters, (int)C, HW, groups, ppc2, (const float*)gamma, (const float*)beta, eps, fuse_silu);
+                int rc = launched();
+                if (rc != (int)cudaErrorCooperativeLaunchTooLarge && rc != (int)cudaErrorNotSupported) return rc;
+                // not schedulable as one gang on this device / partition: the two-pass path below has no rendezvous
+            }
         }
     }
     cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups, st);
@@ -1401,7 +1458,9 @@ int osb_rms_norm(const void* x, int xd, const void* w, int wd, void* y, int yd, 
     if (rows * cols == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = (unsigned)min<int64_t>((rows + 3) / 4, 148 * 8);
-#define OSB_RMS(TI_, TW_, TO_) osb_launch((rms_norm_kernel<TI_, TW_, TO_>), grid, 128, 0, st, (const TI_*)x, (const TW_*)w, (TO_*)y, rows, (int)cols, eps)
+    const bool per_block = rows <= 64 && cols >= 512;
+#define OSB_RMS(TI_, TW_, TO_) do { if (per_block) osb_launch((rms_norm_block_kernel<TI_, TW_, TO_>), (unsigned)rows, 256, 0, st, (const TI_*)x, (const TW_*)w, (TO_*)y, (int)cols, eps); \
+                                    else osb_launch((rms_norm_kernel<TI_, TW_, TO_>), grid, 128, 0, st, (const TI_*)x, (const TW_*)w, (TO_*)y, rows, (int)cols, eps); } while (0)
     if (xd == OSB_F16 && wd == OSB_F16 && yd == OSB_F16) OSB_RMS(__half, __half, __half);
     else if (xd == OSB_F16 && wd == OSB_F16 && yd == OSB_F32) OSB_RMS(__half, __half, float);
     else if (xd == OSB_F16 && wd == OSB_F32 && yd == OSB_F32) OSB_RMS(__half, float, float);
@@ -1409,6 +1468,7 @@ int osb_rms_norm(const void* x, int xd, const void* w, int wd, void* y, int yd, 
     else if (xd == OSB_F32 && wd == OSB_F32 && yd == OSB_F32) OSB_RMS(float, float, float);
     else if (xd == OSB_F32 && wd == OSB_F16 && yd == OSB_F32) OSB_RMS(float, __half, float);
     else if (xd == OSB_F32 && wd == OSB_F32 && yd == OSB_F16) OSB_RMS(float, float, __half);
+    else if (xd == OSB_F32 && wd == OSB_F16 && yd == OSB_F16) OSB_RMS(float, __half, __half);
     else return (int)cudaErrorInvalidValue;
 #undef OSB_RMS
     return launched();

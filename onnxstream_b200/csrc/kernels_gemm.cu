@@ -202,17 +202,16 @@ skinny_gemm_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restri
 // into (256-column x k-slice) panels so that ~2 waves of CTAs stream it with 16-byte loads; partial sums are reduced in
 // shared memory, then added with fp32 atomics into a zeroed scratch row; a second tiny kernel applies bias / residual and
 // rounds to the storage type.  Reads every weight exactly once.
+constexpr int GEMV_U = 8;
 template <typename T, int MAXM>
-__global__ void __launch_bounds__(128)
-gemv_panel_kernel(const T* __restrict__ A, const T* __restrict__ B, float* __restrict__ acc_out, int M, int N, int K, int k_per_cta,
-                  int* __restrict__ counters, T* __restrict__ C, const T* __restrict__ bias, const T* __restrict__ residual)
+__device__ __forceinline__ void gemv_panel_body(const T* __restrict__ A, const T* __restrict__ B, float* __restrict__ acc_out, int M, int N, int K, int k_per_cta,
+                                                int* __restrict__ counter, T* __restrict__ C, const T* __restrict__ bias, const T* __restrict__ residual, int panel, int ldb)
 {
-    osb_pdl_prologue();
     constexpr int VEC = 16 / sizeof(T);           // columns per thread
     constexpr int COLS = 32 * VEC;                // columns per CTA
     __shared__ float red[4][MAXM][COLS];
     const int cg = threadIdx.x & 31, kl = threadIdx.x >> 5;       // 32 column groups x 4 k-lanes
-    const int n0 = blockIdx.x * COLS + cg * VEC;
+    const int n0 = panel * COLS + cg * VEC;
     const int k_lo = blockIdx.y * k_per_cta, k_hi = min(k_lo + k_per_cta, K);
     float acc[MAXM][VEC];
 #pragma unroll
@@ -220,14 +219,27 @@ gemv_panel_kernel(const T* __restrict__ A, const T* __restrict__ B, float* __res
 #pragma unroll
         for (int v = 0; v < VEC; v++) acc[m][v] = 0.f;
     if (n0 < N) {
-        for (int k = k_lo + kl; k < k_hi; k += 4) {
-            Vec<T, VEC> b = load_vec<T, VEC>(B + (int64_t)k * N + n0);
+        // GEMV_U independent 16-byte loads per thread before the first FMA: a decode GEMV is pure weight streaming and one load in
+        // flight per thread left HBM at ~1 TB/s (ncu, r02_launches_llama.csv); 8 x 16 B x 128 threads x 4 CTAs = 64 KB in flight per SM
+        for (int k = k_lo + kl; k < k_hi; k += 4 * GEMV_U) {
+            Vec<T, VEC> b[GEMV_U];
 #pragma unroll
-            for (int m = 0; m < MAXM; m++) {
-                if (m < M) {
-                    float a = to_float(A[(int64_t)m * K + k]);
+            for (int u = 0; u < GEMV_U; u++) {
+                const int kk = k + 4 * u;
+                if (kk < k_hi) b[u] = load_vec<T, VEC>(B + (int64_t)kk * ldb + n0);
+            }
 #pragma unroll
-                    for (int v = 0; v < VEC; v++) acc[m][v] += a * to_float(b.v[v]);
+            for (int u = 0; u < GEMV_U; u++) {
+                const int kk = k + 4 * u;
+                if (kk < k_hi) {
+#pragma unroll
+                    for (int m = 0; m < MAXM; m++) {
+                        if (m < M) {
+                            float a = to_float(A[(int64_t)m * K + kk]);
+#pragma unroll
+                            for (int v = 0; v < VEC; v++) acc[m][v] += a * to_float(b[u].v[v]);
+                        }
+                    }
                 }
             }
         }
@@ -239,7 +251,7 @@ gemv_panel_kernel(const T* __restrict__ A, const T* __restrict__ B, float* __res
     __syncthreads();
     for (int i = threadIdx.x; i < M * COLS; i += 128) {
         int m = i / COLS, c = i % COLS;
-        int n = blockIdx.x * COLS + c;
+        int n = panel * COLS + c;
         if (n >= N) continue;
         float v = 0.f;
 #pragma unroll
@@ -252,13 +264,13 @@ gemv_panel_kernel(const T* __restrict__ A, const T* __restrict__ B, float* __res
     __shared__ int is_last;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) is_last = atomicAdd(&counters[blockIdx.x], 1) == (int)gridDim.y - 1;
+    if (threadIdx.x == 0) is_last = atomicAdd(counter, 1) == (int)gridDim.y - 1;
     __syncthreads();
     if (!is_last) return;
     __threadfence();
     for (int i = threadIdx.x; i < M * COLS; i += 128) {
         int m = i / COLS, c = i % COLS;
-        int n = blockIdx.x * COLS + c;
+        int n = panel * COLS + c;
         if (n >= N) continue;
         float v = __ldcg(&acc_out[(int64_t)m * N + n]);
         acc_out[(int64_t)m * N + n] = 0.f;
@@ -266,7 +278,34 @@ gemv_panel_kernel(const T* __restrict__ A, const T* __restrict__ B, float* __res
         if (residual) v += to_float(residual[(int64_t)m * N + n]);
         C[(int64_t)m * N + n] = from_float<T>(v);
     }
-    if (threadIdx.x == 0) counters[blockIdx.x] = 0;
+    if (threadIdx.x == 0) *counter = 0;
+}
+
+template <typename T, int MAXM>
+__global__ void __launch_bounds__(128)
+gemv_panel_kernel(const T* __restrict__ A, const T* __restrict__ B, float* __restrict__ acc_out, int M, int N, int K, int k_per_cta,
+                  int* __restrict__ counters, T* __restrict__ C, const T* __restrict__ bias, const T* __restrict__ residual, int ldb)
+{
+    osb_pdl_prologue();
+    gemv_panel_body<T, MAXM>(A, B, acc_out, M, N, K, k_per_cta, counters + blockIdx.x, C, bias, residual, (int)blockIdx.x, ldb);
+}
+
+// Up to three GEMVs that share their input row(s) and K (q / k / v projections, gate / up of a gated MLP) as ONE launch: blockIdx.x walks
+// the column panels of all groups, each group with its own weight, output, scratch slice and arrival counters.
+struct GemvGroups {
+    const void* B[3]; void* C[3];
+    int N[3], panel0[4], acc0[3];      // first panel / first scratch float of each group; panel0[groups] = total panels
+    float wscale[3]; int wzp[3];
+    int groups;
+};
+template <typename T, int MAXM>
+__global__ void __launch_bounds__(128)
+gemv_panel_grouped_kernel(const T* __restrict__ A, GemvGroups g, float* __restrict__ acc_out, int M, int K, int k_per_cta, int* __restrict__ counters)
+{
+    osb_pdl_prologue();
+    const int bx = (int)blockIdx.x;
+    const int gi = bx >= g.panel0[2] && g.groups > 2 ? 2 : (bx >= g.panel0[1] ? 1 : 0);
+    gemv_panel_body<T, MAXM>(A, (const T*)g.B[gi], acc_out + g.acc0[gi], M, g.N[gi], K, k_per_cta, counters + bx, (T*)g.C[gi], nullptr, nullptr, bx - g.panel0[gi], g.N[gi]);
 }
 
 // The same panel GEMV with uint8 weights [K, N] (per-tensor scale / zero point), M <= 2: 16 columns per thread per 16-byte load, the
@@ -274,15 +313,13 @@ gemv_panel_kernel(const T* __restrict__ A, const T* __restrict__ B, float* __res
 // builds when it converts a uint8 blob at load time (src/onnxstream.cpp:2885-2890) -- then fp32 FMA.  Half (fp16) / a quarter (fp32) of
 // the HBM bytes of the float GEMV: LLM decode is weight-bandwidth bound.
 template <typename T>
-__global__ void __launch_bounds__(128)
-gemv_w8_panel_kernel(const T* __restrict__ A, const uint8_t* __restrict__ B, float* __restrict__ acc_out, int M, int N, int K, int k_per_cta,
-                     int* __restrict__ counters, T* __restrict__ C, const T* __restrict__ bias, const T* __restrict__ residual, float wscale, int wzp)
+__device__ __forceinline__ void gemv_w8_panel_body(const T* __restrict__ A, const uint8_t* __restrict__ B, float* __restrict__ acc_out, int M, int N, int K, int k_per_cta,
+                                                   int* __restrict__ counter, T* __restrict__ C, const T* __restrict__ bias, const T* __restrict__ residual, float wscale, int wzp, int panel)
 {
-    osb_pdl_prologue();
     constexpr int VEC = 16, COLS = 32 * VEC, MAXM = 2;
     __shared__ float red[4][MAXM][COLS];
     const int cg = threadIdx.x & 31, kl = threadIdx.x >> 5;
-    const int n0 = blockIdx.x * COLS + cg * VEC;
+    const int n0 = panel * COLS + cg * VEC;
     const int k_lo = blockIdx.y * k_per_cta, k_hi = min(k_lo + k_per_cta, K);
     float acc[MAXM][VEC];
 #pragma unroll
@@ -290,18 +327,29 @@ gemv_w8_panel_kernel(const T* __restrict__ A, const uint8_t* __restrict__ B, flo
 #pragma unroll
         for (int v = 0; v < VEC; v++) acc[m][v] = 0.f;
     if (n0 < N) {
-        for (int k = k_lo + kl; k < k_hi; k += 4) {
-            const uint4 raw = *reinterpret_cast<const uint4*>(B + (int64_t)k * N + n0);
-            const uint32_t words[4] = { raw.x, raw.y, raw.z, raw.w };
-            float w[VEC];
+        for (int k = k_lo + kl; k < k_hi; k += 4 * GEMV_U) {
+            uint4 raws[GEMV_U];
 #pragma unroll
-            for (int v = 0; v < VEC; v++) w[v] = to_float(from_float<T>((float)((int)((words[v >> 2] >> (8 * (v & 3))) & 0xFFu) - wzp) * wscale));
+            for (int u = 0; u < GEMV_U; u++) {
+                const int kk = k + 4 * u;
+                if (kk < k_hi) raws[u] = *reinterpret_cast<const uint4*>(B + (int64_t)kk * N + n0);
+            }
 #pragma unroll
-            for (int m = 0; m < MAXM; m++) {
-                if (m < M) {
-                    const float a = to_float(A[(int64_t)m * K + k]);
+            for (int u = 0; u < GEMV_U; u++) {
+                const int kk = k + 4 * u;
+                if (kk < k_hi) {
+                    const uint32_t words[4] = { raws[u].x, raws[u].y, raws[u].z, raws[u].w };
+                    float w[VEC];
 #pragma unroll
-                    for (int v = 0; v < VEC; v++) acc[m][v] += a * w[v];
+                    for (int v = 0; v < VEC; v++) w[v] = to_float(from_float<T>((float)((int)((words[v >> 2] >> (8 * (v & 3))) & 0xFFu) - wzp) * wscale));
+#pragma unroll
+                    for (int m = 0; m < MAXM; m++) {
+                        if (m < M) {
+                            const float a = to_float(A[(int64_t)m * K + kk]);
+#pragma unroll
+                            for (int v = 0; v < VEC; v++) acc[m][v] += a * w[v];
+                        }
+                    }
                 }
             }
         }
@@ -313,7 +361,7 @@ gemv_w8_panel_kernel(const T* __restrict__ A, const uint8_t* __restrict__ B, flo
     __syncthreads();
     for (int i = threadIdx.x; i < M * COLS; i += 128) {
         int m = i / COLS, c = i % COLS;
-        int n = blockIdx.x * COLS + c;
+        int n = panel * COLS + c;
         if (n >= N) continue;
         float v = 0.f;
 #pragma unroll
@@ -323,13 +371,13 @@ gemv_w8_panel_kernel(const T* __restrict__ A, const uint8_t* __restrict__ B, flo
     __shared__ int is_last;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) is_last = atomicAdd(&counters[blockIdx.x], 1) == (int)gridDim.y - 1;
+    if (threadIdx.x == 0) is_last = atomicAdd(counter, 1) == (int)gridDim.y - 1;
     __syncthreads();
     if (!is_last) return;
     __threadfence();
     for (int i = threadIdx.x; i < M * COLS; i += 128) {
         int m = i / COLS, c = i % COLS;
-        int n = blockIdx.x * COLS + c;
+        int n = panel * COLS + c;
         if (n >= N) continue;
         float v = __ldcg(&acc_out[(int64_t)m * N + n]);
         acc_out[(int64_t)m * N + n] = 0.f;
@@ -337,7 +385,26 @@ gemv_w8_panel_kernel(const T* __restrict__ A, const uint8_t* __restrict__ B, flo
         if (residual) v += to_float(residual[(int64_t)m * N + n]);
         C[(int64_t)m * N + n] = from_float<T>(v);
     }
-    if (threadIdx.x == 0) counters[blockIdx.x] = 0;
+    if (threadIdx.x == 0) *counter = 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+gemv_w8_panel_kernel(const T* __restrict__ A, const uint8_t* __restrict__ B, float* __restrict__ acc_out, int M, int N, int K, int k_per_cta,
+                     int* __restrict__ counters, T* __restrict__ C, const T* __restrict__ bias, const T* __restrict__ residual, float wscale, int wzp)
+{
+    osb_pdl_prologue();
+    gemv_w8_panel_body<T>(A, B, acc_out, M, N, K, k_per_cta, counters + blockIdx.x, C, bias, residual, wscale, wzp, (int)blockIdx.x);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+gemv_w8_panel_grouped_kernel(const T* __restrict__ A, GemvGroups g, float* __restrict__ acc_out, int M, int K, int k_per_cta, int* __restrict__ counters)
+{
+    osb_pdl_prologue();
+    const int bx = (int)blockIdx.x;
+    const int gi = bx >= g.panel0[2] && g.groups > 2 ? 2 : (bx >= g.panel0[1] ? 1 : 0);
+    gemv_w8_panel_body<T>(A, (const uint8_t*)g.B[gi], acc_out + g.acc0[gi], M, g.N[gi], K, k_per_cta, counters + bx, (T*)g.C[gi], nullptr, nullptr, g.wscale[gi], g.wzp[gi], bx - g.panel0[gi]);
 }
 
 // ---- softmax with scale + additive mask (score tile of the attention decomposition) ---------------------------
@@ -433,6 +500,129 @@ __global__ void softmax_scaled_smem_kernel(const T* __restrict__ x, T* __restric
 }
 
 // ---- direct attention for short query lengths (decode): one warp per (head, query row), online softmax -------
+// ---- split-KV decode attention: grid (key splits, heads * Tq); each warp scores 32 keys (one per lane), the block folds its 128 keys
+// into one partial (max, sum, acc[dv]) and the last block of a row to arrive (self-resetting ticket) merges the partials.  A decode
+// step at 2048 cached positions becomes 16 x 32 blocks instead of 32 warps walking 2048 keys each.
+constexpr int DEC_KEYS = 128;
+template <typename T>
+__device__ __forceinline__ float dec_dot(const float* qs, const T* kr, int d)
+{
+    float dot = 0.f;
+    for (int c = 0; c < d; c++) dot += qs[c] * to_float(kr[c]);
+    return dot;
+}
+template <>
+__device__ __forceinline__ float dec_dot<__half>(const float* qs, const __half* kr, int d)
+{
+    float dot = 0.f;
+    if ((d & 7) == 0 && ((uintptr_t)kr & 15) == 0) {
+        const uint4* k4 = reinterpret_cast<const uint4*>(kr);
+        for (int c = 0; c < d; c += 8) {
+            uint4 u = k4[c >> 3];
+            const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; j++) { float2 f = __half22float2(h2[j]); dot += qs[c + 2 * j] * f.x + qs[c + 2 * j + 1] * f.y; }
+        }
+    } else {
+        for (int c = 0; c < d; c++) dot += qs[c] * __half2float(kr[c]);
+    }
+    return dot;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) attention_decode_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
+                                                               const T* __restrict__ mask, T* __restrict__ out, float* part, int* tickets,
+                                                               int64_t Tq, int64_t Tk, int d, int dv, float scale, int64_t kv_group, int nsplit)
+{
+    osb_pdl_prologue();
+    extern __shared__ float smem[];   // q [d] | acc of each warp [4][dv] | (max, sum) of each warp [4][2] | p [4][32]
+    float* qs = smem;
+    float* wacc = qs + d;
+    float* wml = wacc + 4 * dv;
+    float* ps = wml + 8;
+    __shared__ int s_last;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t row = blockIdx.y, sp = blockIdx.x;
+    const int64_t h = row / Tq, t = row % Tq, hk = h / kv_group;
+    for (int c = tid; c < d; c += 128) qs[c] = to_float(q[row * d + c]) * scale;
+    __syncthreads();
+    const int64_t s0 = sp * DEC_KEYS + warp * 32, s = s0 + lane;
+    float logit = -INFINITY;
+    if (s < Tk) {
+        logit = dec_dot<T>(qs, k + (hk * Tk + s) * d, d);
+        if (mask) logit += to_float(mask[t * Tk + s]);
+    }
+    const float m = warp_max(logit);
+    const float p = (s < Tk && m > -INFINITY) ? expf(logit - m) : 0.f;
+    const float l = warp_sum(p);
+    ps[warp * 32 + lane] = p;
+    __syncwarp();
+    const int jn = (Tk - s0) < 32 ? (int)max((int64_t)0, Tk - s0) : 32;
+    const T* vb = v + (hk * Tk + s0) * dv;
+    for (int c = lane; c < dv; c += 32) {
+        float a = 0.f;
+#pragma unroll 8
+        for (int j = 0; j < jn; j++) a += ps[warp * 32 + j] * to_float(vb[(int64_t)j * dv + c]);
+        wacc[warp * dv + c] = a;
+    }
+    if (lane == 0) { wml[warp * 2] = m; wml[warp * 2 + 1] = l; }
+    __syncthreads();
+    float* mine = part + (row * nsplit + sp) * (dv + 2);
+    {
+        float M = fmaxf(fmaxf(wml[0], wml[2]), fmaxf(wml[4], wml[6]));
+        float w[4];
+#pragma unroll
+        for (int x = 0; x < 4; x++) w[x] = wml[2 * x] > -INFINITY ? expf(wml[2 * x] - M) : 0.f;
+        for (int c = tid; c < dv; c += 128) __stcg(mine + c, wacc[c] * w[0] + wacc[dv + c] * w[1] + wacc[2 * dv + c] * w[2] + wacc[3 * dv + c] * w[3]);
+        if (tid == 0) { __stcg(mine + dv, M); __stcg(mine + dv + 1, wml[1] * w[0] + wml[3] * w[1] + wml[5] * w[2] + wml[7] * w[3]); }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        int ticket = atomicAdd(&tickets[row], 1);
+        s_last = ticket == nsplit - 1;
+        if (s_last) tickets[row] = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // merge: the per-split (max, sum) pairs are fetched by one thread each (parallel L2 round trips, not a dependent chain), the
+    // weights land in shared memory (ps / wacc are free again), then every output column is a sum of independent loads
+    const float* pr = part + row * nsplit * (dv + 2);
+    float* sw = wacc;                       // [nsplit] weights; nsplit <= 4 * dv is checked by the launcher
+    float Mx = -INFINITY;
+    for (int x0 = 0; x0 < nsplit; x0 += 128) {
+        const int x = x0 + tid;
+        const float mx = x < nsplit ? __ldcg(pr + x * (dv + 2) + dv) : -INFINITY;
+        if (x < nsplit) sw[x] = mx;
+        Mx = fmaxf(Mx, mx);
+    }
+    Mx = warp_max(Mx);
+    if (lane == 0) wml[warp] = Mx;
+    __syncthreads();
+    const float M = fmaxf(fmaxf(wml[0], wml[1]), fmaxf(wml[2], wml[3]));
+    float Lp = 0.f;
+    for (int x0 = 0; x0 < nsplit; x0 += 128) {
+        const int x = x0 + tid;
+        if (x < nsplit) {
+            const float wgt = sw[x] > -INFINITY ? expf(sw[x] - M) : 0.f;
+            Lp += __ldcg(pr + x * (dv + 2) + dv + 1) * wgt;
+            sw[x] = wgt;
+        }
+    }
+    Lp = warp_sum(Lp);
+    __syncthreads();                        // wml[0..3] read by everyone before it is overwritten; sw complete
+    if (lane == 0) wml[4 + warp] = Lp;
+    __syncthreads();
+    const float inv = 1.f / (wml[4] + wml[5] + wml[6] + wml[7]);
+    for (int c = tid; c < dv; c += 128) {
+        float a = 0.f;
+#pragma unroll 8
+        for (int x = 0; x < nsplit; x++) a += __ldcg(pr + x * (dv + 2) + c) * sw[x];
+        out[row * dv + c] = from_float<T>(a * inv);
+    }
+}
+
 template <typename T>
 __global__ void attention_rows_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ mask,
                                       T* __restrict__ out, int64_t heads, int64_t Tq, int64_t Tk, int d, int dv, float scale,
@@ -541,7 +731,8 @@ int osb_gemm_ld(const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
     if (impl == 2 && !tc_ok) return (int)cudaErrorInvalidValue;
     if (tc_ok && impl != 1) return osb_tc_gemm_launch(A, B, C, bias, residual, batch, M, N, K, sa, sb, sc, bt, st, lda, ldb, ldc);
     ConvGeom g{};
-    if (dense && M <= 8 && batch == 1 && !bt && N % 8 == 0 && aligned16(B) && N >= 256 && K >= 64) {
+    // (ldb > N: a row-padded copy of a weight whose N is not a multiple of the 16-byte vector, e.g. a 32003-entry vocabulary)
+    if (lda == K && ldc == N && M <= 8 && batch == 1 && !bt && ldb >= N && ldb % (dtype == OSB_F16 ? 8 : 4) == 0 && aligned16(B) && N >= 256 && K >= 64) {
         // weight-bandwidth path
         // scratch (per-stream, fixed capacity, workspace.h): fp32 sums [M][N] + one arrival counter per column panel; zeroed when
         // allocated, re-armed by the kernel.  Shapes beyond the fixed capacity take the skinny kernel below.
@@ -555,10 +746,12 @@ int osb_gemm_ld(const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
         int k_per = (int)((K + gy - 1) / gy);
         gy = (int)((K + k_per - 1) / k_per);
         dim3 grid(gx, gy);
-        if (dtype == OSB_F16) osb_launch((gemv_panel_kernel<__half, 8>), grid, 128, 0, st, (const __half*)A, (const __half*)B, scratch, (int)M, (int)N, (int)K, k_per,
-                                         counters, (__half*)C, (const __half*)bias, (const __half*)residual);
-        else osb_launch((gemv_panel_kernel<float, 8>), grid, 128, 0, st, (const float*)A, (const float*)B, scratch, (int)M, (int)N, (int)K, k_per,
-                        counters, (float*)C, (const float*)bias, (const float*)residual);
+#define OSB_GEMV(T_, MM_) osb_launch((gemv_panel_kernel<T_, MM_>), grid, 128, 0, st, (const T_*)A, (const T_*)B, scratch, (int)M, (int)N, (int)K, k_per, \
+                                    counters, (T_*)C, (const T_*)bias, (const T_*)residual, (int)ldb)
+        // row-count instantiations: the M = 1 decode GEMV keeps 8 accumulators instead of 64
+        if (dtype == OSB_F16) { if (M == 1) OSB_GEMV(__half, 1); else if (M == 2) OSB_GEMV(__half, 2); else if (M <= 4) OSB_GEMV(__half, 4); else OSB_GEMV(__half, 8); }
+        else { if (M == 1) OSB_GEMV(float, 1); else if (M == 2) OSB_GEMV(float, 2); else if (M <= 4) OSB_GEMV(float, 4); else OSB_GEMV(float, 8); }
+#undef OSB_GEMV
         return launched();
         }
     }
@@ -589,6 +782,48 @@ int osb_gemv_w8(const void* A, const void* Wq, void* C, const void* bias, const 
                                      (__half*)C, (const __half*)bias, (const __half*)residual, wscale, wzp);
     else osb_launch((gemv_w8_panel_kernel<float>), grid, 128, 0, st, (const float*)A, (const uint8_t*)Wq, ws->gemv, (int)M, (int)N, (int)K, k_per, ws->gemv_counters,
                     (float*)C, (const float*)bias, (const float*)residual, wscale, wzp);
+    return launched();
+}
+
+// groups (2 or 3) GEMVs y_g[M,N_g] = x[M,K] . W_g[K,N_g] sharing x, as one launch.  wdtype == OSB_U8: uint8 weights dequantised in
+// registers (M <= 2); otherwise weights of the activation type.  cudaErrorNotSupported = shape outside what the grouped kernels cover
+// (the caller launches the GEMVs one by one).
+int osb_gemv_grouped(const void* A, const void* const* B, void* const* C, const int64_t* N, const float* wscale, const int* wzp, int groups,
+                     int64_t M, int64_t K, int wdtype, int dtype, void* stream)
+{
+    if (groups < 2 || groups > 3 || (dtype != OSB_F16 && dtype != OSB_F32) || M < 1 || K < 64) return (int)cudaErrorNotSupported;
+    const bool w8 = wdtype == OSB_U8;
+    if (!w8 && wdtype != dtype) return (int)cudaErrorNotSupported;
+    if (M > (w8 ? 2 : 8)) return (int)cudaErrorNotSupported;
+    const int cols = w8 ? 512 : (dtype == OSB_F16 ? 256 : 128);
+    GemvGroups g{};
+    g.groups = groups;
+    int panels = 0; int64_t acc = 0;
+    for (int i = 0; i < groups; i++) {
+        if (N[i] < 256 || N[i] % (w8 ? 16 : 8) || !aligned16(B[i])) return (int)cudaErrorNotSupported;
+        g.B[i] = B[i]; g.C[i] = C[i]; g.N[i] = (int)N[i]; g.panel0[i] = panels; g.acc0[i] = (int)acc;
+        g.wscale[i] = w8 ? wscale[i] : 0.f; g.wzp[i] = w8 ? wzp[i] : 0;
+        panels += (int)((N[i] + cols - 1) / cols);
+        acc += M * N[i];
+    }
+    for (int i = groups; i < 4; i++) g.panel0[i] = panels;
+    if (panels > 4096 || (size_t)acc > OSB_WS_GEMV_FLOATS) return (int)cudaErrorNotSupported;
+    cudaStream_t st = (cudaStream_t)stream;
+    OsbWorkspace* ws = osb_workspace(st, OSB_WS_GEMV);
+    if (!ws) return (int)cudaErrorNotSupported;
+    int gy = (int)max<int64_t>(1, min<int64_t>((K + 15) / 16, (592 + panels - 1) / panels));
+    int k_per = (int)((K + gy - 1) / gy);
+    gy = (int)((K + k_per - 1) / k_per);
+    dim3 grid(panels, gy);
+    if (w8) {
+        if (dtype == OSB_F16) osb_launch((gemv_w8_panel_grouped_kernel<__half>), grid, 128, 0, st, (const __half*)A, g, ws->gemv, (int)M, (int)K, k_per, ws->gemv_counters);
+        else osb_launch((gemv_w8_panel_grouped_kernel<float>), grid, 128, 0, st, (const float*)A, g, ws->gemv, (int)M, (int)K, k_per, ws->gemv_counters);
+    } else {
+#define OSB_GEMVG(T_, MM_) osb_launch((gemv_panel_grouped_kernel<T_, MM_>), grid, 128, 0, st, (const T_*)A, g, ws->gemv, (int)M, (int)K, k_per, ws->gemv_counters)
+        if (dtype == OSB_F16) { if (M == 1) OSB_GEMVG(__half, 1); else if (M == 2) OSB_GEMVG(__half, 2); else if (M <= 4) OSB_GEMVG(__half, 4); else OSB_GEMVG(__half, 8); }
+        else { if (M == 1) OSB_GEMVG(float, 1); else if (M == 2) OSB_GEMVG(float, 2); else if (M <= 4) OSB_GEMVG(float, 4); else OSB_GEMVG(float, 8); }
+#undef OSB_GEMVG
+    }
     return launched();
 }
 
@@ -694,6 +929,22 @@ int osb_attention(const void* q, const void* k, const void* v, const void* mask,
     if (heads * Tq * dv == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (kv_group < 1) kv_group = 1;
+    {
+        // long key axis, few query rows (decode): split the keys over the grid
+        static const bool dec = [] { const char* e = getenv("OSB_DECODE_ATTN"); return !(e && e[0] == '0'); }();
+        const int64_t rows = heads * Tq, nsplit = (Tk + DEC_KEYS - 1) / DEC_KEYS;
+        const size_t dsm = (size_t)(d + 4 * dv + 8 + 128) * sizeof(float);
+        if (dec && !k_transposed && Tk >= 256 && rows <= 4096 && nsplit <= 4 * dv && rows * nsplit <= 65535 * 4 && nsplit <= 65535 && rows <= 65535 && dsm <= 48 * 1024 &&
+            (size_t)rows * nsplit * (dv + 2) * sizeof(float) <= OSB_WS_SPLITK_BYTES && (dtype == OSB_F16 || dtype == OSB_F32)) {
+            OsbWorkspace* ws = osb_workspace(st, OSB_WS_SPLITK);
+            if (ws) {
+                dim3 grid((unsigned)nsplit, (unsigned)rows);
+                if (dtype == OSB_F16) osb_launch((attention_decode_kernel<__half>), grid, 128, dsm, st, (const __half*)q, (const __half*)k, (const __half*)v, (const __half*)mask, (__half*)out, ws->splitk, ws->splitk_counters, Tq, Tk, (int)d, (int)dv, scale, kv_group, (int)nsplit);
+                else osb_launch((attention_decode_kernel<float>), grid, 128, dsm, st, (const float*)q, (const float*)k, (const float*)v, (const float*)mask, (float*)out, ws->splitk, ws->splitk_counters, Tq, Tk, (int)d, (int)dv, scale, kv_group, (int)nsplit);
+                return launched();
+            }
+        }
+    }
     int warps = 4;
     size_t smem = (size_t)warps * (d + dv + 32) * sizeof(float);
     if (smem > 48 * 1024) return (int)cudaErrorInvalidValue;

@@ -10,10 +10,11 @@ def summarize(path):
     hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     hdr, data = rows[hi], rows[hi + 1:]
     ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    mi = hdr.index("Metric Name") if "Metric Name" in hdr else None
     agg = collections.defaultdict(lambda: [0, 0.0])
     tot = 0.0
     for r in data:
-        if len(r) <= vi:
+        if len(r) <= vi or (mi is not None and r[mi] != "gpu__time_duration.sum"):
             continue
         m = re.search(r"(\w+_kernel)\b", r[ki])
         key = m.group(1) if m else r[ki][:40]

@@ -582,3 +582,161 @@ def test_geglu(K, dtype, rows, inner):
     scale = ref.abs() + (xd[:, :inner] * gate).abs() + 1.0
     tol = (2.0 ** -10 if dtype == F16 else 2.0 ** -20) * scale
     assert not ((y.double() - ref).abs() > tol).any()
+
+
+ATTN_CASES = [
+    # heads, Tq, Tk, d, dv, kv_group, mask, dtype
+    (32, 1, 2048, 64, 64, 8, True, F16),      # TinyLlama decode: split-KV kernel
+    (32, 1, 2048, 64, 64, 8, True, F32),
+    (8, 1, 300, 64, 64, 2, False, F16),       # ragged last split
+    (4, 3, 515, 80, 40, 1, True, F16),        # several query rows, d != dv, not a multiple of 8 halves per lane chunk
+    (6, 2, 257, 20, 20, 3, True, F32),
+    (4, 1, 100, 64, 64, 2, True, F16),        # short key axis: one warp per row
+]
+
+
+@pytest.mark.parametrize("heads,Tq,Tk,d,dv,group,with_mask,dtype", ATTN_CASES)
+def test_attention_decode_matches_fp64(K, heads, Tq, Tk, d, dv, group, with_mask, dtype):
+    import torch
+    K.osb_attention.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int64] * 5 + [ctypes.c_float, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]
+    ty = torch.float16 if dtype == F16 else torch.float32
+    g = torch.Generator(device="cuda").manual_seed(heads * 1000 + Tk)
+    q = torch.randn(heads, Tq, d, device="cuda", generator=g).to(ty)
+    k = torch.randn(heads // group, Tk, d, device="cuda", generator=g).to(ty)
+    v = torch.randn(heads // group, Tk, dv, device="cuda", generator=g).to(ty)
+    mask = None
+    if with_mask:
+        mask = torch.zeros(Tq, Tk, device="cuda", dtype=ty)
+        mask[:, Tk // 3: Tk // 3 + 40] = -65504.0 if dtype == F16 else -3.0e38     # a band of padded positions
+        mask[:, :5] = -1.5
+    scale = 1.0 / d ** 0.5
+    out = torch.empty(heads, Tq, dv, device="cuda", dtype=ty)
+    for rep in range(2):    # twice: the tickets must re-arm themselves
+        out.zero_()
+        rc = K.osb_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), mask.data_ptr() if with_mask else None, out.data_ptr(), heads, Tq, Tk, d, dv,
+                             scale, 0, group, dtype, _stream())
+        assert rc == 0
+        torch.cuda.synchronize()
+        kk = k.double().repeat_interleave(group, 0); vv = v.double().repeat_interleave(group, 0)
+        s = q.double() @ kk.transpose(1, 2) * scale
+        if with_mask:
+            s = s + mask.double()
+        ref = torch.softmax(s, -1) @ vv
+        tol = 2e-3 if dtype == F16 else 1e-5
+        assert float((out.double() - ref).abs().max()) <= tol * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("rows,cols,xd,wd,yd", [(1, 2048, F16, F16, F16), (3, 64, F32, F16, F32), (5, 1000, F16, F32, F32), (2, 5632, F32, F32, F32)])
+def test_rms_norm_matches_fp64(K, rows, cols, xd, wd, yd):
+    import torch
+    K.osb_rms_norm.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p]
+    T = {F16: torch.float16, F32: torch.float32}
+    g = torch.Generator(device="cuda").manual_seed(rows * cols)
+    x = (torch.randn(rows, cols, device="cuda", generator=g) * 3).to(T[xd])
+    w = torch.randn(cols, device="cuda", generator=g).to(T[wd])
+    y = torch.empty(rows, cols, device="cuda", dtype=T[yd])
+    eps = 1e-5
+    assert K.osb_rms_norm(x.data_ptr(), xd, w.data_ptr(), wd, y.data_ptr(), yd, rows, cols, eps, _stream()) == 0
+    torch.cuda.synchronize()
+    xx = x.double()
+    ref = w.double() * (xx / torch.sqrt((xx * xx).mean(-1, keepdim=True) + eps))
+    tol = 2e-3 if yd == F16 else 2e-6
+    assert float((y.double() - ref).abs().max()) <= tol * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("rows,D,dtype", [(32, 64, F16), (4, 16, F32), (7, 128, F16)])
+def test_rope_matches_the_op_chain(K, rows, D, dtype):
+    """Slice / Neg / Concat / Mul / Mul / Add as separate roundings: the fused kernel must give the same bits in fp32 and the same
+    values within one rounding in fp16 (src/onnxstream.cpp elementwise ops round after each op)."""
+    import torch
+    K.osb_rope.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]
+    ty = torch.float16 if dtype == F16 else torch.float32
+    g = torch.Generator(device="cuda").manual_seed(rows * D)
+    x = torch.randn(rows, D, device="cuda", generator=g).to(ty)
+    ang = torch.rand(D, device="cuda", generator=g) * 6.28
+    cs, sn = torch.cos(ang).to(ty), torch.sin(ang).to(ty)
+    y = torch.empty_like(x)
+    assert K.osb_rope(x.data_ptr(), cs.data_ptr(), sn.data_ptr(), y.data_ptr(), dtype, rows, D, 1, _stream()) == 0
+    torch.cuda.synchronize()
+    rot = torch.cat([-x[:, D // 2:], x[:, :D // 2]], -1)
+    ref = (x * cs).to(ty) + (rot * sn).to(ty)
+    if dtype == F32:
+        assert torch.equal(y, ref)
+    else:
+        assert float((y.float() - ref.float()).abs().max()) <= 2e-3 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("dtype,w8,M,Ns,Kd", [(F16, False, 1, (2048, 256, 256), 2048), (F16, False, 1, (5632, 5632), 2048), (F32, False, 3, (512, 264), 300),
+                                              (F16, True, 1, (2048, 256, 256), 2048), (F16, True, 2, (5632, 5632), 2048), (F32, True, 1, (512, 272), 320)])
+def test_gemv_grouped_matches_fp64(K, dtype, w8, M, Ns, Kd):
+    """q/k/v (or gate/up) decode projections as one launch: every group equals its own fp64 product; run twice (scratch and counters re-arm)."""
+    import torch
+    vp, i64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    K.osb_gemv_grouped.argtypes = [vp, vp, vp, vp, vp, vp, ci, i64, i64, ci, ci, vp]
+    ty = torch.float16 if dtype == F16 else torch.float32
+    g = torch.Generator(device="cuda").manual_seed(sum(Ns) + Kd)
+    a = torch.randn(M, Kd, device="cuda", generator=g).to(ty)
+    n = len(Ns)
+    scales, zps = [0.0031 + 0.001 * i for i in range(n)], [128 + 3 * i for i in range(n)]
+    if w8:
+        ws = [torch.randint(0, 256, (Kd, N), device="cuda", generator=g, dtype=torch.uint8) for N in Ns]
+        wd = [((w.int() - z).float() * np.float32(s)).to(ty).double() for w, s, z in zip(ws, scales, zps)]
+    else:
+        ws = [(torch.randn(Kd, N, device="cuda", generator=g) * 0.05).to(ty) for N in Ns]
+        wd = [w.double() for w in ws]
+    cs = [torch.empty(M, N, device="cuda", dtype=ty) for N in Ns]
+    B = (vp * n)(*[w.data_ptr() for w in ws]); C = (vp * n)(*[c.data_ptr() for c in cs])
+    Nv = (i64 * n)(*Ns); sc = (ctypes.c_float * n)(*scales); zp = (ci * n)(*zps)
+    for rep in range(2):
+        for c in cs:
+            c.zero_()
+        assert K.osb_gemv_grouped(a.data_ptr(), B, C, Nv, sc, zp, n, M, Kd, 1 if w8 else dtype, dtype, _stream()) == 0
+        torch.cuda.synchronize()
+        for c, w in zip(cs, wd):
+            ref = a.double() @ w
+            absref = a.double().abs() @ w.abs()
+            if dtype == F16:
+                _check(c, ref, absref, f"gemv_grouped {M}x{tuple(Ns)}x{Kd}")
+            else:
+                assert float((c.double() - ref).abs().max()) <= 1e-5 * float(absref.max())
+    # shapes the grouped kernels do not cover are refused, not mangled
+    Nbad = (i64 * n)(*([100] * n))
+    assert K.osb_gemv_grouped(a.data_ptr(), B, C, Nbad, sc, zp, n, M, Kd, 1 if w8 else dtype, dtype, _stream()) == 801
+
+
+def test_gemv_padded_rows_and_concat2_and_silu_mul(K):
+    import torch
+    vp, i64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    # GEMV against a row-padded weight (vocabulary 32003 -> ld 32008)
+    K.osb_gemm_ld.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i64, i64, i64, i64, i64, i64, i64, ci, ci, ci, vp]
+    g = torch.Generator(device="cuda").manual_seed(5)
+    N, Np, Kd = 32003, 32008, 512
+    a = torch.randn(1, Kd, device="cuda", generator=g).half()
+    w = torch.zeros(Kd, Np, device="cuda", dtype=torch.half)
+    w[:, :N] = (torch.randn(Kd, N, device="cuda", generator=g) * 0.05).half()
+    w[:, N:] = 7.0                                       # padding must never reach an output
+    c = torch.full((1, N + 8), -1.0, device="cuda", dtype=torch.half)
+    K.osb_launch_count_reset()
+    assert K.osb_gemm_ld(a.data_ptr(), Kd, w.data_ptr(), Np, c.data_ptr(), N, None, None, 1, 1, N, Kd, 0, 0, 0, 0, F16, 0, _stream()) == 0
+    torch.cuda.synchronize()
+    ref = a.double() @ w[:, :N].double()
+    _check(c[:, :N], ref, a.double().abs() @ w[:, :N].double().abs(), "gemv padded ld")
+    assert bool((c[:, N:] == -1.0).all())
+    # two-source concat
+    K.osb_concat2.argtypes = [vp, vp, vp, i64, i64, i64, vp]
+    x = torch.randn(4, 2047, 64, device="cuda", generator=g).half(); y = torch.randn(4, 1, 64, device="cuda", generator=g).half()
+    o = torch.empty(4, 2048, 64, device="cuda", dtype=torch.half)
+    assert K.osb_concat2(x.data_ptr(), y.data_ptr(), o.data_ptr(), 4, 2047 * 64 * 2, 64 * 2, _stream()) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(o, torch.cat([x, y], 1))
+    assert K.osb_concat2(x.data_ptr(), y.data_ptr(), o.data_ptr(), 4, 2047 * 64 * 2, 6, _stream()) == 801     # not 16-byte granular: refused
+    # silu(a) * b
+    K.osb_binary.argtypes = [ci, vp, vp, vp, vp, vp, vp, ci, ci, vp]
+    n = 5632
+    ga = torch.randn(n, device="cuda", generator=g).half() * 3; ub = torch.randn(n, device="cuda", generator=g).half()
+    out = torch.empty(n, device="cuda", dtype=torch.half)
+    one = (i64 * 1)(1); shp = (i64 * 1)(n)
+    assert K.osb_binary(6, ga.data_ptr(), one, ub.data_ptr(), one, out.data_ptr(), shp, 1, F16, _stream()) == 0
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.silu(ga.double()) * ub.double()
+    assert float((out.double() - ref).abs().max()) <= 2e-3 * max(1.0, float(ref.abs().max()))

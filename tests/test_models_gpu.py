@@ -379,6 +379,40 @@ def test_llama_decode_parity(engine_lib, oracle_lib, workdir, mode):
     assert np.array_equal(got["opkv0"][:, :, :-1], ref["opkv0"][:, :, :-1]) or mode == "float16"
 
 
+@pytest.mark.parametrize("wdtype", ["float16", "uint8"])
+def test_llama_decode_midsize_fused_paths(engine_lib, oracle_lib, workdir, wdtype):
+    """The decode-step fusions at a size where they engage (hidden 256, 300 cached positions, 259-entry vocabulary): grouped q/k/v and
+    gate/up GEMVs (fp16 and uint8 weights dequantised in registers), SiLU-gate pass, fused RMSNorm / rotary steps, split-KV decode
+    attention, the row-padded copy of a weight whose N is not 16-byte granular, two-source Concat -- streamed, resident and graph-replay
+    runs against ONE reference run, and the plan must really contain the fused steps."""
+    from onnxstream_b200.model import plan_summary
+    cfg = emit.LlamaConfig(vocab=259, hidden=256, heads=4, kv_heads=2, head_dim=64, mlp=512, layers=2, past=300, max_pos=512)
+    d = os.path.join(workdir, f"llama_mid_{wdtype}") + "/"
+    emit.emit_llama_decode(d, cfg, wdtype)
+    inputs = emit.llama_inputs(cfg)
+    mask = np.ones((1, cfg.past + 1), np.int64); mask[0, 5:40] = 0          # padded positions: the additive mask matters
+    inputs["attention_5F_mask"] = mask
+    opts = ("use_scaled_dp_attn_op", "use_fp16_arithmetic")
+    kw = dict(extra_outputs=("opkv0", "opkv3"), upcast=UPCAST)
+    rep = plan_summary(open(d + "model.txt").read(), use_scaled_dp_attn_op=True, library_path=engine_lib)
+    last = rep.splitlines()[-1]
+    for kind in ("RMSNORM=5", "ROPE=4", "GEMV_GROUP=2", "SWIGLU=2", "SDPA=2", "LINEAR=4"):
+        assert kind in last, last
+    ref = run_model(oracle_lib, d, inputs, ("use_scaled_dp_attn_op",), extra_outputs=("opkv0", "opkv3"))[0]     # fp32 arithmetic on the same blobs
+    ref16 = run_model(oracle_lib, d, inputs, opts, **kw)[0]
+    tol = TOL["float16"] if wdtype == "float16" else 5e-2
+    base_err = report(ref16["logits"], ref["logits"])["rel_to_max"]
+    for b200 in ((), (("b200_resident_weights", 1),), (("b200_resident_weights", 1), ("b200_cuda_graph", 1))):
+        got, m = run_model(engine_lib, d, inputs, opts, wp="ram+nocache", b200_options=b200, runs=4 if b200 else 1, **kw)
+        for n in ("logits", "opkv0", "opkv3"):
+            assert got[n].shape == ref[n].shape
+            assert report(got[n], ref16[n])["rel_to_max"] <= tol, (n, b200)
+        # no further from the fp32-arithmetic result than the reference's own fp16 mode (x2 + slack)
+        assert report(got["logits"], ref["logits"])["rel_to_max"] <= 2 * base_err + 2e-3, b200
+        if len(b200) == 2:
+            assert m.stats()["graph_replays"] >= 1
+
+
 def test_llama_decode_graph_replay_follows_token_ids(engine_lib, workdir):
     """int64 graph inputs and CUDA graphs: token ids / positions / mask reach the device through int64 mirrors (Gather indices, Cast),
     so the captured decode step can be REPLAYED with new ids.  A captured model fed a sequence of different (id, position) pairs must
