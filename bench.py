@@ -586,7 +586,7 @@ def measure(w: Workload, args, dist, clocks=None):
     st_e = mv.stats()
     n_tc, tc_ms, tc_flops, tc_bytes = [float(x) for x in prof]
     achieved_tf = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05 implicit-GEMM conv / GEMM, all launches of one step)",
+    roofline = {"bound": "tensor", "kernel": "tc_gemm_kernel + tc_pair_kernel (tcgen05 implicit-GEMM conv / GEMM: single-CTA and CTA-pair tiles, all launches of one step)",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
                 "peak_source": peak_src, "launches": int(n_tc), "kernel_ms_per_step": tc_ms, "flops_per_step": tc_flops,
                 "algorithmic_bytes_per_step": tc_bytes,
@@ -597,7 +597,7 @@ def measure(w: Workload, args, dist, clocks=None):
         in_bytes = sum(int(v.nbytes) // (2 if v.dtype == np.float32 else 1) for v in inputs.values())     # activations live as fp16
         algo = float(meta["weight_bytes"] + in_bytes)
         ach = algo / (ms_per_step * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "whole step (gemv_panel / gemv_w8_panel + attention_rows + elementwise): weights and KV cache streamed once per token",
+        roofline = {"bound": "hbm", "kernel": "whole step (grouped gemv_panel / gemv_w8_panel + attention_decode + elementwise): weights and KV cache streamed once per token",
                     "achieved": ach, "peak": peak_bw, "unit": "GB/s", "frac": ach / peak_bw, "peak_source": peak_src.replace("sustained bf16 cuBLAS", "STREAM-style copy"),
                     "algorithmic_bytes_per_step": algo, "traffic": None}
     # DRAM traffic of the same kernel from the committed ncu pass (scripts/ncu_traffic.py): per launch, like `achieved`

@@ -41,6 +41,18 @@ int osb_binary(int op, const void* a, const int64_t* a_strides, const void* b, c
 /* Generic strided gather-copy: out[i0..] = in[in_offset + sum_k (i_k / in_div[k]) * in_stride[k]], written at
  * out_offset + sum_k i_k * out_stride[k].  Covers XnnPack::transpose (src/onnxstream.cpp:1748-1809), Concat
  * (4140-4299), Split (5999-6119), Slice (6499-6695), Expand (7154-7351) and nearest Resize (6120-6315, in_div = scale). */
+/* fp32 Conv / MatMul / Gemm on the tensor cores (replaces XnnPack::convolution / matrix_multiply for float, src/onnxstream.cpp:1035-1534):
+   every fp32 operand is split into three bfloat16 parts (24 mantissa bits) and expanded 6x along K so that ONE tcgen05 contraction sums the
+   six significant cross products in its fp32 accumulator.  expand_cols: rows of length L -> rows of 6 L (GEMM A rows, [N][K] weights, NHWC
+   pixels, OHWI taps); expand_rows: a [K][N] weight -> [6 K][N].  b_side: 0 for the A operand, 1 for the B operand (the segment orders pair up).
+   The f32x launchers take the bf16 expansions and fp32 C / bias / residual; cudaErrorNotSupported (801) = shape outside the tensor-core path. */
+int osb_bf16x3_expand_cols(const void* in_f32, void* out_bf16, int64_t rows, int64_t L, int64_t ld_in, int b_side, void* stream);
+int osb_bf16x3_expand_rows(const void* in_f32, void* out_bf16, int64_t K, int64_t N, int b_side, void* stream);
+int osb_tc_gemm_f32x_ok(int64_t M, int64_t N, int64_t K);      /* 1: osb_tc_gemm_f32x takes this fp32 problem (K = the un-expanded depth) */
+int osb_tc_conv_f32x_ok(int64_t H, int64_t W, int64_t Cin, int64_t Cout, int kh, int kw, int stride, int64_t Ho, int64_t Wo);
+int osb_tc_gemm_f32x(const void* A6, const void* B6, void* C_f32, const void* bias_f32, const void* residual_f32, int64_t M, int64_t N, int64_t K6, int b_transposed, void* stream);
+int osb_tc_conv_f32x(const void* x6, const void* w6, const void* bias_f32, const void* residual_f32, void* y_f32, int64_t H, int64_t W, int64_t Cin6, int64_t Cout,
+                     int kh, int kw, int stride, int pad_top, int pad_left, int64_t Ho, int64_t Wo, void* stream);
 /* Concat of two tensors along one axis in one launch (src/onnxstream.cpp Concat branch, two inputs): outer slices of a_bytes / b_bytes each.
    cudaErrorNotSupported (801) unless both slice sizes and all three pointers are multiples of 16 bytes. */
 int osb_concat2(const void* a, const void* b, void* out, int64_t outer, int64_t a_bytes, int64_t b_bytes, void* stream);

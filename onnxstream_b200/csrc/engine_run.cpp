@@ -1049,6 +1049,7 @@ struct Engine::Impl {
     void fused_gemv_group(const Step& s);
     void fused_swiglu(const Step& s);
     bool gemv_group(const Tensor& a, const size_t* op_idx, int n, Tensor* outs);
+    Tensor f32x_operand(const Tensor& t, int64_t rows, int64_t L, bool by_rows, int b_side, const std::string& cache_key);
     void fused_rope(const Step& s);
 
     Tensor binary(int bop, const Tensor& a, const Tensor& b, float out_scale = 0.f, int out_zp = 0);
@@ -1314,9 +1315,20 @@ void Engine::Impl::op_conv(size_t oi, const Tensor* residual, size_t out_op)
             G = stats_groups;
             if (gn_apply_ok(y, Cout, G)) gstats = gn_slot_ptr(gn_slot);
         }
+        bool done = false;
+        if (x.type == DType::f32 && E.gemm_impl != 1 && osb_tc_conv_f32x_ok(H, W, Cin, Cout, kh, kw, stride, Ho, Wo)) {
+            // fp32 conv on the tensor cores: image and OHWI weights as bf16 triple-split expansions (6 Cin channels), fp32 result
+            Tensor x6 = f32x_operand(x, H * W, Cin, false, 0, "");
+            Tensor w6 = f32x_operand(w, Cout * kh * kw, Cin, false, 1, op.in[1].name + "|bf16x6");
+            const int rc = osb_tc_conv_f32x(x6.data(), w6.data(), has_b ? b.data() : nullptr, residual ? rr.data() : nullptr, y.mdata(), H, W, 6 * Cin, Cout, kh, kw, stride,
+                                            pad_top, pad_left, Ho, Wo, st);
+            if (rc != (int)cudaErrorNotSupported) { ck(rc, "osb_tc_conv_f32x"); done = true; }
+        }
+        if (!done) {
         ck(osb_conv2d_ex(x.data(), w.data(), has_b ? b.data() : nullptr, nullptr, residual ? rr.data() : nullptr, y.mdata(), H, W, Cin, Cout, kh, kw, stride, pad_top, pad_left, Ho, Wo,
                          K(x.type), E.gemm_impl, st, gstats, G, &gdone), "osb_conv2d");
         if (gdone) stats_ready_for = stats_want;
+        }
     }
     if (is1d) y.shape.pop_back();
     if (!E.keep_nhwc || is1d) { Tensor t = y; if (is1d) { t.shape.push_back(1); } t = to_plain(t); if (is1d) t.shape.pop_back(); y = t; }
@@ -1393,6 +1405,18 @@ void Engine::Impl::op_matmul(size_t oi, const Tensor* bias, const Tensor* residu
         if (bias) { bb = *bias; if (bb.type != a.type) bb = convert(bb, a.type); }
         if (residual) { rr = to_plain(*residual); if (rr.type != a.type) rr = convert(rr, a.type); }
         y = make(a.type, os);
+        if (a.type == DType::f32 && n == 1 && E.gemm_impl != 1 && osb_tc_gemm_f32x_ok(M, N, Kd)) {
+            // fp32 MatMul on the tensor cores (bf16 triple split); a static [K][N] weight is expanded once when the model is resident
+            const bool stat = op.in[1].wtype != DType::none && op.in[1].shape.size() == 2;
+            Tensor a6 = f32x_operand(a, M, Kd, false, 0, "");
+            Tensor b6 = f32x_operand(b, Kd, N, true, 1, stat ? op.in[1].name + "|bf16x6" : std::string());
+            const int rc = osb_tc_gemm_f32x(a6.data(), b6.data(), y.mdata(), bias ? bb.data() : nullptr, residual ? rr.data() : nullptr, M, N, 6 * Kd, 0, st);
+            if (rc != (int)cudaErrorNotSupported) {
+                ck(rc, "osb_tc_gemm_f32x");
+                push(out_op == (size_t)-1 ? oi : out_op, 0, y);
+                return;
+            }
+        }
         const int64_t vec = 16 / (int64_t)dtype_size(a.type);
         if (E.resident_weights && op.in[1].wtype != DType::none && op.in[1].shape.size() == 2 && n == 1 && M <= 8 && N >= 256 && N % vec != 0 && Kd >= 64) {
             // decode GEMV against a resident weight whose rows are not 16-byte granular (a 32003-entry vocabulary): a row-padded copy,
@@ -1443,6 +1467,12 @@ void Engine::Impl::op_gemm(size_t oi)
     if (b.type != a.type) b = convert(b, a.type);
     if (c.type != a.type) c = convert(c, a.type);
     Tensor y = make(a.type, { M, N });
+    if (a.type == DType::f32 && c.numel() == N && E.gemm_impl != 1 && osb_tc_gemm_f32x_ok(M, N, Kd)) {
+        Tensor a6 = f32x_operand(a, M, Kd, false, 0, "");
+        Tensor b6 = f32x_operand(to_plain(b), Kd, N, true, 1, op.in[1].wtype != DType::none ? op.in[1].name + "|bf16x6" : std::string());
+        const int rc = osb_tc_gemm_f32x(a6.data(), b6.data(), y.mdata(), c.data(), nullptr, M, N, 6 * Kd, 0, st);
+        if (rc != (int)cudaErrorNotSupported) { ck(rc, "osb_tc_gemm_f32x"); push(oi, 0, y); return; }
+    }
     ck(osb_gemm(a.data(), b.data(), y.mdata(), c.data(), nullptr, 1, M, N, Kd, 0, 0, 0, 0, K(a.type), E.gemm_impl, st), "osb_gemm");
     push(oi, 0, y);
 }
@@ -2535,6 +2565,20 @@ void Engine::Impl::fused_rope(const Step& s)
     Tensor y = make(x.type, x.shape);
     ck(osb_rope(x.data(), cs.data(), sn.data(), y.mdata(), K(x.type), x.numel() / D, D, 1, st), "osb_rope");
     push(i + 6, 0, y);
+}
+
+// bf16 triple-split expansion of an fp32 operand for the tensor-core fp32 path (include/onnxstream_b200_kernels.h: osb_tc_gemm_f32x).
+// by_rows: [K = rows][N = L] -> [6 K][N]; otherwise rows of length L -> rows of length 6 L.  A static weight of a resident model is expanded
+// once and kept with the resident weights (cache_key non-empty).
+Tensor Engine::Impl::f32x_operand(const Tensor& t, int64_t rows, int64_t L, bool by_rows, int b_side, const std::string& cache_key)
+{
+    const bool cache = E.resident_weights && !cache_key.empty();
+    if (cache) { auto it = resident.find(cache_key); if (it != resident.end()) return it->second; }
+    Tensor e = make(DType::f16, { rows, 6 * L });          // bfloat16 payload in a 2-byte container type
+    if (by_rows) ck(osb_bf16x3_expand_rows(t.data(), e.mdata(), rows, L, b_side, st), "osb_bf16x3_expand_rows");
+    else ck(osb_bf16x3_expand_cols(t.data(), e.mdata(), rows, L, L, b_side, st), "osb_bf16x3_expand_cols");
+    if (cache) { resident[cache_key] = e; resident_bytes += (size_t)(rows * 6 * L) * 2; }
+    return e;
 }
 
 // n (2 or 3) MatMul nodes x[rows <= 8, K] . W_g[K, N_g] sharing x: one grouped GEMV launch.  false = not expressible (the caller runs the

@@ -68,6 +68,8 @@ struct TcParams {
     double* gn_stats;            // != null: per-group (sum, sum of squares) of the stored output, for the GroupNorm that consumes it
     int gn_cpg, gn_groups;       // channels per group, number of groups (N == gn_cpg * gn_groups)
     int gn_debug;                // bisecting aid (OSB_GN_DEBUG): 1 = skip the per-chunk gathering, 2 = skip the per-tile flush, 3 = both
+    int bf16;                    // operands are bfloat16 (the fp32 path: bf16 triple-split operands, see osb_tc_gemm_f32x)
+    int f32_out;                 // raw fp32 accumulators go to `ws` even when split_k == 1; the reduce kernel writes fp32 C (+ fp32 bias / residual)
     long long stride_c;          // elements between batches
     long long ldc;               // elements between output rows (== N for a dense C)
 };
@@ -75,12 +77,12 @@ struct TcParams {
 using namespace tcptx;
 
 // instruction descriptor for kind::f16: fp16 x fp16 -> fp32, A K-major, B K- or MN-major
-__device__ __forceinline__ uint32_t make_idesc(int b_mn_major, int bn)
+__device__ __forceinline__ uint32_t make_idesc(int b_mn_major, int bn, int bf16 = 0)
 {
     uint32_t d = 0;
     d |= 1u << 4;                              // c_format = F32
-    d |= 0u << 7;                              // a_format = F16
-    d |= 0u << 10;                             // b_format = F16
+    d |= (bf16 ? 1u : 0u) << 7;                // a_format = F16 / BF16
+    d |= (bf16 ? 1u : 0u) << 10;               // b_format = F16 / BF16
     d |= 0u << 15;                             // a_major  = K
     d |= (uint32_t)(b_mn_major ? 1 : 0) << 16; // b_major
     d |= (uint32_t)(bn >> 3) << 17;            // n_dim
@@ -194,7 +196,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (warp-uniform control flow, leader-predicated issue) =====================
-        const uint32_t idesc = make_idesc(p.b_kmajor ? 0 : 1, p.bn);
+        const uint32_t idesc = make_idesc(p.b_kmajor ? 0 : 1, p.bn, p.bf16);
         // Descriptor templates: everything but the 14-bit start address is loop-invariant.
         //   A, K-major SW128: 8-row groups 1024 B apart; K advances 32 B inside the swizzle row.
         //   B, K-major: same.  B, MN-major SW128: two 64-column atoms 8192 B apart (LBO), 8-row k-groups 1024 B apart (SBO);
@@ -257,7 +259,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (p.groups > 1) cbase = b == 0 ? p.C : (b == 1 ? p.C1 : p.C2);    // stride_c == 0 in a grouped launch
             __half* crow = cbase + (long long)b * p.stride_c + out_row * p.ldc;
             const __half* rrow = p.residual ? p.residual + (long long)b * p.stride_c + out_row * p.ldc : nullptr;
-            float* wrow = p.split_k > 1 ? p.ws + (((long long)sp * p.batch + b) * p.M + out_row) * p.N : nullptr;
+            float* wrow = (p.split_k > 1 || p.f32_out) ? p.ws + (((long long)sp * p.batch + b) * p.M + out_row) * p.N : nullptr;
             const bool vec_ok = (p.N & 7) == 0;
             // In-kernel split-K, "last finisher reduces" (no second launch, no co-residency assumption): every CTA of a tile takes a ticket
             // AFTER its main loop.  Tickets 0 .. S-2 publish their fp32 partial and leave; the holder of ticket S-1 -- by construction every
@@ -426,6 +428,21 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, __half* __res
     }
 }
 
+// fp32-output variant (the bf16 triple-split path): out[row][n] = sum_s ws[s][row][n] + bias[n] + residual[row][n], everything fp32, any N
+__global__ void splitk_reduce_f32_kernel(const float* __restrict__ ws, float* __restrict__ out, const float* __restrict__ bias, const float* __restrict__ residual,
+                                         long long rows, int N, int splits)
+{
+    osb_pdl_prologue();
+    const long long total = rows * N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        float a = ws[i];
+        for (int s = 1; s < splits; s++) a += ws[(long long)s * total + i];
+        if (bias) a += bias[(int)(i % N)];
+        if (residual) a += residual[i];
+        out[i] = a;
+    }
+}
+
 #include "gemm_pair.cuh"
 #include "gemm_i8.cuh"
 
@@ -579,6 +596,14 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cuda
     else if (short_k) osb_launch((tc_gemm_kernel<STAGES_SHORT, false>), grid, NUM_THREADS, (size_t)smem_bytes_for(STAGES_SHORT, false), st, ma, mb, mb1, mb2, p);
     else if (extras) osb_launch((tc_gemm_kernel<STAGES_DEEP, true>), grid, NUM_THREADS, (size_t)smem_bytes_for(STAGES_DEEP, true), st, ma, mb, mb1, mb2, p);
     else osb_launch((tc_gemm_kernel<STAGES_DEEP, false>), grid, NUM_THREADS, (size_t)smem_bytes_for(STAGES_DEEP, false), st, ma, mb, mb1, mb2, p);
+    if (p.f32_out) {
+        launched(1);
+        const long long total = (long long)p.batch * p.M * p.N;
+        int rgrid = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+        osb_launch((splitk_reduce_f32_kernel), rgrid, 256, 0, st, (const float*)p.ws, (float*)p.C, (const float*)p.bias, (const float*)p.residual, (long long)p.batch * p.M, p.N, p.split_k);
+        if (g_prof) { cudaEventRecord(rec.b, st); g_prof_list.push_back(rec); }
+        return launched(0);
+    }
     if (p.split_k > 1 && !p.counters) {
         launched(1);
         long long total4 = (long long)p.batch * p.M * p.N / 4;
@@ -859,9 +884,27 @@ bool osb_tc_gemm_ok(int64_t M, int64_t N, int64_t K, int bt, const void* A, cons
     return get_encode() != nullptr || A == nullptr;
 }
 
+// fp32 problems on the tensor cores (osb_tc_gemm_f32x / osb_tc_conv_f32x below): the launch builders run with this flag set -- operands are
+// bf16 triple-split expansions, C / bias / residual are fp32, no CTA-pair tiles, accumulators leave through the fp32 workspace
+static thread_local int g_f32x = 0;
+
+// finish a TcParams for the fp32 path; false = the fp32 partial planes do not fit the fixed workspace
+static bool f32x_params(TcParams& p, OsbWorkspace* wsp, cudaStream_t st)
+{
+    p.bf16 = 1; p.f32_out = 1; p.counters = nullptr;
+    p.bias2 = nullptr; p.gn_stats = nullptr;
+    if ((size_t)p.split_k * p.batch * p.M * p.N * 4 > WS_MAX) p.split_k = 1;
+    if ((size_t)p.batch * p.M * p.N * 4 > WS_MAX) return false;
+    if (!wsp) wsp = osb_workspace(st, OSB_WS_SPLITK);
+    if (!wsp) return false;
+    p.ws = wsp->splitk;
+    return true;
+}
+
 int osb_tc_gemm_launch(const void* A, const void* B, void* C, const void* bias, const void* residual, int64_t batch, int64_t M, int64_t N, int64_t K,
                        int64_t sa, int64_t sb, int64_t sc, int bt, cudaStream_t st, int64_t lda, int64_t ldb, int64_t ldc)
 {
+    if (g_f32x && batch != 1) return (int)cudaErrorNotSupported;
     if (lda <= 0) lda = K;
     if (ldb <= 0) ldb = bt ? K : N;
     if (ldc <= 0) ldc = N;
@@ -885,7 +928,7 @@ int osb_tc_gemm_launch(const void* A, const void* B, void* C, const void* bias, 
         // CTA-pair kernel (256 x bn tiles, TMA-store epilogue) where its cost model wins: dense C only
         int bnp = 0;
         const int k_blocks = (int)((K + BLOCK_K - 1) / BLOCK_K);
-        if (ldc == N && (batch == 1 || sc == M * N) && use_pair(m_tiles, N, batch, bt != 0, k_blocks, bn, &bnp)) {
+        if (!g_f32x && ldc == N && (batch == 1 || sc == M * N) && use_pair(m_tiles, N, batch, bt != 0, k_blocks, bn, &bnp)) {
             CUtensorMap mc;
             int c_swap = 0;
             bool ok = bt ? make_map_rb(&mb, B, (uint64_t)K, (uint64_t)N, bbatch, (uint64_t)ldb * 2, (uint64_t)(sb ? sb : N * ldb) * 2, BLOCK_K, (uint32_t)(bnp / 2), &b_swap)
@@ -920,6 +963,7 @@ int osb_tc_gemm_launch(const void* A, const void* B, void* C, const void* bias, 
     p.ws = wsp ? wsp->splitk : nullptr;
     // in-kernel rendezvous reduction needs every CTA resident at once and float4-aligned rows; otherwise the reduce kernel runs
     p.counters = (p.split_k > 1 && p.N % 8 == 0 && p.ldc % 8 == 0 && (long long)p.m_tiles * p.n_tiles * p.batch <= 2048 && inkernel_reduce() && wsp) ? wsp->splitk_counters : nullptr;
+    if (g_f32x && !f32x_params(p, wsp, st)) return (int)cudaErrorNotSupported;
     p.short_k = short_k_hint(p.taps * p.k_blocks_per_tap, p.split_k);
     return launch(ma, mb, p, st);
 }
@@ -992,7 +1036,7 @@ int osb_tc_conv_launch(const void* x, const void* w, const void* bias, const voi
         // CTA-pair kernel: each CTA of the pair takes one 128-pixel box of the same tiling; output through a (Cout, Wo, Ho) store map
         int bnp = 0;
         const int k_blocks = kh * kw * (int)((Cin + BLOCK_K - 1) / BLOCK_K);
-        if (Cout % 8 == 0 && use_pair(m_tiles_, Cout, 1, true, k_blocks, bn, &bnp)) {
+        if (!g_f32x && Cout % 8 == 0 && use_pair(m_tiles_, Cout, 1, true, k_blocks, bn, &bnp)) {
             CUtensorMap mc;
             const uint32_t box_w = std::min<uint32_t>(bw, 32), box_h = 32 / box_w;
             bool ok = make_map(&mb, w, (uint64_t)Ktot, (uint64_t)Cout, 1, (uint64_t)Ktot * 2, (uint64_t)Ktot * Cout * 2, BLOCK_K, (uint32_t)(bnp / 2), 1) &&
@@ -1037,5 +1081,48 @@ int osb_tc_conv_launch(const void* x, const void* w, const void* bias, const voi
     const bool stats_ok = gn_stats && (p.split_k == 1 || p.counters || gn_cpg % 4 == 0);     // final epilogue (unsplit / last finisher) or the reduce kernel
     if (stats_ok) { p.gn_stats = gn_stats; p.gn_cpg = gn_cpg; p.gn_groups = gn_groups; if (gn_done) *gn_done = 1; }
     { static const int dbg = env_int("OSB_GN_DEBUG"); p.gn_debug = dbg; }
+    if (g_f32x) {
+        if (!f32x_params(p, wsp, st)) return (int)cudaErrorNotSupported;
+        p.short_k = short_k_hint(p.taps * p.k_blocks_per_tap, p.split_k);
+    }
     return launch(ma, mb, p, st);
+}
+
+// ---- fp32 GEMM / conv on the tensor cores: bf16 triple split ------------------------------------------------------------------------
+// x = h + m + l with h = bf16(x), m = bf16(x - h), l = bf16(x - h - m) carries 24 mantissa bits; a.b ~= ah.bh + ah.bm + am.bh + ah.bl + al.bh + am.bm
+// (the dropped terms are below 2^-24 relative).  The six products are ONE tensor-core contraction over a 6x longer K: the caller expands
+// A to [h|h|m|h|l|m] and B to [h|m|h|l|h|m] along K (osb_bf16x3_expand_*), products are exact in fp32 and accumulate in the fp32 TMEM
+// accumulator.  A, B: bf16 expansions (K6 = 6 K); C, bias, residual: fp32; C dense [M][N].  cudaErrorNotSupported: run the CUDA-core kernel.
+// shape predicates of the fp32 tensor-core path (before the caller spends time expanding operands)
+extern "C" int osb_tc_gemm_f32x_ok(int64_t M, int64_t N, int64_t K)
+{
+    static const bool on = [] { const char* e = getenv("OSB_F32_TC"); return !(e && e[0] == '0'); }();
+    return on && M >= 32 && N >= 8 && N % 8 == 0 && K >= 8 && (6 * K) % 8 == 0 && (size_t)M * N * 4 <= WS_MAX && get_encode() != nullptr ? 1 : 0;
+}
+extern "C" int osb_tc_conv_f32x_ok(int64_t H, int64_t W, int64_t Cin, int64_t Cout, int kh, int kw, int stride, int64_t Ho, int64_t Wo)
+{
+    static const bool on = [] { const char* e = getenv("OSB_F32_TC"); return !(e && e[0] == '0'); }();
+    return on && (6 * Cin) % 8 == 0 && 6 * Cin >= 16 && stride >= 1 && stride <= 2 && H * W >= 64 && kh <= 7 && kw <= 7 && (size_t)Ho * Wo * Cout * 4 <= WS_MAX &&
+           get_encode() != nullptr ? 1 : 0;
+}
+
+extern "C" int osb_tc_gemm_f32x(const void* A6, const void* B6, void* C, const void* bias, const void* residual, int64_t M, int64_t N, int64_t K6, int bt, void* stream)
+{
+    const int64_t ldb = bt ? K6 : N;
+    // (ldc is a float pitch here: only 16-byte pointer alignment of C matters to the workspace reduce)
+    if (!osb_tc_gemm_ok(M, N, K6, bt, A6, B6, nullptr, 0, 0, 0, K6, ldb, 8) || (N % 8)) return (int)cudaErrorNotSupported;
+    g_f32x = 1;
+    int r = osb_tc_gemm_launch(A6, B6, C, bias, residual, 1, M, N, K6, 0, 0, M * N, bt, (cudaStream_t)stream, K6, ldb, N);
+    g_f32x = 0;
+    return r;
+}
+
+extern "C" int osb_tc_conv_f32x(const void* x6, const void* w6, const void* bias, const void* residual, void* y, int64_t H, int64_t W, int64_t Cin6, int64_t Cout,
+                     int kh, int kw, int stride, int pad_top, int pad_left, int64_t Ho, int64_t Wo, void* stream)
+{
+    if (!osb_tc_conv_ok(H, W, Cin6, Cout, kh, kw, stride, x6, w6, nullptr)) return (int)cudaErrorNotSupported;
+    g_f32x = 1;
+    int r = osb_tc_conv_launch(x6, w6, bias, residual, y, H, W, Cin6, Cout, kh, kw, stride, pad_top, pad_left, Ho, Wo, (cudaStream_t)stream, nullptr, nullptr, 0, nullptr);
+    g_f32x = 0;
+    return r;
 }

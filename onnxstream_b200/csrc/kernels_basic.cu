@@ -7,6 +7,7 @@
 // multiple of the SM count, fp32 math on fp16 storage, every tensor read once and written once.
 
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include <cstring>
 #include "workspace.h"
 #include <cstdio>
@@ -1101,6 +1102,60 @@ int osb_binary(int op, const void* a, const int64_t* as, const void* b, const in
     if (dtype == OSB_F16) return binary_dispatch<__half, 8>(op, (const __half*)a, as, (const __half*)b, bs, (__half*)out, shape, ndim, st);
     if (dtype == OSB_F32) return binary_dispatch<float, 4>(op, (const float*)a, as, (const float*)b, bs, (float*)out, shape, ndim, st);
     return (int)cudaErrorInvalidValue;
+}
+
+// ---- fp32 -> bf16 triple split, expanded along K for the tensor-core fp32 path (gemm_tcgen05.cu: osb_tc_gemm_f32x) -----------------
+// x = h + m + l, h = bf16(x), m = bf16(x - h), l = bf16(x - h - m).  A side: segments [h|h|m|h|l|m]; B side: [h|m|h|l|h|m], so that
+// segment s of A times segment s of B runs over the six products hh, hm, mh, hl, lh, mm.
+__device__ __forceinline__ void bf16x3_parts(float x, int b_side, __nv_bfloat16* six)
+{
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+    if (b_side) { six[0] = h; six[1] = m; six[2] = h; six[3] = l; six[4] = h; six[5] = m; }
+    else        { six[0] = h; six[1] = h; six[2] = m; six[3] = h; six[4] = l; six[5] = m; }
+}
+// out[r][s * L + j] = part_s(in[r * ld_in + j]): rows of length L become rows of length 6 L (GEMM A rows, K-major B rows, NHWC pixels, OHWI taps)
+__global__ void bf16x3_expand_cols_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t rows, int L, int64_t ld_in, int b_side)
+{
+    osb_pdl_prologue();
+    const int64_t n = rows * L;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / L; const int j = (int)(i - r * L);
+        __nv_bfloat16 six[6];
+        bf16x3_parts(in[r * ld_in + j], b_side, six);
+        __nv_bfloat16* o = out + r * 6 * L + j;
+#pragma unroll
+        for (int s = 0; s < 6; s++) o[(int64_t)s * L] = six[s];
+    }
+}
+// out[s * Kr + k][n] = part_s(in[k][n]): a [K][N] MatMul weight becomes [6 K][N] (MN-major B operand)
+__global__ void bf16x3_expand_rows_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t Kr, int64_t N, int b_side)
+{
+    osb_pdl_prologue();
+    const int64_t n = Kr * N;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        __nv_bfloat16 six[6];
+        bf16x3_parts(in[i], b_side, six);
+#pragma unroll
+        for (int s = 0; s < 6; s++) out[(int64_t)s * n + i] = six[s];
+    }
+}
+
+int osb_bf16x3_expand_cols(const void* in, void* out, int64_t rows, int64_t L, int64_t ld_in, int b_side, void* stream)
+{
+    if (rows * L == 0) return 0;
+    if (L > (1 << 30)) return (int)cudaErrorInvalidValue;
+    osb_launch((bf16x3_expand_cols_kernel), grid_for((size_t)(rows * L), 256), 256, 0, (cudaStream_t)stream, (const float*)in, (__nv_bfloat16*)out, rows, (int)L, ld_in, b_side);
+    return launched();
+}
+
+int osb_bf16x3_expand_rows(const void* in, void* out, int64_t K, int64_t N, int b_side, void* stream)
+{
+    if (K * N == 0) return 0;
+    osb_launch((bf16x3_expand_rows_kernel), grid_for((size_t)(K * N), 256), 256, 0, (cudaStream_t)stream, (const float*)in, (__nv_bfloat16*)out, K, N, b_side);
+    return launched();
 }
 
 // Concat of two sources along one axis as ONE launch: out[o][0:la) = a[o][:], out[o][la:la+lb) = b[o][:], lengths in 16-byte units

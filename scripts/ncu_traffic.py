@@ -15,7 +15,7 @@ def main(src, dst, needle="tc_gemm_kernel"):
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6}
     per = collections.defaultdict(dict)
     for r in rows[hi + 1:]:
-        if len(r) <= vi or needle not in r[ki]:
+        if len(r) <= vi or not any(nd in r[ki] for nd in needle.split(",")):
             continue
         per[r[ii]][r[mi]] = float(r[vi].replace(",", "")) * scale.get(r[ui], 1.0)
     n = len(per)

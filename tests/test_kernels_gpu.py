@@ -740,3 +740,77 @@ def test_gemv_padded_rows_and_concat2_and_silu_mul(K):
     torch.cuda.synchronize()
     ref = torch.nn.functional.silu(ga.double()) * ub.double()
     assert float((out.double() - ref).abs().max()) <= 2e-3 * max(1.0, float(ref.abs().max()))
+
+
+F32X_GEMM = [(77, 768, 768), (77, 3072, 768), (77, 768, 3072), (4096, 320, 320), (256, 64, 40), (1000, 136, 100)]
+
+
+@pytest.mark.parametrize("M,N,Kd", F32X_GEMM)
+def test_f32_gemm_on_tensor_cores_bf16_triple_split(K, M, N, Kd):
+    """fp32 MatMul through tcgen05 (bf16 triple split, six cross products in one contraction): as accurate as an fp32 FMA loop.
+    Bar: |err| <= 2e-6 * sum|a_i b_i| (fp32 rounding of a K-long sum) -- three orders of magnitude below what a single bf16 or tf32 pass gives."""
+    import torch
+    vp, i64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    K.osb_bf16x3_expand_cols.argtypes = [vp, vp, i64, i64, i64, ci, vp]
+    K.osb_bf16x3_expand_rows.argtypes = [vp, vp, i64, i64, ci, vp]
+    K.osb_tc_gemm_f32x.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, ci, vp]
+    K.osb_tc_gemm_f32x_ok.argtypes = [i64, i64, i64]
+    assert K.osb_tc_gemm_f32x_ok(M, N, Kd) == 1
+    g = torch.Generator(device="cuda").manual_seed(M + N + Kd)
+    a = torch.randn(M, Kd, device="cuda", generator=g) * torch.exp(torch.randn(M, 1, device="cuda", generator=g) * 2)     # rows of very different scale
+    b = torch.randn(Kd, N, device="cuda", generator=g) * 0.05
+    bias = torch.randn(N, device="cuda", generator=g); res = torch.randn(M, N, device="cuda", generator=g)
+    a6 = torch.empty(M, 6 * Kd, device="cuda", dtype=torch.bfloat16); b6 = torch.empty(6 * Kd, N, device="cuda", dtype=torch.bfloat16)
+    c = torch.empty(M, N, device="cuda")
+    assert K.osb_bf16x3_expand_cols(a.data_ptr(), a6.data_ptr(), M, Kd, Kd, 0, _stream()) == 0
+    assert K.osb_bf16x3_expand_rows(b.data_ptr(), b6.data_ptr(), Kd, N, 1, _stream()) == 0
+    torch.cuda.synchronize()
+    # the three parts re-assemble the fp32 value to 24 bits
+    parts = a6.view(M, 6, Kd).double()
+    assert float(((parts[:, 0] + parts[:, 2] + parts[:, 4]) - a.double()).abs().max()) <= 2.0 ** -23 * float(a.abs().max())
+    K.osb_launch_count_reset()
+    assert K.osb_tc_gemm_f32x(a6.data_ptr(), b6.data_ptr(), c.data_ptr(), bias.data_ptr(), res.data_ptr(), M, N, 6 * Kd, 0, _stream()) == 0
+    torch.cuda.synchronize()
+    assert K.osb_tc_launch_count() >= 1
+    ref = a.double() @ b.double() + bias.double() + res.double()
+    absref = a.double().abs() @ b.double().abs() + bias.double().abs() + res.double().abs()
+    err = (c.double() - ref).abs()
+    worst = float((err / absref).max())
+    assert worst <= 2e-6, f"f32x gemm {M}x{N}x{Kd}: max err / sum|ab| = {worst:.3g}"
+    # K-major B ([N][K], the conv-weight layout) through expand_cols
+    bt = b.t().contiguous()
+    bt6 = torch.empty(N, 6 * Kd, device="cuda", dtype=torch.bfloat16)
+    assert K.osb_bf16x3_expand_cols(bt.data_ptr(), bt6.data_ptr(), N, Kd, Kd, 1, _stream()) == 0
+    c2 = torch.empty(M, N, device="cuda")
+    assert K.osb_tc_gemm_f32x(a6.data_ptr(), bt6.data_ptr(), c2.data_ptr(), None, None, M, N, 6 * Kd, 1, _stream()) == 0
+    torch.cuda.synchronize()
+    ref2 = a.double() @ b.double()
+    assert float(((c2.double() - ref2).abs() / (a.double().abs() @ b.double().abs())).max()) <= 2e-6
+
+
+@pytest.mark.parametrize("H,W,Cin,Cout,k,stride", [(64, 64, 320, 320, 3, 1), (32, 32, 64, 128, 3, 2), (16, 16, 1280, 640, 1, 1), (40, 24, 12, 40, 3, 1)])
+def test_f32_conv_on_tensor_cores_bf16_triple_split(K, H, W, Cin, Cout, k, stride):
+    import torch
+    vp, i64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    K.osb_bf16x3_expand_cols.argtypes = [vp, vp, i64, i64, i64, ci, vp]
+    K.osb_tc_conv_f32x.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, ci, ci, ci, i64, i64, vp]
+    K.osb_tc_conv_f32x_ok.argtypes = [i64, i64, i64, i64, ci, ci, ci, i64, i64]
+    pad = k // 2
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    assert K.osb_tc_conv_f32x_ok(H, W, Cin, Cout, k, k, stride, Ho, Wo) == 1
+    g = torch.Generator(device="cuda").manual_seed(H * Cin + Cout)
+    x = torch.randn(1, Cin, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) * 0.05
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    xh = x[0].permute(1, 2, 0).contiguous()                     # [H][W][Cin]
+    wo = w.permute(0, 2, 3, 1).contiguous()                     # OHWI
+    x6 = torch.empty(H * W, 6 * Cin, device="cuda", dtype=torch.bfloat16); w6 = torch.empty(Cout * k * k, 6 * Cin, device="cuda", dtype=torch.bfloat16)
+    y = torch.empty(Ho, Wo, Cout, device="cuda")
+    assert K.osb_bf16x3_expand_cols(xh.data_ptr(), x6.data_ptr(), H * W, Cin, Cin, 0, _stream()) == 0
+    assert K.osb_bf16x3_expand_cols(wo.data_ptr(), w6.data_ptr(), Cout * k * k, Cin, Cin, 1, _stream()) == 0
+    assert K.osb_tc_conv_f32x(x6.data_ptr(), w6.data_ptr(), bias.data_ptr(), None, y.data_ptr(), H, W, 6 * Cin, Cout, k, k, stride, pad, pad, Ho, Wo, _stream()) == 0
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), bias.double(), stride=stride, padding=pad)[0].permute(1, 2, 0)
+    absref = torch.nn.functional.conv2d(x.double().abs(), w.double().abs(), bias.double().abs(), stride=stride, padding=pad)[0].permute(1, 2, 0)
+    worst = float(((y.double() - ref).abs() / absref).max())
+    assert worst <= 2e-6, f"f32x conv: max err / sum|xw| = {worst:.3g}"
