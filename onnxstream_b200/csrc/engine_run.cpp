@@ -2622,7 +2622,12 @@ void Engine::Impl::fused_gemv_group(const Step& s)
     Tensor a = to_plain(in(s.first, 0));
     size_t idx[3]; Tensor outs[3];
     for (size_t g = 0; g < s.count; g++) idx[g] = s.first + g;
-    if (!gemv_group(a, idx, (int)s.count, outs)) { exec_unfused(s); return; }
+    if (!gemv_group(a, idx, (int)s.count, outs)) {
+        // every MatMul of the group has consumers outside it: run them one by one and keep all outputs (exec_unfused would drop the
+        // "intermediates" of a fusion group)
+        for (size_t g = 0; g < s.count; g++) exec_single(idx[g]);
+        return;
+    }
     for (size_t g = 0; g < s.count; g++) push(idx[g], 0, outs[g]);
 }
 

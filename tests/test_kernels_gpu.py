@@ -748,7 +748,8 @@ F32X_GEMM = [(77, 768, 768), (77, 3072, 768), (77, 768, 3072), (4096, 320, 320),
 @pytest.mark.parametrize("M,N,Kd", F32X_GEMM)
 def test_f32_gemm_on_tensor_cores_bf16_triple_split(K, M, N, Kd):
     """fp32 MatMul through tcgen05 (bf16 triple split, six cross products in one contraction): as accurate as an fp32 FMA loop.
-    Bar: |err| <= 2e-6 * sum|a_i b_i| (fp32 rounding of a K-long sum) -- three orders of magnitude below what a single bf16 or tf32 pass gives."""
+    Bar: |err| <= 1e-5 * sum|a_i b_i| over every output (a sequential fp32 FMA loop is bounded by K * 2^-24 = 2e-5 at K = 320; the tensor core
+    aligns each group of products to the largest one before adding) -- three orders of magnitude below what a single bf16 or tf32 pass gives."""
     import torch
     vp, i64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
     K.osb_bf16x3_expand_cols.argtypes = [vp, vp, i64, i64, i64, ci, vp]
@@ -776,7 +777,8 @@ def test_f32_gemm_on_tensor_cores_bf16_triple_split(K, M, N, Kd):
     absref = a.double().abs() @ b.double().abs() + bias.double().abs() + res.double().abs()
     err = (c.double() - ref).abs()
     worst = float((err / absref).max())
-    assert worst <= 2e-6, f"f32x gemm {M}x{N}x{Kd}: max err / sum|ab| = {worst:.3g}"
+    print(f"f32x gemm {M}x{N}x{Kd}: max err / sum|ab| = {worst:.3g}")
+    assert worst <= 1e-5, f"f32x gemm {M}x{N}x{Kd}: max err / sum|ab| = {worst:.3g}"
     # K-major B ([N][K], the conv-weight layout) through expand_cols
     bt = b.t().contiguous()
     bt6 = torch.empty(N, 6 * Kd, device="cuda", dtype=torch.bfloat16)
@@ -785,7 +787,8 @@ def test_f32_gemm_on_tensor_cores_bf16_triple_split(K, M, N, Kd):
     assert K.osb_tc_gemm_f32x(a6.data_ptr(), bt6.data_ptr(), c2.data_ptr(), None, None, M, N, 6 * Kd, 1, _stream()) == 0
     torch.cuda.synchronize()
     ref2 = a.double() @ b.double()
-    assert float(((c2.double() - ref2).abs() / (a.double().abs() @ b.double().abs())).max()) <= 2e-6
+    worst2 = float(((c2.double() - ref2).abs() / (a.double().abs() @ b.double().abs())).max())
+    assert worst2 <= 1e-5, f"f32x gemm K-major B {M}x{N}x{Kd}: max err / sum|ab| = {worst2:.3g}"
 
 
 @pytest.mark.parametrize("H,W,Cin,Cout,k,stride", [(64, 64, 320, 320, 3, 1), (32, 32, 64, 128, 3, 2), (16, 16, 1280, 640, 1, 1), (40, 24, 12, 40, 3, 1)])
@@ -813,4 +816,4 @@ def test_f32_conv_on_tensor_cores_bf16_triple_split(K, H, W, Cin, Cout, k, strid
     ref = torch.nn.functional.conv2d(x.double(), w.double(), bias.double(), stride=stride, padding=pad)[0].permute(1, 2, 0)
     absref = torch.nn.functional.conv2d(x.double().abs(), w.double().abs(), bias.double().abs(), stride=stride, padding=pad)[0].permute(1, 2, 0)
     worst = float(((y.double() - ref).abs() / absref).max())
-    assert worst <= 2e-6, f"f32x conv: max err / sum|xw| = {worst:.3g}"
+    assert worst <= 1e-5, f"f32x conv: max err / sum|xw| = {worst:.3g}"
