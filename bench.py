@@ -117,6 +117,25 @@ class SD15UNet(Workload):
         return emit.unet_inputs(self.cfg, seed=seed)
 
 
+class SD15UNetFP32(SD15UNet):
+    """BASELINE config[0]: the SD 1.5 UNet step in fp32 (fp32 blobs, fp32 arithmetic -- the reference's default CPU mode).  On the B200 engine
+    every Conv / MatMul / Gemm runs on the tensor cores through the bf16 triple split (fp32-faithful); the reference arm is the same graph and
+    blobs through XNNPACK f32."""
+    name = "sd15_unet_fp32"
+    metric = "SD1.5 UNet 512x512 bs=1 fp32 denoise steps/s (one UNet Model::run per step)"
+    options = ("fuse_ops_in_attention",)
+    ref_options = ("fuse_ops_in_attention",)
+    dtype = "f32"
+    tol = 2e-4
+
+    def __init__(self, latent=64):
+        super().__init__(latent)
+        self.describe = "SD1.5 UNet-shaped graph (BASELINE config[0]), 4x%dx%d latent, 77x768 context, fp32 weights + fp32 arithmetic (tensor cores via bf16 triple split)" % (latent, latent)
+
+    def emit(self, d):
+        return emit.emit_unet(d, self.cfg, "float32", seed=0)
+
+
 class TinyUNet(SD15UNet):
     name = "tiny_unet_fp16"
     metric = "tiny UNet steps/s (plumbing check)"
@@ -232,6 +251,8 @@ class LlamaDecode(Workload):
 def make_workload(name):
     if name == "sd15_unet_fp16":
         return SD15UNet()
+    if name == "sd15_unet_fp32":
+        return SD15UNetFP32()
     if name == "tiny_unet_fp16":
         return TinyUNet()
     if name == "sdxl_unet_w8":
@@ -249,7 +270,7 @@ def make_workload(name):
     raise SystemExit(f"unknown workload {name}")
 
 
-WORKLOADS = ["sd15_unet_fp16", "tiny_unet_fp16", "sdxl_unet_w8", "sdxl_turbo_w8", "vae_decoder_fp16", "clip_text_fp32", "tinyllama_decode", "tinyllama_decode_w8", "sd15_pipeline"]
+WORKLOADS = ["sd15_unet_fp16", "sd15_unet_fp32", "tiny_unet_fp16", "sdxl_unet_w8", "sdxl_turbo_w8", "vae_decoder_fp16", "clip_text_fp32", "tinyllama_decode", "tinyllama_decode_w8", "sd15_pipeline"]
 
 
 def peaks():
@@ -318,7 +339,9 @@ def dist_setup():
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(0)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", 0))
+    import datetime
+    # a rank that dies or skips a collective must not hold the others (and the GPU box) for NCCL's default 10 minutes
+    dist.init_process_group("nccl", device_id=torch.device("cuda", 0), timeout=datetime.timedelta(seconds=int(os.environ.get("OSB_DIST_TIMEOUT_S", "300"))))
     return dist
 
 
@@ -748,7 +771,7 @@ def main():
 
     dist = dist_setup()
     if args.all_configs:
-        for name in ["sd15_unet_fp16", "sd15_pipeline", "sdxl_unet_w8", "sdxl_turbo_w8", "vae_decoder_fp16", "tinyllama_decode", "tinyllama_decode_w8"]:
+        for name in ["sd15_unet_fp16", "sd15_pipeline", "sdxl_unet_w8", "sdxl_turbo_w8", "vae_decoder_fp16", "clip_text_fp32", "tinyllama_decode", "tinyllama_decode_w8", "sd15_unet_fp32"]:
             a2 = argparse.Namespace(**vars(args)); a2.workload = name
             if name != "sd15_unet_fp16":
                 a2.steps = min(args.steps, 10)

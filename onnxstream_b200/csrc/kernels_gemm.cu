@@ -203,6 +203,8 @@ skinny_gemm_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restri
 // shared memory, then added with fp32 atomics into a zeroed scratch row; a second tiny kernel applies bias / residual and
 // rounds to the storage type.  Reads every weight exactly once.
 constexpr int GEMV_U = 8;
+// CTAs a GEMV launch aims for (4 per SM); OSB_GEMV_CTAS overrides for tuning runs
+static inline int gemv_ctas() { static const int v = [] { const char* e = getenv("OSB_GEMV_CTAS"); int x = e ? atoi(e) : 0; return x > 0 ? x : 592; }(); return v; }
 template <typename T, int MAXM>
 __device__ __forceinline__ void gemv_panel_body(const T* __restrict__ A, const T* __restrict__ B, float* __restrict__ acc_out, int M, int N, int K, int k_per_cta,
                                                 int* __restrict__ counter, T* __restrict__ C, const T* __restrict__ bias, const T* __restrict__ residual, int panel, int ldb)
@@ -559,6 +561,46 @@ __global__ void __launch_bounds__(128) attention_decode_kernel(const T* __restri
     __syncwarp();
     const int jn = (Tk - s0) < 32 ? (int)max((int64_t)0, Tk - s0) : 32;
     const T* vb = v + (hk * Tk + s0) * dv;
+    bool pv_done = false;
+    if constexpr (std::is_same<T, __half>::value) {
+        if ((dv & 7) == 0 && ((uintptr_t)vb & 15) == 0) {
+            // 16-byte V loads: lane = (key group kg of 4, column group cg of 8 halves); every lane has its 8 loads in flight at once, then two
+            // shuffles fold the 4 key groups (the scalar loop below issues 2-byte loads, 64 per lane)
+            const int kg = lane >> 3, cg = lane & 7;
+            for (int c0 = 0; c0 < dv; c0 += 64) {
+                const int c = c0 + cg * 8;
+                float a8[8];
+#pragma unroll
+                for (int t = 0; t < 8; t++) a8[t] = 0.f;
+                if (c < dv) {
+                    uint4 u[8];
+#pragma unroll
+                    for (int jj = 0; jj < 8; jj++) { const int j = jj * 4 + kg; if (j < jn) u[jj] = *reinterpret_cast<const uint4*>(vb + (int64_t)j * dv + c); }
+#pragma unroll
+                    for (int jj = 0; jj < 8; jj++) {
+                        const int j = jj * 4 + kg;
+                        if (j < jn) {
+                            const float pj = ps[warp * 32 + j];
+                            const __half2* h2 = reinterpret_cast<const __half2*>(&u[jj]);
+#pragma unroll
+                            for (int t = 0; t < 4; t++) { const float2 f = __half22float2(h2[t]); a8[2 * t] += pj * f.x; a8[2 * t + 1] += pj * f.y; }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 8; t++) {       // all 32 lanes shuffle (inactive column groups carry zeros)
+                    a8[t] += __shfl_xor_sync(0xffffffffu, a8[t], 8);
+                    a8[t] += __shfl_xor_sync(0xffffffffu, a8[t], 16);
+                }
+                if (kg == 0 && c < dv) {
+#pragma unroll
+                    for (int t = 0; t < 8; t++) wacc[warp * dv + c + t] = a8[t];
+                }
+            }
+            pv_done = true;
+        }
+    }
+    if (!pv_done)
     for (int c = lane; c < dv; c += 32) {
         float a = 0.f;
 #pragma unroll 8
@@ -742,7 +784,7 @@ int osb_gemm_ld(const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
         if (ws) {
         float* scratch = ws->gemv;
         int* counters = ws->gemv_counters;
-        int gy = (int)max<int64_t>(1, min<int64_t>((K + 15) / 16, (592 + gx - 1) / gx));
+        int gy = (int)max<int64_t>(1, min<int64_t>((K + 15) / 16, (gemv_ctas() + gx - 1) / gx));
         int k_per = (int)((K + gy - 1) / gy);
         gy = (int)((K + k_per - 1) / k_per);
         dim3 grid(gx, gy);
@@ -774,7 +816,7 @@ int osb_gemv_w8(const void* A, const void* Wq, void* C, const void* bias, const 
     const int gx = (int)((N + cols - 1) / cols);
     OsbWorkspace* ws = (gx <= 4096 && (size_t)M * N <= OSB_WS_GEMV_FLOATS) ? osb_workspace(st, OSB_WS_GEMV) : nullptr;
     if (!ws) return (int)cudaErrorNotReady;
-    int gy = (int)max<int64_t>(1, min<int64_t>((K + 15) / 16, (592 + gx - 1) / gx));
+    int gy = (int)max<int64_t>(1, min<int64_t>((K + 15) / 16, (gemv_ctas() + gx - 1) / gx));
     int k_per = (int)((K + gy - 1) / gy);
     gy = (int)((K + k_per - 1) / k_per);
     dim3 grid(gx, gy);
@@ -811,7 +853,7 @@ int osb_gemv_grouped(const void* A, const void* const* B, void* const* C, const 
     cudaStream_t st = (cudaStream_t)stream;
     OsbWorkspace* ws = osb_workspace(st, OSB_WS_GEMV);
     if (!ws) return (int)cudaErrorNotSupported;
-    int gy = (int)max<int64_t>(1, min<int64_t>((K + 15) / 16, (592 + panels - 1) / panels));
+    int gy = (int)max<int64_t>(1, min<int64_t>((K + 15) / 16, (gemv_ctas() + panels - 1) / panels));
     int k_per = (int)((K + gy - 1) / gy);
     gy = (int)((K + k_per - 1) / k_per);
     dim3 grid(panels, gy);

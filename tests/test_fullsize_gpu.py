@@ -111,6 +111,8 @@ def test_yolov8n_fp32(engine_lib, oracle_lib, fuse):
         r = report(got[o], ref[o])
         assert r["rel_to_max"] <= 2e-4, (o, r)
     assert m.stats()["kernel_launches"] > 0
+    # fp32 convolutions run on the tensor cores too (bf16 triple split): the fp32 bar above is met THROUGH that path
+    assert m.stats()["tc_launches"] > 40, m.stats()
 
 
 @pytest.mark.skipif(not os.path.exists(YOLO + "model.txt"), reason="YOLOv8n fixture not staged")
