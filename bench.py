@@ -713,7 +713,7 @@ def measure(w: Workload, args, dist, clocks=None):
         try:
             # (DiskNoCache provider: every run re-reads the blobs and re-creates its operators, so the parity run above is a
             # representative run, not a cold outlier)
-            if ref_s is not None and ref_s >= 45:
+            if ref_s is not None and (ref_s >= 45 or getattr(args, "all_configs", None)):     # --all-configs: the parity run IS the sample (bounded total time)
                 v, sample = 1.0 / ref_s, f"1 full run of the whole graph (the parity run), {ref_s:.1f} s"
             else:
                 v, sample, per = time_reference(d, w, w.inputs(0), 2, 1, budget_s=100.0)
