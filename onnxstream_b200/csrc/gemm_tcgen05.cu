@@ -550,11 +550,13 @@ bool inkernel_reduce()
 void prof_begin(ProfRec& rec, const TcParams& p, cudaStream_t st)
 {
     cudaEventCreate(&rec.a); cudaEventCreate(&rec.b);
-    double M = p.M, N = p.N, Kt = (double)p.K * p.taps, B = p.batch;
+    // the fp32 path (bf16 triple split) runs a 6x longer K: ALGORITHMIC work is the fp32 problem's (K / 6, 4-byte elements)
+    const double kdiv = p.bf16 ? 6.0 : 1.0, es = p.bf16 ? 4.0 : 2.0;
+    double M = p.M, N = p.N, Kt = (double)p.K * p.taps / kdiv, B = p.batch;
     rec.flops = 2.0 * M * N * Kt * B;
     // algorithmic bytes: A once (conv: the input image once), B once, C once (+ residual / bias reads)
-    double a_bytes = (p.bh > 0 ? M * p.K : M * Kt) * 2.0 * B;
-    rec.bytes = a_bytes + N * Kt * 2.0 * (p.bh > 0 ? 1.0 : B) + M * N * 2.0 * B * (p.residual ? 2.0 : 1.0) + (p.bias ? N * 2.0 : 0.0);
+    double a_bytes = (p.bh > 0 ? M * (p.K / kdiv) : M * Kt) * es * B;
+    rec.bytes = a_bytes + N * Kt * es * (p.bh > 0 ? 1.0 : B) + M * N * es * B * (p.residual ? 2.0 : 1.0) + (p.bias ? N * es : 0.0);
     rec.M = p.M; rec.N = p.N; rec.K = p.K; rec.taps = p.taps; rec.batch = p.batch; rec.split = p.split_k; rec.conv = p.bh > 0;
     cudaEventRecord(rec.a, st);
 }
