@@ -261,6 +261,18 @@ def test_planner_fusion_on_cpu(engine_lib, workdir):
     emit.emit_llama_decode(d, emit.LlamaConfig.tiny(), "float32")
     repl = plan_summary(open(d + "model.txt").read(), fp16_arithmetic=False, use_scaled_dp_attn_op=True, library_path=engine_lib)
     assert "SDPA=%d" % emit.LlamaConfig.tiny().layers in repl.splitlines()[-1]
+    # ... and so are the decode-block groups: RMSNorm (7 ops, 2 per layer + the final one), rotary embedding (7 ops, q and k), the grouped
+    # q/k/v projections (3 MatMuls sharing their input), the gated MLP (MatMul, Sigmoid, Mul, MatMul, Mul) and the two bias-free
+    # projections whose residual Add rides in the GEMV epilogue; the groups still partition the op list
+    L = emit.LlamaConfig.tiny().layers
+    suml = dict(kv.split("=") for kv in repl.splitlines()[-1].split()[1:])
+    assert int(suml["RMSNORM"]) == 2 * L + 1 and int(suml["ROPE"]) == 2 * L and int(suml["GEMV_GROUP"]) == L and int(suml["SWIGLU"]) == L and int(suml["LINEAR"]) == 2 * L, suml
+    stepsl = [l.split(" ", 3) for l in repl.splitlines() if l and not l.startswith("#")]
+    assert sum(int(t[1]) for t in stepsl) == int(suml["ops"])
+    assert {t[1] for t in stepsl if t[0] == "GEMV_GROUP"} == {"3"} and {t[1] for t in stepsl if t[0] == "SWIGLU"} == {"5"}
+    assert not ({t[2] for t in stepsl if t[0] == "SINGLE"} & {"Pow", "ReduceMean", "Sqrt", "Slice", "Neg", "Sigmoid"})
+    # a prompt-shaped graph (16 rows per MatMul) keeps plain MatMuls: the GEMV groups are for decode
+    # (rows > 8 is checked on the static shapes of model.txt)
     with pytest.raises(Exception):
         plan_summary("not a model line", library_path=engine_lib)
 
