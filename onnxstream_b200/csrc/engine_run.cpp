@@ -1785,7 +1785,9 @@ void Engine::Impl::op_slice(size_t oi)
         if (x.shape.size() != 1 || axes.size() != 1) fail(op, "int64 slice of rank > 1 is not implemented.");
         int64_t n = (int64_t)x.i64->size(), s = (*starts.i64)[0], e = (*ends.i64)[0], stp = steps_[0];
         if (stp != 1) fail(op, "step != 1 not implemented.");
-        if (s < 0) s += n; if (e < 0) e += n; s = std::max<int64_t>(0, std::min(s, n)); e = std::max<int64_t>(0, std::min(e, n));
+        if (s < 0) s += n;
+        if (e < 0) e += n;
+        s = std::max<int64_t>(0, std::min(s, n)); e = std::max<int64_t>(0, std::min(e, n));
         Tensor r; r.type = DType::i64; r.i64 = std::make_shared<std::vector<int64_t>>(x.i64->begin() + s, x.i64->begin() + std::max(s, e));
         r.shape = { (int64_t)r.i64->size() };
         push(oi, 0, r);
@@ -1800,7 +1802,8 @@ void Engine::Impl::op_slice(size_t oi)
         if (ax < 0 || ax >= (int64_t)x.shape.size()) fail(op, "invalid axes.");
         if (steps_[i] != 1) fail(op, "steps != 1 not implemented.");
         int64_t n = x.shape[ax], s = (*starts.i64)[i], e = (*ends.i64)[i];
-        if (s < 0) s += n; if (e < 0) e += n;
+        if (s < 0) s += n;
+        if (e < 0) e += n;
         s = std::max<int64_t>(0, std::min(s, n)); e = std::max<int64_t>(0, std::min(e, n));
         os[ax] = std::max<int64_t>(0, e - s);
         off += s * istr[ax];
@@ -2687,7 +2690,8 @@ void Engine::Impl::fused_geglu(const Step& s)
         int64_t a = (*ax.i64)[0], n = x.shape.empty() ? 0 : x.shape.back();
         if (a < 0) a += (int64_t)x.shape.size();
         int64_t b = (*st_.i64)[0], e = (*en.i64)[0];
-        if (b < 0) b += n; if (e < 0) e += n;
+        if (b < 0) b += n;
+        if (e < 0) e += n;
         e = std::min(e, n);
         return a == (int64_t)x.shape.size() - 1 && (*sp.i64)[0] == 1 && b == lo && e == hi;
     };
