@@ -345,13 +345,34 @@ def dist_setup():
     return dist
 
 
+def dist_device(dist) -> str:
+    """Tensors of a collective live where the backend runs: NCCL on the GPU, gloo (the CPU tests of this host logic) on the host."""
+    return "cuda" if str(dist.get_backend()).lower() == "nccl" else "cpu"
+
+
 def dist_max(dist, x: float) -> float:
     if dist is None:
         return x
     import torch
-    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    t = torch.tensor([x], dtype=torch.float64, device=dist_device(dist))
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def make_comm(lib, dist):
+    """The engine library's own NCCL communicator (weight all-gather / broadcast), bootstrapped over the torch.distributed group:
+    rank 0 creates the 128-byte ncclUniqueId, every rank receives it (onnxstream_b200/multi.py) and joins."""
+    from onnxstream_b200 import multi
+
+    def make_id() -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        assert lib.osb_comm_unique_id(buf) == 0
+        return bytes(buf.raw)
+
+    uid = multi.exchange_unique_id(dist, RANK, make_id)
+    comm = lib.osb_comm_init(WORLD, RANK, uid)
+    assert comm, "ncclCommInitRank failed"
+    return comm
 
 
 def dist_barrier(dist):
@@ -640,14 +661,7 @@ def measure(w: Workload, args, dist, clocks=None):
     comm = None
     me = Model(ENGINE_LIB, 0, "ram")
     if WORLD > 1:
-        import torch.distributed as tdist
-        ident = ctypes.create_string_buffer(128)
-        if RANK == 0:
-            assert me.lib.osb_comm_unique_id(ident) == 0
-        obj = [bytes(ident.raw)]
-        tdist.broadcast_object_list(obj, src=0)
-        comm = me.lib.osb_comm_init(WORLD, RANK, obj[0])
-        assert comm, "ncclCommInitRank failed"
+        comm = make_comm(me.lib, dist)
     me.close()
     me = make_engine_model(d, w, "ram+nocache", resident=False, graph=False, comm=comm)
     for _ in range(max(2, args.warmup)):

@@ -351,20 +351,35 @@ def test_product_does_not_import_oracle():
 
 def _gloo_worker(rank, world, port, q):
     import torch.distributed as dist
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from onnxstream_b200 import multi
-    ident = multi.exchange_unique_id(dist, rank, lambda: bytes(range(128)))
-    cfg = emit.UNetConfig.tiny(8)
-    inputs = multi.rank_inputs(cfg, rank)
-    agg = multi.aggregate_steps_per_sec(dist, world, steps=10, seconds=1.0 + rank)
-    q.put((rank, ident, float(inputs["sample"].sum()), agg))
+    sys.path.insert(0, ROOT)
+    import bench                                   # reads RANK / WORLD_SIZE from the environment at import
+
+    class StubLib:                                 # the two comm entry points of the engine library, without a GPU
+        def __init__(self):
+            self.joined = None
+
+        def osb_comm_unique_id(self, buf):
+            buf.raw = bytes((7 * i + rank) % 256 for i in range(128))      # only rank 0's id may survive
+            return 0
+
+        def osb_comm_init(self, world_, rank_, uid):
+            self.joined = (world_, rank_, bytes(uid))
+            return 0x1234
+
+    lib = StubLib()
+    comm = bench.make_comm(lib, dist)
+    agg_t = bench.dist_max(dist, 1.0 + rank)       # time = max over ranks
+    arr = bench.dist_bcast_array(dist, np.arange(6, dtype=np.float32).reshape(2, 3) if rank == 0 else None)
+    inputs = bench.make_workload("tiny_unet_fp16").inputs(rank)           # rank r = sample r
+    q.put((rank, comm, lib.joined, agg_t, arr.tolist(), float(inputs["sample"].sum())))
     dist.destroy_process_group()
 
 
 def test_multi_rank_host_logic_gloo():
-    """world_size-2 gloo run of the host-side N>1 logic bench.py uses: unique-id exchange, rank -> sample mapping,
-    max-over-ranks aggregation."""
+    """world_size-2 gloo run of the host-side N > 1 logic of bench.py itself: the NCCL-id exchange that bootstraps the engine's communicator
+    (make_comm -> onnxstream_b200/multi.py), max-over-ranks timing, the reference-output broadcast, rank -> sample mapping."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -372,12 +387,16 @@ def test_multi_rank_host_logic_gloo():
     procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=120) for _ in procs)
+    res = sorted(q.get(timeout=180) for _ in procs)
     for p in procs:
         p.join(60)
-    assert res[0][1] == res[1][1] == bytes(range(128))
-    assert res[0][2] != res[1][2]                       # rank r gets sample seed + r
-    assert res[0][3] == res[1][3] == pytest.approx(2 * 10 / 2.0)   # aggregate = world * steps / max(seconds)
+    rank0_id = bytes((7 * i) % 256 for i in range(128))
+    for r, (rank, comm, joined, agg_t, arr, ssum) in enumerate(res):
+        assert rank == r and comm == 0x1234
+        assert joined == (2, r, rank0_id)                  # every rank joined with rank 0's id
+        assert agg_t == pytest.approx(2.0)                 # max over ranks of (1 + rank)
+        assert arr == [[0.0, 1.0, 2.0], [3.0, 4.0, 5.0]]
+    assert res[0][5] != res[1][5]                           # different samples per rank
 
 
 def test_qu8_restatement_bit_exact(oracle_lib, tmp_path):
